@@ -1,0 +1,164 @@
+"""Lazy (meta-device) model construction: build -> shard -> materialise only the local shards.
+
+Parity: reference `colossalai/lazy/lazy_init.py:134-603` (`LazyTensor` op log + `LazyInitContext.materialize`)
+and `lazy/pretrained.py` (deferred `from_pretrained`).  Design here: parameters are created on the `meta` device
+and a TorchFunctionMode records every in-place initialiser call (`normal_`, `uniform_`, `zero_`, `fill_`, ...)
+on them; parallel layers built from a meta module inherit the op log (initialisers are shape-agnostic), and
+`materialize` allocates the *local shard* on the target device and replays the log under the layer's per-rank RNG.
+This lets a 70B model be constructed on 8 GPUs without ever holding a full weight anywhere.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch.overrides import TorchFunctionMode
+
+__all__ = ["LazyInitContext", "LazyTensor", "copy_lazy_ops", "is_lazy"]
+
+_INPLACE_INIT = {"normal_", "uniform_", "zero_", "fill_", "fill_diagonal_", "copy_", "trunc_normal_", "mul_", "add_",
+                 "div_", "clamp_", "bernoulli_", "random_", "exponential_", "erfinv_", "sub_"}
+
+
+class LazyTensor:
+    """Marker namespace kept for API parity (lazy tensors are plain meta tensors carrying `_lazy_ops`)."""
+
+    @staticmethod
+    def is_lazy(t: torch.Tensor) -> bool:
+        return is_lazy(t)
+
+
+def is_lazy(t: torch.Tensor) -> bool:
+    return isinstance(t, torch.Tensor) and t.device.type == "meta"
+
+
+def copy_lazy_ops(src: Optional[torch.Tensor], dst: Optional[torch.Tensor]) -> None:
+    if src is not None and dst is not None and hasattr(src, "_lazy_ops"):
+        dst._lazy_ops = list(src._lazy_ops)
+
+
+class _Recorder(TorchFunctionMode):
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        out = func(*args, **kwargs)
+        name = getattr(func, "__name__", "")
+        if name in _INPLACE_INIT and args and isinstance(args[0], torch.Tensor) and args[0].device.type == "meta":
+            t = args[0]
+            rest = tuple(a for a in args[1:])
+            if any(isinstance(a, torch.Tensor) and a.device.type == "meta" for a in rest):
+                return out  # cannot replay ops that depend on other lazy tensors
+            ops = getattr(t, "_lazy_ops", None)
+            if ops is None:
+                ops = []
+                try:
+                    t._lazy_ops = ops
+                except Exception:
+                    return out
+            ops.append((name, rest, dict(kwargs)))
+        return out
+
+
+class LazyInitContext:
+    """`with LazyInitContext(): model = Model(cfg)` then `ShardFormer.optimize` / `booster.boost` materialises."""
+
+    _replaced = False
+
+    def __init__(self, tensor_cls=None, default_device: Optional[torch.device] = None) -> None:
+        self.default_device = default_device
+        self._dev_ctx = None
+        self._rec = None
+
+    def __enter__(self):
+        self._dev_ctx = torch.device("meta")
+        self._dev_ctx.__enter__()
+        self._rec = _Recorder()
+        self._rec.__enter__()
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self._rec.__exit__(exc_type, exc, tb)
+        self._dev_ctx.__exit__(exc_type, exc, tb)
+
+    # ------------------------------------------------------------------ materialise
+    @staticmethod
+    def _default_fill(name: str, t: torch.Tensor) -> None:
+        if t.dim() >= 2:
+            nn.init.normal_(t, std=0.02)
+        elif "norm" in name and name.endswith("weight"):
+            nn.init.ones_(t)
+        else:
+            nn.init.zeros_(t)
+
+    @staticmethod
+    def _replay(name: str, meta_t: torch.Tensor, real: torch.Tensor) -> None:
+        ops = getattr(meta_t, "_lazy_ops", None)
+        if not ops:
+            LazyInitContext._default_fill(name, real)
+            return
+        with torch.no_grad():
+            for fn, args, kwargs in ops:
+                if fn == "trunc_normal_":
+                    nn.init.trunc_normal_(real, *args, **kwargs)
+                else:
+                    getattr(real, fn)(*args, **kwargs)
+
+    @staticmethod
+    def materialize(module: nn.Module, device: Optional[torch.device] = None, verbose: bool = False) -> nn.Module:
+        """Allocate every meta parameter/buffer of `module` on `device` and replay its initialiser log."""
+        if device is None:
+            from ..accelerator import get_accelerator
+
+            device = get_accelerator().get_current_device()
+        memo = {}
+        n = 0
+        for mod_name, mod in module.named_modules():
+            rnd = getattr(mod, "randomizer", None)
+            for pname, p in list(mod._parameters.items()):
+                if p is None or p.device.type != "meta":
+                    continue
+                if id(p) in memo:
+                    mod._parameters[pname] = memo[id(p)]
+                    continue
+                real = torch.empty(p.shape, dtype=p.dtype, device=device)
+                full = f"{mod_name}.{pname}" if mod_name else pname
+                if rnd is not None:
+                    with rnd.fork_rng(enable_cpu=torch.device(device).type == "cpu"):
+                        LazyInitContext._replay(full, p, real)
+                else:
+                    LazyInitContext._replay(full, p, real)
+                newp = nn.Parameter(real, requires_grad=p.requires_grad)
+                for attr, val in vars(p).items():
+                    if attr in ("_lazy_ops",):
+                        continue
+                    try:
+                        setattr(newp, attr, val)
+                    except Exception:
+                        pass
+                # re-install metadata-preserving detach/clone on the real tensor
+                for a in ("_old_detach", "_old_clone", "detach", "clone", "_pad_old_detach", "_pad_old_clone"):
+                    if a in vars(newp):
+                        delattr(newp, a)
+                if hasattr(newp, "dist_shard") or hasattr(newp, "shard_fn") or hasattr(newp, "dist_layout"):
+                    from ..tensor.d_tensor.api import _hijack_detach_and_clone
+
+                    _hijack_detach_and_clone(newp)
+                if hasattr(newp, "_padding_dim"):
+                    from ..tensor.padded_tensor import _hijack
+
+                    _hijack(newp)
+                zp = getattr(mod, "_zero_padding", None)
+                if pname == "weight" and callable(zp):
+                    zp(newp.data)
+                memo[id(p)] = newp
+                mod._parameters[pname] = newp
+                n += 1
+            for bname, b in list(mod._buffers.items()):
+                if b is None or b.device.type != "meta":
+                    continue
+                real = torch.zeros(b.shape, dtype=b.dtype, device=device)
+                LazyInitContext._replay(bname, b, real) if getattr(b, "_lazy_ops", None) else None
+                mod._buffers[bname] = real
+        if verbose:
+            print(f"LazyInitContext.materialize: allocated {n} parameters on {device}")
+        return module

@@ -1,0 +1,39 @@
+"""Model zoo.  Every family is a thin specialisation of one parallel-aware backbone (`transformer.py`)."""
+from .config import MODEL_ZOO, ModelConfig, MoEConfig, get_config
+from .heads import (
+    TransformerBackboneModel,
+    TransformerForMaskedLM,
+    TransformerForMultipleChoice,
+    TransformerForQuestionAnswering,
+    TransformerForSequenceClassification,
+    TransformerForTokenClassification,
+)
+from .transformer import Attention, DecoderLayer, MLP, SeqMeta, TransformerLMHeadModel, TransformerModel
+from .llama import LlamaForCausalLM, LlamaForSequenceClassification, LlamaModel
+from .gpt2 import GPT2LMHeadModel, GPT2Model
+from .mixtral import MixtralForCausalLM
+from .deepseek import DeepseekForCausalLM
+
+
+def build_model(name_or_config, **overrides):
+    """`build_model("llama3-8b")` or `build_model(ModelConfig(...))` -> causal LM of the right family class."""
+    cfg = get_config(name_or_config, **overrides) if isinstance(name_or_config, str) else name_or_config
+    import importlib
+
+    fam = {"chatglm": ("chatglm", "ChatGLMForConditionalGeneration"), "gpt2": ("gpt2", "GPT2LMHeadModel"),
+           "bert": ("bert", "BertForMaskedLM"), "command": ("command", "CohereForCausalLM"),
+           "deepseek": ("deepseek", "DeepseekForCausalLM"), "deepseek_v3": ("deepseek_v3", "DeepseekV3ForCausalLM"),
+           "gptj": ("gptj", "GPTJForCausalLM"), "opt": ("opt", "OPTForCausalLM")}
+    mod, cls = fam.get(cfg.model_type, (cfg.model_type, cfg.model_type.capitalize() + "ForCausalLM"))
+    try:
+        return getattr(importlib.import_module(f"colossalai_b200.models.{mod}"), cls)(cfg)
+    except (ImportError, AttributeError):
+        return TransformerLMHeadModel(cfg)
+
+
+__all__ = ["MODEL_ZOO", "ModelConfig", "MoEConfig", "get_config", "build_model", "TransformerBackboneModel",
+           "TransformerForMaskedLM", "TransformerForMultipleChoice", "TransformerForQuestionAnswering",
+           "TransformerForSequenceClassification", "TransformerForTokenClassification", "Attention", "DecoderLayer",
+           "MLP", "SeqMeta", "TransformerLMHeadModel", "TransformerModel", "LlamaForCausalLM",
+           "LlamaForSequenceClassification", "LlamaModel", "GPT2LMHeadModel", "GPT2Model", "MixtralForCausalLM",
+           "DeepseekForCausalLM"]

@@ -1,0 +1,37 @@
+"""ChatGLM2/3 (RMSNorm, SwiGLU, multi-query groups, interleaved half-rotary RoPE).
+
+All classes share the generic parallel-aware backbone (`models/transformer.py`); this module pins the family's
+config defaults and exposes the HF-named entry points.  Parity: reference `colossalai/shardformer/policies/chatglm2.py; modeling/chatglm2.py`.
+"""
+from __future__ import annotations
+
+from .config import ModelConfig, get_config
+from .heads import (TransformerBackboneModel, TransformerForMaskedLM, TransformerForMultipleChoice,
+                    TransformerForQuestionAnswering, TransformerForSequenceClassification,
+                    TransformerForTokenClassification)
+from .transformer import TransformerLMHeadModel
+
+DEFAULT_PRESET = "chatglm2-6b"
+FAMILY_DEFAULTS = {}
+
+
+def default_config(**overrides) -> ModelConfig:
+    """The family's reference-size config (override any field, e.g. `num_hidden_layers=2`)."""
+    return get_config(DEFAULT_PRESET, **overrides)
+
+
+class ChatGLMModel(TransformerBackboneModel):
+    """ChatGLMModel — `TransformerBackboneModel` specialised for the chatglm family."""
+
+    def __init__(self, config: ModelConfig = None, **kw) -> None:
+        super().__init__(config if config is not None else default_config(), **kw)
+
+
+class ChatGLMForConditionalGeneration(TransformerLMHeadModel):
+    """ChatGLMForConditionalGeneration — `TransformerLMHeadModel` specialised for the chatglm family."""
+
+    def __init__(self, config: ModelConfig = None, **kw) -> None:
+        super().__init__(config if config is not None else default_config(), **kw)
+
+
+__all__ = ['default_config', 'ChatGLMModel', 'ChatGLMForConditionalGeneration']

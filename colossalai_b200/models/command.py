@@ -1,0 +1,37 @@
+"""Cohere Command-R (parallel block, LayerNorm w/o bias, logit scale, tied embeddings).
+
+All classes share the generic parallel-aware backbone (`models/transformer.py`); this module pins the family's
+config defaults and exposes the HF-named entry points.  Parity: reference `colossalai/shardformer/policies/command.py; modeling/command.py`.
+"""
+from __future__ import annotations
+
+from .config import ModelConfig, get_config
+from .heads import (TransformerBackboneModel, TransformerForMaskedLM, TransformerForMultipleChoice,
+                    TransformerForQuestionAnswering, TransformerForSequenceClassification,
+                    TransformerForTokenClassification)
+from .transformer import TransformerLMHeadModel
+
+DEFAULT_PRESET = "command-r"
+FAMILY_DEFAULTS = {}
+
+
+def default_config(**overrides) -> ModelConfig:
+    """The family's reference-size config (override any field, e.g. `num_hidden_layers=2`)."""
+    return get_config(DEFAULT_PRESET, **overrides)
+
+
+class CohereModel(TransformerBackboneModel):
+    """CohereModel — `TransformerBackboneModel` specialised for the command family."""
+
+    def __init__(self, config: ModelConfig = None, **kw) -> None:
+        super().__init__(config if config is not None else default_config(), **kw)
+
+
+class CohereForCausalLM(TransformerLMHeadModel):
+    """CohereForCausalLM — `TransformerLMHeadModel` specialised for the command family."""
+
+    def __init__(self, config: ModelConfig = None, **kw) -> None:
+        super().__init__(config if config is not None else default_config(), **kw)
+
+
+__all__ = ['default_config', 'CohereModel', 'CohereForCausalLM']

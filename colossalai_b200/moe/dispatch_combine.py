@@ -1,0 +1,62 @@
+"""Expert-parallel dispatch -> grouped experts -> combine.
+
+Parity: reference EP blocks (`shardformer/modeling/mixtral.py:123-208`): sort tokens by expert, exchange sizes,
+uneven all-to-all, local experts, all-to-all back, un-sort, weighted sum.  Baseline (`nccl`) backend below keeps
+that algorithm (dropless) but exchanges sizes as ONE device tensor and grouped-GEMMs the local experts.  The
+`fused` backend (parallel/fused.py, kernel/csrc/moe.cu) removes the host sync by writing rows straight into
+per-expert symmetric receive buffers over NVLink.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..parallel import comm
+from ._operation import AllToAllUneven
+
+__all__ = ["moe_forward"]
+
+
+def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, experts, num_experts: int,
+                ep_group: Optional[dist.ProcessGroup]) -> torch.Tensor:
+    """x [T, H]; topk_w [T, k] fp32; topk_idx [T, k] -> [T, H]."""
+    T, H = x.shape
+    k = topk_idx.shape[1]
+    ep = comm.group_size(ep_group)
+    n_local = num_experts // ep
+    flat_idx = topk_idx.reshape(-1)                                    # [T*k]
+    order = torch.argsort(flat_idx, stable=True)                       # rows grouped by global expert id
+    token_of = order // k
+    xs = x.index_select(0, token_of)                                   # [T*k, H]  (autograd: index_add in bwd)
+    counts = torch.bincount(flat_idx, minlength=num_experts)           # rows per global expert
+    if ep > 1:
+        # exchange per-expert counts: recv_counts[src, e_local]
+        recv_counts = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts, counts, group=ep_group)
+        send_splits = counts.view(ep, n_local).sum(1).tolist()         # host sync (baseline backend)
+        recv_counts_2d = recv_counts.view(ep, n_local)
+        recv_splits = recv_counts_2d.sum(1).tolist()
+        recv = AllToAllUneven.apply(xs, send_splits, recv_splits, ep_group)
+        # received rows are grouped by (src rank, local expert): regroup by local expert
+        rc = recv_counts_2d
+        n_rows = int(sum(recv_splits))
+        seg_expert = torch.arange(n_local, device=x.device).repeat(ep)             # expert id of each segment
+        seg_len = rc.reshape(-1)
+        row_expert = torch.repeat_interleave(seg_expert, seg_len, output_size=n_rows)
+        perm = torch.argsort(row_expert, stable=True)
+        grouped = recv.index_select(0, perm)
+        local_counts = rc.sum(0)
+        y = experts(grouped, local_counts)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(n_rows, device=x.device)
+        y = y.index_select(0, inv)
+        ys = AllToAllUneven.apply(y, recv_splits, send_splits, ep_group)
+    else:
+        ys = experts(xs, counts)
+    # weighted combine back to token order
+    wsorted = topk_w.reshape(-1).index_select(0, order).to(ys.dtype).unsqueeze(-1)
+    out = torch.zeros(T, H, dtype=ys.dtype, device=x.device)
+    out = out.index_add(0, token_of, ys * wsorted)
+    return out

@@ -1,0 +1,92 @@
+"""Policy registry + auto lookup.  Parity: reference `colossalai/shardformer/policies/auto_policy.py`
+(`_POLICY_LIST`, `get_autopolicy`, `import_policy`)."""
+from __future__ import annotations
+
+import importlib
+from dataclasses import dataclass
+from typing import Dict
+
+import torch.nn as nn
+
+from .base_policy import Policy
+
+__all__ = ["PolicyLocation", "get_autopolicy", "import_policy", "register_policy", "_POLICY_LIST"]
+
+
+@dataclass
+class PolicyLocation:
+    file_name: str
+    class_name: str
+
+
+_P = "colossalai_b200.shardformer.policies"
+
+# fully-qualified model class name -> policy location.  All families of our zoo share one backbone, hence one
+# policy implementation with family-specific subclasses kept for discoverability / custom overrides.
+_POLICY_LIST: Dict[str, PolicyLocation] = {}
+
+
+def register_policy(qualname: str, file_name: str, class_name: str) -> None:
+    _POLICY_LIST[qualname] = PolicyLocation(file_name, class_name)
+
+
+for _cls in ("TransformerLMHeadModel", "TransformerModel"):
+    register_policy(f"colossalai_b200.models.transformer.{_cls}", "transformer", "TransformerForCausalLMPolicy")
+
+_FAMILIES = {
+    "llama": ["LlamaModel", "LlamaForCausalLM", "LlamaForSequenceClassification"],
+    "mistral": ["MistralModel", "MistralForCausalLM", "MistralForSequenceClassification"],
+    "qwen2": ["Qwen2Model", "Qwen2ForCausalLM", "Qwen2ForSequenceClassification"],
+    "qwen3": ["Qwen3Model", "Qwen3ForCausalLM", "Qwen3ForSequenceClassification"],
+    "gpt2": ["GPT2Model", "GPT2LMHeadModel", "GPT2DoubleHeadsModel", "GPT2ForQuestionAnswering",
+             "GPT2ForTokenClassification", "GPT2ForSequenceClassification"],
+    "gptj": ["GPTJModel", "GPTJForCausalLM", "GPTJForSequenceClassification", "GPTJForQuestionAnswering"],
+    "opt": ["OPTModel", "OPTForCausalLM", "OPTForSequenceClassification", "OPTForQuestionAnswering"],
+    "bloom": ["BloomModel", "BloomForCausalLM", "BloomForSequenceClassification", "BloomForTokenClassification",
+              "BloomForQuestionAnswering"],
+    "falcon": ["FalconModel", "FalconForCausalLM", "FalconForSequenceClassification",
+               "FalconForTokenClassification", "FalconForQuestionAnswering"],
+    "chatglm": ["ChatGLMModel", "ChatGLMForConditionalGeneration"],
+    "command": ["CohereModel", "CohereForCausalLM"],
+    "mixtral": ["MixtralModel", "MixtralForCausalLM"],
+    "deepseek": ["DeepseekModel", "DeepseekForCausalLM"],
+    "deepseek_v3": ["DeepseekV3Model", "DeepseekV3ForCausalLM"],
+    "bert": ["BertModel", "BertForPreTraining", "BertLMHeadModel", "BertForMaskedLM",
+             "BertForSequenceClassification", "BertForTokenClassification", "BertForNextSentencePrediction",
+             "BertForMultipleChoice", "BertForQuestionAnswering"],
+    "vit": ["ViTModel", "ViTForImageClassification", "ViTForMaskedImageModeling"],
+    "t5": ["T5Model", "T5ForConditionalGeneration", "T5EncoderModel", "T5ForTokenClassification"],
+    "whisper": ["WhisperModel", "WhisperForConditionalGeneration", "WhisperForAudioClassification"],
+    "blip2": ["Blip2Model", "Blip2ForConditionalGeneration"],
+    "sam": ["SamModel"],
+}
+for _fam, _classes in _FAMILIES.items():
+    for _c in _classes:
+        register_policy(f"colossalai_b200.models.{_fam}.{_c}", _fam, f"{_c}Policy")
+
+
+def import_policy(loc: PolicyLocation) -> type:
+    module = importlib.import_module(f"{_P}.{loc.file_name}")
+    return getattr(module, loc.class_name)
+
+
+def _fullname(obj) -> str:
+    klass = obj.__class__
+    module = klass.__module__
+    return klass.__qualname__ if module == "builtins" else module + "." + klass.__qualname__
+
+
+def get_autopolicy(model: nn.Module) -> Policy:
+    name = _fullname(model)
+    loc = _POLICY_LIST.get(name)
+    if loc is None:
+        # subclasses of our generic models inherit the generic policy
+        for klass in model.__class__.__mro__:
+            key = klass.__module__ + "." + klass.__qualname__
+            if key in _POLICY_LIST:
+                loc = _POLICY_LIST[key]
+                break
+    if loc is None:
+        raise NotImplementedError(
+            f"auto policy for {name} is not implemented; supported: {sorted(_POLICY_LIST.keys())}")
+    return import_policy(loc)()
