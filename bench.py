@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Flagship benchmark: Llama-3-8B training step (fwd + bwd + AdamW), tokens/s over the whole job.
+
+    python bench.py --gpus N --steps K --warmup W                 # our framework (N=1 runs in-process)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                    # N > 1, one rank per GPU
+    python bench.py --impl reference ...                          # the UNMODIFIED reference from baseline/_ref
+
+Metric / config follow BASELINE.json: tokens/sec (whole box, device-timed, max over ranks), Llama-3-8B, bf16,
+synthetic tokens, random-init weights, TP = N (+ Megatron-style sequence parallelism) over NVSwitch, weak scaling
+(one 4096-token sequence per GPU per step).  Parity: reference `examples/language/llama/benchmark.py`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASELINE_TOKENS_PER_S_8GPU = 25.83 * 4096      # 25.83 samples/s x 4096 tokens on 8x B200 (7B)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--model", default=os.environ.get("CB200_BENCH_MODEL", "llama3-8b"))
+    p.add_argument("--seq", type=int, default=4096)
+    p.add_argument("--mbs", type=int, default=1, help="sequences per GPU per step (weak scaling)")
+    p.add_argument("--accum", type=int, default=1, help="gradient accumulation micro-steps per optimizer step")
+    p.add_argument("--tp", type=int, default=0, help="tensor parallel size (default: = gpus)")
+    p.add_argument("--pp", type=int, default=1)
+    p.add_argument("--sp-mode", default="split_gather")
+    p.add_argument("--zero", type=int, default=0)
+    p.add_argument("--comm-backend", default=os.environ.get("CB200_COMM_BACKEND", "auto"))
+    p.add_argument("--grad-ckpt", type=float, default=float(os.environ.get("CB200_GRAD_CKPT", "0")))
+    p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the run invalid)")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0) -> None:
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _init_dist(args):
+    import torch
+    import colossalai_b200
+
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        colossalai_b200.launch_from_torch(verbose=False)
+    else:
+        from colossalai_b200.testing import free_port
+
+        colossalai_b200.launch(0, 1, "127.0.0.1", free_port(), verbose=False)
+    return torch.distributed.get_rank(), torch.distributed.get_world_size()
+
+
+def run_ours(args) -> dict:
+    import torch
+    import torch.distributed as dist
+
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.kernel import launch_counter
+    from colossalai_b200.lazy import LazyInitContext
+    from colossalai_b200.models import build_model, get_config
+    from colossalai_b200.nn.optimizer import FusedAdam
+    from colossalai_b200.shardformer import GradientCheckpointConfig
+
+    rank, world = _init_dist(args)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tp = args.tp or world
+    pp = args.pp
+    assert world % (tp * pp) == 0
+    dp = world // (tp * pp)
+    cfg = get_config(args.model)
+    if args.layers:
+        cfg = cfg.replace(num_hidden_layers=args.layers)
+    comm_backend = args.comm_backend
+    if comm_backend == "auto":
+        comm_backend = "nccl"
+        if tp > 1:
+            try:
+                from colossalai_b200.parallel import fused
+
+                comm_backend = "fused" if fused.build_available() else "nccl"
+            except Exception:
+                comm_backend = "nccl"
+    sp_on = tp > 1 and args.sp_mode in ("split_gather", "ring")
+    plugin = HybridParallelPlugin(
+        tp_size=tp, pp_size=pp, precision="bf16", zero_stage=args.zero,
+        enable_sequence_parallelism=sp_on, sequence_parallelism_mode=args.sp_mode if sp_on else None,
+        enable_fused_normalization=True, enable_flash_attention=True, parallel_output=True, max_norm=1.0,
+        num_microbatches=(args.mbs * args.accum if pp > 1 else None),
+        gradient_checkpoint_config=GradientCheckpointConfig(args.grad_ckpt) if args.grad_ckpt > 0 else None,
+        comm_backend=comm_backend)
+    booster = Booster(plugin=plugin)
+    torch.manual_seed(1234)
+    with LazyInitContext():
+        model = build_model(cfg)
+    optimizer = FusedAdam(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1, adamw_mode=True)
+    model, optimizer, _, _, _ = booster.boost(model, optimizer)
+    model.train()
+
+    # ---- data: the TP/SP group consumes `tp * mbs` sequences per micro-step (one 4096-token sequence per GPU)
+    B = args.mbs * tp
+    S = args.seq
+    global_batch = B * dp * args.accum
+    tokens_per_step = global_batch * S
+    gen = torch.Generator().manual_seed(4321 + plugin.pg_mesh.axis_rank("dp"))
+    n_bufs = 4
+    host_ids = [torch.randint(0, cfg.vocab_size, (args.accum, B, S), generator=gen, dtype=torch.int64).pin_memory()
+                for _ in range(n_bufs)]
+    dev_ids = [h.to(dev) for h in host_ids]
+    h2d_bytes = host_ids[0].numel() * host_ids[0].element_size()
+
+    def step(ids_dev) -> torch.Tensor:
+        loss_acc = None
+        for a in range(args.accum):
+            ids = ids_dev[a]
+            out = model(input_ids=ids, labels=ids, return_logits=False)
+            loss = out["loss"] / args.accum
+            last = a == args.accum - 1
+            if last:
+                booster.backward(loss, optimizer)
+            else:
+                with model.no_sync():
+                    optimizer.backward(loss)
+            loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
+        optimizer.step()
+        optimizer.zero_grad()
+        return loss_acc
+
+    def timed(n_steps: int, e2e: bool):
+        dist.barrier()
+        torch.cuda.synchronize()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s_ev.record()
+        last_loss = None
+        for i in range(n_steps):
+            if e2e:
+                ids = host_ids[i % n_bufs].to(dev, non_blocking=True)     # pinned host -> device, every step
+                last_loss = step(ids).item()                               # device -> host read of the result
+            else:
+                last_loss = step(dev_ids[i % n_bufs])
+        e_ev.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = s_ev.elapsed_time(e_ev)
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
+        return t[0].item(), t[1].item(), (last_loss if not torch.is_tensor(last_loss) else last_loss.item())
+
+    for i in range(args.warmup):
+        step(dev_ids[i % n_bufs])
+    torch.cuda.synchronize()
+    launch_counter.reset()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    ms, wall_ms, loss_val = timed(args.steps, e2e=False)
+    launches = launch_counter.count
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e = None
+    if not args.no_e2e:
+        ms_e, wall_e, _ = timed(args.steps, e2e=True)
+        e2e = {"value": tokens_per_step * args.steps / (max(ms_e, wall_e) / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": max(ms_e, wall_e) / args.steps}
+    value = tokens_per_step * args.steps / (ms / 1e3)
+    peak_mem = torch.cuda.max_memory_allocated() / 2**20
+    par = f"tp{tp}" + ("+sp(" + args.sp_mode + ")" if sp_on else "") + (f"xpp{pp}" if pp > 1 else "") + \
+        (f"xdp{dp}" if dp > 1 else "") + (f"+zero{args.zero}" if args.zero else "")
+    result = {
+        "metric": "tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B training step (fwd+bwd+AdamW)",
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / (BASELINE_TOKENS_PER_S_8GPU * world / 8.0), "dtype": "bf16",
+        "data": "synthetic tokens, random-init weights", "impl": "ours",
+        "config": {"model": args.model + (f"[layers={args.layers} DEBUG-INVALID]" if args.layers else ""),
+                   "global_batch": global_batch, "seq_len": S, "parallelism": par, "comm_backend": comm_backend,
+                   "optimizer": "AdamW (fp32 master+moments, fused single-launch, clip 1.0)",
+                   "grad_accum": args.accum, "grad_ckpt_ratio": args.grad_ckpt,
+                   "l2": "working set per step (>= 2 GB weights+activations per layer) >> 126 MB L2; no explicit flush",
+                   "baseline_note": "vs_baseline = value / (published 8xB200 7B number scaled to N GPUs)"},
+        "clocks": clocks, "gpu_launches": launches, "loss": loss_val, "peak_mem_mib": peak_mem,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "tflops_per_gpu": cfg.flops_per_token(S) * tokens_per_step / (ms / args.steps / 1e3) / 1e12 / world,
+    }
+    if e2e is not None:
+        result["e2e"] = e2e
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    dist.barrier()
+    colossalai_b200.initialize.shutdown()
+    return result
+
+
+def run_reference(args) -> None:
+    from baseline.reference_arm import run_reference_arm
+
+    run_reference_arm(args)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

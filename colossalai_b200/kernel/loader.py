@@ -34,7 +34,7 @@ NVCC_FLAGS = [
     "-U__CUDA_NO_HALF_OPERATORS__", "-U__CUDA_NO_HALF_CONVERSIONS__", "-U__CUDA_NO_BFLOAT16_CONVERSIONS__",
     "-U__CUDA_NO_HALF2_OPERATORS__",
 ]
-CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-march=native", "-mavx2", "-mfma"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffast-math", "-fno-finite-math-only"]
 
 # library name -> (sources, kind)
 LIBS: Dict[str, dict] = {
