@@ -23,6 +23,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 BASELINE_TOKENS_PER_S_8GPU = 25.83 * 4096      # 25.83 samples/s x 4096 tokens on 8x B200 (7B)
 

@@ -118,11 +118,7 @@ class MixedPrecisionOptimizer(OptimizerWrapper):
             return torch.zeros(1, device=dev)
         grads = [p.grad for p in params]
         if use_native(grads[0]) and all(g.is_contiguous() for g in grads):
-            key = hash(mt.TensorTable.key_of(grads))
-            tbl = self._tables.get(("n", key))
-            if tbl is None:
-                tbl = self._tables[("n", key)] = mt.TensorTable(grads, grads)
-            return mt.norm_sq(tbl, "grad")[0]
+            return mt.norm_sq(mt.TensorTable(grads, grads), "grad")[0]
         return torch.stack([g.float().pow(2).sum() for g in grads]).sum().reshape(1)
 
     def _compute_grad_norm_sq(self, params: List[Parameter]) -> Tensor:
@@ -156,12 +152,8 @@ class MixedPrecisionOptimizer(OptimizerWrapper):
             if not ps:
                 continue
             group["step"] = group.get("step", 0) + 1
-            key = (gi, hash(mt.TensorTable.key_of(ps, gs, lps)))
-            tbl = self._tables.get(key)
-            if tbl is None:
-                for k in [k for k in self._tables if isinstance(k, tuple) and k[0] == gi]:
-                    del self._tables[k]
-                tbl = self._tables[key] = mt.TensorTable(ps, gs, ms, vs, lps)
+            # gradients are fresh allocations every step -> the descriptor table is rebuilt (cheap: one small H2D)
+            tbl = mt.TensorTable(ps, gs, ms, vs, lps)
             beta1, beta2 = group["betas"]
             mt.adam(tbl, group["lr"], beta1, beta2, group["eps"], group["weight_decay"], group["step"], adamw,
                     group.get("bias_correction", True), inv_scale=1.0 / div_scale, inv_scale_dev=clip_coef_dev)

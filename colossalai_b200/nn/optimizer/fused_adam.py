@@ -61,7 +61,7 @@ class FusedAdam(torch.optim.Optimizer):
         if tbl is None:
             if len(self._tables) > 16:
                 self._tables.clear()
-            tbl = mt.TensorTable(params, grads, ms, vs)
+            tbl = mt.TensorTable(params, grads, ms, vs, keepalive=True)
             self._tables[key] = tbl
         return tbl
 

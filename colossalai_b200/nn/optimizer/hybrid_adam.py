@@ -57,7 +57,7 @@ class HybridAdam(CPUAdam):
                     if tbl is None:
                         if len(self._tables) > 16:
                             self._tables.clear()
-                        tbl = self._tables[key] = mt.TensorTable(gp, gg, gm, gv)
+                        tbl = self._tables[key] = mt.TensorTable(gp, gg, gm, gv, keepalive=True)
                     mt.adam(tbl, group["lr"], beta1, beta2, group["eps"], group["weight_decay"], group_step,
                             self.adamw_mode, group["bias_correction"], inv_scale)
                 else:

@@ -35,7 +35,7 @@ class TensorTable:
 
     def __init__(self, p: Sequence[torch.Tensor], g: Optional[Sequence[torch.Tensor]] = None,
                  m: Optional[Sequence[torch.Tensor]] = None, v: Optional[Sequence[torch.Tensor]] = None,
-                 lp: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
+                 lp: Optional[Sequence[Optional[torch.Tensor]]] = None, keepalive: bool = False) -> None:
         _get_lib()
         n = len(p)
         rows = []
@@ -60,7 +60,9 @@ class TensorTable:
         self.device = p[0].device if n else torch.device("cuda")
         self.table = torch.tensor(rows, dtype=torch.int64).to(self.device) if n else None
         self._partial = None
-        self._keepalive = (list(p), g, m, v, lp)
+        # NOTE: the table stores raw pointers.  Callers own the tensors' lifetime (kernels are stream-ordered, so a
+        # tensor may be released right after the launch); `keepalive=True` pins them for cached tables.
+        self._keepalive = (list(p), g, m, v, lp) if keepalive else None
 
     @staticmethod
     def key_of(*lists) -> tuple:
