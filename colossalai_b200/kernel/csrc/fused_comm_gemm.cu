@@ -1,0 +1,562 @@
+// Fused compute + collective kernels for tensor / sequence parallel linears over NVLink peer memory (sm_100a).
+//
+//   cb_ag_gemm   : Y[T, N]   = all_gather(x_local)[T, K] * B        (col-linear fwd under SP, and dX = AG(dY) * W)
+//   cb_gemm_rs   : y_local   = reduce_scatter(A[T, K] * B)          (row-linear fwd under SP, and dX of col-linear)
+//   cb_all_gather: X_full    = all_gather(x_local)                   (stand-alone pull, used for wgrad re-gather)
+//
+// One persistent launch does both jobs; the transfer overlaps the math tile by tile:
+//   * AG+GEMM: a few "copy CTAs" pull the peers' row chunks over NVLink (16-byte P2P loads from the peers' symmetric
+//     buffers) into the local gathered buffer, publishing one ready-flag per 128-row block; the remaining CTAs run the
+//     tcgen05/TMEM GEMM main loop and their TMA producer only waits for the flag of the A row-block it is about to load.
+//     Tiles are ordered local chunk first, then chunks in arrival order, so compute never idles while data is in flight.
+//   * GEMM+RS: every CTA runs the tcgen05 GEMM, writing bf16 partial tiles into a local symmetric buffer, chunk by
+//     chunk starting with the chunk owned by rank+1; when a rank finishes a chunk it signals the owner; the owner reduces
+//     its chunk straight out of the NVSwitch with multimem.ld_reduce (in-switch fp32 accumulation, falls back to P2P loads
+//     + adds when no multicast mapping exists) while other ranks are still computing later chunks.
+//   * cross-GPU ordering uses release/acquire at .sys scope on 32-bit epoch flags that live in symmetric memory; data
+//     written through the generic proxy and later read by TMA is fenced with fence.proxy.async on both sides.
+//
+// These replace the reference's `dist.all_gather` + `F.linear` / `F.linear` + `dist.reduce_scatter` pairs
+// (shardformer/layer/_operation.py:562-566, 737-751) and its python ring variants (`_ring_as_gather`,
+// `_ring_as_reducescatter`): no NCCL call on these paths.
+#include "common.cuh"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;      // warps 0..5 = GEMM roles, warps 6..7 = NVLink pull (AG) / extra reduce lanes (RS)
+constexpr int COPY_WARPS = 2;
+constexpr int COPY_SEG = 8;           // a 128-row block is pulled as 8 segments of 16 rows by different warps
+constexpr int GROUP_M = 8;
+constexpr int MAX_RANKS = 16;
+
+// flag slots (uint32) inside every rank's symmetric flag page
+constexpr int SLOT_IN_READY = 0;                 // [MAX_RANKS]  peer p wrote: "my input buffer holds epoch e"
+constexpr int SLOT_PULL_DONE = MAX_RANKS;        // [MAX_RANKS]  peer p wrote: "I finished reading your buffer (epoch e)"
+constexpr int SLOT_CHUNK_DONE = 2 * MAX_RANKS;   // [MAX_RANKS]  peer p wrote: "my partial of YOUR chunk is complete"
+constexpr int SLOT_LOCAL = 3 * MAX_RANKS;        // local scratch counters (never written by peers)
+
+template <int BLOCK_N> struct Cfg {
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N >= 512 ? 512 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct CommParams {
+  int rank, world;
+  uint32_t epoch;
+  int n_copy_ctas;                 // (unused by the fused kernels; CTAs of the stand-alone all-gather)
+  int rows_per_chunk;              // T / world
+  const void* peer_in[MAX_RANKS];  // AG: peers' symmetric input buffers [rows_per_chunk, ld_in]
+  uint32_t* peer_flags[MAX_RANKS]; // every rank's flag page (index = rank)
+  void* gathered;                  // AG: local [T, ld_in] gathered buffer (TMA source of A)
+  int ld_in;                       // elements per row of the gathered / input buffers
+  uint32_t* ready;                 // AG: local per-row-block ready flags [T / 128]
+  uint32_t* block_counter;         // AG: local per-row-block segment arrival counters [T / 128]
+  // RS
+  const void* peer_part[MAX_RANKS];  // peers' symmetric partial buffers [T, ldc]
+  const void* mc_part;               // multicast address of the partial buffer (or null)
+  void* out;                         // RS: local output [rows_per_chunk, ld_out]
+  int ld_out;
+  uint32_t* chunk_counter;           // RS: local per-chunk arrival counters [world]
+  int out_dtype;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int ldc;
+  int a_mn_major, b_mn_major;
+  uint32_t idesc;
+  void* C;          // RS: local partial buffer (bf16); AG: output
+  int out_dtype;
+};
+
+// ------------------------------------------------------------------------------------------- flag helpers
+SM100_DEVICE void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+SM100_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SM100_DEVICE void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+SM100_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SM100_DEVICE void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+SM100_DEVICE bool epoch_reached(uint32_t v, uint32_t epoch) { return (int32_t)(v - epoch) >= 0; }
+
+SM100_DEVICE uint4 ld_peer_16B(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+// in-switch reduction of 8 bf16 values held at the same offset on every rank (fp32 accumulate inside the NVSwitch)
+SM100_DEVICE uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc_addr) : "memory");
+  return r;
+}
+
+SM100_DEVICE void tile_coords_rot(int tile, int m_blocks, int n_blocks, int m_rot, int& m_blk, int& n_blk) {
+  const int tiles_per_group = GROUP_M * n_blocks;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(m_blocks - first_m, GROUP_M);
+  const int in_group = tile - group * tiles_per_group;
+  int m = first_m + in_group % gsize;
+  n_blk = in_group / gsize;
+  m_blk = (m + m_rot) % m_blocks;     // rotate so the preferred chunk's row blocks come first
+}
+
+template <typename T16>
+SM100_DEVICE void store_chunk16(T16* __restrict__ dst, const uint32_t (&acc)[32], int n_valid) {
+  if (n_valid >= 32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      Vec16<T16> o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.set(i, __uint_as_float(acc[j + i]));
+      o.store(dst + j);
+    }
+  } else {
+    for (int j = 0; j < n_valid; ++j) dst[j] = from_f32<T16>(__uint_as_float(acc[j]));
+  }
+}
+
+// MODE 0: all-gather + GEMM.  MODE 1: GEMM + reduce-scatter.
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fused_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p, const CommParams c) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int blocks_per_chunk = c.rows_per_chunk / BLOCK_M;
+  uint32_t* my_flags = c.peer_flags[c.rank];
+
+  const int gemm_cta = (int)blockIdx.x;
+  const int gemm_ctas = (int)gridDim.x;
+
+  // ==================================================================== GEMM roles
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // AG: local chunk first.  RS: start with the chunk owned by rank+1, own chunk last.
+  const int m_rot = MODE == 0 ? c.rank * blocks_per_chunk : ((c.rank + 1) % c.world) * blocks_per_chunk;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+      int m_blk, n_blk;
+      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      if (MODE == 0) {
+        // the A rows of this tile must have landed in `gathered`
+        if (lane == 0) {
+          while (!epoch_reached(ld_acquire_gpu(c.ready + m_blk), c.epoch)) {
+          }
+          fence_proxy_async_global();
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn_major) {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (BLOCK_K * 128), m0 + j * 64, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (BLOCK_K * 128), n0 + j * 64, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+    const uint32_t b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+    for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+          const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024)
+                                           : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024)
+                                           : make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16_ss(tmem_d, advance_desc(da, k * a_kstep), advance_desc(db, k * b_kstep), p.idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 6) {
+    if (MODE == 0) {
+      // ================================================================ AG: NVLink pull by the copy warps of ALL CTAs
+      if (blockIdx.x == 0 && warp == 6 && lane < c.world)   // announce: my input buffer is valid for this epoch
+        st_release_sys(c.peer_flags[lane] + SLOT_IN_READY + c.rank, c.epoch);
+      const int vec_per_row = c.ld_in / 8;                  // 16-byte vectors per row
+      const int copy_warp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
+      const int n_copy_warps = (int)gridDim.x * COPY_WARPS;
+      const int units_per_chunk = blocks_per_chunk * COPY_SEG;
+      const int seg_rows = BLOCK_M / COPY_SEG;
+      const size_t seg_vec = (size_t)seg_rows * vec_per_row;
+      int cur_src = -1;
+      for (int u = copy_warp; u < units_per_chunk * c.world; u += n_copy_warps) {
+        const int step = u / units_per_chunk;                // chunks in order rank, rank+1, ...
+        const int src = (c.rank + step) % c.world;
+        const int in_chunk = u - step * units_per_chunk;
+        const int sb = in_chunk / COPY_SEG, seg = in_chunk - sb * COPY_SEG;
+        if (src != cur_src) {
+          if (src != c.rank) {
+            if (lane == 0)
+              while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
+              }
+            __syncwarp();
+          }
+          cur_src = src;
+        }
+        const uint4* sp = reinterpret_cast<const uint4*>(c.peer_in[src]) + ((size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
+        uint4* dp = reinterpret_cast<uint4*>(c.gathered) +
+                    ((size_t)src * c.rows_per_chunk + (size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
+        size_t i = lane;
+        for (; i + 7 * 32 < seg_vec; i += 8 * 32) {          // 8 independent 16-byte loads in flight per lane
+          uint4 t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = ld_peer_16B(sp + i + j * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dp[i + j * 32] = t[j];
+        }
+        for (; i < seg_vec; i += 32) dp[i] = ld_peer_16B(sp + i);
+        fence_proxy_async_global();          // generic-proxy writes -> visible to TMA (async proxy) readers
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const int blk = src * blocks_per_chunk + sb;
+          const uint32_t got = atomicAdd(c.block_counter + blk, 1u) + 1;
+          if (got == (uint32_t)COPY_SEG) {
+            c.block_counter[blk] = 0;
+            __threadfence();
+            st_release_gpu(c.ready + blk, c.epoch);
+          }
+        }
+      }
+      // tell every peer that this rank no longer reads its input buffer (last copy warp to finish signals)
+      if (lane == 0) {
+        const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL, 1u) + 1;
+        if (done == (uint32_t)n_copy_warps) {
+          my_flags[SLOT_LOCAL] = 0;
+          __threadfence_system();
+          for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = gemm_cta; tile < num_tiles; tile += gemm_ctas) {
+      int m_blk, n_blk;
+      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int n0 = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BLOCK_N; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cc, v);
+        tmem_ld_wait();
+        const int n_valid = p.N - (n0 + cc);
+        if (row < p.M && n_valid > 0) {
+          const size_t off = (size_t)row * p.ldc + n0 + cc;
+          if (p.out_dtype == CB_BF16) store_chunk16<__nv_bfloat16>((__nv_bfloat16*)p.C + off, v, n_valid);
+          else store_chunk16<__half>((__half*)p.C + off, v, n_valid);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (MODE == 1) {
+        // publish: this warp's slice of the partial tile is globally visible; count tiles per chunk
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+          const int chunk = m_blk / blocks_per_chunk;
+          const uint32_t got = atomicAdd(c.chunk_counter + chunk, 1u) + 1;
+          const uint32_t need = (uint32_t)blocks_per_chunk * n_blocks * 4;   // 4 epilogue warps per tile
+          if (got == need) {
+            c.chunk_counter[chunk] = 0;
+            __threadfence_system();
+            st_release_sys(c.peer_flags[chunk] + SLOT_CHUNK_DONE + c.rank, c.epoch);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+
+  if (MODE == 1) {
+    // ================================================================== RS: reduce MY chunk out of all partial buffers
+    if (threadIdx.x < c.world) {
+      while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_CHUNK_DONE + threadIdx.x), c.epoch)) {
+      }
+    }
+    __syncthreads();
+    const int vec_per_row = p.N / 8;
+    const size_t row0 = (size_t)c.rank * c.rows_per_chunk;
+    const size_t nvec = (size_t)c.rows_per_chunk * vec_per_row;
+    const size_t ldc_vec = p.ldc / 8;
+    const size_t stride = (size_t)gridDim.x * NUM_THREADS;
+    for (size_t i0 = (size_t)blockIdx.x * NUM_THREADS + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+      uint4 sum[4];
+      size_t dst_off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                           // 4 independent switch reductions in flight per thread
+        const size_t i = i0 + u * stride;
+        if (i >= nvec) { dst_off[u] = (size_t)-1; continue; }
+        const size_t r = i / vec_per_row, cv = i - r * vec_per_row;
+        const size_t src_off = (row0 + r) * ldc_vec + cv;     // 16-byte units inside the partial buffer
+        dst_off[u] = r * (c.ld_out / 8) + cv;
+        if (c.mc_part) {
+          sum[u] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
+        } else {
+          float accf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          for (int rk = 0; rk < c.world; ++rk) {
+            const int src = (c.rank + rk) % c.world;
+            Vec16<__nv_bfloat16> v;
+            v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[src]) + src_off);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) accf[k] += v.get(k);
+          }
+          Vec16<__nv_bfloat16> o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.set(k, accf[k]);
+          sum[u] = o.raw;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst_off[u] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[dst_off[u]] = sum[u];
+    }
+    // everyone may now overwrite their partial buffer again: last CTA of this rank signals all peers
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
+      if (done == gridDim.x) {
+        my_flags[SLOT_LOCAL + 1] = 0;
+        __threadfence_system();
+        for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+      }
+    }
+  }
+}
+
+// Stand-alone all-gather by P2P pull (every CTA is a copy CTA).
+__global__ void __launch_bounds__(256) all_gather_pull_kernel(const CommParams c) {
+  uint32_t* my_flags = c.peer_flags[c.rank];
+  if (blockIdx.x == 0 && threadIdx.x < c.world)
+    st_release_sys(c.peer_flags[threadIdx.x] + SLOT_IN_READY + c.rank, c.epoch);
+  const size_t vec_per_chunk = (size_t)c.rows_per_chunk * (c.ld_in / 8);
+  for (int step = 0; step < c.world; ++step) {
+    const int src = (c.rank + step) % c.world;
+    if (step > 0) {
+      if (threadIdx.x == 0)
+        while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
+        }
+      __syncthreads();
+    }
+    const uint4* s = reinterpret_cast<const uint4*>(c.peer_in[src]);
+    uint4* d = reinterpret_cast<uint4*>(c.gathered) + (size_t)src * vec_per_chunk;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_chunk; i += (size_t)gridDim.x * blockDim.x)
+      d[i] = ld_peer_16B(s + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 2, 1u) + 1;
+    if (done == gridDim.x) {
+      my_flags[SLOT_LOCAL + 2] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
+// Wait until every peer has finished reading this rank's symmetric buffers of `epoch` (buffer-reuse guard).
+__global__ void wait_pull_done_kernel(uint32_t* my_flags, int world, uint32_t epoch) {
+  if (threadIdx.x < world)
+    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_PULL_DONE + threadIdx.x), epoch)) {
+    }
+}
+
+template <int BLOCK_N, int MODE>
+int launch_fused(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_mn, int b_mn, int in_dtype,
+                 GemmParams p, const CommParams& c, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  const bool bf16 = in_dtype == CB_BF16;
+  int r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, BLOCK_M, 64, bf16);
+  if (r) return 1000 + r;
+  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, BLOCK_N, 64, bf16);
+  if (r) return 2000 + r;
+  p.idesc = make_idesc_f16(BLOCK_M, BLOCK_N, bf16 ? 1 : 0, a_mn, b_mn);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fused_gemm_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  // persistent grid: ALL CTAs must be co-resident (flag spinning) -> exactly one CTA per SM
+  const int grid = cb_num_sms();
+  fused_gemm_kernel<BLOCK_N, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, c);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_fused_max_ranks() { return MAX_RANKS; }
+int cb_fused_flag_words() { return 4 * MAX_RANKS; }
+
+// Y[T, N] = gather(x)[T, K] (x) B.   peer_in[r] = rank r's symmetric x_local buffer; `gathered` is a local [T, ld_in]
+// buffer (returned to the caller for the backward pass); `ready` is a local uint32[T/128] array.
+// b_mn_major == 0: B is [N, K] (fwd: W[N_local, K]);  == 1: B is stored [K, N] (dgrad: W[K=N_out_local, N=K_in]).
+int cb_ag_gemm(const void* const* peer_in, uint32_t* const* peer_flags, void* gathered, uint32_t* ready,
+               uint32_t* block_counter,
+               const void* B, void* Y, int T, int N, int K, int ldb, int ldy, int b_mn_major, int in_dtype,
+               int rank, int world, uint32_t epoch, int n_copy_ctas, int block_n, cudaStream_t stream) {
+  if (world > MAX_RANKS || T % (world * BLOCK_M) != 0 || K % 8 != 0) return (int)cudaErrorInvalidValue;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch; c.n_copy_ctas = n_copy_ctas; c.rows_per_chunk = T / world;
+  for (int r = 0; r < world; ++r) { c.peer_in[r] = peer_in[r]; c.peer_flags[r] = peer_flags[r]; }
+  c.gathered = gathered; c.ld_in = K; c.ready = ready; c.block_counter = block_counter;
+  GemmParams p{};
+  p.M = T; p.N = N; p.K = K; p.ldc = ldy; p.a_mn_major = 0; p.b_mn_major = b_mn_major; p.C = Y; p.out_dtype = in_dtype;
+  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (block_n == 256)
+    return launch_fused<256, 0>(gathered, B, T, N, K, K, ldb, 0, b_mn_major, in_dtype, p, c, stream);
+  return launch_fused<128, 0>(gathered, B, T, N, K, K, ldb, 0, b_mn_major, in_dtype, p, c, stream);
+}
+
+// y_local[T/world, N] = reduce_scatter_rows( A[T, K] (x) B ).  `part` is this rank's symmetric [T, N] partial buffer,
+// peer_part[r] the peers' mappings of theirs, mc_part its multicast mapping (may be null).
+int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer_part, const void* mc_part,
+               uint32_t* const* peer_flags, uint32_t* chunk_counter, void* out, int T, int N, int K, int lda, int ldb,
+               int ld_out, int a_mn_major, int b_mn_major, int in_dtype, int rank, int world, uint32_t epoch,
+               int block_n, cudaStream_t stream) {
+  if (world > MAX_RANKS || T % (world * BLOCK_M) != 0 || N % 8 != 0) return (int)cudaErrorInvalidValue;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch; c.rows_per_chunk = T / world;
+  for (int r = 0; r < world; ++r) { c.peer_part[r] = peer_part[r]; c.peer_flags[r] = peer_flags[r]; }
+  c.mc_part = mc_part; c.out = out; c.ld_out = ld_out; c.chunk_counter = chunk_counter; c.out_dtype = in_dtype;
+  GemmParams p{};
+  p.M = T; p.N = N; p.K = K; p.ldc = N; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.C = part;
+  p.out_dtype = in_dtype;
+  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (block_n == 256)
+    return launch_fused<256, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
+  return launch_fused<128, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
+}
+
+int cb_all_gather_pull(const void* const* peer_in, uint32_t* const* peer_flags, void* gathered, int rows_per_chunk,
+                       int ld_elems, int rank, int world, uint32_t epoch, int n_ctas, cudaStream_t stream) {
+  if (world > MAX_RANKS || ld_elems % 8 != 0) return (int)cudaErrorInvalidValue;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch; c.rows_per_chunk = rows_per_chunk; c.ld_in = ld_elems;
+  for (int r = 0; r < world; ++r) { c.peer_in[r] = peer_in[r]; c.peer_flags[r] = peer_flags[r]; }
+  c.gathered = gathered;
+  all_gather_pull_kernel<<<n_ctas, 256, 0, stream>>>(c);
+  return (int)cudaGetLastError();
+}
+
+int cb_wait_pull_done(uint32_t* my_flags, int world, uint32_t epoch, cudaStream_t stream) {
+  wait_pull_done_kernel<<<1, 32, 0, stream>>>(my_flags, world, epoch);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"
