@@ -1,0 +1,266 @@
+"""Fused compute+collective backend ("fused" comm backend) over NVLink peer memory.
+
+Python side of `kernel/csrc/fused_comm_gemm.cu`: symmetric-memory workspaces (allocation + rendezvous through
+`torch.distributed._symmetric_memory`, i.e. cuMem handles exchanged over the bootstrap process group, peer mappings and
+the NVLS multicast mapping), epoch bookkeeping for the flag protocol, and the three entry points used by the TP/SP
+linear layers:
+
+    all_gather_gemm(x_local, w, group)        ->  (gather(x) @ w^T  or  gather(x) @ w,  gathered x)
+    gemm_reduce_scatter(a, w, group)          ->  reduce_scatter_rows(a @ w^T  or  a @ w)
+    all_gather(x_local, group)                ->  gathered rows (P2P pull kernel)
+
+SURVEY §5.8 items 2-4.  Every function falls back to the NCCL composition when a shape does not meet the kernel's
+alignment rules, so callers never need to special-case.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch.distributed import ProcessGroup
+
+from ..kernel import loader
+from ..ops import matmul_nn
+from ..ops._dtypes import code
+from . import comm
+
+__all__ = ["available", "build_available", "all_gather_gemm", "gemm_reduce_scatter", "gemm_all_reduce", "all_gather",
+           "FusedWorkspace", "stats"]
+
+_lib = None
+_workspaces: Dict[int, "FusedWorkspace"] = {}
+_disabled = os.environ.get("CB200_DISABLE_FUSED_COMM", "0") == "1"
+stats = {"ag_gemm": 0, "gemm_rs": 0, "all_gather": 0, "fallback": 0}
+
+
+def _get_lib():
+    global _lib
+    if _lib is None:
+        lib = loader.load("cb200_comm")
+        lib.cb_fused_flag_words.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def build_available() -> bool:
+    if _disabled or not torch.cuda.is_available():
+        return False
+    try:
+        _get_lib()
+        import torch.distributed._symmetric_memory  # noqa: F401
+
+        return True
+    except Exception:
+        return False
+
+
+def available(group: Optional[ProcessGroup]) -> bool:
+    if not build_available() or not dist.is_initialized():
+        return False
+    ws = comm.group_size(group)
+    if ws < 2 or ws > 16:
+        return False
+    try:
+        return workspace(group) is not None
+    except Exception as e:  # pragma: no cover - depends on the box
+        from ..logging import get_dist_logger
+
+        get_dist_logger().warning(f"fused comm backend unavailable ({e}); using NCCL", ranks=[0])
+        _workspaces[id(group)] = None  # type: ignore[assignment]
+        return False
+
+
+class _SymmBuffer:
+    """A symmetric allocation: local tensor + every peer's mapping of its copy (+ multicast mapping)."""
+
+    def __init__(self, nbytes: int, group: ProcessGroup, zero: bool = False) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.nbytes = nbytes
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.tensor = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        if zero:
+            self.tensor.zero_()
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.peer_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        try:
+            if self.handle.has_multicast_support:
+                mc = int(self.handle.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.mc_ptr = mc
+        self.last_epoch = 0
+
+    def ptr_array(self, world: int):
+        return (ctypes.c_void_p * world)(*self.peer_ptrs[:world])
+
+
+class FusedWorkspace:
+    """Per-process-group state of the fused backend."""
+
+    def __init__(self, group: Optional[ProcessGroup]) -> None:
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = comm.group_size(group)
+        self.rank = comm.group_rank(group)
+        lib = _get_lib()
+        self.flags = _SymmBuffer(4 * lib.cb_fused_flag_words(), self.group, zero=True)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)      # flag pages are zero everywhere before first use
+        self.epoch = 0
+        self._in: Dict[int, List[_SymmBuffer]] = {}
+        self._part: Dict[int, List[_SymmBuffer]] = {}
+        self._toggle: Dict[Tuple[str, int], int] = {}
+        self._counters: Dict[int, torch.Tensor] = {}
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.chunk_counter = torch.zeros(64, dtype=torch.int32, device=dev)
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def _pool(self, pools: Dict[int, List[_SymmBuffer]], kind: str, nbytes: int) -> _SymmBuffer:
+        size = 1 << max(20, (nbytes - 1).bit_length())        # power-of-two size classes, >= 1 MiB
+        if size not in pools:
+            pools[size] = [_SymmBuffer(size, self.group), _SymmBuffer(size, self.group)]
+        t = self._toggle.get((kind, size), 0)
+        self._toggle[(kind, size)] = t ^ 1
+        buf = pools[size][t]
+        if buf.last_epoch:
+            # buffer reuse guard: every peer must have finished reading what we published at `last_epoch`
+            lib = _get_lib()
+            loader.check(lib.cb_wait_pull_done(ctypes.c_void_p(self.flags.peer_ptrs[self.rank]), self.world,
+                                               ctypes.c_uint32(buf.last_epoch), loader.stream_ptr()), "wait_pull_done")
+        return buf
+
+    def in_buffer(self, nbytes: int) -> _SymmBuffer:
+        return self._pool(self._in, "in", nbytes)
+
+    def part_buffer(self, nbytes: int) -> _SymmBuffer:
+        return self._pool(self._part, "part", nbytes)
+
+    def counters(self, n_blocks: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(ready flags, block counters): uint32[n_blocks] each, zero-initialised once (epochs make them reusable)."""
+        key = 1 << max(6, (n_blocks - 1).bit_length())
+        if key not in self._counters:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._counters[key] = torch.zeros(2, key, dtype=torch.int32, device=dev)
+        c = self._counters[key]
+        return c[0], c[1]
+
+
+def workspace(group: Optional[ProcessGroup]) -> Optional[FusedWorkspace]:
+    key = id(group)
+    if key not in _workspaces:
+        _workspaces[key] = FusedWorkspace(group)
+    return _workspaces[key]
+
+
+def _aligned(T: int, world: int, *dims: int) -> bool:
+    return T % (world * 128) == 0 and all(d % 8 == 0 for d in dims)
+
+
+def _ok_dtype(*ts: torch.Tensor) -> bool:
+    return all(t.dtype in (torch.bfloat16, torch.float16) and t.dtype == ts[0].dtype for t in ts)
+
+
+# ------------------------------------------------------------------------------------------------ all-gather
+def all_gather(x_local: torch.Tensor, group: Optional[ProcessGroup]) -> torch.Tensor:
+    """Gather rows of every rank's [t, K] tensor -> [t * world, K] by pulling over NVLink."""
+    ws = workspace(group)
+    t, K = x_local.shape
+    if ws is None or not _ok_dtype(x_local) or K % 8 != 0:
+        stats["fallback"] += 1
+        return comm.all_gather(x_local, 0, group)
+    lib = _get_lib()
+    nbytes = x_local.numel() * x_local.element_size()
+    buf = ws.in_buffer(nbytes)
+    buf.tensor[:nbytes].view(x_local.dtype).view(t, K).copy_(x_local)
+    epoch = ws.next_epoch()
+    out = torch.empty(t * ws.world, K, dtype=x_local.dtype, device=x_local.device)
+    n_ctas = 2 * torch.cuda.get_device_properties(x_local.device).multi_processor_count
+    loader.check(lib.cb_all_gather_pull(buf.ptr_array(ws.world), ws.flags.ptr_array(ws.world), loader.ptr(out), t, K,
+                                        ws.rank, ws.world, ctypes.c_uint32(epoch), n_ctas, loader.stream_ptr()),
+                 "all_gather_pull")
+    buf.last_epoch = epoch
+    loader.launch_counter.add("fused_all_gather")
+    stats["all_gather"] += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ AG + GEMM
+def all_gather_gemm(x_local: torch.Tensor, w: torch.Tensor, group: Optional[ProcessGroup], transpose_b: bool = True,
+                    block_n: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """y = gather_rows(x_local) @ (w^T if transpose_b else w).  Returns (y, gathered x)."""
+    ws = workspace(group)
+    t, K = x_local.shape
+    N = w.shape[0] if transpose_b else w.shape[1]
+    kdim_ok = (w.shape[1] == K) if transpose_b else (w.shape[0] == K)
+    assert kdim_ok, f"all_gather_gemm: inner dims mismatch {tuple(x_local.shape)} x {tuple(w.shape)}"
+    world = comm.group_size(group)
+    T = t * world
+    if (ws is None or not _ok_dtype(x_local, w) or not _aligned(T, world, K, N) or not w.is_contiguous()
+            or w.data_ptr() % 16 != 0):
+        stats["fallback"] += 1
+        xf = comm.all_gather(x_local.contiguous(), 0, group)
+        return (torch.nn.functional.linear(xf, w) if transpose_b else matmul_nn(xf, w)), xf
+    lib = _get_lib()
+    nbytes = x_local.numel() * x_local.element_size()
+    buf = ws.in_buffer(nbytes)
+    buf.tensor[:nbytes].view(x_local.dtype).view(t, K).copy_(x_local)
+    epoch = ws.next_epoch()
+    gathered = torch.empty(T, K, dtype=x_local.dtype, device=x_local.device)
+    y = torch.empty(T, N, dtype=x_local.dtype, device=x_local.device)
+    ready, blk_cnt = ws.counters(T // 128)
+    loader.check(lib.cb_ag_gemm(buf.ptr_array(world), ws.flags.ptr_array(world), loader.ptr(gathered),
+                                loader.ptr(ready), loader.ptr(blk_cnt), loader.ptr(w), loader.ptr(y), T, N, K,
+                                w.stride(0), y.stride(0), 0 if transpose_b else 1, code(x_local.dtype), ws.rank, world,
+                                ctypes.c_uint32(epoch), 0, block_n, loader.stream_ptr()), "ag_gemm")
+    buf.last_epoch = epoch
+    loader.launch_counter.add("fused_ag_gemm")
+    stats["ag_gemm"] += 1
+    return y, gathered
+
+
+# ------------------------------------------------------------------------------------------------ GEMM + RS
+def gemm_reduce_scatter(a: torch.Tensor, w: torch.Tensor, group: Optional[ProcessGroup], transpose_b: bool = True,
+                        block_n: int = 0) -> torch.Tensor:
+    """out[T/world, N] = reduce_scatter_rows(a @ (w^T if transpose_b else w))."""
+    ws = workspace(group)
+    T, K = a.shape
+    N = w.shape[0] if transpose_b else w.shape[1]
+    world = comm.group_size(group)
+    if (ws is None or not _ok_dtype(a, w) or not _aligned(T, world, K, N) or not w.is_contiguous()
+            or not a.is_contiguous() or a.data_ptr() % 16 != 0 or w.data_ptr() % 16 != 0):
+        stats["fallback"] += 1
+        full = torch.nn.functional.linear(a, w) if transpose_b else matmul_nn(a, w)
+        return comm.reduce_scatter(full, 0, group)
+    lib = _get_lib()
+    part = ws.part_buffer(T * N * a.element_size())
+    epoch = ws.next_epoch()
+    out = torch.empty(T // world, N, dtype=a.dtype, device=a.device)
+    mc = ctypes.c_void_p(part.mc_ptr) if (part.mc_ptr and a.dtype == torch.bfloat16
+                                          and os.environ.get("CB200_NO_MULTIMEM", "0") != "1") else ctypes.c_void_p(0)
+    loader.check(lib.cb_gemm_rs(loader.ptr(a), loader.ptr(w), ctypes.c_void_p(part.peer_ptrs[ws.rank]),
+                                part.ptr_array(world), mc, ws.flags.ptr_array(world), loader.ptr(ws.chunk_counter),
+                                loader.ptr(out), T, N, K, a.stride(0), w.stride(0), out.stride(0), 0,
+                                0 if transpose_b else 1, code(a.dtype), ws.rank, world, ctypes.c_uint32(epoch), block_n,
+                                loader.stream_ptr()), "gemm_rs")
+    part.last_epoch = epoch
+    loader.launch_counter.add("fused_gemm_rs")
+    stats["gemm_rs"] += 1
+    return out
+
+
+def gemm_all_reduce(a: torch.Tensor, w: torch.Tensor, group: Optional[ProcessGroup]) -> torch.Tensor:
+    """all_reduce(a @ w^T) = fused GEMM+reduce-scatter followed by the NVLink pull all-gather."""
+    world = comm.group_size(group)
+    if a.shape[0] % (world * 128) != 0:
+        stats["fallback"] += 1
+        y = torch.nn.functional.linear(a, w)
+        comm.all_reduce(y, group)
+        return y
+    return all_gather(gemm_reduce_scatter(a, w, group, transpose_b=True), group)

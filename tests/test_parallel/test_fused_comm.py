@@ -1,0 +1,98 @@
+"""Fused compute+collective kernels vs their NCCL + cuBLAS composition (needs >= 2 GPUs on one NVLink box).
+Also times both (device-timed, max over ranks) and prints one JSON line per op for profiles/."""
+import json
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+import colossalai_b200
+from colossalai_b200.testing import rerun_if_address_is_in_use, spawn
+
+pytestmark = pytest.mark.gpu
+
+
+def _time(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / iters], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def _worker(rank, world_size, port, timing=False):
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="nccl", verbose=False)
+    from colossalai_b200.parallel import comm, fused
+
+    group = dist.group.WORLD
+    assert fused.available(group), "fused backend must be available on a multi-GPU B200 box"
+    torch.manual_seed(100 + rank)
+    results = []
+    for (t, K, N) in [(256, 512, 768), (1024, 4096, 6144 // world_size), (2048, 4096, 4096)]:
+        T = t * world_size
+        x_local = (torch.randn(t, K, device="cuda") * 0.5).bfloat16()
+        torch.manual_seed(7)   # identical weights on every rank
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        w2 = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+        torch.manual_seed(100 + rank + t)
+        # ---- all_gather
+        ref_full = comm.all_gather(x_local, 0, group)
+        got_full = fused.all_gather(x_local, group)
+        torch.testing.assert_close(got_full, ref_full, atol=0, rtol=0)
+        # ---- AG + GEMM (both weight layouts)
+        y, gathered = fused.all_gather_gemm(x_local, w, group, transpose_b=True)
+        torch.testing.assert_close(gathered, ref_full, atol=0, rtol=0)
+        torch.testing.assert_close(y.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
+        y2, _ = fused.all_gather_gemm(x_local, w2, group, transpose_b=False)
+        torch.testing.assert_close(y2.float(), ref_full.float() @ w2.float(), atol=0.08, rtol=2e-2)
+        # ---- GEMM + RS: every rank holds a different A (a K-shard of the activations)
+        a = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
+        ref = comm.reduce_scatter((a.float() @ w.float().t()), 0, group)
+        got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True)
+        torch.testing.assert_close(got.float(), ref, atol=0.15, rtol=3e-2)
+        got2 = fused.gemm_reduce_scatter(a, w2, group, transpose_b=False)
+        ref2 = comm.reduce_scatter((a.float() @ w2.float()), 0, group)
+        torch.testing.assert_close(got2.float(), ref2, atol=0.15, rtol=3e-2)
+        # repeated calls exercise buffer reuse / epoch guards
+        for _ in range(5):
+            got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True)
+            y, _ = fused.all_gather_gemm(x_local, w, group, transpose_b=True)
+        torch.testing.assert_close(got.float(), ref, atol=0.15, rtol=3e-2)
+        torch.testing.assert_close(y.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
+        if timing and t >= 1024:
+            t_f = _time(lambda: fused.all_gather_gemm(x_local, w, group))
+            t_n = _time(lambda: torch.nn.functional.linear(comm.all_gather(x_local, 0, group), w))
+            t_f2 = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
+            t_n2 = _time(lambda: comm.reduce_scatter(torch.nn.functional.linear(a, w), 0, group))
+            results.append({"world": world_size, "t_local": t, "K": K, "N": N, "ag_gemm_fused_ms": t_f,
+                            "ag_gemm_nccl_ms": t_n, "gemm_rs_fused_ms": t_f2, "gemm_rs_nccl_ms": t_n2})
+    assert fused.stats["ag_gemm"] > 0 and fused.stats["gemm_rs"] > 0, fused.stats
+    if rank == 0:
+        for r in results:
+            print("FUSED_TIMING " + json.dumps(r), flush=True)
+        print("FUSED_STATS " + json.dumps(fused.stats), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_fused_comm_kernels():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    spawn(_worker, 2)
+
+
+if __name__ == "__main__":
+    n = int(os.environ.get("NGPU", torch.cuda.device_count()))
+    spawn(_worker, n, timing=True)
