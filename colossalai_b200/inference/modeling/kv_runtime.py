@@ -1,0 +1,72 @@
+"""Runtime object handed to the model as `kv_cache`: writes K/V into the paged cache and runs attention.
+
+Replaces the reference's no-padding model forwards + attention backends (`inference/modeling/models/nopadding_llama.py`,
+`modeling/backends/{attention_backend,pre_attention_backend}.py`): our generic model already works on flattened
+un-padded tokens, so inference only has to (a) scatter the step's K/V into the block tables and (b) run varlen
+flash-attention for prefill or the paged split-KV kernel for decode.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from ... import ops
+from ...ops import inference as iops
+
+__all__ = ["PagedKVRuntime"]
+
+
+class PagedKVRuntime:
+    def __init__(self, k_caches: List[torch.Tensor], v_caches: List[torch.Tensor], block_size: int) -> None:
+        self.k_caches, self.v_caches = k_caches, v_caches
+        self.block_size = block_size
+        self.block_tables: Optional[torch.Tensor] = None      # [bsz, max_blocks] int32 (device)
+        self.seq_lens: Optional[torch.Tensor] = None          # [bsz] int32, INCLUDING the tokens of this step
+        self.is_prompt = True
+        self.token_seq: Optional[torch.Tensor] = None         # [tokens] int32 sequence index of every token
+        self.token_pos: Optional[torch.Tensor] = None         # [tokens] int32 position of every token
+        self.cu_seqlens: Optional[torch.Tensor] = None
+        self.max_seqlen: int = 0
+        self.q_per_seq: int = 1                               # decode: tokens verified per sequence (spec-dec)
+
+    def set_step(self, block_tables: torch.Tensor, seq_lens: torch.Tensor, is_prompt: bool, device,
+                 q_per_seq: int = 1) -> torch.Tensor:
+        """Prepare per-step metadata; returns the int64 position of every input token."""
+        self.block_tables = block_tables.to(device=device, dtype=torch.int32).contiguous()
+        self.seq_lens = seq_lens.to(device=device, dtype=torch.int32).contiguous()
+        self.is_prompt = is_prompt
+        self.q_per_seq = q_per_seq
+        lens = seq_lens.tolist()
+        if is_prompt:
+            seq = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens))
+            pos = torch.cat([torch.arange(l) for l in lens])
+            cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+            cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+            self.cu_seqlens = cu.to(device)
+            self.max_seqlen = max(lens)
+        else:
+            seq = torch.repeat_interleave(torch.arange(len(lens)), q_per_seq)
+            pos = torch.cat([torch.arange(l - q_per_seq, l) for l in lens])
+            self.cu_seqlens = None
+        self.token_seq = seq.to(device=device, dtype=torch.int32)
+        self.token_pos = pos.to(device=device, dtype=torch.int32)
+        return pos.to(device=device, dtype=torch.int64)
+
+    def attend(self, layer_idx: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, meta, scale: float) -> torch.Tensor:
+        kc, vc = self.k_caches[layer_idx], self.v_caches[layer_idx]
+        iops.kv_cache_write(k, v, kc, vc, self.block_tables, self.token_seq, self.token_pos)
+        if self.is_prompt:
+            return ops.attention(q, k, v, causal=True, scale=scale, cu_seqlens_q=self.cu_seqlens,
+                                 cu_seqlens_k=self.cu_seqlens, max_seqlen=self.max_seqlen)
+        if self.q_per_seq == 1:
+            return iops.paged_decode_attention(q, kc, vc, self.block_tables, self.seq_lens, scale)
+        # speculative verification: n query tokens per sequence, each sees the cache up to its own position
+        n = self.q_per_seq
+        bsz = self.seq_lens.numel()
+        outs = []
+        for j in range(n):
+            qj = q.view(bsz, n, *q.shape[1:])[:, j]
+            outs.append(iops.paged_decode_attention(qj.contiguous(), kc, vc, self.block_tables,
+                                                    self.seq_lens - (n - 1 - j), scale))
+        return torch.stack(outs, 1).reshape(q.shape)

@@ -1,0 +1,337 @@
+// Paged-KV inference kernels for sm_100a.
+//
+// KV cache layout (both K and V, per layer):  [num_blocks, block_size, kv_heads, head_dim]  (token-major inside a block,
+// 16-byte vectors along head_dim; one (block, head) tile is a strided 2-D box, i.e. directly TMA-addressable).
+//
+//   cb_kv_cache_write        : scatter this step's K,V rows [tokens, kv_heads, D] into their paged slots (prefill: all
+//                              prompt tokens via cu_seqlens; decode: one token per sequence), optional fp8(e5m2) cast
+//   cb_rope_kv_cache_write   : fused RoPE(q,k) in place + cache write of rotated K and of V (decode path)
+//   cb_paged_decode_attention: split-KV flash-decoding: grid (seq, kv_head, split); one CTA serves the whole GQA group
+//                              of a kv head so K/V are read once per group; fp32 online softmax; second pass merges
+//                              splits
+//   cb_gather_cos_sin        : per-token cos/sin rows from the [max_pos, D/2] caches
+//   cb_convert_fp8           : fp16/bf16/fp32 <-> fp8 e5m2 storage
+//
+// Capability parity: reference inference_ops_cuda (extensions/csrc/kernel/cuda/{flash_decoding_attention,
+// decode_kv_cache_memcpy,context_kv_cache_memcpy,fused_rotary_emb_and_cache,get_cos_and_sin,convert_fp8}_kernel.cu,
+// N12-N19) and the Triton twins (kernel/triton/{flash_decoding,kvcache_copy,no_pad_rotary_embedding}.py).
+// Decode attention is HBM-bound (every K/V byte is read once): the design goal is full-sector 16-byte loads and enough
+// CTAs (seqs x kv_heads x splits >= 2 waves of 148 SMs) rather than tensor cores.
+#include "common.cuh"
+
+namespace {
+
+constexpr int DEC_THREADS = 128;
+constexpr int MAX_GROUP = 8;   // q heads per kv head handled by one CTA
+
+template <typename T> CB_DEVICE float kv_to_f32(T v) { return to_f32<T>(v); }
+
+template <typename T, typename TC>
+__global__ void __launch_bounds__(256) kv_cache_write_kernel(const T* __restrict__ k, const T* __restrict__ v,
+                                                             TC* __restrict__ k_cache, TC* __restrict__ v_cache,
+                                                             const int* __restrict__ block_tables,
+                                                             const int* __restrict__ token_seq,   // [tokens] seq id
+                                                             const int* __restrict__ token_pos,   // [tokens] position
+                                                             int tokens, int kv_heads, int D, int block_size,
+                                                             int max_blocks_per_seq, int64_t k_stride,
+                                                             int64_t v_stride) {
+  const int t = blockIdx.x;
+  if (t >= tokens) return;
+  const int seq = token_seq[t], pos = token_pos[t];
+  const int blk = block_tables[seq * max_blocks_per_seq + pos / block_size];
+  const int slot = pos % block_size;
+  const int64_t dst = ((int64_t)blk * block_size + slot) * kv_heads * D;
+  const int n = kv_heads * D;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    k_cache[dst + i] = (TC)k[(int64_t)t * k_stride + i];
+    v_cache[dst + i] = (TC)v[(int64_t)t * v_stride + i];
+  }
+}
+
+// RoPE (half rotation) on q [tokens, Hq, D] and k [tokens, Hkv, D] in place, then K,V -> paged cache.
+template <typename T>
+__global__ void __launch_bounds__(256) rope_kv_cache_write_kernel(T* __restrict__ q, T* __restrict__ k,
+                                                                  const T* __restrict__ v, T* __restrict__ k_cache,
+                                                                  T* __restrict__ v_cache,
+                                                                  const float* __restrict__ cos_c,
+                                                                  const float* __restrict__ sin_c,
+                                                                  const int* __restrict__ block_tables,
+                                                                  const int* __restrict__ token_seq,
+                                                                  const int* __restrict__ token_pos, int tokens, int Hq,
+                                                                  int Hkv, int D, int rot, int block_size,
+                                                                  int max_blocks_per_seq, int64_t q_stride,
+                                                                  int64_t k_stride, int64_t v_stride) {
+  const int t = blockIdx.x;
+  if (t >= tokens) return;
+  const int seq = token_seq[t], pos = token_pos[t];
+  const int half = rot / 2;
+  const float* cp = cos_c + (int64_t)pos * half;
+  const float* sp = sin_c + (int64_t)pos * half;
+  T* qt = q + (int64_t)t * q_stride;
+  T* kt = k + (int64_t)t * k_stride;
+  for (int i = threadIdx.x; i < (Hq + Hkv) * half; i += blockDim.x) {
+    const int h = i / half, j = i - h * half;
+    T* base = h < Hq ? qt + h * D : kt + (h - Hq) * D;
+    const float a = to_f32<T>(base[j]), b = to_f32<T>(base[j + half]), c = cp[j], s = sp[j];
+    base[j] = from_f32<T>(a * c - b * s);
+    base[j + half] = from_f32<T>(b * c + a * s);
+  }
+  __syncthreads();
+  const int blk = block_tables[seq * max_blocks_per_seq + pos / block_size];
+  const int64_t dst = ((int64_t)blk * block_size + pos % block_size) * Hkv * D;
+  for (int i = threadIdx.x; i < Hkv * D; i += blockDim.x) {
+    k_cache[dst + i] = kt[i];
+    v_cache[dst + i] = v[(int64_t)t * v_stride + i];
+  }
+}
+
+// One CTA: sequence `seq`, kv head `kvh`, KV partition `split`.  q: [num_seqs, Hq, D].
+// partial outputs: o_part [num_seqs, Hq, splits, D] fp32, ml_part [num_seqs, Hq, splits, 2] (max, sumexp)
+template <typename T, typename TC, int D>
+__global__ void __launch_bounds__(DEC_THREADS) paged_decode_kernel(
+    const T* __restrict__ q, const TC* __restrict__ k_cache, const TC* __restrict__ v_cache,
+    const int* __restrict__ block_tables, const int* __restrict__ seq_lens, float* __restrict__ o_part,
+    float* __restrict__ ml_part, int Hq, int Hkv, int block_size, int max_blocks_per_seq, int splits, int part_len,
+    float scale, const float* __restrict__ alibi_slopes, int64_t q_stride) {
+  constexpr int VEC = 16 / sizeof(TC);          // cache elements per 16-byte load
+  constexpr int DV = D / 32;                    // output dims owned by a lane
+  const int seq = blockIdx.x, kvh = blockIdx.y, split = blockIdx.z;
+  const int G = Hq / Hkv;
+  const int len = seq_lens[seq];
+  const int t0 = split * part_len, t1 = min(len, t0 + part_len);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = DEC_THREADS / 32;
+  __shared__ float q_s[MAX_GROUP][D];
+  __shared__ float red_m[DEC_THREADS / 32][MAX_GROUP], red_l[DEC_THREADS / 32][MAX_GROUP];
+  __shared__ float red_o[DEC_THREADS / 32][MAX_GROUP][D];
+  for (int i = threadIdx.x; i < G * D; i += DEC_THREADS) {
+    const int g = i / D, d = i - g * D;
+    q_s[g][d] = to_f32<T>(q[(int64_t)seq * q_stride + (int64_t)(kvh * G + g) * D + d]) * scale;
+  }
+  __syncthreads();
+  float m[MAX_GROUP], l[MAX_GROUP], o[MAX_GROUP][DV];
+#pragma unroll
+  for (int g = 0; g < MAX_GROUP; ++g) {
+    m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV; ++j) o[g][j] = 0.f;
+  }
+  const int* bt = block_tables + seq * max_blocks_per_seq;
+  // each warp walks chunks of 32 tokens: lane i scores token (base + i) against all G query heads
+  for (int base = t0 + warp * 32; base < t1; base += nwarps * 32) {
+    const int t = base + lane;
+    float s[MAX_GROUP];
+#pragma unroll
+    for (int g = 0; g < MAX_GROUP; ++g) s[g] = -INFINITY;
+    if (t < t1) {
+      const int blk = bt[t / block_size];
+      const TC* kr = k_cache + (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D;
+#pragma unroll
+      for (int g = 0; g < MAX_GROUP; ++g) if (g < G) s[g] = 0.f;
+#pragma unroll 4
+      for (int d = 0; d < D; d += VEC) {
+        Vec16<TC> kv;
+        kv.load_nc(kr + d);
+#pragma unroll
+        for (int g = 0; g < MAX_GROUP; ++g) {
+          if (g < G) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) s[g] += q_s[g][d + e] * kv.get(e);
+          }
+        }
+      }
+      if (alibi_slopes) {
+#pragma unroll
+        for (int g = 0; g < MAX_GROUP; ++g) if (g < G) s[g] += alibi_slopes[kvh * G + g] * (float)(t - (len - 1));
+      }
+    }
+    // online softmax across the 32 tokens of this chunk
+    float p[MAX_GROUP];
+#pragma unroll
+    for (int g = 0; g < MAX_GROUP; ++g) {
+      if (g < G) {
+        const float cm = warp_max(s[g]);
+        const float nm = fmaxf(m[g], cm);
+        const float corr = __expf(m[g] - nm);
+        p[g] = (t < t1) ? __expf(s[g] - nm) : 0.f;
+        l[g] = l[g] * corr + warp_sum(p[g]);
+        m[g] = nm;
+#pragma unroll
+        for (int j = 0; j < DV; ++j) o[g][j] *= corr;
+      }
+    }
+    // V accumulation: every lane owns DV output dims; token probabilities are broadcast by shuffle
+    const int n_tok = min(32, t1 - base);
+    for (int tt = 0; tt < n_tok; ++tt) {
+      const int tok = base + tt;
+      const int blk = bt[tok / block_size];
+      const TC* vr = v_cache + (((int64_t)blk * block_size + tok % block_size) * Hkv + kvh) * D + lane * DV;
+      float vv[DV];
+#pragma unroll
+      for (int j = 0; j < DV; ++j) vv[j] = kv_to_f32<TC>(vr[j]);
+#pragma unroll
+      for (int g = 0; g < MAX_GROUP; ++g) {
+        if (g < G) {
+          const float pg = __shfl_sync(0xffffffffu, p[g], tt);
+#pragma unroll
+          for (int j = 0; j < DV; ++j) o[g][j] += pg * vv[j];
+        }
+      }
+    }
+  }
+  // merge the warps of this CTA
+  for (int g = 0; g < G; ++g) {
+    if (lane == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
+#pragma unroll
+    for (int j = 0; j < DV; ++j) red_o[warp][g][lane * DV + j] = o[g][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * D; i += DEC_THREADS) {
+    const int g = i / D, d = i - g * D;
+    float gm = -INFINITY;
+    for (int w = 0; w < nwarps; ++w) gm = fmaxf(gm, red_m[w][g]);
+    float acc = 0.f, ls = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      const float c = (red_m[w][g] == -INFINITY) ? 0.f : __expf(red_m[w][g] - gm);
+      acc += red_o[w][g][d] * c;
+      ls += red_l[w][g] * c;
+    }
+    const int64_t oi = (((int64_t)seq * Hq + kvh * G + g) * splits + split);
+    o_part[oi * D + d] = acc;
+    if (d == 0) { ml_part[oi * 2] = gm; ml_part[oi * 2 + 1] = ls; }
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128) decode_reduce_kernel(const float* __restrict__ o_part,
+                                                            const float* __restrict__ ml_part, T* __restrict__ out,
+                                                            int Hq, int splits, int64_t out_stride) {
+  const int seq = blockIdx.x, h = blockIdx.y;
+  const int64_t base = ((int64_t)seq * Hq + h) * splits;
+  float gm = -INFINITY;
+  for (int s = 0; s < splits; ++s) gm = fmaxf(gm, ml_part[(base + s) * 2]);
+  float ls = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float mm = ml_part[(base + s) * 2];
+    ls += (mm == -INFINITY) ? 0.f : ml_part[(base + s) * 2 + 1] * __expf(mm - gm);
+  }
+  const float inv = ls > 0.f ? 1.f / ls : 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float mm = ml_part[(base + s) * 2];
+      if (mm != -INFINITY) acc += o_part[(base + s) * D + d] * __expf(mm - gm);
+    }
+    out[(int64_t)seq * out_stride + (int64_t)h * D + d] = from_f32<T>(acc * inv);
+  }
+}
+
+__global__ void gather_cos_sin_kernel(const float* __restrict__ cos_c, const float* __restrict__ sin_c,
+                                      const int* __restrict__ pos, float* __restrict__ cos_o,
+                                      float* __restrict__ sin_o, int tokens, int half) {
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    cos_o[(int64_t)t * half + i] = cos_c[(int64_t)pos[t] * half + i];
+    sin_o[(int64_t)t * half + i] = sin_c[(int64_t)pos[t] * half + i];
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (TO)(float)in[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+// k, v: [tokens, kv_heads, D] (row strides in elements).  cache dtype == input dtype (fp8 path: cb_convert_fp8 first).
+int cb_kv_cache_write(const void* k, const void* v, void* k_cache, void* v_cache, const int* block_tables,
+                      const int* token_seq, const int* token_pos, int tokens, int kv_heads, int D, int block_size,
+                      int max_blocks_per_seq, int64_t k_stride, int64_t v_stride, int dtype, cudaStream_t s) {
+  if (tokens == 0) return 0;
+  CB_DISPATCH_HALF(dtype, T, {
+    kv_cache_write_kernel<T, T><<<tokens, 256, 0, s>>>((const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_tables,
+                                                      token_seq, token_pos, tokens, kv_heads, D, block_size,
+                                                      max_blocks_per_seq, k_stride, v_stride);
+  });
+  return CB_LAUNCH_CHECK();
+}
+
+int cb_rope_kv_cache_write(void* q, void* k, const void* v, void* k_cache, void* v_cache, const float* cos_c,
+                           const float* sin_c, const int* block_tables, const int* token_seq, const int* token_pos,
+                           int tokens, int Hq, int Hkv, int D, int rot, int block_size, int max_blocks_per_seq,
+                           int64_t q_stride, int64_t k_stride, int64_t v_stride, int dtype, cudaStream_t s) {
+  if (tokens == 0) return 0;
+  CB_DISPATCH_HALF(dtype, T, {
+    rope_kv_cache_write_kernel<T><<<tokens, 256, 0, s>>>((T*)q, (T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, cos_c,
+                                                        sin_c, block_tables, token_seq, token_pos, tokens, Hq, Hkv, D,
+                                                        rot, block_size, max_blocks_per_seq, q_stride, k_stride,
+                                                        v_stride);
+  });
+  return CB_LAUNCH_CHECK();
+}
+
+int cb_decode_num_splits(int num_seqs, int kv_heads, int max_len, int* part_len_out) {
+  // enough CTAs for >= 2 waves, partitions of >= 256 tokens
+  const int target = 2 * cb_num_sms();
+  int splits = (target + num_seqs * kv_heads - 1) / (num_seqs * kv_heads);
+  const int max_splits = (max_len + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int part = (max_len + splits - 1) / splits;
+  part = ((part + 31) / 32) * 32;
+  splits = (max_len + part - 1) / part;
+  if (splits < 1) splits = 1;
+  *part_len_out = part;
+  return splits;
+}
+
+// q: [num_seqs, Hq, D]; out same; caches [nb, bs, Hkv, D]; o_part fp32 [num_seqs, Hq, splits, D]; ml_part [.., 2]
+int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int* block_tables,
+                              const int* seq_lens, void* out, float* o_part, float* ml_part, int num_seqs, int Hq,
+                              int Hkv, int D, int block_size, int max_blocks_per_seq, int splits, int part_len,
+                              float scale, const float* alibi_slopes, int64_t q_stride, int64_t out_stride, int dtype,
+                              cudaStream_t s) {
+  if (num_seqs == 0) return 0;
+  if (Hq % Hkv != 0 || Hq / Hkv > MAX_GROUP) return (int)cudaErrorInvalidValue;
+  dim3 grid(num_seqs, Hkv, splits);
+#define LAUNCH_DEC(T, DD)                                                                                           \
+  paged_decode_kernel<T, T, DD><<<grid, DEC_THREADS, 0, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache,      \
+      block_tables, seq_lens, o_part, ml_part, Hq, Hkv, block_size, max_blocks_per_seq, splits, part_len, scale,     \
+      alibi_slopes, q_stride);                                                                                       \
+  decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride)
+  CB_DISPATCH_HALF(dtype, T, {
+    if (D == 128) { LAUNCH_DEC(T, 128); }
+    else if (D == 64) { LAUNCH_DEC(T, 64); }
+    else if (D == 256) { LAUNCH_DEC(T, 256); }
+    else return (int)cudaErrorInvalidValue;
+  });
+#undef LAUNCH_DEC
+  return CB_LAUNCH_CHECK();
+}
+
+int cb_gather_cos_sin(const float* cos_c, const float* sin_c, const int* pos, float* cos_o, float* sin_o, int tokens,
+                      int half, cudaStream_t s) {
+  if (tokens == 0) return 0;
+  gather_cos_sin_kernel<<<tokens, 128, 0, s>>>(cos_c, sin_c, pos, cos_o, sin_o, tokens, half);
+  return CB_LAUNCH_CHECK();
+}
+
+// direction 0: (fp16|bf16|fp32) -> e5m2 ; 1: e5m2 -> (fp16|bf16|fp32)
+int cb_convert_fp8(const void* in, void* out, int64_t n, int dtype, int direction, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+  if (direction == 0) {
+    if (dtype == CB_BF16) convert_kernel<__nv_bfloat16, __nv_fp8_e5m2><<<grid, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_fp8_e5m2*)out, n);
+    else if (dtype == CB_F16) convert_kernel<__half, __nv_fp8_e5m2><<<grid, 256, 0, s>>>((const __half*)in, (__nv_fp8_e5m2*)out, n);
+    else convert_kernel<float, __nv_fp8_e5m2><<<grid, 256, 0, s>>>((const float*)in, (__nv_fp8_e5m2*)out, n);
+  } else {
+    if (dtype == CB_BF16) convert_kernel<__nv_fp8_e5m2, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_fp8_e5m2*)in, (__nv_bfloat16*)out, n);
+    else if (dtype == CB_F16) convert_kernel<__nv_fp8_e5m2, __half><<<grid, 256, 0, s>>>((const __nv_fp8_e5m2*)in, (__half*)out, n);
+    else convert_kernel<__nv_fp8_e5m2, float><<<grid, 256, 0, s>>>((const __nv_fp8_e5m2*)in, (float*)out, n);
+  }
+  return CB_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -50,7 +50,9 @@ def build_available() -> bool:
         return False
     try:
         _get_lib()
-        import torch.distributed._symmetric_memory  # noqa: F401
+        import importlib
+
+        importlib.import_module("torch.distributed._symmetric_memory")
 
         return True
     except Exception:

@@ -1,0 +1,140 @@
+"""Inference engine: continuous batching + paged KV vs naive full-recompute greedy decoding (CPU tier), scheduler /
+KV manager / batch bucket unit checks (reference: tests/test_infer/test_{batch_bucket,kvcache_manager,
+request_handler,inference_engine,continuous_batching,drafter}.py)."""
+import pytest
+import torch
+
+from colossalai_b200.inference import InferenceConfig, InferenceEngine
+from colossalai_b200.inference.batch_bucket import BatchBucket
+from colossalai_b200.inference.config import GenerationConfig
+from colossalai_b200.inference.kv_cache import KVCacheManager
+from colossalai_b200.inference.struct import Sequence
+from colossalai_b200.models import build_model, get_config
+
+
+def _naive_greedy(model, prompt, n_new):
+    ids = list(prompt)
+    for _ in range(n_new):
+        with torch.no_grad():
+            logits = model(input_ids=torch.tensor([ids]))["logits"]
+        ids.append(int(logits[-1, : model.cfg.vocab_size].argmax()))
+    return ids
+
+
+def test_kvcache_manager_alloc_free():
+    cfg = InferenceConfig(max_batch_size=4, max_input_len=32, max_output_len=32, block_size=8, dtype="fp32")
+    mc = get_config("llama-tiny")
+    mgr = KVCacheManager(cfg, mc)
+    total = mgr.total_num_blocks
+    table = torch.full((mgr.get_max_blocks_per_sequence(),), -1, dtype=torch.int32)
+    mgr.allocate_context_from_block_table(table, 19)
+    assert (table >= 0).sum() == 3 and mgr.num_available_blocks == total - 3
+    mgr.allocate_token_from_block_table(table, 25)          # position 24 -> needs block 3
+    assert (table >= 0).sum() == 4
+    mgr.free_block_table(table)
+    assert mgr.num_available_blocks == total and (table < 0).all()
+
+
+def test_batch_bucket_ops():
+    bb = BatchBucket(4, 16, max_batch_size=4, max_length=64, block_size=8, kv_max_split_num=1)
+    seqs = [Sequence(i, None, list(range(3 + i)), 8, None, 2, 0, 8) for i in range(3)]
+    for s in seqs:
+        bb.add_seq(s, alloc_block_table=torch.full((8,), i, dtype=torch.int32) if (i := s.request_id) >= 0 else None)
+    assert bb.current_batch_size == 3 and bb.seq_lengths[:3].tolist() == [3, 4, 5]
+    bb.append_batch_tokens(torch.tensor([7, 8, 9]))
+    assert seqs[1].output_token_id == [8] and bb.seq_lengths[:3].tolist() == [4, 5, 6]
+    bb.pop_seq_update_batch(0)
+    assert bb.current_batch_size == 2 and bb.is_compact and bb.seq_lengths[:2].tolist() == [5, 6]
+
+
+def test_engine_matches_naive_greedy_with_continuous_batching():
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    cfg = InferenceConfig(max_batch_size=3, max_input_len=24, max_output_len=6, block_size=8, dtype="fp32",
+                          use_cuda_graph=False)
+    engine = InferenceEngine(model, None, cfg)
+    prompts = [[5, 9, 13, 200, 7], [11, 3], [400, 401, 402, 403, 404, 405, 406, 407, 408, 409], [17] * 6, [99, 98, 97]]
+    outs, token_ids = engine.generate(prompts_token_ids=prompts, return_token_ids=True,
+                                      generation_config=GenerationConfig(max_new_tokens=6))
+    assert len(token_ids) == len(prompts)
+    for p, got in zip(prompts, token_ids):
+        ref = _naive_greedy(model, p, 6)
+        # generation may stop early on EOS (id 2)
+        assert got == ref[: len(got)], (p, got, ref)
+        assert len(got) == len(ref) or got[-1] == 2
+
+
+def test_speculative_decoding_matches_plain_greedy():
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    torch.manual_seed(1)
+    drafter = build_model(get_config("llama-tiny", num_hidden_layers=1)).float().eval()
+    cfg = InferenceConfig(max_batch_size=2, max_input_len=16, max_output_len=8, block_size=8, dtype="fp32",
+                          max_n_spec_tokens=4)
+    plain = InferenceEngine(model, None, cfg)
+    prompts = [[5, 9, 13, 200, 7], [11, 3, 4]]
+    _, ref_ids = plain.generate(prompts_token_ids=prompts, return_token_ids=True,
+                                generation_config=GenerationConfig(max_new_tokens=8))
+    spec = InferenceEngine(model, None, cfg)
+    spec.enable_spec_dec(drafter, n_spec_tokens=3)
+    _, got_ids = spec.generate(prompts_token_ids=prompts, return_token_ids=True,
+                               generation_config=GenerationConfig(max_new_tokens=8))
+    for r, g in zip(ref_ids, got_ids):
+        n = min(len(r), len(g))
+        assert r[:n] == g[:n], (r, g)
+
+
+def test_async_engine_and_http_server():
+    import asyncio
+
+    from fastapi.testclient import TestClient
+
+    from colossalai_b200.inference.core.async_engine import AsyncInferenceEngine
+    from colossalai_b200.inference.server.api_server import build_app
+
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    cfg = InferenceConfig(max_batch_size=4, max_input_len=64, max_output_len=8, block_size=8, dtype="fp32")
+
+    async def run():
+        eng = AsyncInferenceEngine(start_engine_loop=True, model_or_path=model, tokenizer=None, inference_config=cfg)
+        outs = await asyncio.gather(*[_collect(eng, i, p) for i, p in enumerate(["hello", "abc", "xyzw"])])
+        assert eng.background_loop_status
+        return outs
+
+    async def _collect(eng, rid, prompt):
+        res = None
+        async for o in eng.generate(rid, prompt):
+            res = o
+        return res
+
+    outs = asyncio.run(run())
+    assert len(outs) == 3 and all(isinstance(o, str) for o in outs)
+
+    eng = AsyncInferenceEngine(start_engine_loop=True, model_or_path=model, tokenizer=None, inference_config=cfg)
+    with TestClient(build_app(eng, "llama-tiny")) as client:
+        assert client.get("/ping").json() == {"status": "Healthy"}
+        r = client.post("/generate", json={"prompt": "hello", "max_new_tokens": 4})
+        assert r.status_code == 200 and "text" in r.json()
+        r = client.post("/completion", json={"prompt": "hi there", "max_new_tokens": 4})
+        assert r.status_code == 200 and r.json()["model"] == "llama-tiny"
+        r = client.post("/chat", json={"messages": [{"role": "user", "content": "hi"}], "max_new_tokens": 4})
+        assert r.status_code == 200 and r.json()["choices"][0]["message"]["role"] == "assistant"
+
+
+def test_rpc_engine_matches_local_engine():
+    from colossalai_b200.inference.core.rpc_engine import RPCInferenceEngine
+
+    cfg = InferenceConfig(max_batch_size=2, max_input_len=16, max_output_len=6, block_size=8, dtype="fp32", tp_size=1)
+    prompts = [[5, 9, 13, 200, 7], [11, 3, 4]]
+    torch.manual_seed(1234)
+    local = InferenceEngine(build_model("llama-tiny").float().eval(), None, cfg)
+    _, ref = local.generate(prompts_token_ids=prompts, return_token_ids=True,
+                            generation_config=GenerationConfig(max_new_tokens=6))
+    rpc = RPCInferenceEngine("llama-tiny", None, cfg)
+    try:
+        _, got = rpc.generate(prompts_token_ids=prompts, return_token_ids=True,
+                              generation_config=GenerationConfig(max_new_tokens=6))
+    finally:
+        rpc.kill_workers()
+    assert got == ref

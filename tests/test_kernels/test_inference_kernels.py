@@ -1,0 +1,108 @@
+"""Paged-KV inference kernels vs fp32 PyTorch references (reference: tests/test_infer/test_kernels/cuda/
+test_{kv_cache_memcpy,flash_decoding_attention,convert_fp8}.py)."""
+import pytest
+import torch
+
+from colossalai_b200.ops import inference as iops
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_cache(n_seqs, max_len, bs, Hkv, D, dtype, dev):
+    max_blocks = (max_len + bs - 1) // bs
+    nb = n_seqs * max_blocks + 3
+    perm = torch.randperm(nb, device=dev)[: n_seqs * max_blocks].to(torch.int32)
+    tables = perm.view(n_seqs, max_blocks).contiguous()
+    kc = torch.randn(nb, bs, Hkv, D, device=dev, dtype=dtype)
+    vc = torch.randn(nb, bs, Hkv, D, device=dev, dtype=dtype)
+    return kc, vc, tables
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("Hq,Hkv", [(8, 8), (32, 8), (16, 2)])
+@pytest.mark.parametrize("bs", [16, 64])
+def test_paged_decode_attention(dtype, D, Hq, Hkv, bs):
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    n, max_len = 7, 700
+    kc, vc, tables = _mk_cache(n, max_len, bs, Hkv, D, dtype, dev)
+    lens = torch.tensor([1, 15, 16, 17, 300, 699, 700], device=dev, dtype=torch.int32)
+    q = torch.randn(n, Hq, D, device=dev, dtype=dtype)
+    out = iops.paged_decode_attention(q, kc, vc, tables, lens)
+    ref = iops.paged_decode_attention_ref(q.float(), kc.float(), vc.float(), tables, lens)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_paged_decode_long_context_split_kv():
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    kc, vc, tables = _mk_cache(2, 8192, 16, 8, 128, torch.bfloat16, dev)
+    lens = torch.tensor([8192, 4097], device=dev, dtype=torch.int32)
+    q = torch.randn(2, 32, 128, device=dev, dtype=torch.bfloat16)
+    out = iops.paged_decode_attention(q, kc, vc, tables, lens)
+    ref = iops.paged_decode_attention_ref(q.float(), kc.float(), vc.float(), tables, lens)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_paged_decode_alibi():
+    dev = torch.device("cuda")
+    torch.manual_seed(2)
+    kc, vc, tables = _mk_cache(3, 256, 16, 8, 128, torch.float16, dev)
+    lens = torch.tensor([5, 100, 256], device=dev, dtype=torch.int32)
+    q = torch.randn(3, 8, 128, device=dev, dtype=torch.float16)
+    slopes = torch.tensor([2 ** (-(i + 1)) for i in range(8)], device=dev, dtype=torch.float32)
+    out = iops.paged_decode_attention(q, kc, vc, tables, lens, alibi_slopes=slopes)
+    ref = iops.paged_decode_attention_ref(q.float(), kc.float(), vc.float(), tables, lens, alibi_slopes=slopes)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_kv_cache_write(dtype):
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    bs, Hkv, D = 16, 4, 128
+    kc, vc, tables = _mk_cache(3, 64, bs, Hkv, D, dtype, dev)
+    kc0, vc0 = kc.clone(), vc.clone()
+    lens = [5, 33, 64]
+    seq = torch.repeat_interleave(torch.arange(3), torch.tensor(lens)).to(dev, torch.int32)
+    pos = torch.cat([torch.arange(l) for l in lens]).to(dev, torch.int32)
+    T = sum(lens)
+    kv = torch.randn(T, 2 * Hkv * D + 7, device=dev, dtype=dtype)   # strided views like a fused qkv output
+    k = kv[:, : Hkv * D].view(T, Hkv, D)
+    v = kv[:, Hkv * D: 2 * Hkv * D].view(T, Hkv, D)
+    iops.kv_cache_write(k, v, kc, vc, tables, seq, pos)
+    blk = tables[seq.long(), (pos // bs).long()].long()
+    slot = (pos % bs).long()
+    kc0[blk, slot] = k
+    vc0[blk, slot] = v
+    assert torch.equal(kc, kc0) and torch.equal(vc, vc0)
+
+
+def test_convert_fp8_roundtrip():
+    dev = torch.device("cuda")
+    x = torch.randn(1000, 130, device=dev, dtype=torch.bfloat16)
+    q = iops.convert_fp8(x, True)
+    ref = x.to(torch.float8_e5m2)
+    assert torch.equal(q, ref.view(torch.uint8))
+    back = iops.convert_fp8(q, False, torch.bfloat16)
+    assert torch.equal(back, ref.to(torch.bfloat16))
+
+
+def test_engine_gpu_cuda_graph_matches_eager():
+    from colossalai_b200.inference import InferenceConfig, InferenceEngine
+    from colossalai_b200.inference.config import GenerationConfig
+    from colossalai_b200.models import build_model
+
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").to(torch.bfloat16).cuda().eval()
+    prompts = [[5, 9, 13, 200, 7], [11, 3], [400, 401, 402, 403, 404, 405, 406, 407, 408, 409]]
+    outs = []
+    for graph in (False, True):
+        cfg = InferenceConfig(max_batch_size=4, max_input_len=32, max_output_len=12, block_size=16, dtype="bf16",
+                              use_cuda_graph=graph)
+        eng = InferenceEngine(model, None, cfg)
+        _, ids = eng.generate(prompts_token_ids=prompts, return_token_ids=True,
+                              generation_config=GenerationConfig(max_new_tokens=12))
+        outs.append(ids)
+    assert outs[0] == outs[1]
