@@ -127,16 +127,28 @@ def run_reference_arm(args) -> None:
                 m = LlamaForCausalLM._from_config(hf_cfg, attn_implementation="sdpa", torch_dtype=torch.bfloat16)
         return m
 
-    attempts = []
+    # transformers-5.x moved the cache classes out of modeling_llama; the reference (written against 4.51) imports them
+    # from there.  Re-export them in place (environment shim — no reference file is touched).
+    try:
+        import transformers.cache_utils as _cu
+        import transformers.models.llama.modeling_llama as _ml
+
+        for _n in ("StaticCache", "DynamicCache", "Cache"):
+            if not hasattr(_ml, _n) and hasattr(_cu, _n):
+                setattr(_ml, _n, getattr(_cu, _n))
+    except Exception:
+        pass
+
+    import gc
+    import traceback
+
     chosen = None
     model = optimizer = booster = None
     errors = []
-    plans = []
-    if world > 1 or True:
-        plans.append(("hybrid_tp", f"tp{world}" + ("+sp(split_gather)" if world > 1 else "")))
-    plans.append(("zero2", f"zero2(dp{world})"))
-    plans.append(("ddp", f"ddp(dp{world})"))
-    for kind, label in plans:
+    plans = [("hybrid_tp", False), ("hybrid_tp", True), ("zero2", False), ("zero2", True), ("ddp", False)]
+    for kind, ckpt in plans:
+        label = {"hybrid_tp": f"tp{world}" + ("+sp(split_gather)" if world > 1 else ""), "zero2": f"zero2(dp{world})",
+                 "ddp": f"ddp(dp{world})"}[kind] + ("+grad_ckpt" if ckpt else "")
         try:
             if kind == "hybrid_tp":
                 from colossalai.booster.plugin import HybridParallelPlugin
@@ -156,32 +168,46 @@ def run_reference_arm(args) -> None:
                 plugin = TorchDDPPlugin()
             booster = Booster(plugin=plugin)
             model = build_model()
+            if ckpt:
+                model.gradient_checkpointing_enable()
             model.train()
             optimizer = torch.optim.AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1)
             model, optimizer, _, _, _ = booster.boost(model, optimizer)
             # one probing step
-            ids = torch.randint(0, hf_cfg.vocab_size, (args.mbs, args.seq), device=dev)
+            nseq = args.mbs * (world if kind == "hybrid_tp" else 1)
+            ids = torch.randint(0, hf_cfg.vocab_size, (nseq, args.seq), device=dev)
             out = model(input_ids=ids, labels=ids)
             booster.backward(out.loss, optimizer)
             optimizer.step()
             optimizer.zero_grad()
             torch.cuda.synchronize()
+            del out, ids
             chosen = (kind, label)
             break
-        except Exception as e:  # try the next stock plugin
-            errors.append(f"{kind}: {type(e).__name__}: {str(e)[:160]}")
-            model = optimizer = booster = None
-            import gc
-
+        except Exception as e:  # try the next stock configuration
+            msg = f"{label}: {type(e).__name__}: {str(e)[:200]}"
+            errors.append(msg)
+            if rank == 0:
+                print("[reference arm] " + msg, file=sys.stderr, flush=True)
+            traceback.clear_frames(e.__traceback__)
+            e = None
+            model = optimizer = booster = plugin = None
             gc.collect()
             torch.cuda.empty_cache()
+            try:
+                torch.cuda.reset_peak_memory_stats()
+            except Exception:
+                pass
     if chosen is None:
-        _unavailable("no stock plugin of the reference runs on this stack: " + " | ".join(errors))
+        _unavailable("no stock plugin of the reference runs on this stack: " + " | ".join(e_[:120] for e_ in errors))
         return
+    tp_mode = chosen[0] == "hybrid_tp"
 
-    B, S = args.mbs, args.seq          # per GPU (data parallel): same tokens per GPU per step as our arm
-    tokens_per_step = B * S * world * args.accum
-    gen = torch.Generator().manual_seed(4321 + rank)
+    # TP: every rank feeds the same global batch of mbs*world sequences (as our arm does); DP: mbs sequences per rank.
+    S = args.seq
+    B = args.mbs * world if tp_mode else args.mbs
+    tokens_per_step = args.mbs * world * S * args.accum
+    gen = torch.Generator().manual_seed(4321 + (0 if tp_mode else rank))
     host_ids = [torch.randint(0, hf_cfg.vocab_size, (args.accum, B, S), generator=gen).pin_memory() for _ in range(4)]
     dev_ids = [h.to(dev) for h in host_ids]
 
@@ -237,7 +263,7 @@ def run_reference_arm(args) -> None:
            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic tokens, random-init weights", "impl": "reference",
-           "config": {"model": args.model, "global_batch": B * world * args.accum, "seq_len": S,
+           "config": {"model": args.model, "global_batch": args.mbs * world * args.accum, "seq_len": S,
                       "parallelism": chosen[1], "reference_plugin": chosen[0], "attn": attn_impl,
                       "optimizer": "torch.optim.AdamW inside the reference's OptimizerWrapper",
                       "skipped_plugins": errors},

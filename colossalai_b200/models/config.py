@@ -220,4 +220,10 @@ def get_config(name: str, **overrides) -> ModelConfig:
     if name not in MODEL_ZOO:
         raise KeyError(f"unknown model preset {name!r}; available: {sorted(MODEL_ZOO)}")
     cfg = MODEL_ZOO[name]
-    return replace(cfg, **overrides) if overrides else replace(cfg)
+    if not overrides:
+        return replace(cfg)
+    # derived fields must be re-derived when the shape changes
+    if ("hidden_size" in overrides or "num_attention_heads" in overrides) and "head_dim" not in overrides \
+            and cfg.head_dim == cfg.hidden_size // cfg.num_attention_heads:
+        overrides["head_dim"] = None
+    return replace(cfg, **overrides)

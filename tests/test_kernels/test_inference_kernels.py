@@ -92,10 +92,13 @@ def test_convert_fp8_roundtrip():
 def test_engine_gpu_cuda_graph_matches_eager():
     from colossalai_b200.inference import InferenceConfig, InferenceEngine
     from colossalai_b200.inference.config import GenerationConfig
-    from colossalai_b200.models import build_model
+    from colossalai_b200.kernel import loader
+    from colossalai_b200.models import build_model, get_config
 
     torch.manual_seed(0)
-    model = build_model("llama-tiny").to(torch.bfloat16).cuda().eval()
+    # head_dim 64 so the decode step runs the native paged kernel (the torch reference path syncs and cannot be captured)
+    model = build_model(get_config("llama-tiny", hidden_size=256, intermediate_size=512)).to(torch.bfloat16).cuda().eval()
+    loader.launch_counter.reset()
     prompts = [[5, 9, 13, 200, 7], [11, 3], [400, 401, 402, 403, 404, 405, 406, 407, 408, 409]]
     outs = []
     for graph in (False, True):
@@ -106,3 +109,4 @@ def test_engine_gpu_cuda_graph_matches_eager():
                               generation_config=GenerationConfig(max_new_tokens=12))
         outs.append(ids)
     assert outs[0] == outs[1]
+    assert loader.launch_counter.by_name.get("paged_decode_attention", 0) > 0
