@@ -23,3 +23,17 @@ class FP8Hook(ColoParamOpHook):
 
     def rewrite_op(self, func):
         return linear_fp8 if func is F.linear else func
+
+
+def convert_linear_to_fp8(module) -> None:
+    """In place: every `nn.Linear` of `module` computes through `linear_fp8` (used by the plugins' `use_fp8` switch)."""
+    import types
+
+    import torch.nn as nn
+
+    def fwd(self, x):
+        return linear_fp8(x, self.weight, self.bias)
+
+    for m in module.modules():
+        if type(m) is nn.Linear:
+            m.forward = types.MethodType(fwd, m)
