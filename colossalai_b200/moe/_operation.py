@@ -149,9 +149,10 @@ class MoeCombine(torch.autograd.Function):
         s, e = logits.shape
         h = expert_tokens.shape[-1]
         et = expert_tokens.reshape(-1, h).contiguous()
-        out = moe_ops.combine_forward(s, e, ec // e if ec >= e else ec, h, et, logits, mask, dest_idx)
+        out = moe_ops.combine_forward(s, e, ec // e, h, et, logits, mask, dest_idx)
         ctx.save_for_backward(et, logits, mask, dest_idx)
         ctx.dims = (s, e, ec, h)
+        ctx.in_shape = expert_tokens.shape
         return out
 
     @staticmethod
@@ -160,9 +161,8 @@ class MoeCombine(torch.autograd.Function):
 
         et, logits, mask, dest_idx = ctx.saved_tensors
         s, e, ec, h = ctx.dims
-        d_expert, d_logits = moe_ops.combine_backward(s, e, ec // e if ec >= e else ec, h, dy.contiguous(), et,
-                                                      logits, mask, dest_idx)
-        return d_expert, d_logits, None, None, None
+        d_expert, d_logits = moe_ops.combine_backward(s, e, ec // e, h, dy.contiguous(), et, logits, mask, dest_idx)
+        return d_expert.view(ctx.in_shape), d_logits, None, None, None
 
 
 class _GradScaler(torch.autograd.Function):

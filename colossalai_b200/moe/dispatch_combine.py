@@ -16,12 +16,42 @@ import torch.distributed as dist
 from ..parallel import comm
 from ._operation import AllToAllUneven
 
-__all__ = ["moe_forward"]
+__all__ = ["moe_forward", "set_moe_backend", "get_moe_backend"]
+
+import os
+
+_BACKEND = os.environ.get("CB200_MOE_BACKEND", "auto")     # auto | nccl | fused
+
+
+def set_moe_backend(name: str) -> None:
+    global _BACKEND
+    assert name in ("auto", "nccl", "fused")
+    _BACKEND = name
+
+
+def get_moe_backend() -> str:
+    return _BACKEND
+
+
+def _use_fused(x: torch.Tensor, num_experts: int, ep_group) -> bool:
+    if _BACKEND == "nccl" or not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16) or x.shape[1] % 8:
+        return False
+    from . import fused_ep
+
+    ok = fused_ep.available(ep_group)
+    if _BACKEND == "fused" and not ok:
+        raise RuntimeError("CB200_MOE_BACKEND=fused but the fused expert-parallel kernels are unavailable")
+    # single-rank groups gain nothing from the symmetric-buffer path unless explicitly requested
+    return ok and (comm.group_size(ep_group) > 1 or _BACKEND == "fused")
 
 
 def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, experts, num_experts: int,
                 ep_group: Optional[dist.ProcessGroup]) -> torch.Tensor:
     """x [T, H]; topk_w [T, k] fp32; topk_idx [T, k] -> [T, H]."""
+    if _use_fused(x, num_experts, ep_group):
+        from . import fused_ep
+
+        return fused_ep.moe_forward_fused(x, topk_w, topk_idx, experts, num_experts, ep_group)
     T, H = x.shape
     k = topk_idx.shape[1]
     ep = comm.group_size(ep_group)
