@@ -46,6 +46,8 @@ def parse_args():
     p.add_argument("--grad-ckpt", type=float, default=float(os.environ.get("CB200_GRAD_CKPT", "0")))
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the run invalid)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profile", default="", help="after the timed region, run ONE extra step under torch.profiler on "
+                                                 "rank 0 and write the per-kernel table to this path")
     return p.parse_args()
 
 
@@ -255,9 +257,43 @@ def run_ours(args) -> dict:
         result["e2e"] = e2e
     if rank == 0:
         print(json.dumps(result), flush=True)
+    if args.profile:
+        _profile_one_step(step, dev_ids[0], args.profile, rank)
     dist.barrier()
     colossalai_b200.initialize.shutdown()
     return result
+
+
+def _profile_one_step(step_fn, ids, path: str, rank: int) -> None:
+    """Kernel-level breakdown of one step (CUPTI through torch.profiler; never used for a reported number)."""
+    from torch.profiler import ProfilerActivity, profile
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn(ids)
+        torch.cuda.synchronize()
+    if rank != 0:
+        return
+    rows = {}
+    total = 0.0
+    for ev in prof.events():
+        if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+            continue
+        dur = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
+        if dur <= 0:
+            dur = float(ev.time_range.elapsed_us()) if hasattr(ev, "time_range") else 0.0
+        name = ev.name
+        r = rows.setdefault(name, [0.0, 0])
+        r[0] += dur
+        r[1] += 1
+        total += dur
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(f"# one training step, rank 0, sum of kernel device time = {total / 1e3:.2f} ms\n")
+        f.write("# ms_total  count  pct  kernel\n")
+        for name, (us, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:80]:
+            f.write(f"{us / 1e3:9.3f} {n:6d} {100 * us / max(total, 1e-9):5.1f}%  {name[:160]}\n")
 
 
 def run_reference(args) -> None:

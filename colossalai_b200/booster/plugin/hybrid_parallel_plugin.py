@@ -40,7 +40,7 @@ from ...shardformer.layer._operation import set_comm_backend
 from ...shardformer.layer.utils import SeqParallelUtils
 from ...shardformer.policies.base_policy import Policy
 from ...tensor.d_tensor import is_distributed_tensor
-from ...tensor.moe_tensor import is_moe_tensor
+from ...tensor.moe_tensor import get_ep_group, is_moe_tensor
 from .plugin_base import PipelinePluginBase, _seed_worker
 
 __all__ = ["HybridParallelPlugin", "HybridParallelModule", "HybridParallelNaiveOptimizer",
@@ -154,6 +154,10 @@ class HybridParallelModule(ModelWrapper, AMPModelMixin):
             return
         grads = [p.grad for p in self.module.parameters() if p.grad is not None and not is_moe_tensor(p)]
         _bucketed_all_reduce(grads, self.dp_group, self.dp_size)
+        moe_dp_group = getattr(self, "moe_dp_group", None)
+        if moe_dp_group is not None and comm.group_size(moe_dp_group) > 1:
+            mg = [p.grad for p in self.module.parameters() if p.grad is not None and is_moe_tensor(p)]
+            _bucketed_all_reduce(mg, moe_dp_group, comm.group_size(moe_dp_group))
 
     def sync_sp_grads(self, grads: Optional[List[Tensor]] = None) -> None:
         """all_to_all / ring_attn: params are replicated over sp -> grads are averaged with dp (handled by using the
@@ -241,8 +245,12 @@ class _HybridNormMixin:
                 stages = sorted(shared.keys())
                 for s in stages[1:]:
                     shared_ids.add(id(shared[s]))
+        moe = []
         for p in params:
             if id(p) in shared_ids:
+                continue
+            if is_moe_tensor(p):
+                moe.append(p)       # expert-parallel shards: summed over the ep group
                 continue
             (sharded if (self.tp_size > 1 and is_distributed_tensor(p)) else replicated).append(p)
         n_sh = local_norm_fn(sharded)
@@ -250,6 +258,12 @@ class _HybridNormMixin:
         if self.tp_size > 1:
             dist.all_reduce(n_sh, group=self.tp_pg)
         total = n_sh + n_rep
+        if moe:
+            n_moe = local_norm_fn(moe)
+            ep_group = get_ep_group(moe[0])
+            if ep_group is not None and comm.group_size(ep_group) > 1:
+                dist.all_reduce(n_moe, group=ep_group)
+            total = total + n_moe
         if self.pp_size > 1:
             dist.all_reduce(total, group=self.pp_pg)
         return total

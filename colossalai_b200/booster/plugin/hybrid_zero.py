@@ -60,41 +60,48 @@ class HybridParallelZeroOptimizer(LowLevelZeroOptimizer):
         super().sync_grad()
 
     def _compute_grad_norm_sq(self) -> Tensor:
-        """Bucket shards mix TP-sharded and replicated params: split the local sum accordingly."""
+        """Bucket shards mix TP-sharded, replicated and expert-parallel params and may live on different dp groups
+        (dense: dp, experts: moe_dp): accumulate [tp-sharded, replicated, moe] per group, reduce each over its group."""
+        from ...tensor.moe_tensor import get_ep_group, is_moe_tensor
+
         dev = self.buckets[0].device if self.buckets else torch.device("cpu")
-        sharded = torch.zeros(1, device=dev)
-        replicated = torch.zeros(1, device=dev)
         shared_ids = set()
         if self.stage_manager is not None:
             for shared in self.shared_params:
                 for s in sorted(shared.keys())[1:]:
                     shared_ids.add(id(shared[s]))
+        per_pg = {}
+        ep_group = None
         for b in self.buckets:
             if b.grad_shard is None:
                 continue
+            acc = per_pg.setdefault(id(b.pg), (b.pg, torch.zeros(3, device=dev)))[1]
             lo, hi = b.my_slice.start, b.my_slice.stop
             for p, o in zip(b.params, b.offsets):
                 s, e = max(o, lo), min(o + p.numel(), hi)
                 if e <= s or id(p) in shared_ids:
                     continue
-                v = b.grad_shard[s - lo:e - lo].float().pow(2).sum().reshape(1)
-                if self.tp_size > 1 and is_distributed_tensor(p):
-                    sharded += v
+                v = b.grad_shard[s - lo:e - lo].float().pow(2).sum()
+                if is_moe_tensor(p):
+                    acc[2] += v
+                    ep_group = get_ep_group(p)
+                elif self.tp_size > 1 and is_distributed_tensor(p):
+                    acc[0] += v
                 else:
-                    replicated += v
-        # sum over the dp group(s): every dp rank holds a different slice
-        by_pg = {}
-        for b in self.buckets:
-            by_pg.setdefault(id(b.pg), b.pg)
-        both = torch.cat([sharded, replicated])
-        for pg in by_pg.values():
-            if comm.group_size(pg) > 1:
-                dist.all_reduce(both, group=pg)
-                break
-        sharded, replicated = both[0:1], both[1:2]
+                    acc[1] += v
+        total3 = torch.zeros(3, device=dev)
+        for pg, acc in per_pg.values():
+            if comm.group_size(pg) > 1:      # every rank of the group holds a different slice
+                dist.all_reduce(acc, group=pg)
+            total3 += acc
+        sharded, replicated, moe = total3[0:1], total3[1:2], total3[2:3]
         if self.tp_size > 1:
             dist.all_reduce(sharded, group=self.tp_pg)
-        total = sharded + replicated
+        if getattr(self, "ep_pg", None) is not None:
+            ep_group = self.ep_pg
+        if ep_group is not None and comm.group_size(ep_group) > 1:
+            dist.all_reduce(moe, group=ep_group)       # collective: every rank of the ep group calls it
+        total = sharded + replicated + moe
         if self.pp_size > 1:
             dist.all_reduce(total, group=self.pp_pg)
         return total

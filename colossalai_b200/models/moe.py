@@ -128,6 +128,10 @@ class SparseMoE(nn.Module):
                 ex.num_local_experts = n_local
         for p in self.experts.parameters():
             set_moe_tensor_ep_group(p, ep_group, getattr(shard_config, "moe_dp_group", None))
+            if self.ep_size > 1:
+                from ..tensor.d_tensor.api import mark_sharded
+
+                mark_sharded(p, 0, ep_group)      # checkpoint IO gathers / re-shards experts like any other shard
 
     def _aux(self, logits: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         m = self.cfg.moe
