@@ -266,6 +266,8 @@ def run_ours(args) -> dict:
 
 def _profile_one_step(step_fn, ids, path: str, rank: int) -> None:
     """Kernel-level breakdown of one step (CUPTI through torch.profiler; never used for a reported number)."""
+    import torch
+    import torch.distributed as dist
     from torch.profiler import ProfilerActivity, profile
 
     torch.cuda.synchronize()
@@ -275,25 +277,20 @@ def _profile_one_step(step_fn, ids, path: str, rank: int) -> None:
         torch.cuda.synchronize()
     if rank != 0:
         return
-    rows = {}
-    total = 0.0
-    for ev in prof.events():
-        if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+    rows = []
+    for e in prof.key_averages():
+        if "cuda" not in str(getattr(e, "device_type", "")).lower():
             continue
-        dur = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
-        if dur <= 0:
-            dur = float(ev.time_range.elapsed_us()) if hasattr(ev, "time_range") else 0.0
-        name = ev.name
-        r = rows.setdefault(name, [0.0, 0])
-        r[0] += dur
-        r[1] += 1
-        total += dur
+        us = float(getattr(e, "self_device_time_total", 0.0) or getattr(e, "device_time_total", 0.0) or 0.0)
+        if us > 0:
+            rows.append((us, int(e.count), str(e.key)))
+    total = sum(r[0] for r in rows)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "w") as f:
         f.write(f"# one training step, rank 0, sum of kernel device time = {total / 1e3:.2f} ms\n")
         f.write("# ms_total  count  pct  kernel\n")
-        for name, (us, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:80]:
-            f.write(f"{us / 1e3:9.3f} {n:6d} {100 * us / max(total, 1e-9):5.1f}%  {name[:160]}\n")
+        for us, n, name in sorted(rows, key=lambda r: -r[0])[:90]:
+            f.write(f"{us / 1e3:9.3f} {n:6d} {100 * us / max(total, 1e-9):5.1f}%  {name[:170]}\n")
 
 
 def run_reference(args) -> None:

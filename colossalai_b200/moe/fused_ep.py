@@ -126,6 +126,11 @@ def ep_workspace(group, hidden: int, dtype: torch.dtype, num_experts: int, rows_
     worst = rows_per_rank * world
     cap = worst if factor <= 0 else min(worst, int(rows_per_rank * factor))
     cap = (cap + 127) // 128 * 128
+    if world > 1:
+        # symmetric allocations must have the same size on every rank: agree on the largest request
+        t = torch.tensor([cap], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        cap = int(t.item())
     key = (id(group), hidden, dtype, num_experts)
     ws = _workspaces.get(key)
     if ws is None or ws.capacity < cap:

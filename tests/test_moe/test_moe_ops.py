@@ -109,8 +109,10 @@ def test_cumsum_and_router_gpu():
         p = lg.float().softmax(-1)
         rw, ridx = p.topk(k, -1)
         torch.testing.assert_close(probs, p, rtol=1e-4, atol=1e-6)
-        assert (idx == ridx).float().mean() > 0.999       # ties in bf16 may order differently
+        # equal probabilities (bf16 ties) may be picked in a different order: compare the selected VALUES
+        torch.testing.assert_close(p.gather(1, idx).sort(-1).values, rw.sort(-1).values, rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(w.sum(-1), torch.ones(777, device="cuda"), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(w, p.gather(1, idx) / p.gather(1, idx).sum(-1, keepdim=True), rtol=1e-4, atol=1e-6)
 
 
 def _fused_vs_nccl(group, T, H, E, K, seed):
