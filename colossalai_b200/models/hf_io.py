@@ -1,0 +1,177 @@
+"""Hugging Face checkpoint <-> colossalai_b200 model conversion.
+
+The reference shards HF `transformers` modules in place, so HF checkpoints load as-is (`checkpoint_io/*`,
+`lazy/pretrained.py`).  Our generic transformer fuses q/k/v into `qkv_proj`, gate/up into `gate_up_proj` and batches the
+experts of an MoE block, so this module maps names and fuses / splits tensors:
+
+    model = load_hf_checkpoint("/path/to/hf_dir", dtype=torch.bfloat16)       # config.json + *.safetensors / *.bin
+    sd    = to_hf_state_dict(model)                                            # export back to HF naming
+
+Supported: llama / mistral / qwen2 / qwen3 (llama-like), mixtral, gpt2.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+from typing import Dict, Iterator, Optional, Tuple
+
+import torch
+
+from .config import ModelConfig, MoEConfig
+
+__all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards"]
+
+_LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral")
+
+
+def config_from_hf(hf: dict) -> ModelConfig:
+    mt = hf.get("model_type", "llama")
+    if mt == "gpt2":
+        return ModelConfig(model_type="gpt2", vocab_size=hf["vocab_size"], hidden_size=hf["n_embd"],
+                           intermediate_size=hf.get("n_inner") or 4 * hf["n_embd"], num_hidden_layers=hf["n_layer"],
+                           num_attention_heads=hf["n_head"], max_position_embeddings=hf["n_positions"],
+                           pos_type="learned", norm_type="layer", hidden_act="gelu_new", glu=False,
+                           attention_bias=True, mlp_bias=True, tie_word_embeddings=True,
+                           norm_eps=hf.get("layer_norm_epsilon", 1e-5))
+    assert mt in _LLAMA_LIKE, f"unsupported HF model_type {mt!r}"
+    kw = dict(model_type=mt, vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+              intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
+              num_attention_heads=hf["num_attention_heads"],
+              num_key_value_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
+              max_position_embeddings=hf.get("max_position_embeddings", 4096),
+              rope_theta=float(hf.get("rope_theta", 10000.0)), norm_eps=hf.get("rms_norm_eps", 1e-6),
+              tie_word_embeddings=hf.get("tie_word_embeddings", False), rope_scaling=hf.get("rope_scaling"))
+    if hf.get("head_dim"):
+        kw["head_dim"] = hf["head_dim"]
+    if mt == "qwen2":
+        kw["attention_bias"], kw["attention_out_bias"] = True, False
+    if mt == "qwen3":
+        kw["qk_norm"] = True
+    if mt == "mixtral":
+        kw["moe"] = MoEConfig(num_experts=hf["num_local_experts"], top_k=hf["num_experts_per_tok"])
+    fields = ModelConfig.__dataclass_fields__
+    return ModelConfig(**{k: v for k, v in kw.items() if k in fields})
+
+
+def iter_hf_shards(path: str) -> Iterator[Dict[str, torch.Tensor]]:
+    files = sorted(f for f in os.listdir(path) if f.endswith((".safetensors", ".bin")) and "optimizer" not in f
+                   and not f.startswith("training_args"))
+    for f in files:
+        full = os.path.join(path, f)
+        if f.endswith(".safetensors"):
+            from safetensors.torch import load_file
+
+            yield load_file(full)
+        else:
+            yield torch.load(full, map_location="cpu", weights_only=True)
+
+
+def convert_hf_state_dict(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    """HF names -> ours (fusing q/k/v, gate/up, stacking experts).  Keys it does not know are passed through."""
+    out: Dict[str, torch.Tensor] = {}
+    if cfg.model_type == "gpt2":
+        for k, v in hf_sd.items():
+            k = k[len("transformer."):] if k.startswith("transformer.") else k
+            m = re.match(r"h\.(\d+)\.(.*)", k)
+            if m:
+                i, rest = m.group(1), m.group(2)
+                pre = f"model.layers.{i}."
+                table = {"ln_1.": "input_layernorm.", "ln_2.": "post_attention_layernorm.",
+                         "attn.c_attn.": "self_attn.qkv_proj.", "attn.c_proj.": "self_attn.o_proj.",
+                         "mlp.c_fc.": "mlp.up_proj.", "mlp.c_proj.": "mlp.down_proj."}
+                for a, b in table.items():
+                    if rest.startswith(a):
+                        t = v.t().contiguous() if (rest.endswith("weight") and ".c_" in rest) else v   # Conv1D -> Linear
+                        out[pre + b + rest[len(a):]] = t
+                        break
+            elif k == "wte.weight":
+                out["model.embed_tokens.weight"] = v
+            elif k == "wpe.weight":
+                out["model.embed_positions.weight"] = v
+            elif k.startswith("ln_f."):
+                out["model.norm." + k[5:]] = v
+            elif k == "lm_head.weight":
+                out["lm_head.weight"] = v
+        return out
+    qkv: Dict[Tuple[str, str], Dict[str, torch.Tensor]] = {}
+    gu: Dict[str, Dict[str, torch.Tensor]] = {}
+    experts: Dict[str, Dict[int, Dict[str, torch.Tensor]]] = {}
+    for k, v in hf_sd.items():
+        m = re.match(r"(model\.layers\.\d+\.self_attn\.)([qkv])_proj\.(weight|bias)", k)
+        if m:
+            qkv.setdefault((m.group(1), m.group(3)), {})[m.group(2)] = v
+            continue
+        m = re.match(r"(model\.layers\.\d+\.mlp\.)(gate|up)_proj\.weight", k)
+        if m:
+            gu.setdefault(m.group(1), {})[m.group(2)] = v
+            continue
+        m = re.match(r"(model\.layers\.\d+\.)block_sparse_moe\.experts\.(\d+)\.(w[123])\.weight", k)
+        if m:
+            experts.setdefault(m.group(1), {}).setdefault(int(m.group(2)), {})[m.group(3)] = v
+            continue
+        m = re.match(r"(model\.layers\.\d+\.)block_sparse_moe\.gate\.weight", k)
+        if m:
+            out[m.group(1) + "mlp.router.gate.weight"] = v
+            continue
+        out[k] = v
+    for (pre, kind), parts in qkv.items():
+        out[f"{pre}qkv_proj.{kind}"] = torch.cat([parts["q"], parts["k"], parts["v"]], dim=0)
+    for pre, parts in gu.items():
+        out[pre + "gate_up_proj.weight"] = torch.cat([parts["gate"], parts["up"]], dim=0)
+    for pre, ex in experts.items():
+        ids = sorted(ex)
+        out[pre + "mlp.experts.w_up"] = torch.stack([torch.cat([ex[i]["w1"], ex[i]["w3"]], 0) for i in ids])
+        out[pre + "mlp.experts.w_down"] = torch.stack([ex[i]["w2"] for i in ids])
+    return out
+
+
+def to_hf_state_dict(model, cfg: Optional[ModelConfig] = None) -> Dict[str, torch.Tensor]:
+    """Inverse of `convert_hf_state_dict` for the llama-like families (un-fuses qkv / gate_up / experts)."""
+    cfg = cfg or model.cfg
+    assert cfg.model_type in _LLAMA_LIKE, "export is implemented for the llama-like families"
+    q, kv = cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in model.state_dict().items():
+        v = v.detach()
+        if k.endswith(("qkv_proj.weight", "qkv_proj.bias")):
+            pre, kind = k.rsplit("qkv_proj.", 1)
+            a, b, c = v.split([q, kv, kv], dim=0)
+            out[pre + "q_proj." + kind], out[pre + "k_proj." + kind], out[pre + "v_proj." + kind] = a, b, c
+        elif k.endswith("gate_up_proj.weight"):
+            pre = k[: -len("gate_up_proj.weight")]
+            g, u = v.chunk(2, dim=0)
+            out[pre + "gate_proj.weight"], out[pre + "up_proj.weight"] = g, u
+        elif k.endswith("mlp.experts.w_up"):
+            pre = k[: -len("mlp.experts.w_up")] + "block_sparse_moe.experts."
+            for i in range(v.shape[0]):
+                w1, w3 = v[i].chunk(2, dim=0)
+                out[f"{pre}{i}.w1.weight"], out[f"{pre}{i}.w3.weight"] = w1, w3
+        elif k.endswith("mlp.experts.w_down"):
+            pre = k[: -len("mlp.experts.w_down")] + "block_sparse_moe.experts."
+            for i in range(v.shape[0]):
+                out[f"{pre}{i}.w2.weight"] = v[i]
+        elif k.endswith("mlp.router.gate.weight"):
+            out[k.replace("mlp.router.gate.weight", "block_sparse_moe.gate.weight")] = v
+        else:
+            out[k] = v
+    return out
+
+
+def load_hf_checkpoint(path: str, dtype: torch.dtype = torch.bfloat16, device: str = "cpu", strict: bool = False):
+    """Build our model from `path/config.json` and load every weight shard found in `path`."""
+    from . import build_model
+
+    with open(os.path.join(path, "config.json")) as f:
+        cfg = config_from_hf(json.load(f))
+    model = build_model(cfg).to(dtype)
+    merged: Dict[str, torch.Tensor] = {}
+    for shard in iter_hf_shards(path):
+        merged.update(shard)        # q/k/v of one layer may sit in different shards -> convert once at the end
+    sd = convert_hf_state_dict(merged, cfg)
+    missing, unexpected = model.load_state_dict({k: v.to(dtype) for k, v in sd.items()}, strict=False)
+    missing = [m for m in missing if not (cfg.tie_word_embeddings and m == "lm_head.weight")]
+    if strict and (missing or unexpected):
+        raise RuntimeError(f"load_hf_checkpoint: missing={missing[:8]} unexpected={unexpected[:8]}")
+    model._pretrained_path = path
+    return model.to(device)
