@@ -37,7 +37,8 @@ def parse_args():
     p.add_argument("--model", default=os.environ.get("CB200_BENCH_MODEL", "llama3-8b"))
     p.add_argument("--seq", type=int, default=4096)
     p.add_argument("--mbs", type=int, default=1, help="sequences per GPU per step (weak scaling)")
-    p.add_argument("--accum", type=int, default=1, help="gradient accumulation micro-steps per optimizer step")
+    p.add_argument("--accum", type=int, default=int(os.environ.get("CB200_BENCH_ACCUM", "8")),
+                   help="gradient accumulation micro-steps per optimizer step (the reference headline uses batch/DP 128)")
     p.add_argument("--tp", type=int, default=0, help="tensor parallel size (default: = gpus)")
     p.add_argument("--pp", type=int, default=1)
     p.add_argument("--sp-mode", default="split_gather")

@@ -16,6 +16,8 @@
 //
 // This kernel replaces the reference's cuBLAS calls (`F.linear` / `torch.matmul` in shardformer/layer/_operation.py)
 // with our own tensor-core path; the comm-fused variants in fused_comm_gemm.cu share its main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -264,6 +266,219 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per cluster of two CTAs.  Each CTA stages its own 128 rows
+// of A and its own 128 columns of B (32 KB / stage instead of 48 KB for a 1-CTA 128x256 tile), the leader CTA issues
+// UMMA 256x256x16 that reads both CTAs' shared memory, and each CTA owns the 128 x 256 fp32 accumulator slice of its
+// rows in its own TMEM.  B is fetched from global memory once per pair, and the operand bytes read from shared memory
+// per MMA flop drop by a third, which is what lifts the tensor pipe from ~71 % to the library's level.
+//   barriers: full[s] lives in the leader (armed with the bytes of BOTH CTAs, completed by both CTAs' TMA),
+//             empty[s] / tmem_full[a] exist in both CTAs and are signalled by multicast tcgen05.commit,
+//             tmem_empty[a] lives in the leader and collects the 2 x 4 epilogue warps (remote arrive from the peer).
+constexpr int PAIR_M = 256;
+constexpr int PAIR_N = 256;
+struct Cfg2 {
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  using C = Cfg2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_pairs = gridDim.x >> 1;
+  const int pair_id = blockIdx.x >> 1;
+  const int m_blocks = (p.M + PAIR_M - 1) / PAIR_M;
+  const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync();                      // both CTAs' barriers exist before anything remote touches them
+  if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+      const int m0 = m_blk * PAIR_M + (int)cta_rank * 128;
+      const int n0 = n_blk * PAIR_N + (int)cta_rank * 128;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn_major) {
+            tma_load_2d_2sm(&tmap_a, fb, sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BLOCK_K * 128), m0 + j * 64, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d_2sm(&tmap_b, fb, sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BLOCK_K * 128), n0 + j * 64, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PAIR_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+            const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024)
+                                             : make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024)
+                                             : make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss_2cta(tmem_d, advance_desc(da, k * a_kstep), advance_desc(db, k * b_kstep), p.idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage], 3);
+            if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (k_blocks == 0 && lane == 0) umma_commit_2cta(&tmem_full[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5, both CTAs)
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+      const int row = m_blk * PAIR_M + (int)cta_rank * 128 + quarter * 32 + lane;
+      const int n0 = n_blk * PAIR_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * PAIR_N + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < PAIR_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c, v);
+        tmem_ld_wait();
+        const int n_valid = p.N - (n0 + c);
+        if (row < p.M && n_valid > 0 && p.K > 0) {
+          const size_t off = (size_t)row * p.ldc + n0 + c;
+          if (p.out_dtype == CB_BF16)
+            store_row_chunk<__nv_bfloat16>((__nv_bfloat16*)p.C + off, v, n_valid, p.accumulate);
+          else if (p.out_dtype == CB_F32)
+            store_row_chunk<float>((float*)p.C + off, v, n_valid, p.accumulate);
+          else
+            store_row_chunk<__half>((__half*)p.C + off, v, n_valid, p.accumulate);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync();                      // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+}
+
+int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                int b_mn, int in_dtype, int out_dtype, int accumulate, cudaStream_t stream) {
+  using C = Cfg2;
+  CUtensorMap ta, tb;
+  const bool bf16 = in_dtype == CB_BF16;
+  int r;
+  r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
+  if (r) return 1000 + r;
+  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
+  if (r) return 2000 + r;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.out_dtype = out_dtype;
+  p.accumulate = accumulate; p.C = Cp;
+  p.idesc = make_idesc_f16(PAIR_M, PAIR_N, bf16 ? 1 : 0, a_mn, b_mn);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = ((M + PAIR_M - 1) / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
+  int pairs = cb_num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  if (pairs <= 0) return 0;
+  gemm_tcgen05_2cta_kernel<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
 template <int BLOCK_N>
 int launch(const void* A, const void* B, void* Cp, int M, int N, int K, int lda, int ldb, int ldc, int a_mn, int b_mn,
            int in_dtype, int out_dtype, int accumulate, cudaStream_t stream) {
@@ -310,6 +525,15 @@ int cb_gemm_tcgen05(const void* A, const void* B, void* C, int M, int N, int K, 
                     cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   if (in_dtype != CB_BF16 && in_dtype != CB_F16) return (int)cudaErrorInvalidValue;
+  static int use_2cta = -1;
+  if (use_2cta < 0) {
+    const char* e = getenv("CB200_GEMM_2CTA");
+    use_2cta = e ? atoi(e) : 1;
+  }
+  // CTA-pair kernel: 256 x 256 tiles; worth it once there are enough tiles to fill the 74 pairs
+  if (block_n == 512 || (block_n == 0 && use_2cta && M >= 256 && N >= 256 &&
+                         ((M + 255) / 256) * ((N + 255) / 256) >= cb_num_sms() / 2))
+    return launch_2cta(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
   if (block_n == 0) {
     const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
     block_n = (tiles256 >= cb_num_sms() || N % 256 == 0 && tiles256 * 2 > cb_num_sms() * 3) ? 256 : 128;

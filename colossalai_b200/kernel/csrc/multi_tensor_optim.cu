@@ -210,7 +210,53 @@ __global__ void __launch_bounds__(OPT_THREADS) multi_tensor_norm_partial_kernel(
     const int64_t n = min((int64_t)CHUNK, t.n - off);
     const void* src = which == 0 ? t.p : (which == 1 ? t.g : t.m);
     const int dt = which == 0 ? t.pd : (which == 1 ? t.gd : CB_F32);
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const int esz = dt == CB_F32 ? 4 : 2;
+    const char* base = reinterpret_cast<const char*>(src) + off * esz;
+    const int per = 16 / esz;                                   // elements per 16-byte vector
+    int64_t head = 0;                                           // scalar prologue up to 16-byte alignment
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(base) & 15;
+    if (mis) head = min(n, (int64_t)((16 - mis) / esz));
+    for (int64_t j = threadIdx.x; j < head; j += blockDim.x) {
+      const float x = ld_any(src, dt, off + j);
+      acc = use_max ? fmaxf(acc, fabsf(x)) : acc + x * x;
+    }
+    const int64_t nvec = (n - head) / per;
+    const uint4* vp = reinterpret_cast<const uint4*>(base + head * esz);
+    float acc2 = 0.f;                                           // two accumulators: more loads in flight
+    for (int64_t j = threadIdx.x; j < nvec; j += 2 * blockDim.x) {
+      uint4 r0, r1 = make_uint4(0, 0, 0, 0);
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "l"(vp + j));
+      const bool two = j + blockDim.x < nvec;
+      if (two)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "l"(vp + j + blockDim.x));
+      const uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w};
+      const uint32_t w1[4] = {r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float a0, a1, b0, b1;
+        if (dt == CB_F32) {
+          a0 = __uint_as_float(w0[q]); a1 = 0.f; b0 = __uint_as_float(w1[q]); b1 = 0.f;
+        } else if (dt == CB_BF16) {
+          a0 = __uint_as_float(w0[q] << 16); a1 = __uint_as_float(w0[q] & 0xffff0000u);
+          b0 = __uint_as_float(w1[q] << 16); b1 = __uint_as_float(w1[q] & 0xffff0000u);
+        } else {
+          const __half2 h0 = *reinterpret_cast<const __half2*>(&w0[q]);
+          const __half2 h1 = *reinterpret_cast<const __half2*>(&w1[q]);
+          a0 = __low2float(h0); a1 = __high2float(h0); b0 = __low2float(h1); b1 = __high2float(h1);
+        }
+        if (use_max) {
+          acc = fmaxf(acc, fmaxf(fabsf(a0), fabsf(a1)));
+          acc2 = fmaxf(acc2, fmaxf(fabsf(b0), fabsf(b1)));
+        } else {
+          acc += a0 * a0 + a1 * a1;
+          acc2 += b0 * b0 + b1 * b1;
+        }
+      }
+    }
+    acc = use_max ? fmaxf(acc, acc2) : acc + acc2;
+    for (int64_t j = head + nvec * per + threadIdx.x; j < n; j += blockDim.x) {     // scalar tail
       const float x = ld_any(src, dt, off + j);
       acc = use_max ? fmaxf(acc, fabsf(x)) : acc + x * x;
     }

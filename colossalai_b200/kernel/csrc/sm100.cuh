@@ -154,6 +154,59 @@ SM100_DEVICE void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
 }
 SM100_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------- CTA pairs (cta_group::2)
+SM100_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SM100_DEVICE void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address of THIS CTA) inside CTA `rank` of the cluster
+SM100_DEVICE uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+SM100_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load issued by either CTA of a pair; the bytes are accounted on the barrier at `bar_cluster_addr`
+// (the leader CTA's full barrier).
+SM100_DEVICE void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0,
+                                  int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int NCOLS> SM100_DEVICE void tmem_alloc_2cta(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+               :: "r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> SM100_DEVICE void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// 256-row MMA across the CTA pair; issued by ONE thread of the leader CTA
+SM100_DEVICE void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in every CTA selected by `cta_mask` once the issued MMAs retire
+SM100_DEVICE void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B.  Byte offsets are encoded without their 4 LSBs.
 //   K-major  : rows of 128 B (64 x 16-bit along K); SBO = stride between 8-row groups (1024 B when rows are packed)

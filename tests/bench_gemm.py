@@ -52,6 +52,10 @@ def main():
             t_o, t_r = timeit(ours), timeit(ref)
             row[label] = {"ours_ms": t_o, "cublas_ms": t_r, "ours_tflops": fl / t_o / 1e9, "cublas_tflops": fl / t_r / 1e9,
                           "frac_of_measured_peak": fl / t_o / 1e9 / peak}
+        # 1-CTA (128x256) vs CTA-pair (256x256) kernels on the forward shape
+        t1 = timeit(lambda: g.gemm_nt(x, w, block_n=256))
+        t2 = timeit(lambda: g.gemm_nt(x, w, block_n=512))
+        row["nt_1cta_tflops"], row["nt_2cta_tflops"] = fl / t1 / 1e9, fl / t2 / 1e9
         out.append(row)
         print(json.dumps(row), flush=True)
 

@@ -14,7 +14,7 @@ SHAPES = [(128, 256, 64), (256, 512, 128), (1000, 768, 520), (4096, 4096, 4096),
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_gemm_nt(M, N, K, block_n, dtype):
     from colossalai_b200.ops import gemm_native as g
@@ -29,7 +29,7 @@ def test_gemm_nt(M, N, K, block_n, dtype):
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 def test_gemm_nn(M, N, K, block_n):
     from colossalai_b200.ops import gemm_native as g
 
@@ -41,7 +41,7 @@ def test_gemm_nn(M, N, K, block_n):
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 def test_gemm_tn(M, N, K, block_n):
     from colossalai_b200.ops import gemm_native as g
 

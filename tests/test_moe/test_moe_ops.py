@@ -144,7 +144,10 @@ def _fused_vs_nccl(group, T, H, E, K, seed):
         outs[name] = (y.detach().float(), xi.grad.float(), li.grad.float(), w.grad.float())
     dc.set_moe_backend("auto")
     for a, b, what in zip(outs["fused"], outs["nccl"], ("y", "dx", "dlogits", "dw")):
-        torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-2, msg=lambda m: f"{what}: {m}")
+        # rows reach the experts in a different order -> bf16 outputs may differ by one ulp: compare in norm
+        err = (a - b).norm() / b.norm().clamp_min(1e-6)
+        assert err < 1e-2, f"{what}: relative error {err:.3e}"
+        assert (a - b).abs().max() <= 0.02 * b.abs().max() + 1e-3, f"{what}: max abs diff {(a - b).abs().max():.3e}"
 
 
 @pytest.mark.gpu
