@@ -19,6 +19,8 @@
 // These replace the reference's `dist.all_gather` + `F.linear` / `F.linear` + `dist.reduce_scatter` pairs
 // (shardformer/layer/_operation.py:562-566, 737-751) and its python ring variants (`_ring_as_gather`,
 // `_ring_as_reducescatter`): no NCCL call on these paths.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -136,6 +138,126 @@ SM100_DEVICE void store_chunk16(T16* __restrict__ dst, const uint32_t (&acc)[32]
     }
   } else {
     for (int j = 0; j < n_valid; ++j) dst[j] = from_f32<T16>(__uint_as_float(acc[j]));
+  }
+}
+
+// NVLink pull executed by warps 6..7 of EVERY CTA (AG+GEMM): 16-row segments of the peers' chunks are copied into the
+// local gathered buffer, one ready flag per 128-row block is published once its 8 segments landed.
+SM100_DEVICE void ag_pull_warps(const CommParams& c, uint32_t* my_flags, int warp, int lane, int blocks_per_chunk) {
+  // ================================================================ AG: NVLink pull by the copy warps of ALL CTAs
+  if (blockIdx.x == 0 && warp == 6 && lane < c.world)   // announce: my input buffer is valid for this epoch
+    st_release_sys(c.peer_flags[lane] + SLOT_IN_READY + c.rank, c.epoch);
+  const int vec_per_row = c.ld_in / 8;                  // 16-byte vectors per row
+  const int copy_warp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
+  const int n_copy_warps = (int)gridDim.x * COPY_WARPS;
+  const int units_per_chunk = blocks_per_chunk * COPY_SEG;
+  const int seg_rows = BLOCK_M / COPY_SEG;
+  const size_t seg_vec = (size_t)seg_rows * vec_per_row;
+  int cur_src = -1;
+  for (int u = copy_warp; u < units_per_chunk * c.world; u += n_copy_warps) {
+    const int step = u / units_per_chunk;                // chunks in order rank, rank+1, ...
+    const int src = (c.rank + step) % c.world;
+    const int in_chunk = u - step * units_per_chunk;
+    const int sb = in_chunk / COPY_SEG, seg = in_chunk - sb * COPY_SEG;
+    if (src != cur_src) {
+      if (src != c.rank) {
+        if (lane == 0)
+          while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
+          }
+        __syncwarp();
+      }
+      cur_src = src;
+    }
+    const uint4* sp = reinterpret_cast<const uint4*>(c.peer_in[src]) + ((size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
+    uint4* dp = reinterpret_cast<uint4*>(c.gathered) +
+                ((size_t)src * c.rows_per_chunk + (size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
+    size_t i = lane;
+    for (; i + 7 * 32 < seg_vec; i += 8 * 32) {          // 8 independent 16-byte loads in flight per lane
+      uint4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = ld_peer_16B(sp + i + j * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dp[i + j * 32] = t[j];
+    }
+    for (; i < seg_vec; i += 32) dp[i] = ld_peer_16B(sp + i);
+    fence_proxy_async_global();          // generic-proxy writes -> visible to TMA (async proxy) readers
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const int blk = src * blocks_per_chunk + sb;
+      const uint32_t got = atomicAdd(c.block_counter + blk, 1u) + 1;
+      if (got == (uint32_t)COPY_SEG) {
+        c.block_counter[blk] = 0;
+        __threadfence();
+        st_release_gpu(c.ready + blk, c.epoch);
+      }
+    }
+  }
+  // tell every peer that this rank no longer reads its input buffer (last copy warp to finish signals)
+  if (lane == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL, 1u) + 1;
+    if (done == (uint32_t)n_copy_warps) {
+      my_flags[SLOT_LOCAL] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
+// Reduce-scatter tail (GEMM+RS): after every peer signalled its partial of MY chunk, sum the chunk out of all partial
+// buffers (in-switch multimem reduction when a multicast mapping exists) and release the partial buffers.
+SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint32_t* my_flags) {
+  // ================================================================== RS: reduce MY chunk out of all partial buffers
+  if (threadIdx.x < c.world) {
+    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_CHUNK_DONE + threadIdx.x), c.epoch)) {
+    }
+  }
+  __syncthreads();
+  const int vec_per_row = p.N / 8;
+  const size_t row0 = (size_t)c.rank * c.rows_per_chunk;
+  const size_t nvec = (size_t)c.rows_per_chunk * vec_per_row;
+  const size_t ldc_vec = p.ldc / 8;
+  const size_t stride = (size_t)gridDim.x * NUM_THREADS;
+  for (size_t i0 = (size_t)blockIdx.x * NUM_THREADS + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+    uint4 sum[4];
+    size_t dst_off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                           // 4 independent switch reductions in flight per thread
+      const size_t i = i0 + u * stride;
+      if (i >= nvec) { dst_off[u] = (size_t)-1; continue; }
+      const size_t r = i / vec_per_row, cv = i - r * vec_per_row;
+      const size_t src_off = (row0 + r) * ldc_vec + cv;     // 16-byte units inside the partial buffer
+      dst_off[u] = r * (c.ld_out / 8) + cv;
+      if (c.mc_part) {
+        sum[u] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
+      } else {
+        float accf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int rk = 0; rk < c.world; ++rk) {
+          const int src = (c.rank + rk) % c.world;
+          Vec16<__nv_bfloat16> v;
+          v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[src]) + src_off);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) accf[k] += v.get(k);
+        }
+        Vec16<__nv_bfloat16> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.set(k, accf[k]);
+        sum[u] = o.raw;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst_off[u] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[dst_off[u]] = sum[u];
+  }
+  // everyone may now overwrite their partial buffer again: last CTA of this rank signals all peers
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
+    if (done == gridDim.x) {
+      my_flags[SLOT_LOCAL + 1] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
   }
 }
 
@@ -270,64 +392,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp >= 6) {
     if (MODE == 0) {
-      // ================================================================ AG: NVLink pull by the copy warps of ALL CTAs
-      if (blockIdx.x == 0 && warp == 6 && lane < c.world)   // announce: my input buffer is valid for this epoch
-        st_release_sys(c.peer_flags[lane] + SLOT_IN_READY + c.rank, c.epoch);
-      const int vec_per_row = c.ld_in / 8;                  // 16-byte vectors per row
-      const int copy_warp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
-      const int n_copy_warps = (int)gridDim.x * COPY_WARPS;
-      const int units_per_chunk = blocks_per_chunk * COPY_SEG;
-      const int seg_rows = BLOCK_M / COPY_SEG;
-      const size_t seg_vec = (size_t)seg_rows * vec_per_row;
-      int cur_src = -1;
-      for (int u = copy_warp; u < units_per_chunk * c.world; u += n_copy_warps) {
-        const int step = u / units_per_chunk;                // chunks in order rank, rank+1, ...
-        const int src = (c.rank + step) % c.world;
-        const int in_chunk = u - step * units_per_chunk;
-        const int sb = in_chunk / COPY_SEG, seg = in_chunk - sb * COPY_SEG;
-        if (src != cur_src) {
-          if (src != c.rank) {
-            if (lane == 0)
-              while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
-              }
-            __syncwarp();
-          }
-          cur_src = src;
-        }
-        const uint4* sp = reinterpret_cast<const uint4*>(c.peer_in[src]) + ((size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
-        uint4* dp = reinterpret_cast<uint4*>(c.gathered) +
-                    ((size_t)src * c.rows_per_chunk + (size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
-        size_t i = lane;
-        for (; i + 7 * 32 < seg_vec; i += 8 * 32) {          // 8 independent 16-byte loads in flight per lane
-          uint4 t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = ld_peer_16B(sp + i + j * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dp[i + j * 32] = t[j];
-        }
-        for (; i < seg_vec; i += 32) dp[i] = ld_peer_16B(sp + i);
-        fence_proxy_async_global();          // generic-proxy writes -> visible to TMA (async proxy) readers
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          const int blk = src * blocks_per_chunk + sb;
-          const uint32_t got = atomicAdd(c.block_counter + blk, 1u) + 1;
-          if (got == (uint32_t)COPY_SEG) {
-            c.block_counter[blk] = 0;
-            __threadfence();
-            st_release_gpu(c.ready + blk, c.epoch);
-          }
-        }
-      }
-      // tell every peer that this rank no longer reads its input buffer (last copy warp to finish signals)
-      if (lane == 0) {
-        const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL, 1u) + 1;
-        if (done == (uint32_t)n_copy_warps) {
-          my_flags[SLOT_LOCAL] = 0;
-          __threadfence_system();
-          for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
-        }
-      }
+      ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
     }
   } else {
     const int quarter = warp & 3;
@@ -380,59 +445,244 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 
   if (MODE == 1) {
-    // ================================================================== RS: reduce MY chunk out of all partial buffers
-    if (threadIdx.x < c.world) {
-      while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_CHUNK_DONE + threadIdx.x), c.epoch)) {
+    rs_reduce_phase(p, c, my_flags);
+  }
+}
+
+// =====================================================================================================================
+// CTA-pair (cta_group::2) version of the fused kernel: one 256 x 256 tile per cluster of two CTAs (see the plain kernel
+// in gemm_tcgen05.cu for the barrier topology).  Communication roles are unchanged: warps 6..7 of every CTA pull peer
+// rows (AG), every epilogue warp publishes its slice of a partial tile (RS).  Each CTA's TMA producer waits for the ready
+// flag of ITS OWN 128-row block of A, so the pair starts a tile as soon as both halves have landed.
+struct Cfg2 {
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+constexpr int PAIR_M = 256;
+constexpr int PAIR_N = 256;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmParams p, const CommParams c) {
+  using C = Cfg2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_pairs = gridDim.x >> 1;
+  const int pair_id = blockIdx.x >> 1;
+  const int m_blocks = (p.M + PAIR_M - 1) / PAIR_M;            // 256-row blocks
+  const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int blocks_per_chunk = c.rows_per_chunk / BLOCK_M;     // 128-row blocks (flag granularity of the pull)
+  const int pair_blocks_per_chunk = c.rows_per_chunk / PAIR_M;
+  uint32_t* my_flags = c.peer_flags[c.rank];
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync();
+  if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int m_rot = MODE == 0 ? c.rank * pair_blocks_per_chunk : ((c.rank + 1) % c.world) * pair_blocks_per_chunk;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      const int m0 = m_blk * PAIR_M + (int)cta_rank * 128;
+      const int n0 = n_blk * PAIR_N + (int)cta_rank * 128;
+      if (MODE == 0) {
+        if (lane == 0) {
+          while (!epoch_reached(ld_acquire_gpu(c.ready + (m_blk * 2 + (int)cta_rank)), c.epoch)) {
+          }
+          fence_proxy_async_global();
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn_major) {
+            tma_load_2d_2sm(&tmap_a, fb, sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BLOCK_K * 128), m0 + j * 64, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d_2sm(&tmap_b, fb, sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BLOCK_K * 128), n0 + j * 64, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncthreads();
-    const int vec_per_row = p.N / 8;
-    const size_t row0 = (size_t)c.rank * c.rows_per_chunk;
-    const size_t nvec = (size_t)c.rows_per_chunk * vec_per_row;
-    const size_t ldc_vec = p.ldc / 8;
-    const size_t stride = (size_t)gridDim.x * NUM_THREADS;
-    for (size_t i0 = (size_t)blockIdx.x * NUM_THREADS + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
-      uint4 sum[4];
-      size_t dst_off[4];
+  } else if (warp == 1) {
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * PAIR_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+            const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024)
+                                             : make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024)
+                                             : make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {                           // 4 independent switch reductions in flight per thread
-        const size_t i = i0 + u * stride;
-        if (i >= nvec) { dst_off[u] = (size_t)-1; continue; }
-        const size_t r = i / vec_per_row, cv = i - r * vec_per_row;
-        const size_t src_off = (row0 + r) * ldc_vec + cv;     // 16-byte units inside the partial buffer
-        dst_off[u] = r * (c.ld_out / 8) + cv;
-        if (c.mc_part) {
-          sum[u] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
-        } else {
-          float accf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          for (int rk = 0; rk < c.world; ++rk) {
-            const int src = (c.rank + rk) % c.world;
-            Vec16<__nv_bfloat16> v;
-            v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[src]) + src_off);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) accf[k] += v.get(k);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss_2cta(tmem_d, advance_desc(da, k * a_kstep), advance_desc(db, k * b_kstep), p.idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage], 3);
+            if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
           }
-          Vec16<__nv_bfloat16> o;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o.set(k, accf[k]);
-          sum[u] = o.raw;
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 6) {
+    if (MODE == 0) ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      const int row = m_blk * PAIR_M + (int)cta_rank * 128 + quarter * 32 + lane;
+      const int n0 = n_blk * PAIR_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * PAIR_N + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < PAIR_N; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cc, v);
+        tmem_ld_wait();
+        const int n_valid = p.N - (n0 + cc);
+        if (row < p.M && n_valid > 0) {
+          const size_t off = (size_t)row * p.ldc + n0 + cc;
+          if (p.out_dtype == CB_BF16) store_chunk16<__nv_bfloat16>((__nv_bfloat16*)p.C + off, v, n_valid);
+          else store_chunk16<__half>((__half*)p.C + off, v, n_valid);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (dst_off[u] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[dst_off[u]] = sum[u];
-    }
-    // everyone may now overwrite their partial buffer again: last CTA of this rank signals all peers
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
-      if (done == gridDim.x) {
-        my_flags[SLOT_LOCAL + 1] = 0;
-        __threadfence_system();
-        for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
       }
+      if (MODE == 1) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+          const int chunk = m_blk / pair_blocks_per_chunk;
+          const uint32_t got = atomicAdd(c.chunk_counter + chunk, 1u) + 1;
+          const uint32_t need = (uint32_t)pair_blocks_per_chunk * n_blocks * 8;   // 2 CTAs x 4 epilogue warps per tile
+          if (got == need) {
+            c.chunk_counter[chunk] = 0;
+            __threadfence_system();
+            st_release_sys(c.peer_flags[chunk] + SLOT_CHUNK_DONE + c.rank, c.epoch);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+  if (MODE == 1) rs_reduce_phase(p, c, my_flags);
+}
+
+template <int MODE>
+int launch_fused_2cta(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_mn, int b_mn,
+                      int in_dtype, GemmParams p, const CommParams& c, cudaStream_t stream) {
+  using C = Cfg2;
+  CUtensorMap ta, tb;
+  const bool bf16 = in_dtype == CB_BF16;
+  int r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
+  if (r) return 1000 + r;
+  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
+  if (r) return 2000 + r;
+  p.idesc = make_idesc_f16(PAIR_M, PAIR_N, bf16 ? 1 : 0, a_mn, b_mn);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fused_gemm_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = cb_num_sms() & ~1;     // all CTAs co-resident (flag spinning): one CTA per SM, whole pairs
+  fused_gemm_2cta_kernel<MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, c);
+  return (int)cudaGetLastError();
+}
+
+// CTA-pair kernels need whole 256-row blocks per rank chunk
+inline bool use_pair_kernel(int T, int world, int N, int block_n) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("CB200_FUSED_2CTA");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (block_n == 512) return true;
+  return enabled && block_n == 0 && (T / world) % PAIR_M == 0 && N >= 256;
 }
 
 // Stand-alone all-gather by P2P pull (every CTA is a copy CTA).
@@ -517,7 +767,9 @@ int cb_ag_gemm(const void* const* peer_in, uint32_t* const* peer_flags, void* ga
   c.gathered = gathered; c.ld_in = K; c.ready = ready; c.block_counter = block_counter;
   GemmParams p{};
   p.M = T; p.N = N; p.K = K; p.ldc = ldy; p.a_mn_major = 0; p.b_mn_major = b_mn_major; p.C = Y; p.out_dtype = in_dtype;
-  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0)
+    return launch_fused_2cta<0>(gathered, B, T, N, K, K, ldb, 0, b_mn_major, in_dtype, p, c, stream);
+  if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
   if (block_n == 256)
     return launch_fused<256, 0>(gathered, B, T, N, K, K, ldb, 0, b_mn_major, in_dtype, p, c, stream);
   return launch_fused<128, 0>(gathered, B, T, N, K, K, ldb, 0, b_mn_major, in_dtype, p, c, stream);
@@ -537,7 +789,9 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
   GemmParams p{};
   p.M = T; p.N = N; p.K = K; p.ldc = N; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.C = part;
   p.out_dtype = in_dtype;
-  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0)
+    return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
+  if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
   if (block_n == 256)
     return launch_fused<256, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
   return launch_fused<128, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);

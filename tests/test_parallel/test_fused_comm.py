@@ -37,7 +37,10 @@ def _worker(rank, world_size, port, timing=False):
     assert fused.available(group), "fused backend must be available on a multi-GPU B200 box"
     torch.manual_seed(100 + rank)
     results = []
-    for (t, K, N) in [(256, 512, 768), (1024, 4096, 6144 // world_size), (2048, 4096, 4096)]:
+    shapes = [(256, 512, 768), (1024, 4096, 6144 // world_size), (2048, 4096, 4096)]
+    if timing:   # Llama-3-8B per-layer shapes at this TP degree (4096 tokens per rank)
+        shapes += [(4096, 4096, 28672 // world_size), (4096, 14336 // world_size, 4096)]
+    for (t, K, N) in shapes:
         T = t * world_size
         x_local = (torch.randn(t, K, device="cuda") * 0.5).bfloat16()
         torch.manual_seed(7)   # identical weights on every rank
@@ -62,6 +65,11 @@ def _worker(rank, world_size, port, timing=False):
         got2 = fused.gemm_reduce_scatter(a, w2, group, transpose_b=False)
         ref2 = comm.reduce_scatter((a.float() @ w2.float()), 0, group)
         torch.testing.assert_close(got2.float(), ref2, atol=0.15, rtol=3e-2)
+        # the 1-CTA (128x256 tile) kernels stay available behind block_n=256; block_n=0 picks the CTA-pair kernels
+        y1, _ = fused.all_gather_gemm(x_local, w, group, transpose_b=True, block_n=256)
+        torch.testing.assert_close(y1.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
+        got1 = fused.gemm_reduce_scatter(a, w, group, transpose_b=True, block_n=256)
+        torch.testing.assert_close(got1.float(), ref, atol=0.15, rtol=3e-2)
         # repeated calls exercise buffer reuse / epoch guards
         for _ in range(5):
             got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True)
@@ -70,11 +78,14 @@ def _worker(rank, world_size, port, timing=False):
         torch.testing.assert_close(y.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
         if timing and t >= 1024:
             t_f = _time(lambda: fused.all_gather_gemm(x_local, w, group))
+            t_f1 = _time(lambda: fused.all_gather_gemm(x_local, w, group, block_n=256))
             t_n = _time(lambda: torch.nn.functional.linear(comm.all_gather(x_local, 0, group), w))
             t_f2 = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
+            t_f21 = _time(lambda: fused.gemm_reduce_scatter(a, w, group, block_n=256))
             t_n2 = _time(lambda: comm.reduce_scatter(torch.nn.functional.linear(a, w), 0, group))
             results.append({"world": world_size, "t_local": t, "K": K, "N": N, "ag_gemm_fused_ms": t_f,
-                            "ag_gemm_nccl_ms": t_n, "gemm_rs_fused_ms": t_f2, "gemm_rs_nccl_ms": t_n2})
+                            "ag_gemm_fused_1cta_ms": t_f1, "ag_gemm_nccl_cublas_ms": t_n, "gemm_rs_fused_ms": t_f2,
+                            "gemm_rs_fused_1cta_ms": t_f21, "gemm_rs_nccl_cublas_ms": t_n2})
     assert fused.stats["ag_gemm"] > 0 and fused.stats["gemm_rs"] > 0, fused.stats
     if rank == 0:
         for r in results:
