@@ -98,7 +98,8 @@ def _bucketed_all_reduce(grads: List[Tensor], group: ProcessGroup, average_by: i
 class HybridParallelModule(ModelWrapper, AMPModelMixin):
     def __init__(self, module: Module, precision: str, shard_config: ShardConfig, dp_group: ProcessGroup,
                  tp_group: ProcessGroup, sp_group: ProcessGroup, use_ddp: bool, ddp_config: dict,
-                 custom_policy: Policy, overlap_allgather: bool = False, use_fp8: bool = False) -> None:
+                 custom_policy: Policy, overlap_allgather: bool = False, use_fp8: bool = False,
+                 inplace_wgrad: bool = False) -> None:
         self.stage_manager = shard_config.pipeline_stage_manager
         self.shard_config = shard_config
         self.dp_group, self.tp_group, self.sp_group = dp_group, tp_group, sp_group
@@ -128,6 +129,24 @@ class HybridParallelModule(ModelWrapper, AMPModelMixin):
             from ...quantization.fp8_hook import convert_linear_to_fp8
 
             convert_linear_to_fp8(self.module)
+        elif inplace_wgrad:
+            self._enable_inplace_wgrad()
+
+    def _enable_inplace_wgrad(self) -> None:
+        """Gradient accumulation inside the wgrad GEMM epilogue (`grad += dY^T X` with beta = 1): plain `nn.Linear`s
+        are routed through our autograd function, every 2-D linear weight is flagged (see `_accumulate_wgrad`)."""
+        from ...shardformer.layer._operation import linear_with_grad_accum
+
+        def fwd(mod, x):
+            return linear_with_grad_accum(x, mod.weight, mod.bias)
+
+        for m in self.module.modules():
+            w = getattr(m, "weight", None)
+            if not isinstance(w, nn.Parameter) or w.dim() != 2 or isinstance(m, nn.Embedding):
+                continue
+            if type(m) is nn.Linear:
+                m.forward = MethodType(fwd, m)
+            w._cb200_inplace_wgrad = True
 
     # ------------------------------------------------------------------ grad syncs
     def sync_shared_params(self) -> None:
@@ -553,7 +572,8 @@ class HybridParallelPlugin(PipelinePluginBase):
             model = HybridParallelModule(model, precision=self.precision, shard_config=self.shard_config,
                                          dp_group=self.mixed_dp_group, tp_group=self.tp_group, sp_group=self.sp_group,
                                          use_ddp=use_ddp, ddp_config=self.ddp_config, custom_policy=self.custom_policy,
-                                         overlap_allgather=self.zero_config["overlap_allgather"], use_fp8=self.use_fp8)
+                                         overlap_allgather=self.zero_config["overlap_allgather"], use_fp8=self.use_fp8,
+                                         inplace_wgrad=(self.zero_stage == 0))
             model.dp_size = self.dp_size_for_grads
         if optimizer is not None and not isinstance(optimizer, OptimizerWrapper):
             from ...nn.optimizer import cast_to_distributed

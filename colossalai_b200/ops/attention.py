@@ -28,6 +28,12 @@ class AttnMaskType:
 def _sdpa(q, k, v, causal, scale, attn_mask=None):
     # q [B,Hq,Sq,D], k/v [B,Hkv,Sk,D]
     Hq, Hkv = q.shape[1], k.shape[1]
+    if Hq != Hkv and q.is_cuda and attn_mask is None and q.shape[2] == k.shape[2]:
+        # grouped-query attention handled inside the library kernel: no 4x K/V expansion, no reduce in backward
+        try:
+            return F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale, enable_gqa=True)
+        except (TypeError, RuntimeError):
+            pass
     if Hq != Hkv:
         rep = Hq // Hkv
         k = k.repeat_interleave(rep, dim=1)

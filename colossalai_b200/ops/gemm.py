@@ -55,6 +55,11 @@ def matmul_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = No
         n = _try_native()
         if n and n.supported_tn(a, b):
             return n.gemm_tn(a, b, out=out, accumulate=accumulate)
+    if out is not None and a.is_cuda and out.dtype == a.dtype and out.is_contiguous():
+        # library path: accumulate inside the GEMM epilogue (beta = 1) instead of a separate add pass
+        if accumulate:
+            return out.addmm_(a.t(), b)
+        return torch.mm(a.t(), b, out=out)
     c = a.t() @ b
     if out is not None:
         if accumulate:

@@ -54,6 +54,12 @@ def _use_fused(x: torch.Tensor, group) -> bool:
 def _accumulate_wgrad(weight: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor) -> Optional[torch.Tensor]:
     """dW = dy2^T @ x2.  When the parameter carries a persistent `main_grad` buffer (fp32 or bf16 flat gradient
     arena owned by the optimizer wrapper) the GEMM accumulates straight into it and autograd gets None."""
+    if getattr(weight, "_cb200_inplace_wgrad", False) and weight.grad is not None \
+            and weight.grad.dtype == dy2.dtype and weight.grad.is_contiguous():
+        # gradient accumulation (micro-batches): fold `grad += dW` into the GEMM epilogue.  Only enabled by plugins
+        # that do not hang post-accumulate hooks on the parameter (autograd receives None for this weight).
+        ops.matmul_tn(dy2, x2, out=weight.grad, accumulate=True)
+        return None
     mg = getattr(weight, "main_grad", None)
     if mg is not None:
         if mg.dtype == dy2.dtype:

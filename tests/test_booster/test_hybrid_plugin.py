@@ -60,8 +60,51 @@ def _run(cfg):
     del plugin
 
 
+def _run_accum(plugin_kw):
+    """Two micro-batches per optimizer step: the second wgrad accumulates inside the GEMM (in-place path)."""
+    torch.manual_seed(42)
+    base = build_model("llama-tiny")
+    model = copy.deepcopy(base)
+    ref_opt = torch.optim.AdamW(base.parameters(), lr=1e-2, weight_decay=0.0)
+    opt = FusedAdam(model.parameters(), lr=1e-2, weight_decay=0.0)
+    plugin = HybridParallelPlugin(precision="fp32", **plugin_kw)
+    booster = Booster(plugin=plugin)
+    model, opt, *_ = booster.boost(model, opt)
+    flagged = [p for p in model.unwrap().parameters() if getattr(p, "_cb200_inplace_wgrad", False)]
+    assert flagged, "in-place wgrad accumulation should be enabled without ZeRO"
+    torch.manual_seed(100)
+    ids = torch.randint(0, 512, (2, 2 * plugin.dp_size, 32))
+    dp_rank = plugin.pg_mesh.axis_rank("dp")
+    for step in range(2):
+        for mb in range(2):
+            mine = ids[mb, dp_rank: dp_rank + 1]
+            loss = model(input_ids=mine, labels=mine)["loss"] / 2
+            if mb == 0:
+                with model.no_sync():
+                    opt.backward(loss)
+            else:
+                booster.backward(loss, opt)
+            for r in range(plugin.dp_size):
+                x = ids[mb, r: r + 1]
+                (base(input_ids=x, labels=x)["loss"] / 2 / plugin.dp_size).backward()
+        opt.step()
+        opt.zero_grad()
+        ref_opt.step()
+        ref_opt.zero_grad()
+    ref_params = dict(base.named_parameters())
+    for name, p in model.unwrap().named_parameters():
+        full = _gather_param(p)
+        r = ref_params[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        torch.testing.assert_close(full, r.detach(), atol=2e-4, rtol=2e-3, msg=lambda m: f"accum {name}: {m}")
+    del plugin
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    _run_accum(dict(tp_size=2, pp_size=1, enable_sequence_parallelism=True, sequence_parallelism_mode="split_gather"))
+    _run_accum(dict(tp_size=1, pp_size=1))
     _run(dict(plugin=dict(tp_size=2, pp_size=1)))
     _run(dict(plugin=dict(tp_size=2, pp_size=1, enable_sequence_parallelism=True,
                           sequence_parallelism_mode="split_gather"), max_norm=0.5))
