@@ -70,6 +70,10 @@ struct CommParams {
   int ld_out;
   uint32_t* chunk_counter;           // RS: local per-chunk arrival counters [world]
   int out_dtype;
+  // RS, CTA-pair kernel: tile-granular pipeline (reduce of a tile starts as soon as every rank finished that tile)
+  uint32_t* peer_tile_flags[MAX_RANKS];  // symmetric [MAX_RANKS][tile_flag_stride] epoch flags (index = writer rank)
+  int tile_flag_stride;                  // flags per writer rank
+  uint32_t* tile_counter;                // local per-tile epilogue-warp arrival counters [m_blocks * n_blocks]
 };
 
 struct GemmParams {
@@ -254,6 +258,85 @@ SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint
   if (threadIdx.x == 0) {
     const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
     if (done == gridDim.x) {
+      my_flags[SLOT_LOCAL + 1] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
+// GEMM+RS, CTA-pair kernel: warps 6..7 of every CTA reduce MY chunk tile by tile while the GEMM roles are still
+// producing later tiles.  A 256 x 256 tile of my chunk is reduced (multimem.ld_reduce in the switch, or P2P loads) as soon
+// as every rank's partial of that tile is complete; the tiles of my chunk are visited in the order my own GEMM produces
+// them (they come last in the rotated tile order), so only the final tiles' reduction is exposed.
+SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int warp, int lane,
+                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot) {
+  const int num_tiles = m_blocks * n_blocks;
+  const int rwarp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
+  const int n_rwarps = (int)gridDim.x * COPY_WARPS;
+  const uint32_t* my_tile_flags = c.peer_tile_flags[c.rank];
+  const size_t ldc_vec = p.ldc / 8;
+  const size_t ldo_vec = c.ld_out / 8;
+  const int my_first_blk = c.rank * pair_blocks_per_chunk;
+  // walk the tile order of the GEMM roles, keep the tiles of MY chunk (they come last when chunks align with the
+  // rasterisation groups) and deal them round-robin to the reduce warps of the whole grid
+  int mine = 0;
+  for (int t = 0; t < num_tiles; ++t) {
+    int m_blk, n_blk;
+    tile_coords_rot(t, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+    if (m_blk < my_first_blk || m_blk >= my_first_blk + pair_blocks_per_chunk) continue;
+    if ((mine++) % n_rwarps != rwarp) continue;
+    const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
+    if (lane < c.world) {
+      const uint32_t* f = my_tile_flags + (size_t)lane * c.tile_flag_stride + slot;
+      while (!epoch_reached(ld_acquire_sys(f), c.epoch)) __nanosleep(200);
+    }
+    __syncwarp();
+    const int row0 = m_blk * 256;                               // global row in [T]
+    const int rows = min(256, p.M - row0);
+    const int col0 = n_blk * 256;
+    const int cols = min(256, p.N - col0);
+    const int vec_per_row = cols / 8;                           // N % 8 == 0 is enforced by the launcher
+    const int out_row0 = row0 - c.rank * c.rows_per_chunk;
+    const int nvec = rows * vec_per_row;
+    for (int i0 = lane; i0 < nvec; i0 += 4 * 32) {
+      uint4 sum[4];
+      int ok[4];
+      size_t doff[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 32;
+        ok[j] = i < nvec;
+        if (!ok[j]) continue;
+        const int r = i / vec_per_row, cv = i - r * vec_per_row;
+        const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
+        doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+        if (c.mc_part) {
+          sum[j] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
+        } else {
+          float accf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          for (int rk = 0; rk < c.world; ++rk) {
+            Vec16<__nv_bfloat16> v;
+            v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[(c.rank + rk) % c.world]) + src_off);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) accf[k] += v.get(k);
+          }
+          Vec16<__nv_bfloat16> o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.set(k, accf[k]);
+          sum[j] = o.raw;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ok[j]) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
+    }
+  }
+  // every partial buffer of this epoch has been consumed by me: last reduce warp tells the peers
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
+    if (done == (uint32_t)n_rwarps) {
       my_flags[SLOT_LOCAL + 1] = 0;
       __threadfence_system();
       for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
@@ -597,6 +680,7 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp >= 6) {
     if (MODE == 0) ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
+    else rs_reduce_tiles(p, c, my_flags, warp, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot);
   } else {
     const int quarter = warp & 3;
     int acc = 0;
@@ -631,13 +715,15 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         __threadfence_system();
         __syncwarp();
         if (lane == 0) {
+          // tile-granular publication: the 8th epilogue warp (2 CTAs x 4) of a tile tells the chunk owner
           const int chunk = m_blk / pair_blocks_per_chunk;
-          const uint32_t got = atomicAdd(c.chunk_counter + chunk, 1u) + 1;
-          const uint32_t need = (uint32_t)pair_blocks_per_chunk * n_blocks * 8;   // 2 CTAs x 4 epilogue warps per tile
-          if (got == need) {
-            c.chunk_counter[chunk] = 0;
+          uint32_t* ctr = c.tile_counter + (size_t)m_blk * n_blocks + n_blk;
+          const uint32_t got = atomicAdd(ctr, 1u) + 1;
+          if (got == 8u) {
+            *ctr = 0;
             __threadfence_system();
-            st_release_sys(c.peer_flags[chunk] + SLOT_CHUNK_DONE + c.rank, c.epoch);
+            const int slot = (m_blk - chunk * pair_blocks_per_chunk) * n_blocks + n_blk;
+            st_release_sys(c.peer_tile_flags[chunk] + (size_t)c.rank * c.tile_flag_stride + slot, c.epoch);
           }
         }
       }
@@ -648,7 +734,6 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tc_fence_before();
   cluster_sync();
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
-  if (MODE == 1) rs_reduce_phase(p, c, my_flags);
 }
 
 template <int MODE>
@@ -780,7 +865,8 @@ int cb_ag_gemm(const void* const* peer_in, uint32_t* const* peer_flags, void* ga
 int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer_part, const void* mc_part,
                uint32_t* const* peer_flags, uint32_t* chunk_counter, void* out, int T, int N, int K, int lda, int ldb,
                int ld_out, int a_mn_major, int b_mn_major, int in_dtype, int rank, int world, uint32_t epoch,
-               int block_n, cudaStream_t stream) {
+               int block_n, uint32_t* const* peer_tile_flags, int tile_flag_stride, uint32_t* tile_counter,
+               int tile_counter_len, cudaStream_t stream) {
   if (world > MAX_RANKS || T % (world * BLOCK_M) != 0 || N % 8 != 0) return (int)cudaErrorInvalidValue;
   CommParams c{};
   c.rank = rank; c.world = world; c.epoch = epoch; c.rows_per_chunk = T / world;
@@ -789,8 +875,15 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
   GemmParams p{};
   p.M = T; p.N = N; p.K = K; p.ldc = N; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.C = part;
   p.out_dtype = in_dtype;
-  if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0)
+  const int pair_tiles_chunk = ((T / world) / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
+  const int pair_tiles = (T / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
+  if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0 && peer_tile_flags && tile_counter &&
+      pair_tiles_chunk <= tile_flag_stride && pair_tiles <= tile_counter_len) {
+    for (int r = 0; r < world; ++r) c.peer_tile_flags[r] = peer_tile_flags[r];
+    c.tile_flag_stride = tile_flag_stride;
+    c.tile_counter = tile_counter;
     return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
+  }
   if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
   if (block_n == 256)
     return launch_fused<256, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);

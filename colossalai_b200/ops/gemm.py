@@ -7,6 +7,7 @@ call site in the reference's `shardformer/layer/_operation.py:90-737`.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -15,10 +16,26 @@ import torch.nn.functional as F
 from ._dispatch import use_native
 
 _native = None
+# plain (un-fused) GEMMs: "cublas" = library GEMM through torch (default: the library's 2x2-cluster kernels are still
+# ~8 % ahead of our CTA-pair kernel, see profiles/gemm_tcgen05_2cta_vs_cublas_r1.jsonl), "native" = our tcgen05 kernel.
+# The comm-fused GEMMs (parallel/fused.py) always run our main loop - there is no library equivalent.
+_BACKEND = os.environ.get("CB200_GEMM_BACKEND", "cublas")
+
+
+def set_gemm_backend(name: str) -> None:
+    global _BACKEND
+    assert name in ("cublas", "native")
+    _BACKEND = name
+
+
+def get_gemm_backend() -> str:
+    return _BACKEND
 
 
 def _try_native():
     global _native
+    if _BACKEND != "native":
+        return False
     if _native is None:
         try:
             from . import gemm_native

@@ -110,6 +110,9 @@ class FusedWorkspace:
         self.rank = comm.group_rank(group)
         lib = _get_lib()
         self.flags = _SymmBuffer(4 * lib.cb_fused_flag_words(), self.group, zero=True)
+        # tile-granular GEMM->RS pipeline: symmetric epoch flags [16 writer ranks][tile_flag_stride]
+        self.tile_flag_stride = 8192
+        self.tile_flags = _SymmBuffer(4 * 16 * self.tile_flag_stride, self.group, zero=True)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)      # flag pages are zero everywhere before first use
         self.epoch = 0
@@ -119,6 +122,7 @@ class FusedWorkspace:
         self._counters: Dict[int, torch.Tensor] = {}
         dev = torch.device("cuda", torch.cuda.current_device())
         self.chunk_counter = torch.zeros(64, dtype=torch.int32, device=dev)
+        self.tile_counter = torch.zeros(1 << 16, dtype=torch.int32, device=dev)
 
     def next_epoch(self) -> int:
         self.epoch += 1
@@ -250,7 +254,8 @@ def gemm_reduce_scatter(a: torch.Tensor, w: torch.Tensor, group: Optional[Proces
                                 part.ptr_array(world), mc, ws.flags.ptr_array(world), loader.ptr(ws.chunk_counter),
                                 loader.ptr(out), T, N, K, a.stride(0), w.stride(0), out.stride(0), 0,
                                 0 if transpose_b else 1, code(a.dtype), ws.rank, world, ctypes.c_uint32(epoch), block_n,
-                                loader.stream_ptr()), "gemm_rs")
+                                ws.tile_flags.ptr_array(world), ws.tile_flag_stride, loader.ptr(ws.tile_counter),
+                                ws.tile_counter.numel(), loader.stream_ptr()), "gemm_rs")
     part.last_epoch = epoch
     loader.launch_counter.add("fused_gemm_rs")
     stats["gemm_rs"] += 1

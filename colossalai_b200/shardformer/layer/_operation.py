@@ -11,6 +11,7 @@ multimem traffic over NVLink).  Weight-gradient GEMMs can be deferred (`WeightGr
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -30,6 +31,9 @@ __all__ = [
 ]
 
 _COMM_BACKEND = "nccl"
+
+
+_SAVE_GATHERED = os.environ.get("CB200_SP_SAVE_GATHERED", "1") != "0"
 
 
 def set_comm_backend(name: str) -> None:
@@ -168,10 +172,19 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
         ctx.group, ctx.dim, ctx.ring, ctx.use_zbv = group, dim, ring, use_zbv
         ctx.use_bias = bias is not None
         ctx.fused = _use_fused(x_local, group) and dim == 0 and x_local.dim() == 2
+        ctx.saved_gathered = False
         if ctx.fused:
             from ...parallel import fused
 
-            y, _ = fused.all_gather_gemm(x_local, weight, group)
+            y, gathered = fused.all_gather_gemm(x_local, weight, group)
+            if _SAVE_GATHERED:
+                # keep the gathered activations for the wgrad GEMM instead of pulling them again in backward
+                # (T x K bf16 per column-parallel linear; set CB200_SP_SAVE_GATHERED=0 to trade it for a re-gather)
+                if bias is not None:
+                    y = y + bias
+                ctx.saved_gathered = True
+                ctx.save_for_backward(gathered, weight)
+                return y
         elif ring and comm.group_size(group) > 1:
             y, _ = _ring_gather_gemm(x_local, weight, group, dim)
         else:
@@ -191,8 +204,8 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
         if ctx.fused:
             from ...parallel import fused
 
-            # dX = dY @ W fused with the reduce-scatter; X re-gathered by the fused AG for the wgrad GEMM
-            x_full = fused.all_gather(x_local, group)
+            # dX = dY @ W fused with the reduce-scatter; X comes from forward (saved) or is re-gathered over NVLink
+            x_full = x_local if ctx.saved_gathered else fused.all_gather(x_local, group)
             dx_local = fused.gemm_reduce_scatter(dy2, weight, group, transpose_b=False)
             dw = _maybe_defer_wgrad(weight, dy2, x_full, ctx.use_zbv)
             db = dy2.sum(0) if ctx.use_bias else None

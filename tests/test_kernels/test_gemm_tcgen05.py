@@ -67,13 +67,22 @@ def test_gemm_tn_accumulate(out_dtype):
 def test_linear_autograd_through_native_gemm():
     """The op-level entry points (`ops.linear_forward / matmul_nn / matmul_tn`) used by every parallel linear."""
     from colossalai_b200 import ops
+    from colossalai_b200.kernel import loader
+    from colossalai_b200.ops import gemm as gemm_ops
     from colossalai_b200.shardformer.layer._operation import linear_with_grad_accum
 
     torch.manual_seed(0)
     x = _mk(1024, 512).requires_grad_(True)
     w = _mk(768, 512).requires_grad_(True)
-    y = linear_with_grad_accum(x, w)
-    (y.float() * 0.01).sum().backward()
+    old = gemm_ops.get_gemm_backend()
+    gemm_ops.set_gemm_backend("native")
+    before = loader.launch_counter.count
+    try:
+        y = linear_with_grad_accum(x, w)
+        (y.float() * 0.01).sum().backward()
+    finally:
+        gemm_ops.set_gemm_backend(old)
+    assert loader.launch_counter.count >= before + 3, "the tcgen05 GEMM must have run for fwd, dgrad and wgrad"
     xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
     ((xr @ wr.t()) * 0.01).sum().backward()
     torch.testing.assert_close(y.float(), xr @ wr.t(), atol=0.2, rtol=2e-2)
