@@ -176,7 +176,14 @@ SM100_DEVICE void ag_pull_warps(const CommParams& c, uint32_t* my_flags, int war
     uint4* dp = reinterpret_cast<uint4*>(c.gathered) +
                 ((size_t)src * c.rows_per_chunk + (size_t)sb * BLOCK_M + seg * seg_rows) * vec_per_row;
     size_t i = lane;
-    for (; i + 7 * 32 < seg_vec; i += 8 * 32) {          // 8 independent 16-byte loads in flight per lane
+    for (; i + 15 * 32 < seg_vec; i += 16 * 32) {        // 16 independent 16-byte loads in flight per lane
+      uint4 t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = ld_peer_16B(sp + i + j * 32);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dp[i + j * 32] = t[j];
+    }
+    for (; i + 7 * 32 < seg_vec; i += 8 * 32) {
       uint4 t[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) t[j] = ld_peer_16B(sp + i + j * 32);
@@ -299,15 +306,16 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
     const int vec_per_row = cols / 8;                           // N % 8 == 0 is enforced by the launcher
     const int out_row0 = row0 - c.rank * c.rows_per_chunk;
     const int nvec = rows * vec_per_row;
-    for (int i0 = lane; i0 < nvec; i0 += 4 * 32) {
-      uint4 sum[4];
-      int ok[4];
-      size_t doff[4];
+    // 16 independent 16-byte reductions in flight per lane: the NVLink round trip (~2-3 us) must be covered by
+    // memory-level parallelism of only two warps per SM
+    constexpr int RU = 16;
+    for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
+      uint4 sum[RU];
+      size_t doff[RU];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < RU; ++j) {
         const int i = i0 + j * 32;
-        ok[j] = i < nvec;
-        if (!ok[j]) continue;
+        if (i >= nvec) { doff[j] = (size_t)-1; continue; }
         const int r = i / vec_per_row, cv = i - r * vec_per_row;
         const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
         doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
@@ -328,8 +336,8 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (ok[j]) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
+      for (int j = 0; j < RU; ++j)
+        if (doff[j] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
     }
   }
   // every partial buffer of this epoch has been consumed by me: last reduce warp tells the peers

@@ -40,6 +40,8 @@ def _worker(rank, world_size, port, timing=False):
     shapes = [(256, 512, 768), (1024, 4096, 6144 // world_size), (2048, 4096, 4096)]
     if timing:   # Llama-3-8B per-layer shapes at this TP degree (4096 tokens per rank)
         shapes += [(4096, 4096, 28672 // world_size), (4096, 14336 // world_size, 4096)]
+        if world_size >= 4:   # the skinny projections of high TP degrees (qkv: small N, o_proj: small K)
+            shapes += [(4096, 4096, 6144 // world_size), (4096, 4096 // world_size, 4096)]
     for (t, K, N) in shapes:
         T = t * world_size
         x_local = (torch.randn(t, K, device="cuda") * 0.5).bfloat16()
