@@ -277,19 +277,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 //             tmem_empty[a] lives in the leader and collects the 2 x 4 epilogue warps (remote arrive from the peer).
 constexpr int PAIR_M = 256;
 constexpr int PAIR_N = 256;
-struct Cfg2 {
-  static constexpr int STAGES = 6;
-  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
-  static constexpr int B_BYTES = 128 * BLOCK_K * 2;
+template <int BK_, int STAGES_> struct Cfg2 {
+  static constexpr int BK = BK_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = 128 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+template <int BK, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-  using C = Cfg2;
+  using C = Cfg2<BK, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -310,7 +312,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int m_blocks = (p.M + PAIR_M - 1) / PAIR_M;
   const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
   const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int k_blocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
@@ -350,18 +352,20 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * BK;
           if (!p.a_mn_major) {
-            tma_load_2d_2sm(&tmap_a, fb, sa, k0, m0);
+#pragma unroll
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (128 * 128), k0 + j * 64, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BLOCK_K * 128), m0 + j * 64, k0);
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BK * 128), m0 + j * 64, k0);
           }
           if (!p.b_mn_major) {
-            tma_load_2d_2sm(&tmap_b, fb, sb, k0, n0);
+#pragma unroll
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (128 * 128), k0 + j * 64, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BLOCK_K * 128), n0 + j * 64, k0);
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BK * 128), n0 + j * 64, k0);
           }
         }
         __syncwarp();
@@ -387,14 +391,19 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
             const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
-            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024)
+            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BK * 128, 1024)
                                              : make_smem_desc_sw128(sa, 16, 1024);
-            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024)
+            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BK * 128, 1024)
                                              : make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss_2cta(tmem_d, advance_desc(da, k * a_kstep), advance_desc(db, k * b_kstep), p.idesc,
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: 64-wide swizzled sub-tiles of 128 rows (16 KB each), 4 k-steps of 32 B inside a sub-tile;
+              // MN-major: one 16-k-row slab (2 KB) per step
+              const uint32_t ao = p.a_mn_major ? k * a_kstep : (k >> 2) * (128 * 128) + (k & 3) * a_kstep;
+              const uint32_t bo = p.b_mn_major ? k * b_kstep : (k >> 2) * (128 * 128) + (k & 3) * b_kstep;
+              umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
                                (kb > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit_2cta(&empty_bar[stage], 3);
             if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
           }
@@ -450,15 +459,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
 }
 
+template <int BK, int STAGES>
 int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                 int b_mn, int in_dtype, int out_dtype, int accumulate, cudaStream_t stream) {
-  using C = Cfg2;
+  using C = Cfg2<BK, STAGES>;
   CUtensorMap ta, tb;
   const bool bf16 = in_dtype == CB_BF16;
   int r;
-  r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
+  r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BK, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
   if (r) return 1000 + r;
-  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
+  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BK, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
   if (r) return 2000 + r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.out_dtype = out_dtype;
@@ -466,7 +476,7 @@ int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int
   p.idesc = make_idesc_f16(PAIR_M, PAIR_N, bf16 ? 1 : 0, a_mn, b_mn);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -475,7 +485,7 @@ int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int
   int pairs = cb_num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
   if (pairs <= 0) return 0;
-  gemm_tcgen05_2cta_kernel<<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_2cta_kernel<BK, STAGES><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -533,7 +543,18 @@ int cb_gemm_tcgen05(const void* A, const void* B, void* C, int M, int N, int K, 
   // CTA-pair kernel: 256 x 256 tiles; worth it once there are enough tiles to fill the 74 pairs
   if (block_n == 512 || (block_n == 0 && use_2cta && M >= 256 && N >= 256 &&
                          ((M + 255) / 256) * ((N + 255) / 256) >= cb_num_sms() / 2))
-    return launch_2cta(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
+  {
+    static int variant = -1;           // main-loop shape of the CTA-pair kernel: 0 = BK64 x 6 stages, 1 = BK64 x 7, 2 = BK128 x 3
+    if (variant < 0) {
+      const char* e = getenv("CB200_GEMM_2CTA_VARIANT");
+      variant = e ? atoi(e) : 0;
+    }
+    if (variant == 1)
+      return launch_2cta<64, 7>(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
+    if (variant == 2)
+      return launch_2cta<128, 3>(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
+    return launch_2cta<64, 6>(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
+  }
   if (block_n == 0) {
     const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
     block_n = (tiles256 >= cb_num_sms() || N % 256 == 0 && tiles256 * 2 > cb_num_sms() * 3) ? 256 : 128;
