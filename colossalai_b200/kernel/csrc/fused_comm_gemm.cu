@@ -808,6 +808,75 @@ __global__ void __launch_bounds__(256) all_gather_pull_kernel(const CommParams c
   }
 }
 
+// Stand-alone reduce-scatter over symmetric memory: every rank has written its full [world * rows_per_chunk, ld] input
+// into its symmetric buffer; rank r sums chunk r over all ranks (fp32 accumulation: in-switch `multimem.ld_reduce` when a
+// multicast mapping exists, otherwise 16-byte P2P loads) and writes it to `out`.  ELEM: 0 = bf16, 1 = fp32.
+SM100_DEVICE uint4 multimem_ld_reduce_f32x4(const void* mc_addr) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc_addr) : "memory");
+  return r;
+}
+
+template <int ELEM>
+__global__ void __launch_bounds__(256) reduce_scatter_kernel(const CommParams c, size_t vec_per_chunk) {
+  uint32_t* my_flags = c.peer_flags[c.rank];
+  // publish "my input buffer is complete" and wait for every peer's
+  if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.peer_flags[threadIdx.x] + SLOT_IN_READY + c.rank, c.epoch);
+  if (threadIdx.x < c.world)
+    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + threadIdx.x), c.epoch)) {
+    }
+  __syncthreads();
+  const size_t base = (size_t)c.rank * vec_per_chunk;          // 16-byte units
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < vec_per_chunk; i0 += 8 * stride) {
+    uint4 sum[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i >= vec_per_chunk) continue;
+      if (c.mc_part) {
+        const uint4* a = reinterpret_cast<const uint4*>(c.mc_part) + base + i;
+        sum[u] = ELEM == 0 ? multimem_ld_reduce_bf16x8(a) : multimem_ld_reduce_f32x4(a);
+      } else if (ELEM == 0) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int rk = 0; rk < c.world; ++rk) {
+          Vec16<__nv_bfloat16> v;
+          v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[(c.rank + rk) % c.world]) + base + i);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += v.get(k);
+        }
+        Vec16<__nv_bfloat16> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.set(k, acc[k]);
+        sum[u] = o.raw;
+      } else {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int rk = 0; rk < c.world; ++rk) {
+          const uint4 v = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[(c.rank + rk) % c.world]) + base + i);
+          acc.x += __uint_as_float(v.x); acc.y += __uint_as_float(v.y);
+          acc.z += __uint_as_float(v.z); acc.w += __uint_as_float(v.w);
+        }
+        sum[u] = make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z), __float_as_uint(acc.w));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < vec_per_chunk) reinterpret_cast<uint4*>(c.out)[i] = sum[u];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 2, 1u) + 1;
+    if (done == gridDim.x) {
+      my_flags[SLOT_LOCAL + 2] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
 // Wait until every peer has finished reading this rank's symmetric buffers of `epoch` (buffer-reuse guard).
 __global__ void wait_pull_done_kernel(uint32_t* my_flags, int world, uint32_t epoch) {
   if (threadIdx.x < world)
@@ -906,6 +975,21 @@ int cb_all_gather_pull(const void* const* peer_in, uint32_t* const* peer_flags, 
   for (int r = 0; r < world; ++r) { c.peer_in[r] = peer_in[r]; c.peer_flags[r] = peer_flags[r]; }
   c.gathered = gathered;
   all_gather_pull_kernel<<<n_ctas, 256, 0, stream>>>(c);
+  return (int)cudaGetLastError();
+}
+
+// out[chunk_bytes] = sum over ranks of (rank's symmetric buffer)[my chunk].  elem: 0 = bf16, 1 = fp32.
+int cb_reduce_scatter(const void* const* peer_part, const void* mc_part, uint32_t* const* peer_flags, void* out,
+                      int64_t chunk_bytes, int elem, int rank, int world, uint32_t epoch, int n_ctas,
+                      cudaStream_t stream) {
+  if (world > MAX_RANKS || chunk_bytes % 16 != 0) return (int)cudaErrorInvalidValue;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch;
+  for (int r = 0; r < world; ++r) { c.peer_part[r] = peer_part[r]; c.peer_flags[r] = peer_flags[r]; }
+  c.mc_part = mc_part; c.out = out;
+  const size_t vec = (size_t)chunk_bytes / 16;
+  if (elem == 0) reduce_scatter_kernel<0><<<n_ctas, 256, 0, stream>>>(c, vec);
+  else reduce_scatter_kernel<1><<<n_ctas, 256, 0, stream>>>(c, vec);
   return (int)cudaGetLastError();
 }
 

@@ -28,6 +28,7 @@ from ..ops._dtypes import code
 from . import comm
 
 __all__ = ["available", "build_available", "all_gather_gemm", "gemm_reduce_scatter", "gemm_all_reduce", "all_gather",
+           "reduce_scatter",
            "FusedWorkspace", "stats"]
 
 _lib = None
@@ -194,6 +195,33 @@ def all_gather(x_local: torch.Tensor, group: Optional[ProcessGroup]) -> torch.Te
     buf.last_epoch = epoch
     loader.launch_counter.add("fused_all_gather")
     stats["all_gather"] += 1
+    return out
+
+
+def reduce_scatter(x: torch.Tensor, group: Optional[ProcessGroup]) -> torch.Tensor:
+    """Sum `x` ([world * t, ...], bf16 or fp32) over the group and return this rank's chunk [t, ...]: every rank
+    publishes its tensor in symmetric memory and reduces its own chunk straight out of the NVSwitch."""
+    ws = workspace(group)
+    world = comm.group_size(group)
+    nbytes = x.numel() * x.element_size()
+    if (ws is None or x.dtype not in (torch.bfloat16, torch.float32) or x.shape[0] % world != 0
+            or (nbytes // world) % 16 != 0 or not x.is_cuda):
+        stats["fallback"] += 1
+        return comm.reduce_scatter(x.contiguous(), 0, group)
+    part = ws.part_buffer(nbytes)
+    part.tensor[:nbytes].view(x.dtype).view(x.shape).copy_(x)
+    epoch = ws.next_epoch()
+    out = torch.empty((x.shape[0] // world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    use_mc = part.mc_ptr and os.environ.get("CB200_NO_MULTIMEM", "0") != "1"
+    n_ctas = 2 * torch.cuda.get_device_properties(x.device).multi_processor_count
+    loader.check(_get_lib().cb_reduce_scatter(part.ptr_array(world), ctypes.c_void_p(part.mc_ptr if use_mc else 0),
+                                              ws.flags.ptr_array(world), loader.ptr(out),
+                                              ctypes.c_int64(nbytes // world), 0 if x.dtype == torch.bfloat16 else 1,
+                                              ws.rank, world, ctypes.c_uint32(epoch), n_ctas, loader.stream_ptr()),
+                 "reduce_scatter")
+    part.last_epoch = epoch
+    loader.launch_counter.add("fused_reduce_scatter")
+    stats["reduce_scatter"] = stats.get("reduce_scatter", 0) + 1
     return out
 
 

@@ -97,11 +97,30 @@ def _merge(out: Optional[torch.Tensor], lse: Optional[torch.Tensor], blk_out: to
     return out * w_old + blk_out.float() * w_new, new_lse
 
 
+def _to_bhsd(x: torch.Tensor, batch: int, rep: int = 1) -> torch.Tensor:
+    T, H, D = x.shape
+    xb = x.view(batch, T // batch, H, D).transpose(1, 2)
+    return xb if rep == 1 else xb.repeat_interleave(rep, dim=1)
+
+
+def _lib_flash_ok(q: torch.Tensor) -> bool:
+    return q.is_cuda and q.dtype in (torch.float16, torch.bfloat16) and q.shape[-1] <= 256 and q.shape[-1] % 8 == 0 \
+        and hasattr(torch.ops.aten, "_scaled_dot_product_flash_attention")
+
+
 def _block_fwd(q, k, v, batch, causal, scale):
+    """One attention block returning (out [T,Hq,D], lse [T,Hq] fp32).  CUDA: the library flash kernel through aten (it
+    returns the log-sum-exp needed by the online-softmax merge) until the tcgen05 kernel lands; CPU: explicit softmax."""
     from ...ops import flash_attn_native as fa
 
     if q.is_cuda and fa.supported(q, k, v, None):
         return fa.flash_attention_with_lse(q, k, v, batch=batch, causal=causal, scale=scale)
+    if _lib_flash_ok(q) and (not causal or q.shape[0] == k.shape[0]):
+        g = q.shape[1] // k.shape[1]
+        res = torch.ops.aten._scaled_dot_product_flash_attention(_to_bhsd(q, batch), _to_bhsd(k, batch, g),
+                                                                 _to_bhsd(v, batch, g), 0.0, causal, False, scale=scale)
+        out, lse = res[0], res[1]                       # [B,H,S,D], [B,H,S]
+        return out.transpose(1, 2).reshape(q.shape), lse.transpose(1, 2).reshape(q.shape[0], q.shape[1])
     return attention_with_lse_ref(q, k, v, batch=batch, causal=causal, scale=scale)
 
 
@@ -111,6 +130,22 @@ def _block_bwd(do, q, k, v, o, lse, batch, causal, scale):
 
     if q.is_cuda and fa.supported(q, k, v, None) and hasattr(fa, "flash_attention_bwd"):
         return fa.flash_attention_bwd(do, q, k, v, o, lse, batch=batch, causal=causal, scale=scale)
+    if _lib_flash_ok(q) and (not causal or q.shape[0] == k.shape[0]) \
+            and hasattr(torch.ops.aten, "_scaled_dot_product_flash_attention_backward"):
+        Hq, Hkv = q.shape[1], k.shape[1]
+        g = Hq // Hkv
+        Sq, Sk = q.shape[0] // batch, k.shape[0] // batch
+        qb, kb, vb = _to_bhsd(q, batch), _to_bhsd(k, batch, g), _to_bhsd(v, batch, g)
+        ob, dob = _to_bhsd(o.to(q.dtype), batch), _to_bhsd(do.to(q.dtype), batch)
+        lb = lse.view(batch, Sq, Hq).transpose(1, 2).contiguous().float()
+        z = torch.zeros((), dtype=torch.int64, device=q.device)
+        dq, dk, dv = torch.ops.aten._scaled_dot_product_flash_attention_backward(
+            dob.contiguous(), qb.contiguous(), kb.contiguous(), vb.contiguous(), ob.contiguous(), lb, None, None, Sq, Sk,
+            0.0, causal, z, z, scale=scale)
+        dq = dq.transpose(1, 2).reshape(q.shape).float()
+        dk = dk.float().view(batch, Hkv, g, Sk, -1).sum(2).transpose(1, 2).reshape(k.shape)
+        dv = dv.float().view(batch, Hkv, g, Sk, -1).sum(2).transpose(1, 2).reshape(v.shape)
+        return dq, dk, dv
     T, Hq, D = q.shape
     Tk, Hkv = k.shape[0], k.shape[1]
     Sq, Sk, g = T // batch, Tk // batch, Hq // Hkv
@@ -136,6 +171,26 @@ def _block_bwd(do, q, k, v, o, lse, batch, causal, scale):
     dk = dk.view(batch, Hkv, g, Sk, D).sum(2).transpose(1, 2).reshape(Tk, Hkv, D)
     dv = dv.view(batch, Hkv, g, Sk, D).sum(2).transpose(1, 2).reshape(Tk, Hkv, D)
     return dq, dk, dv
+
+
+def _p2p_gather_kv(kv: torch.Tensor, sp_group) -> Optional[torch.Tensor]:
+    """[2, T, Hkv, D] local KV -> [sp, 2, T, Hkv, D] from every rank by the P2P pull kernel, or None if unavailable."""
+    import os
+
+    if not kv.is_cuda or kv.dtype not in (torch.float16, torch.bfloat16) \
+            or os.environ.get("CB200_RING_ATTN_P2P", "1") == "0":
+        return None
+    try:
+        from ...parallel import fused
+
+        if not fused.available(sp_group):
+            return None
+        flat = kv.reshape(1, -1)
+        if flat.shape[1] % 8 != 0:
+            return None
+        return fused.all_gather(flat, sp_group).view((comm.group_size(sp_group),) + tuple(kv.shape))
+    except Exception:
+        return None
 
 
 def _halves(x: torch.Tensor, batch: int):
@@ -172,11 +227,17 @@ class RingAttention(torch.autograd.Function):
         q0, q1 = _halves(q, batch)
         out1 = lse1 = None  # second-half accumulators when only half of q participates
         cur = kv
+        # NVSwitch path: every rank publishes its KV once in symmetric memory and the peers PULL all blocks in one
+        # P2P kernel (no ring forwarding, no NCCL); the loop below then only indexes the gathered blocks
+        kv_all = _p2p_gather_kv(kv, sp_group) if sp > 1 else None
+        ctx.p2p = kv_all is not None
         for step in range(sp):
             nxt = None
-            if step < sp - 1:
-                nxt = ring.send_recv(cur)
             src = (r - step) % sp
+            if kv_all is not None:
+                cur = kv_all[src]
+            elif step < sp - 1:
+                nxt = ring.send_recv(cur)
             kk, vv = cur[0], cur[1]
             if step == 0:
                 # local block.  zigzag halves: q0 x k0 causal; q1 x (k0 full, k1 causal)
@@ -217,6 +278,8 @@ class RingAttention(torch.autograd.Function):
         sp, r = comm.group_size(sp_group), comm.group_rank(sp_group)
         kv_ring, dkv_ring = RingComm(sp_group), RingComm(sp_group)
         dout = dout.contiguous()
+        if getattr(ctx, "p2p", False):
+            return RingAttention._backward_p2p(ctx, dout, q, k, v, out, lse)
         q0, q1 = _halves(q, batch)
         do0, do1 = _halves(dout, batch)
         o0, o1 = _halves(out, batch)
@@ -269,6 +332,52 @@ class RingAttention(torch.autograd.Function):
             dkv_recv = dkv_ring.send_recv(dkv.contiguous())
         dkv_ring.wait()
         dkv = dkv_recv
+        dq = _join_halves(dq0, dq1, batch)
+        return dq.to(q.dtype), dkv[0].to(k.dtype), dkv[1].to(v.dtype), None, None, None
+
+    @staticmethod
+    def _backward_p2p(ctx, dout, q, k, v, out, lse):
+        """Backward of the NVSwitch path: KV blocks are pulled again in one P2P kernel, every rank computes the dKV
+        contributions of ALL blocks locally (fp32) and one fused reduce-scatter (in-switch reduction) returns each
+        block's gradient to its owner."""
+        from ...parallel import fused
+
+        sp_group, batch, scale = ctx.sp_group, ctx.batch, ctx.scale
+        sp, r = comm.group_size(sp_group), comm.group_rank(sp_group)
+        kv_all = _p2p_gather_kv(torch.stack([k, v], 0).contiguous(), sp_group)
+        q0, q1 = _halves(q, batch)
+        do0, do1 = _halves(dout, batch)
+        o0, o1 = _halves(out, batch)
+        l0, l1 = _halves(lse, batch)
+        dq0 = torch.zeros_like(q0, dtype=torch.float32)
+        dq1 = torch.zeros_like(q1, dtype=torch.float32)
+        dkv_all = torch.zeros((sp,) + tuple(kv_all.shape[1:]), dtype=torch.float32, device=q.device)
+        for src in range(sp):
+            kk, vv = kv_all[src][0], kv_all[src][1]
+            k0, k1 = _halves(kk, batch)
+            v0, v1 = _halves(vv, batch)
+            if src == r:
+                a, b, c = _block_bwd(do0, q0, k0, v0, o0, l0, batch, True, scale)
+                dq0 += a
+                dk0, dv0 = b.clone(), c.clone()
+                a, b, c = _block_bwd(do1, q1, k0, v0, o1, l1, batch, False, scale)
+                dq1 += a; dk0 += b; dv0 += c
+                a, dk1, dv1 = _block_bwd(do1, q1, k1, v1, o1, l1, batch, True, scale)
+                dq1 += a
+                dkv_all[src, 0] = _join_halves(dk0, dk1, batch)
+                dkv_all[src, 1] = _join_halves(dv0, dv1, batch)
+            elif src < r:
+                a, b, c = _block_bwd(dout, q, k0, v0, out, lse, batch, False, scale)
+                a0, a1 = _halves(a, batch)
+                dq0 += a0; dq1 += a1
+                z = torch.zeros_like(b)
+                dkv_all[src, 0] = _join_halves(b, z, batch)
+                dkv_all[src, 1] = _join_halves(c, z, batch)
+            else:
+                a, b, c = _block_bwd(do1, q1, kk, vv, o1, l1, batch, False, scale)
+                dq1 += a
+                dkv_all[src, 0], dkv_all[src, 1] = b, c
+        dkv = fused.reduce_scatter(dkv_all.view(sp, -1), sp_group).view(kv_all.shape[1:])
         dq = _join_halves(dq0, dq1, batch)
         return dq.to(q.dtype), dkv[0].to(k.dtype), dkv[1].to(v.dtype), None, None, None
 
