@@ -141,7 +141,9 @@ SM100_DEVICE void store_chunk16(T16* __restrict__ dst, const uint32_t (&acc)[32]
       o.store(dst + j);
     }
   } else {
-    for (int j = 0; j < n_valid; ++j) dst[j] = from_f32<T16>(__uint_as_float(acc[j]));
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid) dst[j] = from_f32<T16>(__uint_as_float(acc[j]));
   }
 }
 

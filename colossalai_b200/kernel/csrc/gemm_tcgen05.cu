@@ -78,7 +78,10 @@ SM100_DEVICE void store_row_chunk<float>(float* __restrict__ dst, const uint32_t
       *reinterpret_cast<float4*>(dst + j) = v;
     }
   } else {
-    for (int j = 0; j < n_valid; ++j) dst[j] = __uint_as_float(acc[j]) + (accumulate ? dst[j] : 0.f);
+    // fully unrolled + predicated: a dynamically indexed `acc[j]` would force the whole fragment into local memory
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid) dst[j] = __uint_as_float(acc[j]) + (accumulate ? dst[j] : 0.f);
   }
 }
 
@@ -94,8 +97,9 @@ SM100_DEVICE void store_row_chunk_16(T16* __restrict__ dst, const uint32_t (&acc
       o.store(dst + j);
     }
   } else {
-    for (int j = 0; j < n_valid; ++j)
-      dst[j] = from_f32<T16>(__uint_as_float(acc[j]) + (accumulate ? to_f32<T16>(dst[j]) : 0.f));
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid) dst[j] = from_f32<T16>(__uint_as_float(acc[j]) + (accumulate ? to_f32<T16>(dst[j]) : 0.f));
   }
 }
 template <>
@@ -429,20 +433,28 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * PAIR_N + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < PAIR_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c, v);
+      for (int c = 0; c < PAIR_N; c += 64) {
+        // two 32-column TMEM loads in flight per wait: halves the exposed tcgen05.ld latency of the epilogue
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(taddr + c, v0);
+        tmem_ld_32x32b_x32(taddr + c + 32, v1);
         tmem_ld_wait();
-        const int n_valid = p.N - (n0 + c);
-        if (row < p.M && n_valid > 0 && p.K > 0) {
-          const size_t off = (size_t)row * p.ldc + n0 + c;
-          if (p.out_dtype == CB_BF16)
-            store_row_chunk<__nv_bfloat16>((__nv_bfloat16*)p.C + off, v, n_valid, p.accumulate);
-          else if (p.out_dtype == CB_F32)
-            store_row_chunk<float>((float*)p.C + off, v, n_valid, p.accumulate);
-          else
-            store_row_chunk<__half>((__half*)p.C + off, v, n_valid, p.accumulate);
+#define CB_EPI_STORE(V, CC)                                                                              \
+        {                                                                                                  \
+          const int n_valid = p.N - (n0 + (CC));                                                           \
+          if (row < p.M && n_valid > 0 && p.K > 0) {                                                       \
+            const size_t off = (size_t)row * p.ldc + n0 + (CC);                                            \
+            if (p.out_dtype == CB_BF16)                                                                    \
+              store_row_chunk<__nv_bfloat16>((__nv_bfloat16*)p.C + off, V, n_valid, p.accumulate);         \
+            else if (p.out_dtype == CB_F32)                                                                \
+              store_row_chunk<float>((float*)p.C + off, V, n_valid, p.accumulate);                         \
+            else                                                                                           \
+              store_row_chunk<__half>((__half*)p.C + off, V, n_valid, p.accumulate);                       \
+          }                                                                                                \
         }
+        CB_EPI_STORE(v0, c)
+        CB_EPI_STORE(v1, c + 32)
+#undef CB_EPI_STORE
       }
       tc_fence_before();
       __syncwarp();
