@@ -19,6 +19,7 @@
 // These replace the reference's `dist.all_gather` + `F.linear` / `F.linear` + `dist.reduce_scatter` pairs
 // (shardformer/layer/_operation.py:562-566, 737-751) and its python ring variants (`_ring_as_gather`,
 // `_ring_as_reducescatter`): no NCCL call on these paths.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -105,6 +106,24 @@ SM100_DEVICE uint32_t ld_acquire_gpu(const uint32_t* p) {
 SM100_DEVICE void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 SM100_DEVICE bool epoch_reached(uint32_t v, uint32_t epoch) { return (int32_t)(v - epoch) >= 0; }
 
+// Bounded spin on an epoch flag: a peer that never arrives (crashed rank, mismatched call sequence) must not hang the
+// GPU forever - after ~20 s the kernel reports and traps, which surfaces as a CUDA error in the host process.
+constexpr long long SPIN_TIMEOUT_CYCLES = 40LL * 1000 * 1000 * 1000;
+template <bool SYS>
+SM100_DEVICE void wait_epoch(const uint32_t* flag, uint32_t epoch) {
+  if (epoch_reached(SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag), epoch)) return;
+  const long long t0 = clock64();
+  uint32_t it = 0;
+  while (!epoch_reached(SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag), epoch)) {
+    __nanosleep(100);
+    if ((++it & 0x3fff) == 0 && clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+      printf("[cb200 fused comm] timeout waiting for epoch %u on flag %p (have %u), block %d\n", epoch, (const void*)flag,
+             *flag, (int)blockIdx.x);
+      __trap();
+    }
+  }
+}
+
 SM100_DEVICE uint4 ld_peer_16B(const void* p) {
   uint4 r;
   asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -168,8 +187,7 @@ SM100_DEVICE void ag_pull_warps(const CommParams& c, uint32_t* my_flags, int war
     if (src != cur_src) {
       if (src != c.rank) {
         if (lane == 0)
-          while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
-          }
+          wait_epoch<true>(my_flags + SLOT_IN_READY + src, c.epoch);
         __syncwarp();
       }
       cur_src = src;
@@ -222,8 +240,7 @@ SM100_DEVICE void ag_pull_warps(const CommParams& c, uint32_t* my_flags, int war
 SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint32_t* my_flags) {
   // ================================================================== RS: reduce MY chunk out of all partial buffers
   if (threadIdx.x < c.world) {
-    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_CHUNK_DONE + threadIdx.x), c.epoch)) {
-    }
+    wait_epoch<true>(my_flags + SLOT_CHUNK_DONE + threadIdx.x, c.epoch);
   }
   __syncthreads();
   const int vec_per_row = p.N / 8;
@@ -298,7 +315,7 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
     const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
     if (lane < c.world) {
       const uint32_t* f = my_tile_flags + (size_t)lane * c.tile_flag_stride + slot;
-      while (!epoch_reached(ld_acquire_sys(f), c.epoch)) __nanosleep(200);
+      wait_epoch<true>(f, c.epoch);
     }
     __syncwarp();
     const int row0 = m_blk * 256;                               // global row in [T]
@@ -417,8 +434,7 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (MODE == 0) {
         // the A rows of this tile must have landed in `gathered`
         if (lane == 0) {
-          while (!epoch_reached(ld_acquire_gpu(c.ready + m_blk), c.epoch)) {
-          }
+          wait_epoch<false>(c.ready + m_blk, c.epoch);
           fence_proxy_async_global();
         }
         __syncwarp();
@@ -621,8 +637,7 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const int n0 = n_blk * PAIR_N + (int)cta_rank * 128;
       if (MODE == 0) {
         if (lane == 0) {
-          while (!epoch_reached(ld_acquire_gpu(c.ready + (m_blk * 2 + (int)cta_rank)), c.epoch)) {
-          }
+          wait_epoch<false>(c.ready + (m_blk * 2 + (int)cta_rank), c.epoch);
           fence_proxy_async_global();
         }
         __syncwarp();
@@ -790,8 +805,7 @@ __global__ void __launch_bounds__(256) all_gather_pull_kernel(const CommParams c
     const int src = (c.rank + step) % c.world;
     if (step > 0) {
       if (threadIdx.x == 0)
-        while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + src), c.epoch)) {
-        }
+        wait_epoch<true>(my_flags + SLOT_IN_READY + src, c.epoch);
       __syncthreads();
     }
     const uint4* s = reinterpret_cast<const uint4*>(c.peer_in[src]);
@@ -826,8 +840,7 @@ __global__ void __launch_bounds__(256) reduce_scatter_kernel(const CommParams c,
   // publish "my input buffer is complete" and wait for every peer's
   if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.peer_flags[threadIdx.x] + SLOT_IN_READY + c.rank, c.epoch);
   if (threadIdx.x < c.world)
-    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_IN_READY + threadIdx.x), c.epoch)) {
-    }
+    wait_epoch<true>(my_flags + SLOT_IN_READY + threadIdx.x, c.epoch);
   __syncthreads();
   const size_t base = (size_t)c.rank * vec_per_chunk;          // 16-byte units
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -882,8 +895,7 @@ __global__ void __launch_bounds__(256) reduce_scatter_kernel(const CommParams c,
 // Wait until every peer has finished reading this rank's symmetric buffers of `epoch` (buffer-reuse guard).
 __global__ void wait_pull_done_kernel(uint32_t* my_flags, int world, uint32_t epoch) {
   if (threadIdx.x < world)
-    while (!epoch_reached(ld_acquire_sys(my_flags + SLOT_PULL_DONE + threadIdx.x), epoch)) {
-    }
+    wait_epoch<true>(my_flags + SLOT_PULL_DONE + threadIdx.x, epoch);
 }
 
 template <int BLOCK_N, int MODE>

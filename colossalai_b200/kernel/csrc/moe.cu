@@ -16,6 +16,8 @@
 //        * and on the way back PULLS its k expert outputs per token from the owners' output buffers with 16-byte P2P
 //          loads, doing the weighted combine on the fly.
 //      No host synchronisation, no NCCL call, no re-sort.  Flags are epoch-valued words in a symmetric flag page.
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace {
@@ -216,7 +218,16 @@ CB_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 CB_DEVICE void spin_until(const uint32_t* p, uint32_t epoch) {
   // epochs only grow; a later epoch also satisfies the wait (the producer has moved on, data of this epoch landed)
-  while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) __nanosleep(64);
+  if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return;
+  const long long t0 = clock64();
+  uint32_t it = 0;
+  while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+    __nanosleep(100);
+    if ((++it & 0x3fff) == 0 && clock64() - t0 > 40LL * 1000 * 1000 * 1000) {   // ~20 s: a peer never arrived
+      printf("[cb200 moe] timeout waiting for epoch %u on flag %p\n", epoch, (const void*)p);
+      __trap();
+    }
+  }
 }
 
 // histogram of the routing choices: counts[e] += 1 for every (t, k)
