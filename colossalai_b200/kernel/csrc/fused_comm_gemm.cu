@@ -75,6 +75,7 @@ struct CommParams {
   uint32_t* peer_tile_flags[MAX_RANKS];  // symmetric [MAX_RANKS][tile_flag_stride] epoch flags (index = writer rank)
   int tile_flag_stride;                  // flags per writer rank
   uint32_t* tile_counter;                // local per-tile epilogue-warp arrival counters [m_blocks * n_blocks]
+  uint32_t* reduce_ticket;               // local work-queue head of the tile-granular reduction
 };
 
 struct GemmParams {
@@ -295,39 +296,51 @@ SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint
 // producing later tiles.  A 256 x 256 tile of my chunk is reduced (multimem.ld_reduce in the switch, or P2P loads) as soon
 // as every rank's partial of that tile is complete; the tiles of my chunk are visited in the order my own GEMM produces
 // them (they come last in the rotated tile order), so only the final tiles' reduction is exposed.
-SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int warp, int lane,
-                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot) {
+SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int lane,
+                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot, int total_warps) {
+  // Work units = 32-row slices of the 256 x 256 tiles of MY chunk, handed out through a ticket counter in the order
+  // the GEMM roles produce the tiles.  Warps 6..7 start pulling tickets immediately (overlap with the main loop);
+  // warps 0..5 join when their GEMM role is done, so a communication-bound shape finishes with every warp reducing.
+  constexpr int SUB = 8;                                        // slices per tile
   const int num_tiles = m_blocks * n_blocks;
-  const int rwarp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
-  const int n_rwarps = (int)gridDim.x * COPY_WARPS;
+  const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
+  const int n_units = tiles_per_chunk * SUB;
   const uint32_t* my_tile_flags = c.peer_tile_flags[c.rank];
   const size_t ldc_vec = p.ldc / 8;
   const size_t ldo_vec = c.ld_out / 8;
   const int my_first_blk = c.rank * pair_blocks_per_chunk;
-  // walk the tile order of the GEMM roles, keep the tiles of MY chunk (they come last when chunks align with the
-  // rasterisation groups) and deal them round-robin to the reduce warps of the whole grid
-  int mine = 0;
-  for (int t = 0; t < num_tiles; ++t) {
-    int m_blk, n_blk;
-    tile_coords_rot(t, m_blocks, n_blocks, m_rot, m_blk, n_blk);
-    if (m_blk < my_first_blk || m_blk >= my_first_blk + pair_blocks_per_chunk) continue;
-    if ((mine++) % n_rwarps != rwarp) continue;
-    const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
-    if (lane < c.world) {
-      const uint32_t* f = my_tile_flags + (size_t)lane * c.tile_flag_stride + slot;
-      wait_epoch<true>(f, c.epoch);
+  int t_cursor = 0, mine_cursor = 0, cur_m = -1, cur_n = -1;   // incremental scan of the rotated tile order
+  int ready_tile = -1;
+  while (true) {
+    int u = 0;
+    if (lane == 0) u = (int)atomicAdd(c.reduce_ticket, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_units) break;
+    const int tile_idx = u / SUB, sub = u - tile_idx * SUB;
+    while (mine_cursor <= tile_idx) {                            // tickets only grow: keep scanning forward
+      int mb, nb;
+      tile_coords_rot(t_cursor, m_blocks, n_blocks, m_rot, mb, nb);
+      ++t_cursor;
+      if (mb < my_first_blk || mb >= my_first_blk + pair_blocks_per_chunk) continue;
+      cur_m = mb; cur_n = nb;
+      ++mine_cursor;
+      if (t_cursor > num_tiles) break;
     }
-    __syncwarp();
-    const int row0 = m_blk * 256;                               // global row in [T]
-    const int rows = min(256, p.M - row0);
+    const int m_blk = cur_m, n_blk = cur_n;
+    if (ready_tile != tile_idx) {
+      const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
+      if (lane < c.world) wait_epoch<true>(my_tile_flags + (size_t)lane * c.tile_flag_stride + slot, c.epoch);
+      __syncwarp();
+      ready_tile = tile_idx;
+    }
+    const int row0 = m_blk * 256 + sub * 32;                    // global row in [T]
+    const int rows = max(0, min(32, p.M - row0));
     const int col0 = n_blk * 256;
     const int cols = min(256, p.N - col0);
     const int vec_per_row = cols / 8;                           // N % 8 == 0 is enforced by the launcher
     const int out_row0 = row0 - c.rank * c.rows_per_chunk;
     const int nvec = rows * vec_per_row;
-    // 16 independent 16-byte reductions in flight per lane: the NVLink round trip (~2-3 us) must be covered by
-    // memory-level parallelism of only two warps per SM
-    constexpr int RU = 16;
+    constexpr int RU = 16;                                      // independent 16-byte reductions in flight per lane
     for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
       uint4 sum[RU];
       size_t doff[RU];
@@ -359,12 +372,14 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
         if (doff[j] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
     }
   }
-  // every partial buffer of this epoch has been consumed by me: last reduce warp tells the peers
+  // every partial buffer of this epoch has been consumed by me: the last warp of the grid resets the ticket and tells
+  // the peers that their partial buffers may be overwritten
   __syncwarp();
   if (lane == 0) {
     const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
-    if (done == (uint32_t)n_rwarps) {
+    if (done == (uint32_t)total_warps) {
       my_flags[SLOT_LOCAL + 1] = 0;
+      *c.reduce_ticket = 0;
       __threadfence_system();
       for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
     }
@@ -705,7 +720,6 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp >= 6) {
     if (MODE == 0) ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
-    else rs_reduce_tiles(p, c, my_flags, warp, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot);
   } else {
     const int quarter = warp & 3;
     int acc = 0;
@@ -756,6 +770,8 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   }
+  if (MODE == 1)   // warps 6..7 arrive here at once, the GEMM roles when their tiles are done
+    rs_reduce_tiles(p, c, my_flags, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot, (int)gridDim.x * 8);
   tc_fence_before();
   cluster_sync();
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
@@ -969,10 +985,11 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
   const int pair_tiles_chunk = ((T / world) / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
   const int pair_tiles = (T / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
   if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0 && peer_tile_flags && tile_counter &&
-      pair_tiles_chunk <= tile_flag_stride && pair_tiles <= tile_counter_len) {
+      pair_tiles_chunk <= tile_flag_stride && pair_tiles < tile_counter_len) {
     for (int r = 0; r < world; ++r) c.peer_tile_flags[r] = peer_tile_flags[r];
     c.tile_flag_stride = tile_flag_stride;
     c.tile_counter = tile_counter;
+    c.reduce_ticket = tile_counter + (tile_counter_len - 1);
     return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
   }
   if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
