@@ -340,36 +340,72 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
     const int vec_per_row = cols / 8;                           // N % 8 == 0 is enforced by the launcher
     const int out_row0 = row0 - c.rank * c.rows_per_chunk;
     const int nvec = rows * vec_per_row;
-    constexpr int RU = 16;                                      // independent 16-byte reductions in flight per lane
-    for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
-      uint4 sum[RU];
-      size_t doff[RU];
+    if (c.mc_part) {
+      constexpr int RU = 16;                                    // independent in-switch reductions in flight per lane
+      for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
+        uint4 sum[RU];
+        size_t doff[RU];
 #pragma unroll
-      for (int j = 0; j < RU; ++j) {
-        const int i = i0 + j * 32;
-        if (i >= nvec) { doff[j] = (size_t)-1; continue; }
-        const int r = i / vec_per_row, cv = i - r * vec_per_row;
-        const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
-        doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
-        if (c.mc_part) {
+        for (int j = 0; j < RU; ++j) {
+          const int i = i0 + j * 32;
+          if (i >= nvec) { doff[j] = (size_t)-1; continue; }
+          const int r = i / vec_per_row, cv = i - r * vec_per_row;
+          const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
+          doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
           sum[j] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
-        } else {
-          float accf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          for (int rk = 0; rk < c.world; ++rk) {
-            Vec16<__nv_bfloat16> v;
-            v.raw = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[(c.rank + rk) % c.world]) + src_off);
+        }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) accf[k] += v.get(k);
+        for (int j = 0; j < RU; ++j)
+          if (doff[j] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
+      }
+    } else {
+      // P2P path: issue the loads of up to 8 ranks for two vectors first (16 x 16 B in flight), then add in fp32
+      for (int i0 = lane; i0 < nvec; i0 += 2 * 32) {
+        float accf[2][8];
+        size_t doff[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) accf[j][k] = 0.f;
+        }
+        for (int rbase = 0; rbase < c.world; rbase += 8) {
+          uint4 raw[2][8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int i = i0 + j * 32;
+            doff[j] = (size_t)-1;
+            if (i >= nvec) continue;
+            const int r = i / vec_per_row, cv = i - r * vec_per_row;
+            const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
+            doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+#pragma unroll
+            for (int rk = 0; rk < 8; ++rk)
+              if (rbase + rk < c.world)
+                raw[j][rk] = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[rbase + rk]) + src_off);
           }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (doff[j] == (size_t)-1) continue;
+#pragma unroll
+            for (int rk = 0; rk < 8; ++rk) {
+              if (rbase + rk < c.world) {
+                Vec16<__nv_bfloat16> v;
+                v.raw = raw[j][rk];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) accf[j][k] += v.get(k);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (doff[j] == (size_t)-1) continue;
           Vec16<__nv_bfloat16> o;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o.set(k, accf[k]);
-          sum[j] = o.raw;
+          for (int k = 0; k < 8; ++k) o.set(k, accf[j][k]);
+          reinterpret_cast<uint4*>(c.out)[doff[j]] = o.raw;
         }
       }
-#pragma unroll
-      for (int j = 0; j < RU; ++j)
-        if (doff[j] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
     }
   }
   // every partial buffer of this epoch has been consumed by me: the last warp of the grid resets the ticket and tells

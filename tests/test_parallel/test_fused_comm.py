@@ -84,10 +84,17 @@ def _worker(rank, world_size, port, timing=False):
             t_n = _time(lambda: torch.nn.functional.linear(comm.all_gather(x_local, 0, group), w))
             t_f2 = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
             t_f21 = _time(lambda: fused.gemm_reduce_scatter(a, w, group, block_n=256))
+            os.environ["CB200_NO_MULTIMEM"] = "1"          # reduction by P2P loads instead of the in-switch reduction
+            got_p2p = fused.gemm_reduce_scatter(a, w, group)
+            torch.testing.assert_close(got_p2p.float(), comm.reduce_scatter((a.float() @ w.float().t()), 0, group),
+                                       atol=0.15, rtol=3e-2)
+            t_f2p = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
+            os.environ["CB200_NO_MULTIMEM"] = "0"
             t_n2 = _time(lambda: comm.reduce_scatter(torch.nn.functional.linear(a, w), 0, group))
             results.append({"world": world_size, "t_local": t, "K": K, "N": N, "ag_gemm_fused_ms": t_f,
                             "ag_gemm_fused_1cta_ms": t_f1, "ag_gemm_nccl_cublas_ms": t_n, "gemm_rs_fused_ms": t_f2,
-                            "gemm_rs_fused_1cta_ms": t_f21, "gemm_rs_nccl_cublas_ms": t_n2})
+                            "gemm_rs_fused_1cta_ms": t_f21, "gemm_rs_fused_p2p_ms": t_f2p,
+                            "gemm_rs_nccl_cublas_ms": t_n2})
     assert fused.stats["ag_gemm"] > 0 and fused.stats["gemm_rs"] > 0, fused.stats
     if rank == 0:
         for r in results:
