@@ -138,3 +138,31 @@ def test_rpc_engine_matches_local_engine():
     finally:
         rpc.kill_workers()
     assert got == ref
+
+
+def _tp_worker(rank, world_size, port):
+    import copy
+
+    import torch.distributed as dist
+
+    import colossalai_b200
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    prompts = [[5, 9, 13, 200, 7], [11, 3], [17] * 6]
+    gen = GenerationConfig(max_new_tokens=6)
+    kw = dict(max_batch_size=4, max_input_len=16, max_output_len=6, block_size=8, dtype="fp32")
+    _, ref_ids = InferenceEngine(copy.deepcopy(model), None, InferenceConfig(**kw)).generate(
+        prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    eng = InferenceEngine(model, None, InferenceConfig(tp_size=2, **kw))        # TP-sharded through the policy
+    _, ids = eng.generate(prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    assert ids == ref_ids, (ids, ref_ids)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tensor_parallel_engine_matches_single_rank():
+    from colossalai_b200.testing import spawn
+
+    spawn(_tp_worker, 2)
