@@ -86,10 +86,20 @@ class LLMEngine(BaseEngine):
 
     # ------------------------------------------------------------------ model
     def init_model(self, model_or_path, model_policy=None, model_shard_infer_config=None) -> None:
+        hf_dir = None
         if isinstance(model_or_path, str):
-            from ...models.hf_io import load_hf_checkpoint
+            import json
+            import os
 
-            self.model = load_hf_checkpoint(model_or_path, dtype=self.dtype)
+            from ...models.hf_io import config_from_hf, load_hf_checkpoint
+
+            if self.inference_config.tp_size > 1:
+                # build the skeleton, shard it, then stream each rank's slices in (InferCheckpoint_io)
+                with open(os.path.join(model_or_path, "config.json")) as f:
+                    self.model = build_model(config_from_hf(json.load(f)))
+                hf_dir = model_or_path
+            else:
+                self.model = load_hf_checkpoint(model_or_path, dtype=self.dtype)
         elif isinstance(model_or_path, ModelConfig):
             self.model = build_model(model_or_path)
         else:
@@ -103,6 +113,10 @@ class LLMEngine(BaseEngine):
             self.pg_mesh = DeviceMesh(pp=dist.get_world_size() // tp, tp=tp)
             self.tp_group = self.pg_mesh.group("tp")
             self.model = self._shardformer(self.model, model_policy, model_shard_infer_config, None, self.tp_group)
+            if hf_dir is not None:
+                from .plugin import InferCheckpoint_io
+
+                InferCheckpoint_io().load_model(self.model, hf_dir)
         self.model = self.model.to(self.device)
 
     def _verify_args(self) -> None:

@@ -166,3 +166,36 @@ def test_tensor_parallel_engine_matches_single_rank():
     from colossalai_b200.testing import spawn
 
     spawn(_tp_worker, 2)
+
+
+def _tp_ckpt_worker(rank, world_size, port, tmp):
+    import torch.distributed as dist
+    import transformers
+
+    import colossalai_b200
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    if rank == 0:
+        torch.manual_seed(0)
+        hf = transformers.LlamaForCausalLM(transformers.LlamaConfig(
+            vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+            num_key_value_heads=2, max_position_embeddings=64))
+        hf.save_pretrained(tmp, safe_serialization=True)
+    dist.barrier()
+    prompts = [[5, 9, 13, 20, 7], [11, 3]]
+    gen = GenerationConfig(max_new_tokens=5)
+    kw = dict(max_batch_size=2, max_input_len=16, max_output_len=5, block_size=8, dtype="fp32")
+    _, ref_ids = InferenceEngine(tmp, None, InferenceConfig(**kw)).generate(
+        prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    _, ids = InferenceEngine(tmp, None, InferenceConfig(tp_size=2, **kw)).generate(
+        prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    assert ids == ref_ids, (ids, ref_ids)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tp_engine_loads_hf_checkpoint(tmp_path):
+    pytest.importorskip("transformers")
+    from colossalai_b200.testing import spawn
+
+    spawn(_tp_ckpt_worker, 2, tmp=str(tmp_path))
