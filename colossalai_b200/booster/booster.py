@@ -71,6 +71,14 @@ class Booster:
         from ..interface.pretrained import get_pretrained_path, set_pretrained_path
 
         pretrained_path = get_pretrained_path(model)
+        # lazily built models: plugins that shard through ShardFormer materialise AFTER sharding (each rank only allocates
+        # its slices); every other plugin gets real tensors before it wraps the module
+        if not getattr(self.plugin, "materializes_lazy_models", False) and not isinstance(model, ModelWrapper):
+            from ..lazy import LazyInitContext
+            from ..lazy.lazy_init import is_lazy
+
+            if any(is_lazy(p) or p.device.type == "meta" for p in model.parameters()):
+                LazyInitContext.materialize(model)
         if self.plugin:
             model, optimizer, criterion, dataloader, lr_scheduler = self.plugin.configure(
                 model, optimizer, criterion, dataloader, lr_scheduler)

@@ -380,6 +380,8 @@ class HybridParallelPlugin(PipelinePluginBase):
     >>> model, optimizer, criterion, dataloader, _ = booster.boost(model, optimizer, criterion, dataloader)
     """
 
+    materializes_lazy_models = True      # ShardFormer materialises lazily built models after sharding
+
     def __init__(self, tp_size: int, pp_size: int, sp_size: int = None, precision: str = "fp16", zero_stage: int = 0,
                  enable_all_optimization: bool = False, enable_fused_normalization: bool = False,
                  enable_flash_attention: bool = False, enable_jit_fused: bool = False,

@@ -56,7 +56,9 @@ def main():
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, sp_size=args.sp if args.sp > 1 else None,
                                       zero_stage=args.zero, precision=args.precision,
                                       enable_sequence_parallelism=args.sp_mode is not None,
-                                      sequence_parallelism_mode=args.sp_mode, microbatch_size=args.mbs,
+                                      sequence_parallelism_mode=args.sp_mode,
+                                      microbatch_size=None if args.pp_style == "zbv" else args.mbs,
+                                      num_microbatches=(args.batch_size // args.mbs) if args.pp_style == "zbv" else None,
                                       pp_style=args.pp_style, num_model_chunks=args.n_chunks, max_norm=1.0,
                                       comm_backend=args.comm_backend)
     elif args.plugin in ("zero1", "zero2"):
