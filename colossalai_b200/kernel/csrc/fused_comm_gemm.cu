@@ -296,126 +296,100 @@ SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint
 // producing later tiles.  A 256 x 256 tile of my chunk is reduced (multimem.ld_reduce in the switch, or P2P loads) as soon
 // as every rank's partial of that tile is complete; the tiles of my chunk are visited in the order my own GEMM produces
 // them (they come last in the rotated tile order), so only the final tiles' reduction is exposed.
-SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int lane,
-                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot, int total_warps) {
-  // Work units = 32-row slices of the 256 x 256 tiles of MY chunk, handed out through a ticket counter in the order
-  // the GEMM roles produce the tiles.  Warps 6..7 start pulling tickets immediately (overlap with the main loop);
-  // warps 0..5 join when their GEMM role is done, so a communication-bound shape finishes with every warp reducing.
-  constexpr int SUB = 8;                                        // slices per tile
+// GEMM+RS, CTA-pair kernel: staggered pull-accumulate by warps 6..7 of every CTA.
+// Rank q computes the chunks in the order q+1, q+2, ..., q, so the partial of MY chunk r becomes available on rank r-k
+// during time slot k (k = 1..world-1) and my own partial in the last slot.  The reduce warps therefore pull slice by
+// slice from rank r-1, then r-2, ... while the GEMM roles are still busy with later chunks: every slot moves one
+// chunk-partial per rank over a distinct NVLink peer (a permutation -> all links busy), and only the last, LOCAL
+// accumulation step runs after the main loop.  Accumulation is bf16 in `out` with fp32 adds (the precision of a ring
+// reduce-scatter); work units (32-row slices of 256 x 256 tiles) are statically owned by one warp, so the k-steps of a
+// unit are naturally ordered.
+SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int warp, int lane,
+                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot) {
+  constexpr int SUB = 8;                                        // 32-row slices per 256-row tile
   const int num_tiles = m_blocks * n_blocks;
-  const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
-  const int n_units = tiles_per_chunk * SUB;
+  const int rwarp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
+  const int n_rwarps = (int)gridDim.x * COPY_WARPS;
   const uint32_t* my_tile_flags = c.peer_tile_flags[c.rank];
   const size_t ldc_vec = p.ldc / 8;
   const size_t ldo_vec = c.ld_out / 8;
   const int my_first_blk = c.rank * pair_blocks_per_chunk;
-  int t_cursor = 0, mine_cursor = 0, cur_m = -1, cur_n = -1;   // incremental scan of the rotated tile order
-  int ready_tile = -1;
-  while (true) {
-    int u = 0;
-    if (lane == 0) u = (int)atomicAdd(c.reduce_ticket, 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u >= n_units) break;
-    const int tile_idx = u / SUB, sub = u - tile_idx * SUB;
-    while (mine_cursor <= tile_idx) {                            // tickets only grow: keep scanning forward
-      int mb, nb;
-      tile_coords_rot(t_cursor, m_blocks, n_blocks, m_rot, mb, nb);
-      ++t_cursor;
-      if (mb < my_first_blk || mb >= my_first_blk + pair_blocks_per_chunk) continue;
-      cur_m = mb; cur_n = nb;
-      ++mine_cursor;
-      if (t_cursor > num_tiles) break;
-    }
-    const int m_blk = cur_m, n_blk = cur_n;
-    if (ready_tile != tile_idx) {
-      const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
-      if (lane < c.world) wait_epoch<true>(my_tile_flags + (size_t)lane * c.tile_flag_stride + slot, c.epoch);
-      __syncwarp();
-      ready_tile = tile_idx;
-    }
-    const int row0 = m_blk * 256 + sub * 32;                    // global row in [T]
-    const int rows = max(0, min(32, p.M - row0));
-    const int col0 = n_blk * 256;
-    const int cols = min(256, p.N - col0);
-    const int vec_per_row = cols / 8;                           // N % 8 == 0 is enforced by the launcher
-    const int out_row0 = row0 - c.rank * c.rows_per_chunk;
-    const int nvec = rows * vec_per_row;
-    if (c.mc_part) {
-      constexpr int RU = 16;                                    // independent in-switch reductions in flight per lane
-      for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
-        uint4 sum[RU];
-        size_t doff[RU];
-#pragma unroll
-        for (int j = 0; j < RU; ++j) {
-          const int i = i0 + j * 32;
-          if (i >= nvec) { doff[j] = (size_t)-1; continue; }
-          const int r = i / vec_per_row, cv = i - r * vec_per_row;
-          const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
-          doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
-          sum[j] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_part) + src_off);
+  for (int k = 1; k <= c.world; ++k) {
+    const int src = (c.rank - k + 2 * c.world) % c.world;       // k == world -> my own partial
+    const uint4* src_part = reinterpret_cast<const uint4*>(c.peer_part[src]);
+    // units u = tile_in_chunk * SUB + slice, dealt round-robin over the reduce warps of the grid.  When chunks align
+    // with the rasterisation groups my chunk's tiles are the LAST tiles of the rotated order (direct indexing);
+    // otherwise fall back to scanning the order.
+    const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
+    const bool aligned = (pair_blocks_per_chunk % GROUP_M == 0) || (m_blocks <= GROUP_M);
+    int scan_t = 0, scan_mine = 0;
+    for (int u = rwarp; u < tiles_per_chunk * SUB; u += n_rwarps) {
+      const int tile_in_chunk = u / SUB;
+      const int first_sub = u - tile_in_chunk * SUB;
+      int m_blk = 0, n_blk = 0;
+      if (aligned) {
+        tile_coords_rot(num_tiles - tiles_per_chunk + tile_in_chunk, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      } else {
+        while (scan_mine <= tile_in_chunk && scan_t < num_tiles) {
+          int mb, nb;
+          tile_coords_rot(scan_t++, m_blocks, n_blocks, m_rot, mb, nb);
+          if (mb < my_first_blk || mb >= my_first_blk + pair_blocks_per_chunk) continue;
+          m_blk = mb; n_blk = nb;
+          ++scan_mine;
         }
-#pragma unroll
-        for (int j = 0; j < RU; ++j)
-          if (doff[j] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[j]] = sum[j];
       }
-    } else {
-      // P2P path: issue the loads of up to 8 ranks for two vectors first (16 x 16 B in flight), then add in fp32
-      for (int i0 = lane; i0 < nvec; i0 += 2 * 32) {
-        float accf[2][8];
-        size_t doff[2];
+      const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
+      if (lane == 0) wait_epoch<true>(my_tile_flags + (size_t)src * c.tile_flag_stride + slot, c.epoch);
+      __syncwarp();
+      const int col0 = n_blk * 256;
+      const int cols = min(256, p.N - col0);
+      const int vec_per_row = cols / 8;
+      for (int sub = first_sub; sub < SUB; sub += n_rwarps) {
+        const int row0 = m_blk * 256 + sub * 32;
+        const int rows = max(0, min(32, p.M - row0));
+        const int out_row0 = row0 - c.rank * c.rows_per_chunk;
+        const int nvec = rows * vec_per_row;
+        constexpr int RU = 8;
+        for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
+          uint4 in[RU], cur[RU];
+          size_t doff[RU];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) accf[j][k] = 0.f;
-        }
-        for (int rbase = 0; rbase < c.world; rbase += 8) {
-          uint4 raw[2][8];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < RU; ++j) {
             const int i = i0 + j * 32;
             doff[j] = (size_t)-1;
             if (i >= nvec) continue;
             const int r = i / vec_per_row, cv = i - r * vec_per_row;
-            const size_t src_off = (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv;
             doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+            in[j] = ld_peer_16B(src_part + (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv);
+          }
+          if (k > 1) {
 #pragma unroll
-            for (int rk = 0; rk < 8; ++rk)
-              if (rbase + rk < c.world)
-                raw[j][rk] = ld_peer_16B(reinterpret_cast<const uint4*>(c.peer_part[rbase + rk]) + src_off);
+            for (int j = 0; j < RU; ++j)
+              if (doff[j] != (size_t)-1) cur[j] = reinterpret_cast<const uint4*>(c.out)[doff[j]];
           }
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < RU; ++j) {
             if (doff[j] == (size_t)-1) continue;
+            if (k > 1) {
+              Vec16<__nv_bfloat16> a, b2, o;
+              a.raw = in[j];
+              b2.raw = cur[j];
 #pragma unroll
-            for (int rk = 0; rk < 8; ++rk) {
-              if (rbase + rk < c.world) {
-                Vec16<__nv_bfloat16> v;
-                v.raw = raw[j][rk];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) accf[j][k] += v.get(k);
-              }
+              for (int e = 0; e < 8; ++e) o.set(e, a.get(e) + b2.get(e));
+              in[j] = o.raw;
             }
+            reinterpret_cast<uint4*>(c.out)[doff[j]] = in[j];
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (doff[j] == (size_t)-1) continue;
-          Vec16<__nv_bfloat16> o;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o.set(k, accf[j][k]);
-          reinterpret_cast<uint4*>(c.out)[doff[j]] = o.raw;
         }
       }
     }
   }
-  // every partial buffer of this epoch has been consumed by me: the last warp of the grid resets the ticket and tells
-  // the peers that their partial buffers may be overwritten
+  // every partial buffer of this epoch has been consumed by me: the last reduce warp tells the peers
   __syncwarp();
   if (lane == 0) {
     const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
-    if (done == (uint32_t)total_warps) {
+    if (done == (uint32_t)n_rwarps) {
       my_flags[SLOT_LOCAL + 1] = 0;
-      *c.reduce_ticket = 0;
       __threadfence_system();
       for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
     }
@@ -756,6 +730,7 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp >= 6) {
     if (MODE == 0) ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
+    else rs_reduce_tiles(p, c, my_flags, warp, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot);
   } else {
     const int quarter = warp & 3;
     int acc = 0;
@@ -806,8 +781,6 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   }
-  if (MODE == 1)   // warps 6..7 arrive here at once, the GEMM roles when their tiles are done
-    rs_reduce_tiles(p, c, my_flags, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot, (int)gridDim.x * 8);
   tc_fence_before();
   cluster_sync();
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
