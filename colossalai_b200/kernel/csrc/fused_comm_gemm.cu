@@ -349,7 +349,7 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
         const int rows = max(0, min(32, p.M - row0));
         const int out_row0 = row0 - c.rank * c.rows_per_chunk;
         const int nvec = rows * vec_per_row;
-        constexpr int RU = 8;
+        constexpr int RU = 16;     // 16 x 16 B peer loads in flight per lane (NVLink round trip ~3 us)
         for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
           uint4 in[RU], cur[RU];
           size_t doff[RU];
