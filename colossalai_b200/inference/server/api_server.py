@@ -39,6 +39,19 @@ def build_app(async_engine: AsyncInferenceEngine, served_model: str = "model", t
     def health_check():
         return JSONResponse({"status": "Healthy"})
 
+    @app.get("/metrics")
+    def metrics():
+        """Prometheus text exposition of the scheduler state (requests waiting / running, KV blocks in use)."""
+        rh = async_engine.engine.engine.request_handler
+        cm = rh.cache_manager
+        waiting = sum(len(l) for l in rh.waiting_list)
+        running = rh.total_requests_in_batch_bucket()
+        lines = ["# TYPE cb200_requests_waiting gauge", f"cb200_requests_waiting {waiting}",
+                 "# TYPE cb200_requests_running gauge", f"cb200_requests_running {running}",
+                 "# TYPE cb200_kv_blocks_total gauge", f"cb200_kv_blocks_total {cm.total_num_blocks}",
+                 "# TYPE cb200_kv_blocks_free gauge", f"cb200_kv_blocks_free {cm.num_available_blocks}"]
+        return Response(content="\n".join(lines) + "\n", media_type="text/plain; version=0.0.4")
+
     @app.get("/engine_check")
     def engine_check():
         return JSONResponse({"status": "Running" if async_engine.background_loop_status else "Error"})

@@ -87,6 +87,9 @@ class _SymmBuffer:
         self.tensor = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
         if zero:
             self.tensor.zero_()
+        elif os.environ.get("CB200_POISON_SYMM", "0") == "1":
+            # debug: data buffers start as 0xFF (bf16 NaN) so a read-before-write in a flag protocol shows up as NaNs
+            self.tensor.fill_(0xFF)
         self.handle = symm_mem.rendezvous(self.tensor, group)
         self.peer_ptrs: List[int] = [int(p) for p in self.handle.buffer_ptrs]
         mc = 0

@@ -114,6 +114,7 @@ def test_async_engine_and_http_server():
     eng = AsyncInferenceEngine(start_engine_loop=True, model_or_path=model, tokenizer=None, inference_config=cfg)
     with TestClient(build_app(eng, "llama-tiny")) as client:
         assert client.get("/ping").json() == {"status": "Healthy"}
+        assert "cb200_kv_blocks_free" in client.get("/metrics").text
         r = client.post("/generate", json={"prompt": "hello", "max_new_tokens": 4})
         assert r.status_code == 200 and "text" in r.json()
         r = client.post("/completion", json={"prompt": "hi there", "max_new_tokens": 4})
