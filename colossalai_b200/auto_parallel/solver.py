@@ -23,6 +23,7 @@ class LayerStrategy:
     param_bytes: float
     out_sharded: bool              # activation leaving the layer is feature-sharded
     in_sharded: bool               # layer expects a feature-sharded input
+    out_features: int = 0          # width of the activation leaving the layer
 
 
 @dataclass
@@ -45,17 +46,20 @@ def _layer_candidates(name: str, m: nn.Module, tokens: int, mesh: DeviceMesh, ax
         act_out = tokens * fout * elem
         act_in = tokens * fin * elem
         return [
-            LayerStrategy(name, "replicate", flops / peak_flops, 0.0, pbytes, False, False),
+            LayerStrategy(name, "replicate", flops / peak_flops, 0.0, pbytes, False, False, fout),
             # column: no fwd comm, dgrad needs an all-reduce of the input gradient
-            LayerStrategy(name, "col", flops / n / peak_flops, mesh.all_reduce_cost(act_in, axis), pbytes / n, True, False),
+            LayerStrategy(name, "col", flops / n / peak_flops, mesh.all_reduce_cost(act_in, axis), pbytes / n, True, False,
+                          fout),
             # row: fwd all-reduce of the output
-            LayerStrategy(name, "row", flops / n / peak_flops, mesh.all_reduce_cost(act_out, axis), pbytes / n, False, True),
+            LayerStrategy(name, "row", flops / n / peak_flops, mesh.all_reduce_cost(act_out, axis), pbytes / n, False, True,
+                          fout),
         ]
     if isinstance(m, nn.Embedding):
         pbytes = m.num_embeddings * m.embedding_dim * elem
         act = tokens * m.embedding_dim * elem
-        return [LayerStrategy(name, "replicate", 0.0, 0.0, pbytes, False, False),
-                LayerStrategy(name, "row", 0.0, mesh.all_reduce_cost(act, axis), pbytes / n, False, False)]
+        return [LayerStrategy(name, "replicate", 0.0, 0.0, pbytes, False, False, m.embedding_dim),
+                LayerStrategy(name, "row", 0.0, mesh.all_reduce_cost(act, axis), pbytes / n, False, False,
+                              m.embedding_dim)]
     return []
 
 
@@ -83,7 +87,7 @@ def solve_chain(layers: List[List[LayerStrategy]], mesh: DeviceMesh, axis: int, 
         for i in range(1, len(layers)):
             for j, s in enumerate(layers[i]):
                 for k, p in enumerate(layers[i - 1]):
-                    c = best[i - 1][k] + reshard(p, s, tokens * elem * 1.0 * _width(p)) + s.compute_s + s.comm_s \
+                    c = best[i - 1][k] + reshard(p, s, float(tokens) * elem * max(p.out_features, 1)) + s.compute_s + s.comm_s \
                         + lmbda * s.param_bytes
                     if c < best[i][j]:
                         best[i][j], back[i][j] = c, k
@@ -94,13 +98,6 @@ def solve_chain(layers: List[List[LayerStrategy]], mesh: DeviceMesh, axis: int, 
             choice.append(j)
         return best[-1][choice[0]], choice[::-1]
 
-    def _width(s: LayerStrategy) -> float:
-        return 1.0 if s.param_bytes == 0 else max(s.param_bytes, 1.0) ** 0.0 * _out_features.get(s.name, 1.0)
-
-    _out_features: Dict[str, float] = {}
-    for cands in layers:
-        for s in cands:
-            _out_features.setdefault(s.name, 1.0)
     lmbda, plan_choice = 0.0, None
     for _ in range(40):
         _, choice = run(lmbda)
