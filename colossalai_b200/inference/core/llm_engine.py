@@ -73,6 +73,12 @@ class LLMEngine(BaseEngine):
         self.kv_runtime = PagedKVRuntime(k_caches, v_caches, self.inference_config.block_size)
         self.counter = count()
         self.use_cuda_graph = self.inference_config.use_cuda_graph and torch.cuda.is_available()
+        if self.use_cuda_graph and (self.model_config.head_dim not in (64, 128, 256)
+                                    or self.dtype not in (torch.float16, torch.bfloat16)):
+            # the decode step must stay on the native paged kernel to be capturable (the reference path syncs)
+            self.logger.warning("CUDA graphs disabled: the native paged-decode kernel needs fp16/bf16 and head_dim in "
+                                "{64, 128, 256}", ranks=[0])
+            self.use_cuda_graph = False
         self.graph_runners: Dict[int, CUDAGraphRunner] = {}
         self.graph_memory_pool = None
         self.use_spec_dec = False

@@ -321,7 +321,7 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
     // with the rasterisation groups my chunk's tiles are the LAST tiles of the rotated order (direct indexing);
     // otherwise fall back to scanning the order.
     const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
-    const bool aligned = (pair_blocks_per_chunk % GROUP_M == 0) || (m_blocks <= GROUP_M);
+    const bool aligned = (pair_blocks_per_chunk % GROUP_M == 0);      // whole rasterisation groups per chunk
     int scan_t = 0, scan_mine = 0;
     for (int u = rwarp; u < tiles_per_chunk * SUB; u += n_rwarps) {
       const int tile_in_chunk = u / SUB;
@@ -588,10 +588,11 @@ fused_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // in gemm_tcgen05.cu for the barrier topology).  Communication roles are unchanged: warps 6..7 of every CTA pull peer
 // rows (AG), every epilogue warp publishes its slice of a partial tile (RS).  Each CTA's TMA producer waits for the ready
 // flag of ITS OWN 128-row block of A, so the pair starts a tile as soon as both halves have landed.
-struct Cfg2 {
-  static constexpr int STAGES = 6;
-  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
-  static constexpr int B_BYTES = 128 * BLOCK_K * 2;
+template <int BK_, int STAGES_> struct Cfg2 {
+  static constexpr int BK = BK_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = 128 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
@@ -599,11 +600,11 @@ struct Cfg2 {
 constexpr int PAIR_M = 256;
 constexpr int PAIR_N = 256;
 
-template <int MODE>
+template <int MODE, int BK, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const GemmParams p, const CommParams c) {
-  using C = Cfg2;
+  using C = Cfg2<BK, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -624,7 +625,7 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int m_blocks = (p.M + PAIR_M - 1) / PAIR_M;            // 256-row blocks
   const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
   const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int k_blocks = (p.K + BK - 1) / BK;
   const int blocks_per_chunk = c.rows_per_chunk / BLOCK_M;     // 128-row blocks (flag granularity of the pull)
   const int pair_blocks_per_chunk = c.rows_per_chunk / PAIR_M;
   uint32_t* my_flags = c.peer_flags[c.rank];
@@ -674,18 +675,20 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * BK;
           if (!p.a_mn_major) {
-            tma_load_2d_2sm(&tmap_a, fb, sa, k0, m0);
+#pragma unroll
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (128 * 128), k0 + j * 64, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BLOCK_K * 128), m0 + j * 64, k0);
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BK * 128), m0 + j * 64, k0);
           }
           if (!p.b_mn_major) {
-            tma_load_2d_2sm(&tmap_b, fb, sb, k0, n0);
+#pragma unroll
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (128 * 128), k0 + j * 64, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BLOCK_K * 128), n0 + j * 64, k0);
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BK * 128), n0 + j * 64, k0);
           }
         }
         __syncwarp();
@@ -710,14 +713,17 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           if (lane == 0) {
             const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
             const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
-            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024)
+            const uint64_t da = p.a_mn_major ? make_smem_desc_sw128(sa, BK * 128, 1024)
                                              : make_smem_desc_sw128(sa, 16, 1024);
-            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024)
+            const uint64_t db = p.b_mn_major ? make_smem_desc_sw128(sb, BK * 128, 1024)
                                              : make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss_2cta(tmem_d, advance_desc(da, k * a_kstep), advance_desc(db, k * b_kstep), p.idesc,
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t ao = p.a_mn_major ? k * a_kstep : (k >> 2) * (128 * 128) + (k & 3) * a_kstep;
+              const uint32_t bo = p.b_mn_major ? k * b_kstep : (k >> 2) * (128 * 128) + (k & 3) * b_kstep;
+              umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
                                (kb > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit_2cta(&empty_bar[stage], 3);
             if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
           }
@@ -786,26 +792,26 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
 }
 
-template <int MODE>
+template <int MODE, int BK = 128, int STAGES = 3>
 int launch_fused_2cta(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_mn, int b_mn,
                       int in_dtype, GemmParams p, const CommParams& c, cudaStream_t stream) {
-  using C = Cfg2;
+  using C = Cfg2<BK, STAGES>;
   CUtensorMap ta, tb;
   const bool bf16 = in_dtype == CB_BF16;
-  int r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
+  int r = a_mn ? make_tmap_2d_16b(&ta, A, K, M, lda, BK, 64, bf16) : make_tmap_2d_16b(&ta, A, M, K, lda, 128, 64, bf16);
   if (r) return 1000 + r;
-  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BLOCK_K, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
+  r = b_mn ? make_tmap_2d_16b(&tb, B, K, N, ldb, BK, 64, bf16) : make_tmap_2d_16b(&tb, B, N, K, ldb, 128, 64, bf16);
   if (r) return 2000 + r;
   p.idesc = make_idesc_f16(PAIR_M, PAIR_N, bf16 ? 1 : 0, a_mn, b_mn);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fused_gemm_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fused_gemm_2cta_kernel<MODE, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int grid = cb_num_sms() & ~1;     // all CTAs co-resident (flag spinning): one CTA per SM, whole pairs
-  fused_gemm_2cta_kernel<MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, c);
+  fused_gemm_2cta_kernel<MODE, BK, STAGES><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, c);
   return (int)cudaGetLastError();
 }
 

@@ -43,7 +43,12 @@ class _Recorder(TorchFunctionMode):
         kwargs = kwargs or {}
         out = func(*args, **kwargs)
         name = getattr(func, "__name__", "")
-        if name in _INPLACE_INIT and args and isinstance(args[0], torch.Tensor) and args[0].device.type == "meta":
+        # NB: `torch.nn.init.*` wrappers dispatch as a whole (name e.g. "kaiming_uniform_") and are deliberately NOT
+        # recorded: module constructors call them as throw-away defaults.  Only tensor-level in-place initialisers
+        # (`w.normal_()`, `w.fill_()`, ...) are replayed; everything else gets `_default_fill` (or the model's own
+        # `_init_weights` after materialisation).
+        if getattr(func, "__module__", "") != "torch.nn.init" and name in _INPLACE_INIT and args \
+                and isinstance(args[0], torch.Tensor) and args[0].device.type == "meta":
             t = args[0]
             rest = tuple(a for a in args[1:])
             if any(isinstance(a, torch.Tensor) and a.device.type == "meta" for a in rest):
@@ -98,7 +103,9 @@ class LazyInitContext:
             return
         with torch.no_grad():
             for fn, args, kwargs in ops:
-                if fn == "trunc_normal_":
+                if fn.startswith("init:"):
+                    getattr(nn.init, fn[5:])(real, *args, **kwargs)
+                elif fn == "trunc_normal_":
                     nn.init.trunc_normal_(real, *args, **kwargs)
                 else:
                     getattr(real, fn)(*args, **kwargs)

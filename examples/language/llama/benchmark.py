@@ -23,7 +23,6 @@ from colossalai_b200.booster.plugin import (GeminiPlugin, HybridParallelPlugin, 
 from colossalai_b200.lazy import LazyInitContext  # noqa: E402
 from colossalai_b200.models import build_model, get_config  # noqa: E402
 from colossalai_b200.nn.optimizer import HybridAdam  # noqa: E402
-from colossalai_b200.utils.timer import CudaEventTimer  # noqa: E402
 from data_utils import RandomDataset, format_numel_str, get_model_numel  # noqa: E402
 
 
@@ -85,13 +84,14 @@ def main():
     if rank == 0:
         print(f"model {args.config}: {format_numel_str(get_model_numel(model))} params on this rank, plugin {args.plugin}")
     dev = colossalai_b200.accelerator.get_accelerator().get_current_device()
-    timer = CudaEventTimer() if dev.type == "cuda" else None
+    use_events = dev.type == "cuda"
     times = []
     it = iter(loader)
     for step in range(args.num_steps):
         t0 = time.perf_counter()
-        if timer:
-            timer.start()
+        if use_events:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if args.plugin == "3d" and args.pp > 1:
             out = booster.execute_pipeline(it, model, lambda o, b: o["loss"], optimizer, return_loss=True)
             loss = out["loss"]
@@ -101,7 +101,12 @@ def main():
             booster.backward(loss, optimizer)
         optimizer.step()
         optimizer.zero_grad()
-        dt = timer.stop() / 1e3 if timer else time.perf_counter() - t0
+        if use_events:
+            ev1.record()
+            torch.cuda.synchronize()
+            dt = ev0.elapsed_time(ev1) / 1e3
+        else:
+            dt = time.perf_counter() - t0
         if step >= args.ignore_steps:
             times.append(dt)
         if rank == 0:
