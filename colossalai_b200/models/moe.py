@@ -106,7 +106,9 @@ class SparseMoE(nn.Module):
     def setup_parallel(self, shard_config) -> None:
         ep_group = shard_config.ep_group
         self.ep_group = ep_group
-        self.ep_size, self.ep_rank = comm.group_size(ep_group), comm.group_rank(ep_group)
+        # no ep group configured = experts are replicated (plain data / tensor parallel run), NOT "the world"
+        self.ep_size = comm.group_size(ep_group) if ep_group is not None else 1
+        self.ep_rank = comm.group_rank(ep_group) if ep_group is not None else 0
         if self.ep_size > 1:
             assert self.num_experts % self.ep_size == 0
             n_local = self.num_experts // self.ep_size
@@ -126,6 +128,16 @@ class SparseMoE(nn.Module):
                     ex.w_up = nn.Parameter(ex.w_up.data[s:s + n_local].clone())
                     ex.w_down = nn.Parameter(ex.w_down.data[s:s + n_local].clone())
                 ex.num_local_experts = n_local
+        # Megatron-style sequence parallelism: the block sees only this rank's sequence shard, so the gradients of its
+        # replicated (non-TP, non-EP) parameters are partial sums -> all-reduced over the tp group with the norm grads
+        sp_mode = getattr(shard_config, "sp_mode", None)
+        if sp_mode in ("split_gather", "ring") and getattr(shard_config, "sequence_parallel_size", 1) > 1:
+            from ..tensor.d_tensor import is_distributed_tensor
+
+            for name, p in self.named_parameters():
+                if is_distributed_tensor(p) or (self.ep_size > 1 and name.startswith("experts.")):
+                    continue
+                p.partial_derived = True
         for p in self.experts.parameters():
             set_moe_tensor_ep_group(p, ep_group, getattr(shard_config, "moe_dp_group", None))
             if self.ep_size > 1:

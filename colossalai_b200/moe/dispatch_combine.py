@@ -42,7 +42,7 @@ def _use_fused(x: torch.Tensor, num_experts: int, ep_group) -> bool:
     if _BACKEND == "fused" and not ok:
         raise RuntimeError("CB200_MOE_BACKEND=fused but the fused expert-parallel kernels are unavailable")
     # single-rank groups gain nothing from the symmetric-buffer path unless explicitly requested
-    return ok and (comm.group_size(ep_group) > 1 or _BACKEND == "fused")
+    return ok and ((ep_group is not None and comm.group_size(ep_group) > 1) or _BACKEND == "fused")
 
 
 def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, experts, num_experts: int,
@@ -54,7 +54,7 @@ def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, e
         return fused_ep.moe_forward_fused(x, topk_w, topk_idx, experts, num_experts, ep_group)
     T, H = x.shape
     k = topk_idx.shape[1]
-    ep = comm.group_size(ep_group)
+    ep = comm.group_size(ep_group) if ep_group is not None else 1     # None = no expert parallelism (NOT the world)
     n_local = num_experts // ep
     flat_idx = topk_idx.reshape(-1)                                    # [T*k]
     order = torch.argsort(flat_idx, stable=True)                       # rows grouped by global expert id

@@ -62,7 +62,7 @@ class EPWorkspace:
 
     def __init__(self, group, hidden: int, dtype: torch.dtype, num_experts: int, capacity_rows: int) -> None:
         self.group = group
-        self.world = comm.group_size(group) if group is not None or dist.is_initialized() else 1
+        self.world = comm.group_size(group) if group is not None else 1      # None = single-rank (no EP)
         self.rank = comm.group_rank(group) if self.world > 1 else 0
         self.hidden, self.dtype, self.E = hidden, dtype, num_experts
         self.capacity = capacity_rows
@@ -112,7 +112,7 @@ def available(group) -> bool:
         _get_lib()
     except Exception:
         return False
-    world = comm.group_size(group) if dist.is_initialized() else 1
+    world = comm.group_size(group) if (dist.is_initialized() and group is not None) else 1
     if world == 1:
         return True
     from ..parallel import fused
@@ -121,7 +121,7 @@ def available(group) -> bool:
 
 
 def ep_workspace(group, hidden: int, dtype: torch.dtype, num_experts: int, rows_per_rank: int) -> EPWorkspace:
-    world = comm.group_size(group) if dist.is_initialized() else 1
+    world = comm.group_size(group) if (dist.is_initialized() and group is not None) else 1
     factor = float(os.environ.get("CB200_EP_CAPACITY_FACTOR", "0"))
     worst = rows_per_rank * world
     cap = worst if factor <= 0 else min(worst, int(rows_per_rank * factor))

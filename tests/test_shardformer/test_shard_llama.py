@@ -85,6 +85,9 @@ def _worker(rank, world_size, port):
         _run_one("llama-tiny", cfg)
     _run_one("gpt2-tiny", dict(tp=2, sp_mode=None))
     _run_one("gpt2-tiny", dict(tp=2, sp_mode="split_gather"))
+    for name in ("mixtral-tiny", "deepseek-tiny"):      # MoE blocks under pure TP / TP+SP (experts replicated)
+        _run_one(name, dict(tp=2, sp_mode=None), atol=1e-4)
+        _run_one(name, dict(tp=2, sp_mode="split_gather"), atol=1e-4)
     dist.destroy_process_group()
 
 
