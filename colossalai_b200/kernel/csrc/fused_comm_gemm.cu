@@ -76,6 +76,7 @@ struct CommParams {
   int tile_flag_stride;                  // flags per writer rank
   uint32_t* tile_counter;                // local per-tile epilogue-warp arrival counters [m_blocks * n_blocks]
   uint32_t* reduce_ticket;               // local work-queue head of the tile-granular reduction
+  uint32_t* rs_progress;                 // local per-slice progress words ((epoch << 5) | steps accumulated)
 };
 
 struct GemmParams {
@@ -296,100 +297,109 @@ SM100_DEVICE void rs_reduce_phase(const GemmParams& p, const CommParams& c, uint
 // producing later tiles.  A 256 x 256 tile of my chunk is reduced (multimem.ld_reduce in the switch, or P2P loads) as soon
 // as every rank's partial of that tile is complete; the tiles of my chunk are visited in the order my own GEMM produces
 // them (they come last in the rotated tile order), so only the final tiles' reduction is exposed.
-// GEMM+RS, CTA-pair kernel: staggered pull-accumulate by warps 6..7 of every CTA.
+// GEMM+RS, CTA-pair kernel: staggered pull-accumulate.
 // Rank q computes the chunks in the order q+1, q+2, ..., q, so the partial of MY chunk r becomes available on rank r-k
-// during time slot k (k = 1..world-1) and my own partial in the last slot.  The reduce warps therefore pull slice by
-// slice from rank r-1, then r-2, ... while the GEMM roles are still busy with later chunks: every slot moves one
-// chunk-partial per rank over a distinct NVLink peer (a permutation -> all links busy), and only the last, LOCAL
-// accumulation step runs after the main loop.  Accumulation is bf16 in `out` with fp32 adds (the precision of a ring
-// reduce-scatter); work units (32-row slices of 256 x 256 tiles) are statically owned by one warp, so the k-steps of a
-// unit are naturally ordered.
-SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int warp, int lane,
-                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot) {
+// during time slot k (k = 1..world-1) and my own partial in the last slot.  Work units (32-row slices of the 256 x 256
+// tiles of my chunk, one per source rank) are handed out through a ticket counter in exactly that order: step k pulls
+// from rank r-k - a different NVLink peer per step, a permutation over the ranks, so every link is busy - and adds into
+// `out` (bf16 with fp32 adds: the precision of a ring reduce-scatter).  Warps 6..7 of every CTA take tickets from the
+// start (overlap with the main loop); warps 0..5 join when their GEMM role is finished, so a communication-bound
+// projection ends with all eight warps per SM pulling.  Step k of a slice waits for step k-1 of the same slice through
+// a per-slice progress word (tickets of step k-1 were issued earlier, so the wait is bounded).
+SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int lane,
+                                  int m_blocks, int n_blocks, int pair_blocks_per_chunk, int m_rot, int total_warps) {
   constexpr int SUB = 8;                                        // 32-row slices per 256-row tile
   const int num_tiles = m_blocks * n_blocks;
-  const int rwarp = (int)blockIdx.x * COPY_WARPS + (warp - 6);
-  const int n_rwarps = (int)gridDim.x * COPY_WARPS;
+  const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
+  const int n_units = tiles_per_chunk * SUB;
   const uint32_t* my_tile_flags = c.peer_tile_flags[c.rank];
   const size_t ldc_vec = p.ldc / 8;
   const size_t ldo_vec = c.ld_out / 8;
   const int my_first_blk = c.rank * pair_blocks_per_chunk;
-  for (int k = 1; k <= c.world; ++k) {
-    const int src = (c.rank - k + 2 * c.world) % c.world;       // k == world -> my own partial
-    const uint4* src_part = reinterpret_cast<const uint4*>(c.peer_part[src]);
-    // units u = tile_in_chunk * SUB + slice, dealt round-robin over the reduce warps of the grid.  When chunks align
-    // with the rasterisation groups my chunk's tiles are the LAST tiles of the rotated order (direct indexing);
-    // otherwise fall back to scanning the order.
-    const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
-    const bool aligned = (pair_blocks_per_chunk % GROUP_M == 0);      // whole rasterisation groups per chunk
-    int scan_t = 0, scan_mine = 0;
-    for (int u = rwarp; u < tiles_per_chunk * SUB; u += n_rwarps) {
-      const int tile_in_chunk = u / SUB;
-      const int first_sub = u - tile_in_chunk * SUB;
-      int m_blk = 0, n_blk = 0;
-      if (aligned) {
-        tile_coords_rot(num_tiles - tiles_per_chunk + tile_in_chunk, m_blocks, n_blocks, m_rot, m_blk, n_blk);
-      } else {
-        while (scan_mine <= tile_in_chunk && scan_t < num_tiles) {
-          int mb, nb;
-          tile_coords_rot(scan_t++, m_blocks, n_blocks, m_rot, mb, nb);
-          if (mb < my_first_blk || mb >= my_first_blk + pair_blocks_per_chunk) continue;
-          m_blk = mb; n_blk = nb;
-          ++scan_mine;
-        }
+  const bool aligned = (pair_blocks_per_chunk % GROUP_M == 0);  // whole rasterisation groups per chunk
+  const uint32_t prog_base = c.epoch << 5;                      // progress word = (epoch << 5) | steps done
+  int scan_k = 0, scan_t = 0, scan_mine = 0, scan_m = 0, scan_n = 0;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = (int)atomicAdd(c.reduce_ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= n_units * c.world) break;
+    const int k = t / n_units + 1;                              // 1 .. world (world = my own partial)
+    const int u = t - (k - 1) * n_units;
+    const int tile_in_chunk = u / SUB, sub = u - tile_in_chunk * SUB;
+    int m_blk, n_blk;
+    if (aligned) {
+      tile_coords_rot(num_tiles - tiles_per_chunk + tile_in_chunk, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+    } else {
+      if (scan_k != k) { scan_k = k; scan_t = 0; scan_mine = 0; }
+      while (scan_mine <= tile_in_chunk && scan_t < num_tiles) {
+        int mb, nb;
+        tile_coords_rot(scan_t++, m_blocks, n_blocks, m_rot, mb, nb);
+        if (mb < my_first_blk || mb >= my_first_blk + pair_blocks_per_chunk) continue;
+        scan_m = mb; scan_n = nb;
+        ++scan_mine;
       }
-      const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
-      if (lane == 0) wait_epoch<true>(my_tile_flags + (size_t)src * c.tile_flag_stride + slot, c.epoch);
-      __syncwarp();
-      const int col0 = n_blk * 256;
-      const int cols = min(256, p.N - col0);
-      const int vec_per_row = cols / 8;
-      for (int sub = first_sub; sub < SUB; sub += n_rwarps) {
-        const int row0 = m_blk * 256 + sub * 32;
-        const int rows = max(0, min(32, p.M - row0));
-        const int out_row0 = row0 - c.rank * c.rows_per_chunk;
-        const int nvec = rows * vec_per_row;
-        constexpr int RU = 16;     // 16 x 16 B peer loads in flight per lane (NVLink round trip ~3 us)
-        for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
-          uint4 in[RU], cur[RU];
-          size_t doff[RU];
+      m_blk = scan_m; n_blk = scan_n;
+    }
+    const int src = (c.rank - k + 2 * c.world) % c.world;
+    const uint4* src_part = reinterpret_cast<const uint4*>(c.peer_part[src]);
+    const int slot = (m_blk - my_first_blk) * n_blocks + n_blk;
+    if (lane == 0) {
+      wait_epoch<true>(my_tile_flags + (size_t)src * c.tile_flag_stride + slot, c.epoch);     // partial tile exists
+      if (k > 1) wait_epoch<false>(c.rs_progress + u, prog_base + (uint32_t)(k - 1));          // previous step landed
+    }
+    __syncwarp();
+    const int col0 = n_blk * 256;
+    const int cols = min(256, p.N - col0);
+    const int vec_per_row = cols / 8;
+    const int row0 = m_blk * 256 + sub * 32;
+    const int rows = max(0, min(32, p.M - row0));
+    const int out_row0 = row0 - c.rank * c.rows_per_chunk;
+    const int nvec = rows * vec_per_row;
+    constexpr int RU = 16;                                      // 16 x 16 B peer loads in flight per lane
+    for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
+      uint4 in[RU], cur[RU];
+      size_t doff[RU];
 #pragma unroll
-          for (int j = 0; j < RU; ++j) {
-            const int i = i0 + j * 32;
-            doff[j] = (size_t)-1;
-            if (i >= nvec) continue;
-            const int r = i / vec_per_row, cv = i - r * vec_per_row;
-            doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
-            in[j] = ld_peer_16B(src_part + (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv);
-          }
-          if (k > 1) {
+      for (int j = 0; j < RU; ++j) {
+        const int i = i0 + j * 32;
+        doff[j] = (size_t)-1;
+        if (i >= nvec) continue;
+        const int r = i / vec_per_row, cv = i - r * vec_per_row;
+        doff[j] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+        in[j] = ld_peer_16B(src_part + (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv);
+      }
+      if (k > 1) {
 #pragma unroll
-            for (int j = 0; j < RU; ++j)
-              if (doff[j] != (size_t)-1) cur[j] = reinterpret_cast<const uint4*>(c.out)[doff[j]];
-          }
+        for (int j = 0; j < RU; ++j)
+          if (doff[j] != (size_t)-1) cur[j] = reinterpret_cast<const uint4*>(c.out)[doff[j]];
+      }
 #pragma unroll
-          for (int j = 0; j < RU; ++j) {
-            if (doff[j] == (size_t)-1) continue;
-            if (k > 1) {
-              Vec16<__nv_bfloat16> a, b2, o;
-              a.raw = in[j];
-              b2.raw = cur[j];
+      for (int j = 0; j < RU; ++j) {
+        if (doff[j] == (size_t)-1) continue;
+        if (k > 1) {
+          Vec16<__nv_bfloat16> a, b2, o;
+          a.raw = in[j];
+          b2.raw = cur[j];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o.set(e, a.get(e) + b2.get(e));
-              in[j] = o.raw;
-            }
-            reinterpret_cast<uint4*>(c.out)[doff[j]] = in[j];
-          }
+          for (int e = 0; e < 8; ++e) o.set(e, a.get(e) + b2.get(e));
+          in[j] = o.raw;
         }
+        reinterpret_cast<uint4*>(c.out)[doff[j]] = in[j];
       }
     }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu(c.rs_progress + u, prog_base + (uint32_t)k);
   }
-  // every partial buffer of this epoch has been consumed by me: the last reduce warp tells the peers
+  // every partial buffer of this epoch has been consumed by me: the last warp of the grid resets the ticket and tells
+  // the peers that their partial buffers may be overwritten
   __syncwarp();
   if (lane == 0) {
     const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
-    if (done == (uint32_t)n_rwarps) {
+    if (done == (uint32_t)total_warps) {
       my_flags[SLOT_LOCAL + 1] = 0;
+      *c.reduce_ticket = 0;
       __threadfence_system();
       for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
     }
@@ -736,7 +746,6 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   } else if (warp >= 6) {
     if (MODE == 0) ag_pull_warps(c, my_flags, warp, lane, blocks_per_chunk);
-    else rs_reduce_tiles(p, c, my_flags, warp, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot);
   } else {
     const int quarter = warp & 3;
     int acc = 0;
@@ -787,6 +796,8 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   }
+  if (MODE == 1)   // warps 6..7 arrive here at once, the GEMM roles when their tiles are done
+    rs_reduce_tiles(p, c, my_flags, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot, (int)gridDim.x * 8);
   tc_fence_before();
   cluster_sync();
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
@@ -988,7 +999,7 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
                uint32_t* const* peer_flags, uint32_t* chunk_counter, void* out, int T, int N, int K, int lda, int ldb,
                int ld_out, int a_mn_major, int b_mn_major, int in_dtype, int rank, int world, uint32_t epoch,
                int block_n, uint32_t* const* peer_tile_flags, int tile_flag_stride, uint32_t* tile_counter,
-               int tile_counter_len, cudaStream_t stream) {
+               int tile_counter_len, uint32_t* rs_progress, int rs_progress_len, cudaStream_t stream) {
   if (world > MAX_RANKS || T % (world * BLOCK_M) != 0 || N % 8 != 0) return (int)cudaErrorInvalidValue;
   CommParams c{};
   c.rank = rank; c.world = world; c.epoch = epoch; c.rows_per_chunk = T / world;
@@ -1000,11 +1011,13 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
   const int pair_tiles_chunk = ((T / world) / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
   const int pair_tiles = (T / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
   if (use_pair_kernel(T, world, N, block_n) && (T / world) % PAIR_M == 0 && peer_tile_flags && tile_counter &&
+      rs_progress && pair_tiles_chunk * 8 <= rs_progress_len && epoch < (1u << 26) &&
       pair_tiles_chunk <= tile_flag_stride && pair_tiles < tile_counter_len) {
     for (int r = 0; r < world; ++r) c.peer_tile_flags[r] = peer_tile_flags[r];
     c.tile_flag_stride = tile_flag_stride;
     c.tile_counter = tile_counter;
     c.reduce_ticket = tile_counter + (tile_counter_len - 1);
+    c.rs_progress = rs_progress;
     return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
   }
   if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;

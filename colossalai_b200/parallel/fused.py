@@ -127,6 +127,7 @@ class FusedWorkspace:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.chunk_counter = torch.zeros(64, dtype=torch.int32, device=dev)
         self.tile_counter = torch.zeros(1 << 16, dtype=torch.int32, device=dev)
+        self.rs_progress = torch.zeros(1 << 17, dtype=torch.int32, device=dev)
 
     def next_epoch(self) -> int:
         self.epoch += 1
@@ -286,7 +287,8 @@ def gemm_reduce_scatter(a: torch.Tensor, w: torch.Tensor, group: Optional[Proces
                                 loader.ptr(out), T, N, K, a.stride(0), w.stride(0), out.stride(0), 0,
                                 0 if transpose_b else 1, code(a.dtype), ws.rank, world, ctypes.c_uint32(epoch), block_n,
                                 ws.tile_flags.ptr_array(world), ws.tile_flag_stride, loader.ptr(ws.tile_counter),
-                                ws.tile_counter.numel(), loader.stream_ptr()), "gemm_rs")
+                                ws.tile_counter.numel(), loader.ptr(ws.rs_progress), ws.rs_progress.numel(),
+                                loader.stream_ptr()), "gemm_rs")
     part.last_epoch = epoch
     loader.launch_counter.add("fused_gemm_rs")
     stats["gemm_rs"] += 1

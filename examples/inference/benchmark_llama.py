@@ -1,0 +1,76 @@
+"""Decode / prefill throughput of the inference engine (reference: examples/inference/llama/benchmark_llama.py).
+
+    python examples/inference/benchmark_llama.py -m llama3-8b -b 32 --in_len 512 --out_len 128 [--cuda_graph] [--layers 8]
+
+Prints one JSON line: prefill tokens/s, decode tokens/s (device-timed with CUDA events), per-step latency."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+
+from colossalai_b200.inference import GenerationConfig, InferenceConfig, InferenceEngine  # noqa: E402
+from colossalai_b200.kernel import loader  # noqa: E402
+from colossalai_b200.lazy import LazyInitContext  # noqa: E402
+from colossalai_b200.models import build_model, get_config  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-m", "--model", default="llama3-8b")
+    ap.add_argument("-b", "--batch_size", type=int, default=32)
+    ap.add_argument("--in_len", type=int, default=512)
+    ap.add_argument("--out_len", type=int, default=128)
+    ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count")
+    ap.add_argument("--cuda_graph", action="store_true")
+    ap.add_argument("--dtype", default="bf16")
+    args = ap.parse_args()
+    assert torch.cuda.is_available(), "this benchmark needs a GPU"
+    cfg = get_config(args.model, **({"num_hidden_layers": args.layers} if args.layers else {}))
+    torch.manual_seed(0)
+    with LazyInitContext():
+        model = build_model(cfg)
+    LazyInitContext.materialize(model)
+    icfg = InferenceConfig(max_batch_size=args.batch_size, max_input_len=args.in_len, max_output_len=args.out_len,
+                           dtype=args.dtype, use_cuda_graph=args.cuda_graph, block_size=64, ignore_eos=True)
+    engine = InferenceEngine(model, None, icfg)
+    g = torch.Generator().manual_seed(1)
+    prompts = torch.randint(3, cfg.vocab_size, (args.batch_size, args.in_len), generator=g).tolist()
+    gen = GenerationConfig(max_new_tokens=args.out_len)
+    eng = engine.engine
+    eng.generation_config, eng.generation_config_dict = gen, gen.to_dict()
+
+    def run():
+        eng.add_request(prompts_token_ids=prompts, generation_config=gen)
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        eng.step()                                  # prefill of the whole batch
+        e1.record()
+        steps = 1
+        while eng.request_handler.check_unfinished_reqs():
+            eng.step()
+            steps += 1
+        e2.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), steps
+
+    run()                                           # warm-up (graph capture, allocator)
+    loader.launch_counter.reset()
+    t_prefill, t_decode, steps = run()
+    out = {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""), "batch": args.batch_size,
+           "in_len": args.in_len, "out_len": args.out_len, "cuda_graph": args.cuda_graph, "dtype": args.dtype,
+           "prefill_ms": t_prefill, "prefill_tokens_per_s": args.batch_size * args.in_len / (t_prefill / 1e3),
+           "decode_ms_per_step": t_decode / max(steps - 1, 1),
+           "decode_tokens_per_s": args.batch_size * (steps - 1) / (t_decode / 1e3),
+           "our_kernel_launches": loader.launch_counter.count,
+           "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
