@@ -64,8 +64,7 @@ class GeminiCheckpointIO(GeneralCheckpointIO):
         if os.path.isfile(checkpoint_path):
             return
         Path(checkpoint_path).mkdir(parents=True, exist_ok=True)
-        shards = model.state_dict_shard(max_shard_size=max_shard_size, only_rank_0=True, dtype=torch.float32
-                                        if False else model.mixed_precision)
+        shards = model.state_dict_shard(max_shard_size=max_shard_size, only_rank_0=True, dtype=model.mixed_precision)
         weights_name, save_index_file = get_model_base_filenames(prefix, use_safetensors)
         index_file = CheckpointIndexFile(checkpoint_path)
         is_master = self.coordinator.is_master()

@@ -155,8 +155,6 @@ class HybridParallelModule(ModelWrapper, AMPModelMixin):
                 p = shared[self.stage_manager.stage]
                 if p.grad is not None:
                     dist.all_reduce(p.grad, group=group)
-        if self.shared_params:
-            dist.barrier() if False else None
 
     @contextmanager
     def no_sync(self):
@@ -295,7 +293,7 @@ class HybridParallelNaiveOptimizer(OptimizerWrapper, _HybridNormMixin):
                  max_norm: float = 0, tp_process_group: Optional[ProcessGroup] = None,
                  pp_process_group: Optional[ProcessGroup] = None) -> None:
         self.param_info = param_info
-        _reassign_params(optim, model) if use_pipeline or True else None
+        _reassign_params(optim, model)
         self.model = model
         self.stage_manager = model.stage_manager
         self.shared_params = model.shared_params

@@ -55,7 +55,7 @@ class MoeHybridParallelPlugin(HybridParallelPlugin):
         world = dist.get_world_size()
         if ep_size == 1:
             # degenerate: experts are plain data-parallel parameters
-            self.ep_group = dist.new_group([dist.get_rank()]) if False else self._self_group()
+            self.ep_group = self._self_group()
             self.moe_dp_group = self.dp_group
             self.moe_mesh = None
         else:

@@ -94,8 +94,6 @@ class HierarchicalAllToAll(torch.autograd.Function):
         dist.gather(x, outs, dst=src_rank, group=intra)
         if dist.get_rank() == src_rank:
             t = torch.cat(outs, dim=0)
-            shape = t.shape
-            t = t.view(num_group, local_ws, -1, shape[-1]) if False else t
             recv = torch.empty_like(t)
             dist.all_to_all_single(recv, t.contiguous(), group=inter)
             outs = list(recv.chunk(local_ws, dim=0))

@@ -250,8 +250,6 @@ class GeminiDDP(ModelWrapper):
         gchunk.tensor_trans_state(p, TensorState.READY_FOR_REDUCE)
         cm.trans_tensor_state(p, TensorState.HOLD_AFTER_BWD)
         if gchunk.can_reduce:
-            if gchunk.l2_norm_flag or True:
-                pass
             cm.reduce_chunk(gchunk)
             if gchunk.has_inf_or_nan:
                 self.overflow_counter += 1

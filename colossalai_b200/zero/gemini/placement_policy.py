@@ -71,7 +71,6 @@ class StaticPlacementPolicy(PlacementPolicy):
         can_shard = 0
         for c in can_evict_chunks:
             can_shard += c.chunk_mem - c.shard_mem
-        target = sum(c.chunk_mem for c in can_evict_chunks) - self.keep_gathered_chunk_mem if False else 0
         # static policy: chunks are released by the DDP wrapper right after use; param offload happens here
         vol = 0
         start = time()
