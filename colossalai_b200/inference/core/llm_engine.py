@@ -190,6 +190,7 @@ class LLMEngine(BaseEngine):
         self.drafter_model = self.drafter = None
         torch.cuda.empty_cache() if torch.cuda.is_available() else None
 
+    @torch.inference_mode()
     def steps_spec_dec(self) -> List[Sequence]:
         """One speculative round: draft n tokens per sequence, verify them with ONE target-model pass, keep the longest
         matching prefix (+1 corrected token), roll back the rest."""
@@ -330,6 +331,7 @@ class LLMEngine(BaseEngine):
         self.request_handler.append_next_tokens(next_tokens.cpu())
         return self.request_handler.update()
 
+    @torch.inference_mode()
     def step(self) -> List[Sequence]:
         batch = self.request_handler.schedule()
         if batch.is_empty:
