@@ -15,10 +15,28 @@ from .mixtral import MixtralForCausalLM
 from .deepseek import DeepseekForCausalLM
 
 
+_EXTRA_FAMILIES = [("vit", "VIT_ZOO", "ViTForImageClassification"), ("t5", "T5_ZOO", "T5ForConditionalGeneration"),
+                   ("whisper", "WHISPER_ZOO", "WhisperForConditionalGeneration"),
+                   ("blip2", "BLIP2_ZOO", "Blip2ForConditionalGeneration"), ("sam", "SAM_ZOO", "SamModel")]
+
+
 def build_model(name_or_config, **overrides):
     """`build_model("llama3-8b")` or `build_model(ModelConfig(...))` -> causal LM of the right family class."""
-    cfg = get_config(name_or_config, **overrides) if isinstance(name_or_config, str) else name_or_config
     import importlib
+
+    # vision / encoder-decoder / multimodal families carry their own config types and zoos
+    for mod, zoo, cls in _EXTRA_FAMILIES:
+        m = None
+        if isinstance(name_or_config, str):
+            m = importlib.import_module(f"colossalai_b200.models.{mod}")
+            z = getattr(m, zoo)
+            if name_or_config in z:
+                cfg = z[name_or_config]
+                return getattr(m, cls)(cfg.replace(**overrides) if overrides else cfg)
+        elif getattr(name_or_config, "model_type", None) == mod:
+            m = importlib.import_module(f"colossalai_b200.models.{mod}")
+            return getattr(m, cls)(name_or_config)
+    cfg = get_config(name_or_config, **overrides) if isinstance(name_or_config, str) else name_or_config
 
     fam = {"chatglm": ("chatglm", "ChatGLMForConditionalGeneration"), "gpt2": ("gpt2", "GPT2LMHeadModel"),
            "bert": ("bert", "BertForMaskedLM"), "command": ("command", "CohereForCausalLM"),

@@ -277,16 +277,17 @@ class TransformerModel(nn.Module):
         self.gradient_checkpointing = True
 
     # ------------------------------------------------------------------ forward
-    def embed(self, input_ids: torch.Tensor, meta: SeqMeta, positions_local: torch.Tensor,
-              token_type_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def embed(self, input_ids: Optional[torch.Tensor], meta: SeqMeta, positions_local: torch.Tensor,
+              token_type_ids: Optional[torch.Tensor] = None,
+              inputs_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
         cfg = self.cfg
-        x = self.embed_tokens(input_ids)
+        x = inputs_embeds if inputs_embeds is not None else self.embed_tokens(input_ids)
         if cfg.embed_scale != 1.0:
             x = x * cfg.embed_scale
         if cfg.pos_type == "learned":
             x = x + self.embed_positions(positions_local)
         if cfg.type_vocab_size > 0:
-            tt = token_type_ids if token_type_ids is not None else torch.zeros_like(input_ids)
+            tt = token_type_ids if token_type_ids is not None else positions_local.new_zeros(x.shape[0])
             x = x + self.embed_token_types(tt)
         if cfg.embed_norm:
             x = self.embed_layernorm(x)
@@ -297,8 +298,10 @@ class TransformerModel(nn.Module):
     def forward(self, input_ids: Optional[torch.Tensor] = None, hidden_states: Optional[torch.Tensor] = None,
                 attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
                 token_type_ids: Optional[torch.Tensor] = None, batch: Optional[int] = None,
-                seqlen: Optional[int] = None, kv_cache=None, meta: Optional[SeqMeta] = None) -> torch.Tensor:
-        """`input_ids` [B, S] on the first stage (or `hidden_states` [T_local, H] from the previous stage).
+                seqlen: Optional[int] = None, kv_cache=None, meta: Optional[SeqMeta] = None,
+                inputs_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`input_ids` [B, S] on the first stage (or `hidden_states` [T_local, H] from the previous stage, or
+        `inputs_embeds` [B, S, H] replacing the token-embedding lookup — multimodal prefixes).
         Returns token-major hidden states in the stage's activation layout."""
         cfg, sc = self.cfg, self.shard_config
         sm = sc.pipeline_stage_manager if sc is not None else None
@@ -310,6 +313,9 @@ class TransformerModel(nn.Module):
         if input_ids is not None:
             B, S = input_ids.shape
             device = input_ids.device
+        elif inputs_embeds is not None:
+            B, S = inputs_embeds.shape[:2]
+            device = inputs_embeds.device
         else:
             assert batch is not None and seqlen is not None, "later PP stages need batch/seqlen"
             B, S, device = batch, seqlen, hidden_states.device
@@ -330,7 +336,14 @@ class TransformerModel(nn.Module):
                 positions = pos_full
                 local_S = S
             meta = SeqMeta(batch=B, seqlen=S, positions=positions, attn_mask=attention_mask, local_seqlen=local_S)
-        if first:
+        if first and inputs_embeds is not None:
+            assert not (sp_mode in ("ring_attn", "all_to_all") and sp > 1), \
+                "inputs_embeds is not supported together with ring_attn / all_to_all sequence parallelism"
+            x = self.embed(None, meta, meta.positions, None if token_type_ids is None else token_type_ids.reshape(-1),
+                           inputs_embeds=inputs_embeds.reshape(B * S, -1))
+            if sp_mode in ("split_gather", "ring") and sp > 1:
+                x = split_forward_gather_backward(x, 0, sp_group)
+        elif first:
             ids = input_ids
             tt = token_type_ids
             if sp_mode == "ring_attn" and sp > 1:
@@ -405,16 +418,19 @@ class TransformerLMHeadModel(nn.Module):
                 attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
                 hidden_states: Optional[torch.Tensor] = None, token_type_ids: Optional[torch.Tensor] = None,
                 batch: Optional[int] = None, seqlen: Optional[int] = None, return_logits: bool = True,
-                kv_cache=None, meta=None, **unused) -> Dict[str, torch.Tensor]:
+                kv_cache=None, meta=None, inputs_embeds: Optional[torch.Tensor] = None,
+                **unused) -> Dict[str, torch.Tensor]:
         cfg, sc = self.cfg, self.shard_config
         sm = sc.pipeline_stage_manager if sc is not None else None
         if input_ids is not None:
             B, S = input_ids.shape
+        elif inputs_embeds is not None:
+            B, S = inputs_embeds.shape[:2]
         else:
             B, S = batch, seqlen
         h = self.model(input_ids=input_ids, hidden_states=hidden_states, attention_mask=attention_mask,
                        position_ids=position_ids, token_type_ids=token_type_ids, batch=B, seqlen=S,
-                       kv_cache=kv_cache, meta=meta)
+                       kv_cache=kv_cache, meta=meta, inputs_embeds=inputs_embeds)
         if sm is not None and not sm.is_last_stage():
             return {"hidden_states": h}
         sp_mode = sc.sp_mode if sc is not None else None

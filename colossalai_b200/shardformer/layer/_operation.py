@@ -55,6 +55,17 @@ def _use_fused(x: torch.Tensor, group) -> bool:
     return fused.available(group)
 
 
+_FUSED_RS_MIN_K = int(os.environ.get("CB200_FUSED_RS_MIN_K", "2048"))
+
+
+def _fused_rs_profitable(k_local: int) -> bool:
+    """GEMM->reduce-scatter as ONE kernel pays when the GEMM (2*M*N*K flops) is long enough to hide the M*N
+    partial-sum traffic; below ~2k of reduction depth the op is pure communication and the in-switch NCCL
+    reduce-scatter behind a cuBLAS GEMM is faster (measured at TP=4 and TP=8: profiles/fused_comm_n{4,8}_timing_v3.log:
+    K=512..1792 -> 0.53-0.72 ms NCCL vs 0.93-0.98 ms fused; K>=3584 -> fused wins)."""
+    return k_local >= _FUSED_RS_MIN_K
+
+
 def _accumulate_wgrad(weight: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor) -> Optional[torch.Tensor]:
     """dW = dy2^T @ x2.  When the parameter carries a persistent `main_grad` buffer (fp32 or bf16 flat gradient
     arena owned by the optimizer wrapper) the GEMM accumulates straight into it and autograd gets None."""
@@ -206,9 +217,19 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
 
             # dX = dY @ W fused with the reduce-scatter; X comes from forward (saved) or is re-gathered over NVLink
             x_full = x_local if ctx.saved_gathered else fused.all_gather(x_local, group)
-            dx_local = fused.gemm_reduce_scatter(dy2, weight, group, transpose_b=False)
+            h_rs = None
+            if _fused_rs_profitable(dy2.shape[1]):
+                dx_local = fused.gemm_reduce_scatter(dy2, weight, group, transpose_b=False)
+            else:
+                # communication-bound shape: cuBLAS dgrad, NCCL reduce-scatter in flight under the wgrad GEMM
+                dx_full = ops.matmul_nn(dy2, weight)
+                dx_local = torch.empty((dx_full.shape[0] // ws, dx_full.shape[1]), dtype=dx_full.dtype,
+                                       device=dx_full.device)
+                h_rs = dist.reduce_scatter_tensor(dx_local, dx_full, group=group, async_op=True)
             dw = _maybe_defer_wgrad(weight, dy2, x_full, ctx.use_zbv)
             db = dy2.sum(0) if ctx.use_bias else None
+            if h_rs is not None:
+                h_rs.wait()
             return dx_local, dw, db, None, None, None, None
         # re-gather X (async) while computing dX
         x_local_c = x_local.contiguous()
@@ -276,10 +297,12 @@ class _LinearReduceScatterFwdGatherBwd(torch.autograd.Function):
         ctx.use_bias = bias is not None
         ctx.fused = _use_fused(x, group) and dim == 0 and x.dim() == 2
         ctx.save_for_backward(x, weight)
-        if ctx.fused:
+        if ctx.fused and _fused_rs_profitable(x.shape[1]):
             from ...parallel import fused
 
             y = fused.gemm_reduce_scatter(x, weight, group, transpose_b=True)
+        elif ctx.fused:
+            y = comm.reduce_scatter(ops.linear_forward(x, weight), dim, group)
         elif ring and comm.group_size(group) > 1:
             y = _ring_gemm_reducescatter(x, weight, group, dim)
         else:
