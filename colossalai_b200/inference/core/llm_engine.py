@@ -205,7 +205,15 @@ class LLMEngine(BaseEngine):
         drafted = []
         for s in seqs:
             ctx = torch.tensor([s.input_token_id + s.output_token_id], device=self.device)
-            out = self.drafter.speculate(ctx, n)
+            glide = None
+            if self.use_glide:
+                # the drafter glimpses the target model's last-layer KV of the tokens verified so far
+                i = len(drafted)
+                glide = GlideInput(block_tables=batch.block_tables[i: i + 1].to(self.device),
+                                   large_k_cache=self.kv_runtime.k_caches[-1],
+                                   large_v_cache=self.kv_runtime.v_caches[-1],
+                                   sequence_lengths=batch._sequence_lengths[i: i + 1] - 1, n_spec_tokens=n)
+            out = self.drafter.speculate(ctx, n, glide_input=glide)
             drafted.append(out.next_tokens.tolist())
         for s, d in zip(seqs, drafted):
             s.output_token_id += d

@@ -53,9 +53,22 @@ class PagedKVRuntime:
         self.token_pos = pos.to(device=device, dtype=torch.int32)
         return pos.to(device=device, dtype=torch.int64)
 
-    def attend(self, layer_idx: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, meta, scale: float) -> torch.Tensor:
+    def attend(self, layer_idx: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, meta, scale: float,
+               alibi_slopes: Optional[torch.Tensor] = None) -> torch.Tensor:
         kc, vc = self.k_caches[layer_idx], self.v_caches[layer_idx]
         iops.kv_cache_write(k, v, kc, vc, self.block_tables, self.token_seq, self.token_pos)
+        if alibi_slopes is not None:
+            # ALiBi families (Baichuan-13B, BLOOM): biased varlen prefill through the reference backend, the paged
+            # decode kernel takes the slopes natively
+            from .backends.attention_backend import AttentionMetaData, ReferenceAttentionBackend
+
+            if self.is_prompt:
+                md = AttentionMetaData(q, k, v, kc, vc, self.block_tables, self.block_size, cu_seqlens=self.cu_seqlens,
+                                       sm_scale=scale, alibi_slopes=alibi_slopes)
+                return ReferenceAttentionBackend().prefill(md)
+            assert self.q_per_seq == 1, "speculative verification is not implemented for ALiBi models"
+            return iops.paged_decode_attention(q, kc, vc, self.block_tables, self.seq_lens, scale,
+                                               alibi_slopes=alibi_slopes)
         if self.is_prompt:
             return ops.attention(q, k, v, causal=True, scale=scale, cu_seqlens_q=self.cu_seqlens,
                                  cu_seqlens_k=self.cu_seqlens, max_seqlen=self.max_seqlen)

@@ -38,8 +38,11 @@ class Drafter:
             input_ids = input_ids.unsqueeze(0)
         ids = input_ids.to(self._device)
         toks, all_logits = [], []
+        use_glide = glide_input is not None and glide_input.glimpse_ready and \
+            hasattr(self._drafter_model, "model") and hasattr(self._drafter_model.model.layers[0], "cross_attn")
         for _ in range(n_spec_tokens):
-            out = self._drafter_model(input_ids=ids)
+            out = self._drafter_model(input_ids=ids, glide_input=glide_input) if use_glide \
+                else self._drafter_model(input_ids=ids)
             logits = out["logits"] if isinstance(out, dict) else out.logits
             logits = logits.view(ids.shape[0], ids.shape[1], -1)[:, -1]
             nxt = logits.argmax(-1)

@@ -66,6 +66,7 @@ class ModelConfig:
     attn_dropout: float = 0.0
     hidden_dropout: float = 0.0
     sliding_window: Optional[int] = None
+    norm_head: bool = False           # Baichuan-2 NormHead: L2-normalised LM-head rows
     moe: Optional[MoEConfig] = None
     pad_token_id: Optional[int] = None
     bos_token_id: int = 1
@@ -210,6 +211,15 @@ MODEL_ZOO: Dict[str, ModelConfig] = {
                                num_hidden_layers=28, num_attention_heads=32, num_key_value_heads=2,
                                max_position_embeddings=32768, attention_bias=True, attention_out_bias=False,
                                rope_interleaved=True, partial_rotary_factor=0.5),
+    "baichuan-7b": ModelConfig(model_type="baichuan", vocab_size=64000, hidden_size=4096, intermediate_size=11008,
+                               num_hidden_layers=32, num_attention_heads=32, max_position_embeddings=4096,
+                               norm_eps=1e-6),
+    "baichuan2-13b": ModelConfig(model_type="baichuan", vocab_size=125696, hidden_size=5120, intermediate_size=13696,
+                                 num_hidden_layers=40, num_attention_heads=40, max_position_embeddings=4096,
+                                 pos_type="alibi", norm_eps=1e-6, norm_head=True),
+    "baichuan-tiny": ModelConfig(model_type="baichuan", vocab_size=512, hidden_size=64, intermediate_size=128,
+                                 num_hidden_layers=2, num_attention_heads=4, max_position_embeddings=256,
+                                 pos_type="alibi", norm_head=True),
     "command-r": ModelConfig(model_type="command", vocab_size=256000, hidden_size=8192, intermediate_size=22528,
                              num_hidden_layers=40, num_attention_heads=64, num_key_value_heads=64, norm_type="layer",
                              parallel_block=True, tie_word_embeddings=True, logit_scale=0.0625, rope_theta=8e6),

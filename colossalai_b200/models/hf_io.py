@@ -22,7 +22,7 @@ from .config import ModelConfig, MoEConfig
 
 __all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards"]
 
-_LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral")
+_LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral", "baichuan")
 
 
 def config_from_hf(hf: dict) -> ModelConfig:
@@ -48,6 +48,11 @@ def config_from_hf(hf: dict) -> ModelConfig:
         kw["attention_bias"], kw["attention_out_bias"] = True, False
     if mt == "qwen3":
         kw["qk_norm"] = True
+    if mt == "baichuan":
+        # 13B checkpoints (hidden 5120) use ALiBi instead of RoPE; Baichuan-2 (vocab 125696) has the NormHead
+        kw["pos_type"] = "alibi" if hf["hidden_size"] >= 5120 else "rope"
+        kw["norm_head"] = hf["vocab_size"] == 125696
+        kw["max_position_embeddings"] = hf.get("max_position_embeddings", hf.get("model_max_length", 4096))
     if mt == "mixtral":
         kw["moe"] = MoEConfig(num_experts=hf["num_local_experts"], top_k=hf["num_experts_per_tok"])
     fields = ModelConfig.__dataclass_fields__
@@ -101,6 +106,10 @@ def convert_hf_state_dict(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> D
         m = re.match(r"(model\.layers\.\d+\.self_attn\.)([qkv])_proj\.(weight|bias)", k)
         if m:
             qkv.setdefault((m.group(1), m.group(3)), {})[m.group(2)] = v
+            continue
+        m = re.match(r"(model\.layers\.\d+\.self_attn\.)W_pack\.(weight|bias)", k)
+        if m:       # Baichuan: already fused [q; k; v]
+            out[f"{m.group(1)}qkv_proj.{m.group(2)}"] = v
             continue
         m = re.match(r"(model\.layers\.\d+\.mlp\.)(gate|up)_proj\.weight", k)
         if m:

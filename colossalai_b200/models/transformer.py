@@ -120,7 +120,8 @@ class Attention(nn.Module):
         q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
         q, k, v = q.reshape(T, hq, D), k.reshape(T, hkv, D), v.reshape(T, hkv, D)
         if kv_cache is not None:
-            o = kv_cache.attend(self.layer_idx, q, k, v, meta, self.scale)
+            slopes = self._local_alibi_slopes(q.device) if cfg.pos_type == "alibi" else None
+            o = kv_cache.attend(self.layer_idx, q, k, v, meta, self.scale, alibi_slopes=slopes)
         elif sp_mode == "ring_attn" and comm.group_size(sp_group) > 1:
             o = RingAttention.attention(q, k, v, sp_group, batch=meta.batch, scale=self.scale)
         else:
@@ -137,6 +138,13 @@ class Attention(nn.Module):
             o = all_to_all_comm(o.reshape(B, S, hq, D), sp_group, scatter_dim=1, gather_dim=2)
             o = o.reshape(B * (S // sp), hq * sp * D)
         return self.o_proj(o)
+
+    def _local_alibi_slopes(self, device) -> torch.Tensor:
+        sc = self.shard_config
+        slopes = _alibi_slopes(self.cfg.num_attention_heads).to(device=device, dtype=torch.float32)
+        if sc is not None and sc.enable_tensor_parallelism and sc.tensor_parallel_size > 1:
+            slopes = slopes.chunk(sc.tensor_parallel_size)[comm.group_rank(sc.tp_group)]
+        return slopes.contiguous()
 
     def _build_mask(self, meta: SeqMeta, T: int, hq: int, device, dtype) -> torch.Tensor:
         """Additive/boolean mask [B, H, S, S] for ALiBi and padded encoder inputs (reference path only)."""
@@ -442,7 +450,10 @@ class TransformerLMHeadModel(nn.Module):
         if sp_mode in ("all_to_all", "ring_attn") and not keep_sp_sharded and comm.group_size(sp_group) > 1:
             Sl = h.shape[0] // B
             h = gather_sp_output(h.view(B, Sl, -1), sp_group, sp_mode, sp_dim=1).reshape(B * S, -1)
-        logits = self.lm_head(h)
+        if cfg.norm_head and isinstance(self.lm_head, nn.Linear):
+            logits = F.linear(h, F.normalize(self.lm_head.weight, dim=-1))
+        else:   # sharded heads: NormHead is folded into the weight at load time (inference) — see models/baichuan.py
+            logits = self.lm_head(h)
         if cfg.logit_scale != 1.0:
             logits = logits * cfg.logit_scale
         out: Dict[str, torch.Tensor] = {}

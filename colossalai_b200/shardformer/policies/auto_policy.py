@@ -54,6 +54,7 @@ _FAMILIES = {
     "bert": ["BertModel", "BertForPreTraining", "BertLMHeadModel", "BertForMaskedLM",
              "BertForSequenceClassification", "BertForTokenClassification", "BertForNextSentencePrediction",
              "BertForMultipleChoice", "BertForQuestionAnswering"],
+    "baichuan": ["BaichuanModel", "BaichuanForCausalLM", "BaichuanForSequenceClassification"],
     "vit": ["ViTModel", "ViTForImageClassification", "ViTForMaskedImageModeling"],
     "t5": ["T5Model", "T5ForConditionalGeneration", "T5EncoderModel", "T5ForTokenClassification"],
     "whisper": ["WhisperModel", "WhisperForConditionalGeneration", "WhisperForAudioClassification"],
