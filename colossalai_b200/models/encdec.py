@@ -71,6 +71,7 @@ class MultiHeadAttention(nn.Module):
         self.o_proj = nn.Linear(inner, cfg.hidden_size, bias=cfg.out_bias)
         self.scale = cfg.attn_scale if cfg.attn_scale is not None else 1.0 / math.sqrt(cfg.head_dim)
         self.shard_config = None
+        self.kv_exchange = None
 
     def project_memory(self, memory: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """K/V of the encoder memory `[B, Sk, H]` -> two `[B, heads_local, Sk, D]` tensors (cacheable across decode steps)."""
@@ -98,6 +99,8 @@ class MultiHeadAttention(nn.Module):
             q, k, v = (t.reshape(B, Sq, h, D).transpose(1, 2) for t in (q, k, v))
             if past_kv is not None:
                 k, v = torch.cat([past_kv[0], k], dim=2), torch.cat([past_kv[1], v], dim=2)
+            if self.kv_exchange is not None:      # patch parallelism: keys/values of the other ranks' tokens
+                k, v = self.kv_exchange(k, v, token_dim=2)
         Sk = k.shape[2]
         mask = bias
         causal = self.causal and not self.cross and Sq > 1
