@@ -1,6 +1,8 @@
 """Booster façade.  Parity: reference `colossalai/booster/booster.py:33-433`."""
 from __future__ import annotations
 
+import os
+
 from contextlib import contextmanager
 from typing import Any, Callable, Dict, Iterator, List, Optional, Union
 
@@ -91,7 +93,13 @@ class Booster:
             if optimizer is not None and not isinstance(optimizer, OptimizerWrapper):
                 optimizer = OptimizerWrapper(optimizer)
         if pretrained_path:
-            self.load_model(model, pretrained_path)
+            from ..lazy.pretrained import is_hf_checkpoint_dir, load_pretrained_into
+
+            if is_hf_checkpoint_dir(pretrained_path) and not os.path.isfile(
+                    os.path.join(pretrained_path, "cb200_format")):
+                load_pretrained_into(model, pretrained_path)      # HF naming -> fused / sharded parameters
+            else:
+                self.load_model(model, pretrained_path)
             orig = model.unwrap() if isinstance(model, ModelWrapper) else model
             set_pretrained_path(orig, None)
         return model, optimizer, criterion, dataloader, lr_scheduler

@@ -58,3 +58,37 @@ def test_mixtral_and_gpt2():
         pytest.skip(f"installed transformers uses a different Mixtral layout: {e}")
     g2 = transformers.GPT2Config(vocab_size=128, n_embd=64, n_layer=2, n_head=4, n_positions=64)
     _check(transformers.GPT2LMHeadModel(g2))
+
+
+def _lazy_worker(rank, world_size, port, ckpt):
+    import torch.distributed as dist
+
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.lazy import from_pretrained
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    model = from_pretrained(ckpt, lazy=True)
+    assert all(p.device.type == "meta" or getattr(p, "_is_lazy", True) for p in model.parameters())
+    plugin = HybridParallelPlugin(tp_size=2, pp_size=1, precision="fp32", parallel_output=False)
+    model, *_ = Booster(plugin=plugin).boost(model)
+    hf = transformers.LlamaForCausalLM.from_pretrained(ckpt).float().eval()
+    ids = torch.randint(0, 128, (2, 8), generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        got = model(input_ids=ids)["logits"].view(2, 8, -1)[..., :128]
+        torch.testing.assert_close(got, hf(input_ids=ids).logits, atol=3e-4, rtol=1e-3)
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+def test_lazy_from_pretrained_then_boost_tp2():
+    """70B-style flow at toy size: lazy skeleton -> shard -> stream the HF weights into the TP slices."""
+    from colossalai_b200.testing import spawn
+
+    torch.manual_seed(0)
+    hf_cfg = transformers.LlamaConfig(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64)
+    with tempfile.TemporaryDirectory() as tmp:
+        transformers.LlamaForCausalLM(hf_cfg).save_pretrained(tmp, safe_serialization=True)
+        spawn(_lazy_worker, 2, ckpt=tmp)
