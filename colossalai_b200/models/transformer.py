@@ -121,7 +121,8 @@ class Attention(nn.Module):
         q, k, v = q.reshape(T, hq, D), k.reshape(T, hkv, D), v.reshape(T, hkv, D)
         if kv_cache is not None:
             slopes = self._local_alibi_slopes(q.device) if cfg.pos_type == "alibi" else None
-            o = kv_cache.attend(self.layer_idx, q, k, v, meta, self.scale, alibi_slopes=slopes)
+            extra = {} if slopes is None else {"alibi_slopes": slopes}
+            o = kv_cache.attend(self.layer_idx, q, k, v, meta, self.scale, **extra)
         elif sp_mode == "ring_attn" and comm.group_size(sp_group) > 1:
             o = RingAttention.attention(q, k, v, sp_group, batch=meta.batch, scale=self.scale)
         else:

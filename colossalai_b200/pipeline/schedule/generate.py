@@ -35,8 +35,11 @@ class DenseKVCache:
         self.k: Dict[int, torch.Tensor] = {}
         self.v: Dict[int, torch.Tensor] = {}
 
-    def attend(self, layer_idx: int, q, k, v, meta, scale: float):
+    def attend(self, layer_idx: int, q, k, v, meta, scale: float, alibi_slopes=None):
         from ... import ops
+
+        if alibi_slopes is not None:
+            raise NotImplementedError("pipeline generation with ALiBi models: use the paged inference engine")
 
         B = self.batch
         kb = k.view(B, -1, *k.shape[1:])

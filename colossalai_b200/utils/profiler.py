@@ -169,7 +169,19 @@ class CommProfiler:
         self._orig.clear()
         return False
 
-    def result_str(self) -> str:
+    # legacy `ProfilerContext` protocol
+    name, priority = "Comm", 5
+
+    def enable(self) -> None:
+        self.__enter__()
+
+    def disable(self) -> None:
+        self.__exit__(None, None, None)
+
+    def show(self) -> None:
+        print(self.result_str())
+
+    def result_str(self, sep: str = "\n") -> str:
         lines = ["collective            calls        MiB   host s"]
         for k, s in sorted(self.stats.items(), key=lambda kv: -kv[1]["bytes"]):
             lines.append(f"{k:20s} {int(s['count']):6d} {s['bytes'] / 2**20:10.1f} {s['host_seconds']:8.3f}")

@@ -179,3 +179,79 @@ def _zero_v2(rank, world_size, port):
 @rerun_if_address_is_in_use()
 def test_legacy_zero_v2_adapters():
     spawn(_zero_v2, 2)
+
+
+def test_registry_builder_checkpoint_sampler_profilers():
+    from colossalai_b200.legacy.builder import build_from_registry
+    from colossalai_b200.legacy.registry import LAYERS, OPTIMIZERS, Registry
+    from colossalai_b200.legacy.utils import DataParallelSampler, checkpoint, clip_grad_norm_fp32
+    from colossalai_b200.legacy.utils.profiler import MemProfiler, PcieProfiler, ProfilerContext
+    from colossalai_b200.utils.profiler import CommProfiler
+
+    reg = Registry("toy")
+
+    @reg.register_module
+    class Foo:
+        def __init__(self, a=1):
+            self.a = a
+
+    assert build_from_registry(dict(type="Foo", a=3), reg).a == 3 and LAYERS.has("Linear")
+    lin = build_from_registry(dict(type="Linear", in_features=4, out_features=2), LAYERS)
+    opt = OPTIMIZERS.get_module("SGD")(lin.parameters(), lr=0.1)
+    assert isinstance(opt, torch.optim.SGD)
+    # activation checkpoint with offload and dropout RNG replay
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Dropout(0.5), torch.nn.Linear(8, 8))
+    x = torch.randn(4, 8, requires_grad=True)
+    torch.manual_seed(5)
+    y = checkpoint(net, True, x)
+    y.sum().backward()
+    g1 = x.grad.clone()
+    x.grad = None
+    torch.manual_seed(5)
+    net(x).sum().backward()
+    torch.testing.assert_close(g1, x.grad)
+    # sampler: 2 replicas would partition, single replica sees everything exactly once
+    s = DataParallelSampler(list(range(10)), shuffle=True, seed=3)
+    assert sorted(iter(s)) == list(range(10)) and len(s) == 10
+    p = torch.nn.Parameter(torch.ones(4))
+    p.grad = torch.full((4,), 3.0)
+    n = clip_grad_norm_fp32([p], max_norm=1.0)
+    assert abs(float(n) - 6.0) < 1e-5 and abs(float(p.grad.norm()) - 1.0) < 1e-3
+    with ProfilerContext([CommProfiler(), PcieProfiler(), MemProfiler()]) as prof:
+        prof.profilers[0].step("a") if hasattr(prof.profilers[0], "step") else None
+        torch.randn(8, 8) @ torch.randn(8, 8)
+    assert "Pcie profiling result" in "".join(p.result_str() for p in prof.profilers)
+
+
+def _legacy_init(rank, world_size, port):
+    from colossalai_b200.legacy.amp import AMP_TYPE
+    from colossalai_b200.legacy.context import ParallelMode, global_context as gpc
+    from colossalai_b200.legacy.initialize import initialize, launch
+
+    launch(dict(parallel=dict(pipeline=1, tensor=dict(size=1, mode="1d")), clip_grad_norm=1.0,
+                fp16=dict(mode=AMP_TYPE.NAIVE, dtype=torch.bfloat16)),
+           rank=rank, world_size=world_size, host="127.0.0.1", port=port, backend="gloo", verbose=False)
+    assert gpc.get_world_size(ParallelMode.DATA) == 2 and gpc.get_world_size(ParallelMode.TENSOR) == 1
+    torch.manual_seed(rank)            # replicas start different; initialize() must sync them
+    model = torch.nn.Linear(8, 2)
+    engine, *_ = initialize(model, torch.optim.SGD(model.parameters(), lr=0.1), torch.nn.MSELoss())
+    w = engine.model.weight.detach().float().clone()
+    dist.all_reduce(w)
+    torch.testing.assert_close(w / 2, engine.model.weight.detach().float())
+    engine.train()
+    x = torch.randn(4, 8, generator=torch.Generator().manual_seed(rank)).bfloat16()
+    loss = engine.criterion(engine(x).float(), torch.zeros(4, 2))
+    engine.zero_grad()
+    engine.optimizer.backward(loss) if hasattr(engine.optimizer, "backward") else engine.backward(loss)
+    engine.step()
+    w2 = engine.model.weight.detach().float().clone()
+    dist.all_reduce(w2)
+    torch.testing.assert_close(w2 / 2, engine.model.weight.detach().float())     # replicas stay in lock-step
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_legacy_initialize_engine():
+    spawn(_legacy_init, 2)
