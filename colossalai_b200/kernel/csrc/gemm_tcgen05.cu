@@ -48,6 +48,8 @@ struct GemmParams {
   int accumulate;     // D += existing C
   uint32_t idesc;
   void* C;
+  const float* scale_a = nullptr;   // fp8 path: per-tensor dequantisation scales (device pointers, may be null)
+  const float* scale_b = nullptr;
 };
 
 SM100_DEVICE void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
@@ -291,11 +293,16 @@ template <int BK_, int STAGES_> struct Cfg2 {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BK, int STAGES>
+// F8 = true: 8-bit float operands (K-major only).  Byte-wise the pipeline is identical to the 16-bit one — a 128-byte
+// swizzle row holds 128 fp8 values and one tcgen05.mma consumes 32 of them (32 bytes, like 16 bf16) — so only the
+// element-space K coordinates double and the MMA kind changes; the epilogue applies scale_a * scale_b.
+template <int BK, int STAGES, bool F8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
   using C = Cfg2<BK, STAGES>;
+  constexpr int KE = F8 ? 2 * BK : BK;      // K elements per stage
+  constexpr int SUB = F8 ? 128 : 64;        // K elements per 128-byte swizzled sub-tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -316,7 +323,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int m_blocks = (p.M + PAIR_M - 1) / PAIR_M;
   const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
   const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (p.K + BK - 1) / BK;
+  const int k_blocks = (p.K + KE - 1) / KE;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
@@ -356,17 +363,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = kb * KE;
           if (!p.a_mn_major) {
 #pragma unroll
-            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (128 * 128), k0 + j * 64, m0);
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (128 * 128), k0 + j * SUB, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BK * 128), m0 + j * 64, k0);
           }
           if (!p.b_mn_major) {
 #pragma unroll
-            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (128 * 128), k0 + j * 64, n0);
+            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (128 * 128), k0 + j * SUB, n0);
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BK * 128), n0 + j * 64, k0);
@@ -405,8 +412,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               // MN-major: one 16-k-row slab (2 KB) per step
               const uint32_t ao = p.a_mn_major ? k * a_kstep : (k >> 2) * (128 * 128) + (k & 3) * a_kstep;
               const uint32_t bo = p.b_mn_major ? k * b_kstep : (k >> 2) * (128 * 128) + (k & 3) * b_kstep;
-              umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
-                               (kb > 0 || k > 0) ? 1u : 0u);
+              if constexpr (F8)
+                umma_f8_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit_2cta(&empty_bar[stage], 3);
             if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
@@ -424,6 +435,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float alpha = 1.0f;
+    if constexpr (F8) {
+      if (p.scale_a) alpha *= __ldg(p.scale_a);
+      if (p.scale_b) alpha *= __ldg(p.scale_b);
+    }
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
@@ -439,6 +455,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tmem_ld_32x32b_x32(taddr + c, v0);
         tmem_ld_32x32b_x32(taddr + c + 32, v1);
         tmem_ld_wait();
+        if constexpr (F8) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = __float_as_uint(__uint_as_float(v0[i]) * alpha);
+            v1[i] = __float_as_uint(__uint_as_float(v1[i]) * alpha);
+          }
+        }
 #define CB_EPI_STORE(V, CC)                                                                              \
         {                                                                                                  \
           const int n_valid = p.N - (n0 + (CC));                                                           \
@@ -498,6 +521,39 @@ int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int
   if (tiles < pairs) pairs = tiles;
   if (pairs <= 0) return 0;
   gemm_tcgen05_2cta_kernel<BK, STAGES><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+// fp8 (E4M3 / E5M2) x fp8 -> bf16 / fp16 / fp32, both operands K-major: A [M, K], B [N, K] bytes.
+template <int BK, int STAGES>
+int launch_2cta_f8(const void* A, const void* B, void* Cp, int M, int N, int K, int lda, int ldb, int ldc, int a_fmt,
+                   int b_fmt, int out_dtype, int accumulate, const float* scale_a, const float* scale_b,
+                   cudaStream_t stream) {
+  using C = Cfg2<BK, STAGES>;
+  CUtensorMap ta, tb;
+  int r = make_tmap_2d_8b(&ta, A, M, K, lda, 128, 128);
+  if (r) return 1000 + r;
+  r = make_tmap_2d_8b(&tb, B, N, K, ldb, 128, 128);
+  if (r) return 2000 + r;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn_major = 0; p.b_mn_major = 0; p.out_dtype = out_dtype;
+  p.accumulate = accumulate; p.C = Cp; p.scale_a = scale_a; p.scale_b = scale_b;
+  uint32_t d = make_idesc_f16(PAIR_M, PAIR_N, 0, 0, 0);
+  d |= (uint32_t)(a_fmt & 7) << 7;              // 0 = E4M3, 1 = E5M2
+  d |= (uint32_t)(b_fmt & 7) << 10;
+  p.idesc = d;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BK, STAGES, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = ((M + PAIR_M - 1) / PAIR_M) * ((N + PAIR_N - 1) / PAIR_N);
+  int pairs = cb_num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  if (pairs <= 0) return 0;
+  gemm_tcgen05_2cta_kernel<BK, STAGES, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
 
@@ -577,6 +633,18 @@ int cb_gemm_tcgen05(const void* A, const void* B, void* C, int M, int N, int K, 
   if (block_n == 256)
     return launch<256>(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
   return launch<128>(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, in_dtype, out_dtype, accumulate, stream);
+}
+
+// D[M,N] (+)= scale_a * scale_b * (A[M,K] x B[N,K]^T) with 8-bit float operands on the CTA-pair tcgen05 kernel
+// (kind::f8f6f4, 256x256 tiles, 256 K-elements per stage).  a_fmt / b_fmt: 0 = E4M3, 1 = E5M2.  Requirements:
+// 16-byte aligned bases, lda / ldb multiples of 16 bytes.  scale pointers are device fp32 scalars or null.
+int cb_gemm_fp8_tcgen05(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                        int a_fmt, int b_fmt, int out_dtype, int accumulate, const float* scale_a,
+                        const float* scale_b, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if ((lda & 15) || (ldb & 15)) return (int)cudaErrorInvalidValue;
+  return launch_2cta_f8<128, 3>(A, B, C, M, N, K, lda, ldb, ldc, a_fmt, b_fmt, out_dtype, accumulate, scale_a,
+                                scale_b, stream);
 }
 
 int cb_gemm_smem_bytes(int block_n) { return block_n == 256 ? Cfg<256>::SMEM_BYTES : Cfg<128>::SMEM_BYTES; }

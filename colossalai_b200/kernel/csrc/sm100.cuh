@@ -200,6 +200,16 @@ SM100_DEVICE void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t de
       :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 8-bit floating point operands (E4M3 / E5M2, formats chosen in the instruction descriptor): K = 32 per instruction
+SM100_DEVICE void umma_f8_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this smem offset in every CTA selected by `cta_mask` once the issued MMAs retire
 SM100_DEVICE void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
@@ -265,6 +275,21 @@ inline int make_tmap_2d_16b(CUtensorMap* out, const void* base, uint64_t rows, u
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+// 2-D row-major tensor [rows, cols] of 8-bit elements (fp8 payloads travel as raw bytes); box = [box_rows, box_cols].
+inline int make_tmap_2d_8b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }
 

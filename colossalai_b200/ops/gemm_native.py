@@ -96,3 +96,46 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     assert out.stride(1) == 1 and out.dtype in (torch.float32, torch.bfloat16, torch.float16)
     _launch(a, b, out, M, N, red, a.stride(0), b.stride(0), 1, 1, accumulate, block_n)
     return out
+
+
+# ---- fp8: c[M,N] = scale_a * scale_b * (a[M,K] @ b[N,K]^T), operands e4m3 / e5m2, both K-major
+_FP8_FMT = {getattr(torch, "float8_e4m3fn", None): 0, getattr(torch, "float8_e5m2", None): 1}
+_FP8_BACKEND = os.environ.get("CB200_FP8_GEMM", "cublaslt")      # "native" -> CTA-pair tcgen05 kind::f8f6f4 kernel
+
+
+def fp8_backend() -> str:
+    return _FP8_BACKEND
+
+
+def set_fp8_backend(name: str) -> None:
+    global _FP8_BACKEND
+    assert name in ("native", "cublaslt")
+    _FP8_BACKEND = name
+
+
+def supported_fp8_nt(a: torch.Tensor, b: torch.Tensor) -> bool:
+    def ok(t):
+        return (t.dim() == 2 and t.dtype in _FP8_FMT and t.stride(1) == 1 and t.stride(0) % 16 == 0
+                and t.data_ptr() % 16 == 0 and t.stride(0) >= t.shape[1])
+
+    if not (a.is_cuda and ok(a) and ok(b) and a.shape[1] == b.shape[1]):
+        return False
+    M, K, N = a.shape[0], a.shape[1], b.shape[0]
+    return M >= 256 and N >= 256 and K >= 256 and N % 8 == 0 and ((M + 255) // 256) * ((N + 255) // 256) >= 37
+
+
+def gemm_fp8_nt(a: torch.Tensor, b: torch.Tensor, scale_a: Optional[torch.Tensor], scale_b: Optional[torch.Tensor],
+                out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a [M, K] fp8, b [N, K] fp8 (rows contiguous); scales are fp32 device scalars (dequantisation factors)."""
+    M, K = a.shape
+    N = b.shape[0]
+    c = out if out is not None else torch.empty(M, N, dtype=out_dtype, device=a.device)
+    sa = None if scale_a is None else scale_a.reshape(1).to(device=a.device, dtype=torch.float32)
+    sb = None if scale_b is None else scale_b.reshape(1).to(device=a.device, dtype=torch.float32)
+    lib = _get_lib()
+    rc = lib.cb_gemm_fp8_tcgen05(loader.ptr(a), loader.ptr(b), loader.ptr(c), M, N, K, a.stride(0), b.stride(0),
+                                 c.stride(0), _FP8_FMT[a.dtype], _FP8_FMT[b.dtype], code(c.dtype), 0,
+                                 loader.ptr(sa), loader.ptr(sb), loader.stream_ptr())
+    loader.check(rc, "gemm_fp8_tcgen05")
+    loader.launch_counter.add("gemm_fp8_tcgen05")
+    return c

@@ -5,7 +5,8 @@ all_to_all_single_fp8:258, cast_{to,from}_fp8_pipeline:285/327, reduce_scatter_f
 all_to_all_fp8:648, all_gather_fp8:680, linear_fp8:842).
 
 B200 design: the amax reduction + scaled cast run as native kernels (kernel/csrc/quant.cu), payloads travel as raw bytes
-(`uint8` views) so the same code drives NCCL and gloo; the FP8 matmul is cuBLASLt's scaled GEMM (`torch._scaled_mm`).
+(`uint8` views) so the same code drives NCCL and gloo; the FP8 matmul is cuBLASLt's scaled GEMM (`torch._scaled_mm`) or, with
+`CB200_FP8_GEMM=native`, the hand-written CTA-pair tcgen05 `kind::f8f6f4` kernel (kernel/csrc/gemm_tcgen05.cu).
 """
 from __future__ import annotations
 
@@ -376,6 +377,12 @@ def fp8_compress_fsdp_params_comm_hook(state: object, padded_unsharded_flat_para
 def _scaled_mm(a_q, a_sinv, b_q_t, b_sinv, out_dtype):
     """a_q [M,K] row-major fp8, b_q_t [K,N] column-major fp8 (i.e. the transpose view of a row-major [N,K])."""
     if a_q.is_cuda:
+        from ..ops import gemm_native
+
+        if gemm_native.fp8_backend() == "native" and gemm_native.available():
+            b_nk = b_q_t.t()                       # the row-major [N, K] view behind the column-major operand
+            if gemm_native.supported_fp8_nt(a_q, b_nk):
+                return gemm_native.gemm_fp8_nt(a_q, b_nk, a_sinv, b_sinv, out_dtype)
         return torch._scaled_mm(a_q, b_q_t, scale_a=a_sinv.reshape(()).float(), scale_b=b_sinv.reshape(()).float(),
                                 out_dtype=out_dtype)
     return ((a_q.float() * a_sinv.reshape(())) @ (b_q_t.float() * b_sinv.reshape(()))).to(out_dtype)
