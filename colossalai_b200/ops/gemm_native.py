@@ -100,7 +100,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
 
 # ---- fp8: c[M,N] = scale_a * scale_b * (a[M,K] @ b[N,K]^T), operands e4m3 / e5m2, both K-major
 _FP8_FMT = {getattr(torch, "float8_e4m3fn", None): 0, getattr(torch, "float8_e5m2", None): 1}
-_FP8_BACKEND = os.environ.get("CB200_FP8_GEMM", "cublaslt")      # "native" -> CTA-pair tcgen05 kind::f8f6f4 kernel
+_FP8_BACKEND = os.environ.get("CB200_FP8_GEMM", "native")      # "native" -> CTA-pair tcgen05 kind::f8f6f4 kernel
 
 
 def fp8_backend() -> str:
