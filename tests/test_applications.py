@@ -1,0 +1,205 @@
+"""ColossalChat (coati) on tiny models: objectives against hand-computed values, every trainer makes progress, the
+producer -> consumer GRPO loop learns a verifiable reward (reference: applications/ColossalChat/tests/*)."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "ColossalChat"))
+
+from coati.dataset import (Conversation, DataCollatorForKTODataset, DataCollatorForPreferenceDataset,  # noqa: E402
+                           DataCollatorForPromptDataset, DataCollatorForSupervisedDataset, ListDataset, tokenize_kto,
+                           tokenize_preference, tokenize_prompt, tokenize_sft)
+from coati.distributed import (GRPOConsumer, ModelRolloutBackend, Producer, boxed_math_reward, extract_boxed,  # noqa: E402
+                               format_reward, launch_distributed)
+from coati.experience import NaiveExperienceMaker  # noqa: E402
+from coati.models import (Critic, DpoLoss, KTOLoss, LogSigLoss, OddsRatioLoss, PolicyLoss, RewardModel, ValueLoss,  # noqa: E402
+                          calc_action_log_probs, compute_reward, generate, get_logits)
+from coati.trainer import (DPOTrainer, GRPOTrainer, KTOTrainer, ORPOTrainer, PPOTrainer, RewardModelTrainer,  # noqa: E402
+                           SFTTrainer)
+from coati.trainer.grpo import group_advantages  # noqa: E402
+from colossalai_b200.models import build_model, get_config  # noqa: E402
+
+
+def _tok(text):           # byte-level toy tokenizer (ids 3..258), 0 pad / 1 bos / 2 eos
+    return [3 + b for b in text.encode()]
+
+
+def _tiny(seed=0, **kw):
+    torch.manual_seed(seed)
+    return build_model(get_config("llama-tiny", num_hidden_layers=2, **kw)).float()
+
+
+def test_losses_match_formulas():
+    lp, old = torch.tensor([[-1.0, -2.0]]), torch.tensor([[-1.2, -1.5]])
+    adv = torch.tensor([[1.0, -1.0]])
+    loss, skipped, _ = PolicyLoss(0.2)(lp, old, adv, torch.ones(1, 2))
+    r = (lp - old).exp()
+    expect = -torch.min(r * adv, r.clamp(0.8, 1.2) * adv).mean()
+    assert not skipped and torch.allclose(loss, expect)
+    assert PolicyLoss(0.2, skip_threshold=1.1)(lp, old - 5, adv, torch.ones(1, 2))[1]          # off-policy batch skipped
+    v = ValueLoss(0.2)(torch.tensor([[1.0]]), torch.tensor([[0.5]]), torch.tensor([[2.0]]))
+    assert torch.allclose(v, torch.tensor(0.5 * max((0.7 - 2) ** 2, (1.0 - 2) ** 2)))
+    m = torch.ones(2, 3)
+    pc, pr, rc, rr = torch.full((2, 3), -1.0), torch.full((2, 3), -2.0), torch.full((2, 3), -1.5), torch.full((2, 3), -1.5)
+    d, cw, rw = DpoLoss(0.1)(pc, pr, rc, rr, m, m)
+    assert torch.allclose(d, -F.logsigmoid(torch.tensor(0.1 * 3.0))) and (cw > rw).all()
+    assert torch.allclose(LogSigLoss()(torch.tensor([2.0]), torch.tensor([0.0])), -F.logsigmoid(torch.tensor(2.0)))
+    o, lo = OddsRatioLoss()(torch.full((1, 2), -0.1), torch.full((1, 2), -2.0), torch.ones(1, 2), torch.ones(1, 2))
+    assert lo.item() > 0 and o.item() < math.log(2)
+    k, *_ = KTOLoss(0.1)(torch.tensor([-1.0]), torch.tensor([-3.0]), torch.tensor([-2.0, -2.0]), torch.tensor([-2.0]),
+                         torch.tensor([-2.0]), torch.tensor([-2.0, -2.0]))
+    assert 0 < k.item() < 1
+    g = group_advantages(torch.tensor([1.0, 0.0, 0.0, 1.0, 5.0, 5.0, 5.0, 5.0]), 4)
+    assert torch.allclose(g[:4].sum(), torch.tensor(0.0), atol=1e-5) and torch.all(g[4:] == 0)
+    r, kl = compute_reward(torch.tensor([1.0]), 0.1, torch.tensor([[-1.0, -1.0, -1.0]]), torch.tensor([[-1.5, -1.5, -1.5]]),
+                           torch.tensor([[1.0, 1.0, 0.0]]))
+    assert torch.allclose(r, torch.tensor([[-0.05, 0.95, 0.0]])) and torch.allclose(kl, torch.tensor([0.5]))
+
+
+def test_dataset_tokenisation_and_rewards():
+    msgs = [{"role": "user", "content": "hi"}, {"role": "assistant", "content": "yo"}]
+    s = tokenize_sft(msgs, _tok)
+    trained = bytes(t - 3 for t, l in zip(s["input_ids"], s["labels"]) if l != -100).decode()
+    assert trained == "yo<|end|>\n" and len(s["input_ids"]) == len(s["labels"])
+    p = tokenize_prompt(msgs[:1], _tok)
+    assert bytes(t - 3 for t in p["input_ids"]).decode().endswith("<|assistant|>\n")
+    pref = tokenize_preference(msgs[:1], "good", "bad!", _tok)
+    batch = DataCollatorForPreferenceDataset()([pref, pref])
+    assert batch["chosen_input_ids"].shape[0] == 2 and batch["rejected_loss_mask"].sum() == 2 * len(_tok("bad!<|end|>\n"))
+    kb = DataCollatorForKTODataset()([tokenize_kto(msgs[:1], "a", True, _tok), tokenize_kto(msgs[:1], "bcd", False, _tok)])
+    assert kb["label"].tolist() == [True, False] and kb["kl_input_ids"].shape[0] == 2
+    pb = DataCollatorForPromptDataset()([{"input_ids": [5, 6, 7]}, {"input_ids": [8]}])
+    assert pb["input_ids"].tolist() == [[5, 6, 7], [0, 0, 8]] and pb["attention_mask"].tolist() == [[1, 1, 1], [0, 0, 1]]
+    assert extract_boxed("so \\boxed{\\frac{1}{2}} and \\boxed{42}.") == "42"
+    assert boxed_math_reward("answer \\boxed{42.0}", "42") == 1.0 and boxed_math_reward("no box", "42") == 0.0
+    assert boxed_math_reward("\\boxed{7}", "42", format_score=0.1) == 0.1
+    assert format_reward("<think>a</think><answer>b</answer>") == 1.0 and format_reward("<answer>b</answer>") == 0.0
+
+
+def _pref_loader(n=8):
+    torch.manual_seed(0)
+    items = [tokenize_preference([{"role": "user", "content": f"q{i}"}], "yes " * 3, "no " * 3, _tok) for i in range(n)]
+    return torch.utils.data.DataLoader(ListDataset(items), batch_size=4, collate_fn=DataCollatorForPreferenceDataset())
+
+
+def test_supervised_style_trainers_learn():
+    sft_items = [tokenize_sft([{"role": "user", "content": "ping"}, {"role": "assistant", "content": "pong"}], _tok)] * 8
+    dl = torch.utils.data.DataLoader(ListDataset(sft_items), batch_size=4, collate_fn=DataCollatorForSupervisedDataset())
+    m = _tiny()
+    h = SFTTrainer(m, None, torch.optim.AdamW(m.parameters(), lr=3e-3), max_epochs=6).fit(dl)
+    assert h[-1]["loss"] < 0.5 * h[0]["loss"]
+    rm = RewardModel(_tiny(1))
+    h = RewardModelTrainer(rm, None, torch.optim.AdamW(rm.parameters(), lr=3e-3), max_epochs=6).fit(_pref_loader())
+    assert h[-1]["accuracy"] == 1.0 and h[-1]["loss"] < h[0]["loss"]
+    actor, ref = _tiny(2), _tiny(2)
+    h = DPOTrainer(actor, ref, None, torch.optim.AdamW(actor.parameters(), lr=2e-3), beta=0.5, max_epochs=5).fit(_pref_loader())
+    assert h[-1]["loss"] < h[0]["loss"] and h[-1]["accuracy"] == 1.0
+    actor = _tiny(3)      # SimPO flavour: no reference, length-normalised, margin
+    h = DPOTrainer(actor, None, None, torch.optim.AdamW(actor.parameters(), lr=2e-3), beta=2.0, gamma=0.5,
+                   length_normalization=True, max_epochs=4).fit(_pref_loader())
+    assert h[-1]["loss"] < h[0]["loss"]
+    actor = _tiny(4)
+    h = ORPOTrainer(actor, None, torch.optim.AdamW(actor.parameters(), lr=2e-3), lam=0.5, max_epochs=4).fit(_pref_loader())
+    assert h[-1]["loss"] < h[0]["loss"] and h[-1]["log_odds_ratio"] > h[0]["log_odds_ratio"]
+    kto_items = [tokenize_kto([{"role": "user", "content": f"q{i}"}], "yes yes" if i % 2 == 0 else "no no", i % 2 == 0, _tok)
+                 for i in range(8)]
+    kdl = torch.utils.data.DataLoader(ListDataset(kto_items), batch_size=4, collate_fn=DataCollatorForKTODataset())
+    actor, ref = _tiny(5), _tiny(5)
+    h = KTOTrainer(actor, ref, None, torch.optim.AdamW(actor.parameters(), lr=2e-3), beta=0.5, max_epochs=5).fit(kdl)
+    assert h[-1]["loss"] < h[0]["loss"] and h[-1]["chosen_reward"] > h[-1]["rejected_reward"]
+
+
+TARGET = 7      # the "verifiable" task: emit token 7 as often as possible
+
+
+def _count_reward(seq, prompt_len, **_):
+    return (seq[:, prompt_len:] == TARGET).float().mean(-1)
+
+
+def _prompt_loader():
+    items = [{"input_ids": [1, 10 + i, 11 + i]} for i in range(4)]
+    return torch.utils.data.DataLoader(ListDataset(items), batch_size=4, collate_fn=DataCollatorForPromptDataset())
+
+
+def test_gae_and_ppo_improves_reward():
+    v = torch.zeros(1, 3)
+    r = torch.tensor([[0.0, 0.0, 1.0]])
+    adv = NaiveExperienceMaker.gae(v, r, torch.ones(1, 3), gamma=1.0, lam=1.0)
+    assert torch.allclose(adv, torch.ones(1, 3))
+    actor, init = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    critic = Critic(_tiny(1, vocab_size=32))
+    tr = PPOTrainer(None, None, actor, critic, None, init, torch.optim.AdamW(actor.parameters(), lr=3e-3),
+                    torch.optim.AdamW(critic.parameters(), lr=3e-3), kl_coef=0.0, train_batch_size=16,
+                    reward_fn=_count_reward, generate_kwargs=dict(max_new_tokens=6))
+    torch.manual_seed(0)
+    h = tr.fit(_prompt_loader(), num_episodes=12, num_collect_steps=4, num_update_steps=3)
+    first = sum(x["reward"] for x in h[:6]) / 6
+    last = sum(x["reward"] for x in h[-6:]) / 6
+    assert last > first + 0.05, (first, last)
+
+
+def test_grpo_trainer_and_producer_consumer_loop():
+    actor, init = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    tr = GRPOTrainer(None, actor, init, torch.optim.AdamW(actor.parameters(), lr=3e-3), _count_reward,
+                     num_generations=8, beta=0.01, clip_eps_low=0.2, clip_eps_high=0.28, loss_variation="token_level",
+                     filter_uniform_groups=True, generate_kwargs=dict(max_new_tokens=6))
+    torch.manual_seed(0)
+    h = tr.fit(_prompt_loader(), num_episodes=15, num_collect_steps=1, num_update_steps=1)
+    assert sum(x["reward"] for x in h[-4:]) / 4 > sum(x["reward"] for x in h[:4]) / 4 + 0.05
+    # producer / consumer with periodic weight sync (single-process launch)
+    policy, sampler = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    prod = Producer(ModelRolloutBackend(sampler, dict(max_new_tokens=6)), _prompt_loader(), num_generations=8)
+    cons = GRPOConsumer(policy, torch.optim.AdamW(policy.parameters(), lr=3e-3), _count_reward, num_generations=8,
+                        minibatch_size=16)
+    torch.manual_seed(0)
+    h = launch_distributed(prod, cons, num_steps=15, sync_every=2)
+    assert sum(x["reward"] for x in h[-4:]) / 4 > sum(x["reward"] for x in h[:4]) / 4 + 0.05
+    assert prod.model_version >= 14 and max(x["staleness"] for x in h) <= 2
+    for a, b in zip(policy.parameters(), sampler.parameters()):       # last sync landed on step 14 of 15
+        assert a.shape == b.shape
+
+
+def test_colossal_llama_eval_and_qa_utilities(tmp_path):
+    for sub in ("Colossal-LLaMA", "ColossalEval", "ColossalQA"):
+        sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", sub))
+    from colossal_eval import Evaluator, exact_match, f1_score, perplexity, rouge_l
+    from colossal_llama import ClosedToConstantLengthSplicedDataset, expand_vocab, supervised_tokenize_pretrain
+    from colossalqa import EmbeddingIndex, RetrievalQA, split_text
+
+    # spliced dataset: every sample appears once, items are exactly max_length, little padding
+    samples = [supervised_tokenize_pretrain({"source": "s" * (i % 3), "target": "t" * (5 + 3 * i)}, _tok) for i in range(12)]
+    ds = list(ClosedToConstantLengthSplicedDataset(samples, max_length=64, num_packed_sequences=6))
+    assert all(d["input_ids"].shape == (64,) for d in ds)
+    assert sum(int(d["attention_mask"].sum()) for d in ds) == sum(s["seq_length"] for s in samples)
+    assert sum(int(d["attention_mask"].sum()) for d in ds) / (64 * len(ds)) > 0.75
+    assert all(int(d["seq_boundaries"][-1]) == int(d["attention_mask"].sum()) for d in ds)
+    assert samples[1]["labels"][:2] == [-100, -100] and samples[1]["labels"][-1] == 2
+    # vocabulary expansion keeps old logits and mean-initialises the new rows
+    m = _tiny(0, vocab_size=32)
+    ids = torch.randint(0, 32, (1, 6))
+    before = m(input_ids=ids)["logits"][:, :32].clone()
+    m = expand_vocab(m, 40, {32: [3, 4]})
+    after = m(input_ids=ids)["logits"]
+    assert after.shape[-1] == 40 and torch.allclose(after[:, :32], before, atol=1e-5)
+    w = m.model.embed_tokens.weight
+    assert torch.allclose(w[32], (w[3] + w[4]) / 2, atol=1e-6)
+    # metrics + evaluator
+    assert exact_match("The Cat.", "cat") == 1.0 and 0 < f1_score("a big cat", "big dog") < 1 and rouge_l("x y z", "x z") > 0.7
+    ev = Evaluator(_tiny(1), _tok, max_new_tokens=2)
+    res = ev.evaluate({"mc": [{"instruction": "2+2=", "choices": ["4", "5"], "answer": 0}],
+                       "gen": [{"instruction": "hi", "target": "zzz"}]}, {"gen": ["exact_match", "f1"]})
+    assert set(res) == {"mc", "gen"} and res["mc"]["accuracy"] in (0.0, 1.0) and perplexity(_tiny(1), _tok, ["abc"]) > 1
+    # retrieval QA
+    doc = ("The B200 has 148 streaming multiprocessors. Its HBM3e capacity is 180 gigabytes. "
+           "NVLink 5 gives every GPU 900 gigabytes per second to each peer. Bananas are yellow.")
+    chunks = split_text(doc, chunk_size=70, chunk_overlap=10)
+    assert len(chunks) >= 3 and all(len(c) <= 70 for c in chunks)
+    index = EmbeddingIndex()
+    assert index.add_documents(chunks, source="b200.txt") == len(chunks) and index.add_documents(chunks, source="b200.txt") == 0
+    qa = RetrievalQA(index, generate=lambda prompt: prompt.split("context:\n")[1].split("\n")[0])
+    ans, src = qa.run("How many streaming multiprocessors does the B200 have?")
+    assert "148" in ans and src and "question:" in qa.build_prompt("x")[0] and len(qa.memory.turns) == 1
