@@ -7,7 +7,8 @@ experts of an MoE block, so this module maps names and fuses / splits tensors:
     model = load_hf_checkpoint("/path/to/hf_dir", dtype=torch.bfloat16)       # config.json + *.safetensors / *.bin
     sd    = to_hf_state_dict(model)                                            # export back to HF naming
 
-Supported: llama / mistral / qwen2 / qwen3 (llama-like), mixtral, gpt2.
+Supported: llama / mistral / qwen2 / qwen3 / baichuan (llama-like), mixtral, gpt2, opt, bloom, falcon (7B-style
+multi-query layout) and the bert backbone.
 """
 from __future__ import annotations
 
@@ -34,6 +35,46 @@ def config_from_hf(hf: dict) -> ModelConfig:
                            pos_type="learned", norm_type="layer", hidden_act="gelu_new", glu=False,
                            attention_bias=True, mlp_bias=True, tie_word_embeddings=True,
                            norm_eps=hf.get("layer_norm_epsilon", 1e-5))
+    if mt == "opt":
+        assert hf.get("do_layer_norm_before", True) and hf.get("word_embed_proj_dim", hf["hidden_size"]) == hf["hidden_size"], \
+            "OPT-350m style post-LN / projected embeddings are not supported"
+        return ModelConfig(model_type="opt", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+                           intermediate_size=hf["ffn_dim"], num_hidden_layers=hf["num_hidden_layers"],
+                           num_attention_heads=hf["num_attention_heads"],
+                           max_position_embeddings=hf["max_position_embeddings"], norm_type="layer",
+                           hidden_act=hf.get("activation_function", "relu"), glu=False, attention_bias=True, mlp_bias=True,
+                           pos_type="learned", tie_word_embeddings=hf.get("tie_word_embeddings", True), norm_eps=1e-5,
+                           pad_token_id=hf.get("pad_token_id"), bos_token_id=hf.get("bos_token_id", 2),
+                           eos_token_id=hf.get("eos_token_id", 2))
+    if mt == "bloom":
+        h = hf.get("hidden_size", hf.get("n_embed"))
+        return ModelConfig(model_type="bloom", vocab_size=hf["vocab_size"], hidden_size=h, intermediate_size=4 * h,
+                           num_hidden_layers=hf.get("n_layer", hf.get("num_hidden_layers")),
+                           num_attention_heads=hf.get("n_head", hf.get("num_attention_heads")), norm_type="layer",
+                           hidden_act="gelu_new", glu=False, attention_bias=True, mlp_bias=True, pos_type="alibi",
+                           embed_norm=True, tie_word_embeddings=True, norm_eps=hf.get("layer_norm_epsilon", 1e-5))
+    if mt == "falcon":
+        assert not hf.get("new_decoder_architecture", False) and hf.get("parallel_attn", True) and not hf.get("alibi", False), \
+            "only the falcon-7b style layout (parallel attention, rotary, single layer norm) is mapped"
+        nh = hf["num_attention_heads"]
+        nkv = 1 if hf.get("multi_query", True) else nh
+        return ModelConfig(model_type="falcon", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+                           intermediate_size=hf.get("ffn_hidden_size") or 4 * hf["hidden_size"],
+                           num_hidden_layers=hf["num_hidden_layers"], num_attention_heads=nh, num_key_value_heads=nkv,
+                           norm_type="layer", hidden_act="gelu", glu=False, parallel_block=True,
+                           attention_bias=hf.get("bias", False), mlp_bias=hf.get("bias", False),
+                           rope_theta=float(hf.get("rope_theta", 10000.0)),
+                           max_position_embeddings=hf.get("max_position_embeddings", 2048),
+                           tie_word_embeddings=hf.get("tie_word_embeddings", True),
+                           norm_eps=hf.get("layer_norm_epsilon", 1e-5))
+    if mt == "bert":
+        return ModelConfig(model_type="bert", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+                           intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
+                           num_attention_heads=hf["num_attention_heads"],
+                           max_position_embeddings=hf["max_position_embeddings"], norm_type="layer",
+                           hidden_act=hf.get("hidden_act", "gelu"), glu=False, attention_bias=True, mlp_bias=True,
+                           pos_type="learned", causal=False, type_vocab_size=hf.get("type_vocab_size", 2), post_norm=True,
+                           final_norm=False, embed_norm=True, norm_eps=hf.get("layer_norm_eps", 1e-12))
     assert mt in _LLAMA_LIKE, f"unsupported HF model_type {mt!r}"
     kw = dict(model_type=mt, vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
               intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
@@ -99,6 +140,8 @@ def convert_hf_state_dict(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> D
             elif k == "lm_head.weight":
                 out["lm_head.weight"] = v
         return out
+    if cfg.model_type in _FAMILY_CONVERTERS:
+        return _FAMILY_CONVERTERS[cfg.model_type](hf_sd, cfg)
     qkv: Dict[Tuple[str, str], Dict[str, torch.Tensor]] = {}
     gu: Dict[str, Dict[str, torch.Tensor]] = {}
     experts: Dict[str, Dict[int, Dict[str, torch.Tensor]]] = {}
@@ -133,6 +176,136 @@ def convert_hf_state_dict(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> D
         out[pre + "mlp.experts.w_up"] = torch.stack([torch.cat([ex[i]["w1"], ex[i]["w3"]], 0) for i in ids])
         out[pre + "mlp.experts.w_down"] = torch.stack([ex[i]["w2"] for i in ids])
     return out
+
+
+def _strip(k: str, *prefixes: str) -> str:
+    for p in prefixes:
+        if k.startswith(p):
+            return k[len(p):]
+    return k
+
+
+def _convert_opt(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    parts: Dict[Tuple[str, str], Dict[str, torch.Tensor]] = {}
+    for k, v in hf_sd.items():
+        k = _strip(k, "model.decoder.", "decoder.")
+        m = re.match(r"layers\.(\d+)\.(.*)", k)
+        if m:
+            pre, rest = f"model.layers.{m.group(1)}.", m.group(2)
+            mm = re.match(r"self_attn\.([qkv])_proj\.(weight|bias)", rest)
+            if mm:
+                parts.setdefault((pre, mm.group(2)), {})[mm.group(1)] = v
+                continue
+            for a, b in {"self_attn.out_proj.": "self_attn.o_proj.", "self_attn_layer_norm.": "input_layernorm.",
+                         "final_layer_norm.": "post_attention_layernorm.", "fc1.": "mlp.up_proj.",
+                         "fc2.": "mlp.down_proj."}.items():
+                if rest.startswith(a):
+                    out[pre + b + rest[len(a):]] = v
+                    break
+        elif k == "embed_tokens.weight":
+            out["model.embed_tokens.weight"] = v
+        elif k == "embed_positions.weight":
+            out["model.embed_positions.weight"] = v[2:]          # OPT reserves two offset rows
+        elif k.startswith("final_layer_norm."):
+            out["model.norm." + k[len("final_layer_norm."):]] = v
+        elif k == "lm_head.weight":
+            out["lm_head.weight"] = v
+    for (pre, kind), p in parts.items():
+        out[f"{pre}self_attn.qkv_proj.{kind}"] = torch.cat([p["q"], p["k"], p["v"]], 0)
+    return out
+
+
+def _convert_bloom(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    H, D = cfg.num_attention_heads, cfg.head_dim
+    for k, v in hf_sd.items():
+        k = _strip(k, "transformer.")
+        m = re.match(r"h\.(\d+)\.(.*)", k)
+        if m:
+            pre, rest = f"model.layers.{m.group(1)}.", m.group(2)
+            if rest.startswith("self_attention.query_key_value."):
+                # BLOOM interleaves per head: rows are [head, (q, k, v), head_dim] -> ours is [q heads | k heads | v heads]
+                kind = rest.rsplit(".", 1)[1]
+                t = v.reshape(H, 3, D, *v.shape[1:]).transpose(0, 1).reshape(3 * H * D, *v.shape[1:])
+                out[pre + "self_attn.qkv_proj." + kind] = t.contiguous()
+                continue
+            for a, b in {"self_attention.dense.": "self_attn.o_proj.", "mlp.dense_h_to_4h.": "mlp.up_proj.",
+                         "mlp.dense_4h_to_h.": "mlp.down_proj.", "input_layernorm.": "input_layernorm.",
+                         "post_attention_layernorm.": "post_attention_layernorm."}.items():
+                if rest.startswith(a):
+                    out[pre + b + rest[len(a):]] = v
+                    break
+        elif k == "word_embeddings.weight":
+            out["model.embed_tokens.weight"] = v
+        elif k.startswith("word_embeddings_layernorm."):
+            out["model.embed_layernorm." + k.rsplit(".", 1)[1]] = v
+        elif k.startswith("ln_f."):
+            out["model.norm." + k[5:]] = v
+        elif k == "lm_head.weight":
+            out["lm_head.weight"] = v
+    return out
+
+
+def _convert_falcon(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in hf_sd.items():
+        k = _strip(k, "transformer.")
+        m = re.match(r"h\.(\d+)\.(.*)", k)
+        if m:
+            pre, rest = f"model.layers.{m.group(1)}.", m.group(2)
+            if rest.startswith("self_attention.query_key_value.") and cfg.num_key_value_heads != 1:
+                # multi-head falcon (rw-1b style) interleaves like BLOOM
+                H, D = cfg.num_attention_heads, cfg.head_dim
+                v = v.reshape(H, 3, D, *v.shape[1:]).transpose(0, 1).reshape(3 * H * D, *v.shape[1:]).contiguous()
+            for a, b in {"self_attention.query_key_value.": "self_attn.qkv_proj.",
+                         "self_attention.dense.": "self_attn.o_proj.", "mlp.dense_h_to_4h.": "mlp.up_proj.",
+                         "mlp.dense_4h_to_h.": "mlp.down_proj.", "input_layernorm.": "input_layernorm."}.items():
+                if rest.startswith(a):
+                    out[pre + b + rest[len(a):]] = v
+                    break
+        elif k == "word_embeddings.weight":
+            out["model.embed_tokens.weight"] = v
+        elif k.startswith("ln_f."):
+            out["model.norm." + k[5:]] = v
+        elif k == "lm_head.weight":
+            out["lm_head.weight"] = v
+    return out
+
+
+def _convert_bert(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    parts: Dict[Tuple[str, str], Dict[str, torch.Tensor]] = {}
+    emb = {"embeddings.word_embeddings.weight": "model.embed_tokens.weight",
+           "embeddings.position_embeddings.weight": "model.embed_positions.weight",
+           "embeddings.token_type_embeddings.weight": "model.embed_token_types.weight",
+           "embeddings.LayerNorm.weight": "model.embed_layernorm.weight",
+           "embeddings.LayerNorm.bias": "model.embed_layernorm.bias"}
+    for k, v in hf_sd.items():
+        k = _strip(k, "bert.")
+        if k in emb:
+            out[emb[k]] = v
+            continue
+        m = re.match(r"encoder\.layer\.(\d+)\.(.*)", k)
+        if not m:
+            continue
+        pre, rest = f"model.layers.{m.group(1)}.", m.group(2)
+        mm = re.match(r"attention\.self\.(query|key|value)\.(weight|bias)", rest)
+        if mm:
+            parts.setdefault((pre, mm.group(2)), {})[mm.group(1)[0]] = v
+            continue
+        for a, b in {"attention.output.dense.": "self_attn.o_proj.", "attention.output.LayerNorm.": "input_layernorm.",
+                     "intermediate.dense.": "mlp.up_proj.", "output.dense.": "mlp.down_proj.",
+                     "output.LayerNorm.": "post_attention_layernorm."}.items():
+            if rest.startswith(a):
+                out[pre + b + rest[len(a):]] = v
+                break
+    for (pre, kind), p in parts.items():
+        out[f"{pre}self_attn.qkv_proj.{kind}"] = torch.cat([p["q"], p["k"], p["v"]], 0)
+    return out
+
+
+_FAMILY_CONVERTERS = {"opt": _convert_opt, "bloom": _convert_bloom, "falcon": _convert_falcon, "bert": _convert_bert}
 
 
 def to_hf_state_dict(model, cfg: Optional[ModelConfig] = None) -> Dict[str, torch.Tensor]:
