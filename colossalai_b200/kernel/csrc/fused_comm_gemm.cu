@@ -77,6 +77,7 @@ struct CommParams {
   uint32_t* tile_counter;                // local per-tile epilogue-warp arrival counters [m_blocks * n_blocks]
   uint32_t* reduce_ticket;               // local work-queue head of the tile-granular reduction
   uint32_t* rs_progress;                 // local per-slice progress words ((epoch << 5) | steps accumulated)
+  int rs_stream;                         // 1: uniform interleaved tile order + streamed in-switch reduction (below)
 };
 
 struct GemmParams {
@@ -406,6 +407,79 @@ SM100_DEVICE void rs_reduce_tiles(const GemmParams& p, const CommParams& c, uint
   }
 }
 
+// GEMM+RS, CTA-pair kernel, "stream" variant (CB200_RS_STREAM=1, needs the multicast mapping).
+// EVERY rank walks the output tiles in the same interleaved order - tile t belongs to chunk t % world and is the
+// (t / world)-th tile of that chunk - so the partials of tile j of chunk c complete on all ranks at about the same
+// time, and the owner of chunk c can reduce that tile INSIDE THE SWITCH (`multimem.ld_reduce`, fp32 accumulate) while
+// all ranks are already computing tile j+1.  The reduction streams through the whole GEMM instead of leaving the
+// owner's own partial for last (the problem of a rotated order), each output byte crosses NVLink once as a reduced
+// value, and only the last round of tiles is exposed.
+SM100_DEVICE void tile_coords_stream(int tile, int n_blocks, int pair_blocks_per_chunk, int world, int& m_blk,
+                                     int& n_blk) {
+  const int chunk = tile % world;
+  const int j = tile / world;
+  n_blk = j / pair_blocks_per_chunk;                 // consecutive tiles of a chunk share the B columns (L2 reuse)
+  m_blk = chunk * pair_blocks_per_chunk + (j - n_blk * pair_blocks_per_chunk);
+}
+
+SM100_DEVICE void rs_reduce_tiles_stream(const GemmParams& p, const CommParams& c, uint32_t* my_flags, int lane,
+                                         int n_blocks, int pair_blocks_per_chunk, int total_warps) {
+  constexpr int SUB = 8;                                        // 32-row slices per 256-row tile
+  const int tiles_per_chunk = pair_blocks_per_chunk * n_blocks;
+  const int n_units = tiles_per_chunk * SUB;
+  const uint32_t* my_tile_flags = c.peer_tile_flags[c.rank];
+  const size_t ldc_vec = p.ldc / 8;
+  const size_t ldo_vec = c.ld_out / 8;
+  const uint4* mc = reinterpret_cast<const uint4*>(c.mc_part);
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = (int)atomicAdd(c.reduce_ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= n_units) break;
+    const int j = t / SUB, sub = t - j * SUB;
+    const int n_blk = j / pair_blocks_per_chunk;
+    const int mb = j - n_blk * pair_blocks_per_chunk;             // row block inside my chunk
+    const int slot = mb * n_blocks + n_blk;
+    if (lane < c.world)                                           // one lane per writer rank polls its (local) flag
+      wait_epoch<true>(my_tile_flags + (size_t)lane * c.tile_flag_stride + slot, c.epoch);
+    __syncwarp();
+    const int col0 = n_blk * 256;
+    const int cols = min(256, p.N - col0);
+    const int vec_per_row = cols / 8;
+    const int out_row0 = mb * 256 + sub * 32;                     // row inside my chunk == row of `out`
+    const int row0 = c.rank * c.rows_per_chunk + out_row0;        // row inside the [T, N] partial buffers
+    const int rows = max(0, min(32, c.rows_per_chunk - out_row0));
+    const int nvec = rows * vec_per_row;
+    constexpr int RU = 8;                                         // 8 switch reductions in flight per lane
+    for (int i0 = lane; i0 < nvec; i0 += RU * 32) {
+      uint4 v[RU];
+      size_t doff[RU];
+#pragma unroll
+      for (int q = 0; q < RU; ++q) {
+        const int i = i0 + q * 32;
+        doff[q] = (size_t)-1;
+        if (i >= nvec) continue;
+        const int r = i / vec_per_row, cv = i - r * vec_per_row;
+        doff[q] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+        v[q] = multimem_ld_reduce_bf16x8(mc + (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv);
+      }
+#pragma unroll
+      for (int q = 0; q < RU; ++q)
+        if (doff[q] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[q]] = v[q];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
+    if (done == (uint32_t)total_warps) {
+      my_flags[SLOT_LOCAL + 1] = 0;
+      *c.reduce_ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
 // MODE 0: all-gather + GEMM.  MODE 1: GEMM + reduce-scatter.
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -661,6 +735,7 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const bool stream = MODE == 1 && c.rs_stream != 0;
   const int m_rot = MODE == 0 ? c.rank * pair_blocks_per_chunk : ((c.rank + 1) % c.world) * pair_blocks_per_chunk;
 
   if (warp == 0) {
@@ -668,7 +743,8 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint32_t phase = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
-      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      if (stream) tile_coords_stream(tile, n_blocks, pair_blocks_per_chunk, c.world, m_blk, n_blk);
+      else tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
       const int m0 = m_blk * PAIR_M + (int)cta_rank * 128;
       const int n0 = n_blk * PAIR_N + (int)cta_rank * 128;
       if (MODE == 0) {
@@ -752,7 +828,8 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint32_t acc_phase = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
-      tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
+      if (stream) tile_coords_stream(tile, n_blocks, pair_blocks_per_chunk, c.world, m_blk, n_blk);
+      else tile_coords_rot(tile, m_blocks, n_blocks, m_rot, m_blk, n_blk);
       const int row = m_blk * PAIR_M + (int)cta_rank * 128 + quarter * 32 + lane;
       const int n0 = n_blk * PAIR_N;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -796,8 +873,10 @@ fused_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   }
-  if (MODE == 1)   // warps 6..7 arrive here at once, the GEMM roles when their tiles are done
-    rs_reduce_tiles(p, c, my_flags, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot, (int)gridDim.x * 8);
+  if (MODE == 1) {   // warps 6..7 arrive here at once, the GEMM roles when their tiles are done
+    if (stream) rs_reduce_tiles_stream(p, c, my_flags, lane, n_blocks, pair_blocks_per_chunk, (int)gridDim.x * 8);
+    else rs_reduce_tiles(p, c, my_flags, lane, m_blocks, n_blocks, pair_blocks_per_chunk, m_rot, (int)gridDim.x * 8);
+  }
   tc_fence_before();
   cluster_sync();
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
@@ -1018,6 +1097,13 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
     c.tile_counter = tile_counter;
     c.reduce_ticket = tile_counter + (tile_counter_len - 1);
     c.rs_progress = rs_progress;
+    // CB200_RS_STREAM=1: uniform tile order + streamed in-switch reduction (bf16 partials, multicast mapping needed)
+    static int rs_stream = -1;
+    if (rs_stream < 0) {
+      const char* e = getenv("CB200_RS_STREAM");
+      rs_stream = e ? atoi(e) : 0;
+    }
+    c.rs_stream = (rs_stream && mc_part != nullptr && in_dtype == CB_BF16 && N % 256 == 0) ? 1 : 0;
     return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
   }
   if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
