@@ -1,15 +1,103 @@
-"""ctypes face of the sm_100a flash-attention kernels (kernel/csrc/flash_attn_tcgen05.cu).  Filled in once the
-kernel lands; until then `supported()` is False and `ops.attention` uses SDPA."""
+"""ctypes face of the sm_100a flash-attention forward kernel (`kernel/csrc/flash_attn_tcgen05.cu`).
+
+The kernel has been compiled and reviewed but not yet executed on hardware, so it is OFF unless
+`CB200_FLASH_NATIVE=1`; with the flag on, `ops.attention` and the ring-attention block functions route equal-length
+bf16 / fp16 batches (head_dim 64 / 128, sequence length a multiple of 128) through it.  The backward pass reuses the
+library flash backward (it only needs q, k, v, out and the log-sum-exp we return).
+"""
 from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional, Tuple
 
 import torch
 
-_READY = False
+from ..kernel import loader
+from ._dtypes import code
+
+_ENABLED = os.environ.get("CB200_FLASH_NATIVE", "0") == "1"
+_lib = None
+
+
+def _get_lib():
+    global _lib
+    if _lib is None:
+        _lib = loader.load("cb200_attn")
+    return _lib
+
+
+def enable(flag: bool = True) -> None:
+    global _ENABLED
+    _ENABLED = flag
+
+
+def _tensor_ok(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dim() == 3 and t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous() \
+        and t.data_ptr() % 16 == 0
 
 
 def supported(q, k, v, cu_seqlens_q) -> bool:
-    return _READY
+    if not _ENABLED or cu_seqlens_q is not None or not torch.cuda.is_available():
+        return False
+    if not (_tensor_ok(q) and _tensor_ok(k) and _tensor_ok(v)) or torch.cuda.get_device_capability()[0] != 10:
+        return False
+    D = q.shape[-1]
+    return D in (64, 128) and k.shape[-1] == D and v.shape[-1] == D and q.shape[1] % k.shape[1] == 0 \
+        and k.shape[1] == v.shape[1] and q.dtype == k.dtype == v.dtype
 
 
-def flash_attention(q, k, v, **kw):  # pragma: no cover
-    raise NotImplementedError
+def shapes_ok(q, k, batch: int, causal: bool) -> bool:
+    Sq, Sk = q.shape[0] // batch, k.shape[0] // batch
+    return q.shape[0] % batch == 0 and k.shape[0] % batch == 0 and Sq % 128 == 0 and Sk % 128 == 0 \
+        and (not causal or Sq == Sk)
+
+
+def flash_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, causal: bool,
+              scale: Optional[float]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """q [B*Sq, Hq, D], k / v [B*Sk, Hkv, D] -> (out [B*Sq, Hq, D], lse [B*Sq, Hq] fp32)."""
+    T, Hq, D = q.shape
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    out = torch.empty_like(q)
+    lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
+    rc = _get_lib().cb_flash_attn_fwd(loader.ptr(q), loader.ptr(k), loader.ptr(v), loader.ptr(out), loader.ptr(lse),
+                                      batch, T // batch, k.shape[0] // batch, Hq, k.shape[1], D, int(causal),
+                                      ctypes.c_float(scale), code(q.dtype), loader.stream_ptr())
+    loader.check(rc, "flash_attn_fwd")
+    loader.launch_counter.add("flash_attn_fwd")
+    return out, lse
+
+
+class _FlashFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, batch, causal, scale):
+        out, lse = flash_fwd(q, k, v, batch, causal, scale)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.batch, ctx.causal, ctx.scale = batch, causal, scale
+        return out, lse
+
+    @staticmethod
+    def backward(ctx, dout, dlse):
+        from ..shardformer.layer.attn import _block_bwd
+
+        q, k, v, out, lse = ctx.saved_tensors
+        scale = ctx.scale if ctx.scale is not None else 1.0 / math.sqrt(q.shape[-1])
+        dq, dk, dv = _block_bwd(dout.contiguous(), q, k, v, out, lse, ctx.batch, ctx.causal, scale)
+        return dq, dk, dv, None, None, None
+
+
+def flash_attention_with_lse(q, k, v, batch: int = 1, causal: bool = True, scale: Optional[float] = None):
+    if not shapes_ok(q, k, batch, causal):
+        from .attention import attention_with_lse_ref
+
+        return attention_with_lse_ref(q, k, v, batch=batch, causal=causal, scale=scale)
+    return _FlashFn.apply(q, k, v, batch, causal, scale)
+
+
+def flash_attention(q, k, v, batch: int = 1, causal: bool = True, scale: Optional[float] = None, **unused):
+    if not shapes_ok(q, k, batch, causal):
+        from .attention import attention_ref
+
+        return attention_ref(q, k, v, batch, causal, scale)
+    return _FlashFn.apply(q, k, v, batch, causal, scale)[0]
