@@ -66,6 +66,7 @@ class ModelConfig:
     attn_dropout: float = 0.0
     hidden_dropout: float = 0.0
     sliding_window: Optional[int] = None
+    lm_head_bias: bool = False        # GPT-J
     norm_head: bool = False           # Baichuan-2 NormHead: L2-normalised LM-head rows
     moe: Optional[MoEConfig] = None
     pad_token_id: Optional[int] = None
@@ -206,7 +207,7 @@ MODEL_ZOO: Dict[str, ModelConfig] = {
     "gptj-6b": ModelConfig(model_type="gptj", vocab_size=50400, hidden_size=4096, intermediate_size=16384,
                            num_hidden_layers=28, num_attention_heads=16, max_position_embeddings=2048,
                            norm_type="layer", hidden_act="gelu_new", glu=False, mlp_bias=True, parallel_block=True,
-                           rope_interleaved=True, partial_rotary_factor=0.25),
+                           rope_interleaved=True, partial_rotary_factor=0.25, lm_head_bias=True),
     "chatglm2-6b": ModelConfig(model_type="chatglm", vocab_size=65024, hidden_size=4096, intermediate_size=13696,
                                num_hidden_layers=28, num_attention_heads=32, num_key_value_heads=2,
                                max_position_embeddings=32768, attention_bias=True, attention_out_bias=False,
@@ -222,7 +223,8 @@ MODEL_ZOO: Dict[str, ModelConfig] = {
                                  pos_type="alibi", norm_head=True),
     "command-r": ModelConfig(model_type="command", vocab_size=256000, hidden_size=8192, intermediate_size=22528,
                              num_hidden_layers=40, num_attention_heads=64, num_key_value_heads=64, norm_type="layer",
-                             parallel_block=True, tie_word_embeddings=True, logit_scale=0.0625, rope_theta=8e6),
+                             parallel_block=True, tie_word_embeddings=True, logit_scale=0.0625, rope_theta=8e6,
+                             rope_interleaved=True),
 }
 
 

@@ -23,7 +23,7 @@ from .config import ModelConfig, MoEConfig
 
 __all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards"]
 
-_LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral", "baichuan")
+_LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral", "baichuan", "command")
 
 
 def config_from_hf(hf: dict) -> ModelConfig:
@@ -67,6 +67,25 @@ def config_from_hf(hf: dict) -> ModelConfig:
                            max_position_embeddings=hf.get("max_position_embeddings", 2048),
                            tie_word_embeddings=hf.get("tie_word_embeddings", True),
                            norm_eps=hf.get("layer_norm_epsilon", 1e-5))
+    if mt == "gptj":
+        return ModelConfig(model_type="gptj", vocab_size=hf["vocab_size"], hidden_size=hf["n_embd"],
+                           intermediate_size=hf.get("n_inner") or 4 * hf["n_embd"], num_hidden_layers=hf["n_layer"],
+                           num_attention_heads=hf["n_head"], max_position_embeddings=hf.get("n_positions", 2048),
+                           norm_type="layer", hidden_act=hf.get("activation_function", "gelu_new"), glu=False,
+                           mlp_bias=True, parallel_block=True, rope_interleaved=True,
+                           partial_rotary_factor=hf["rotary_dim"] / (hf["n_embd"] // hf["n_head"]), lm_head_bias=True,
+                           norm_eps=hf.get("layer_norm_epsilon", 1e-5), tie_word_embeddings=False)
+    if mt == "cohere":
+        assert not hf.get("use_qk_norm", False), "Cohere checkpoints with per-head LayerNorm qk-norm are not mapped"
+        return ModelConfig(model_type="command", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+                           intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
+                           num_attention_heads=hf["num_attention_heads"],
+                           num_key_value_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
+                           max_position_embeddings=hf.get("max_position_embeddings", 8192), norm_type="layer",
+                           parallel_block=True, tie_word_embeddings=hf.get("tie_word_embeddings", True),
+                           logit_scale=hf.get("logit_scale", 0.0625), rope_theta=float(hf.get("rope_theta", 10000.0)),
+                           rope_interleaved=True, norm_eps=hf.get("layer_norm_eps", 1e-5),
+                           attention_bias=hf.get("attention_bias", False))
     if mt == "bert":
         return ModelConfig(model_type="bert", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
                            intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
@@ -305,7 +324,35 @@ def _convert_bert(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str,
     return out
 
 
-_FAMILY_CONVERTERS = {"opt": _convert_opt, "bloom": _convert_bloom, "falcon": _convert_falcon, "bert": _convert_bert}
+def _convert_gptj(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    parts: Dict[str, Dict[str, torch.Tensor]] = {}
+    for k, v in hf_sd.items():
+        k = _strip(k, "transformer.")
+        m = re.match(r"h\.(\d+)\.(.*)", k)
+        if m:
+            pre, rest = f"model.layers.{m.group(1)}.", m.group(2)
+            mm = re.match(r"attn\.([qkv])_proj\.weight", rest)
+            if mm:
+                parts.setdefault(pre, {})[mm.group(1)] = v
+                continue
+            for a, b in {"attn.out_proj.": "self_attn.o_proj.", "ln_1.": "input_layernorm.", "mlp.fc_in.": "mlp.up_proj.",
+                         "mlp.fc_out.": "mlp.down_proj."}.items():
+                if rest.startswith(a):
+                    out[pre + b + rest[len(a):]] = v
+                    break
+        elif k == "wte.weight":
+            out["model.embed_tokens.weight"] = v
+        elif k.startswith("ln_f."):
+            out["model.norm." + k[5:]] = v
+        elif k.startswith("lm_head."):
+            out[k] = v
+    for pre, p in parts.items():
+        out[pre + "self_attn.qkv_proj.weight"] = torch.cat([p["q"], p["k"], p["v"]], 0)
+    return out
+
+
+_FAMILY_CONVERTERS = {"gptj": _convert_gptj, "opt": _convert_opt, "bloom": _convert_bloom, "falcon": _convert_falcon, "bert": _convert_bert}
 
 
 def to_hf_state_dict(model, cfg: Optional[ModelConfig] = None) -> Dict[str, torch.Tensor]:

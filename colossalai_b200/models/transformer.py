@@ -394,7 +394,7 @@ class TransformerLMHeadModel(nn.Module):
         self.cfg = cfg
         self.config = cfg
         self.model = TransformerModel(cfg)
-        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
+        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=cfg.lm_head_bias)
         if cfg.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self.shard_config = None

@@ -189,3 +189,25 @@ def test_vit_t5_whisper_match_transformers():
         ref = hf(input_features=feats, decoder_input_ids=dec).logits
         got = ours(input_features=feats, decoder_input_ids=dec)["logits"]
     torch.testing.assert_close(got, ref, atol=3e-4, rtol=1e-3)
+
+
+def test_more_decoder_families_match_transformers():
+    """mistral / qwen2 (qkv bias) / qwen3 (per-head q/k RMSNorm) / gptj (partial interleaved rotary, parallel block,
+    LM-head bias) / cohere (interleaved rotary, bias-free LayerNorm, parallel block, logit scale)."""
+    torch.manual_seed(0)
+    ids = torch.randint(3, 128, (2, 12))
+    kw = dict(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+              num_key_value_heads=2, max_position_embeddings=64)
+    _logits_match(transformers.MistralForCausalLM(transformers.MistralConfig(**kw)), ids)
+    _logits_match(transformers.Qwen2ForCausalLM(transformers.Qwen2Config(**kw)), ids)
+    _logits_match(transformers.Qwen3ForCausalLM(transformers.Qwen3Config(head_dim=16, **kw)), ids)
+    _logits_match(transformers.GPTJForCausalLM(transformers.GPTJConfig(vocab_size=128, n_embd=64, n_layer=2, n_head=4,
+                                                                       rotary_dim=8, n_positions=64, n_inner=128)), ids)
+    hf = transformers.CohereForCausalLM(transformers.CohereConfig(**kw)).float().eval()
+    cfg = config_from_hf(hf.config.to_dict())
+    ours = build_model(cfg).float().eval()
+    missing, _ = ours.load_state_dict(convert_hf_state_dict(hf.state_dict(), cfg), strict=False)
+    assert all(m.endswith("layernorm.bias") or m in ("model.norm.bias", "lm_head.weight") for m in missing), missing
+    with torch.no_grad():
+        torch.testing.assert_close(ours(input_ids=ids)["logits"].view(2, 12, -1)[..., :128], hf(input_ids=ids).logits,
+                                   atol=1e-3, rtol=1e-3)
