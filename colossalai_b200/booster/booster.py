@@ -72,6 +72,20 @@ class Booster:
               dataloader: Optional[DataLoader] = None, lr_scheduler: Optional[LRScheduler] = None) -> List[Any]:
         from ..interface.pretrained import get_pretrained_path, set_pretrained_path
 
+        # reference-style user code hands over a Hugging Face model instance: convert it to our implementation
+        from ..models.hf_io import from_hf_model, is_hf_model
+
+        if is_hf_model(model):
+            self.logger.info(f"converting {type(model).__name__} (transformers) to the colossalai_b200 model of the "
+                             "same family; rebuild the optimizer over the returned model's parameters", ranks=[0])
+            if optimizer is not None:
+                hf_ids = {id(p) for p in model.parameters()}
+                opt_ids = {id(p) for g in optimizer.param_groups for p in g["params"]}
+                assert not (opt_ids & hf_ids), (
+                    "the optimizer was built over the Hugging Face model's parameters, which are replaced by the "
+                    "conversion: call `colossalai_b200.models.hf_io.from_hf_model(model)` first and build the "
+                    "optimizer over the converted model")
+            model = from_hf_model(model)
         pretrained_path = get_pretrained_path(model)
         # lazily built models: plugins that shard through ShardFormer materialise AFTER sharding (each rank only allocates
         # its slices); every other plugin gets real tensors before it wraps the module

@@ -21,7 +21,8 @@ import torch
 
 from .config import ModelConfig, MoEConfig
 
-__all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards"]
+__all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards",
+           "from_hf_model", "is_hf_model"]
 
 _LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral", "baichuan", "command")
 
@@ -404,3 +405,62 @@ def load_hf_checkpoint(path: str, dtype: torch.dtype = torch.bfloat16, device: s
         raise RuntimeError(f"load_hf_checkpoint: missing={missing[:8]} unexpected={unexpected[:8]}")
     model._pretrained_path = path
     return model.to(device)
+
+
+def is_hf_model(model) -> bool:
+    """A `transformers.PreTrainedModel` instance (duck-typed: no hard dependency on transformers)."""
+    mod = type(model).__module__ or ""
+    return mod.startswith("transformers.") and hasattr(model, "config") and hasattr(model.config, "to_dict")
+
+
+def from_hf_model(hf_model, dtype: Optional[torch.dtype] = None):
+    """Convert an instantiated Hugging Face model into the equivalent colossalai_b200 model (same weights).
+
+    This is what lets reference-style user code (`model = LlamaForCausalLM.from_pretrained(...)`;
+    `booster.boost(model, ...)`) run unchanged: `Booster.boost` calls this for HF instances.  Decoder families go
+    through `convert_hf_state_dict`; ViT / T5 / Whisper through `hf_io_encdec`."""
+    hf_cfg = hf_model.config.to_dict()
+    mt = hf_cfg.get("model_type", "")
+    dtype = dtype or next(hf_model.parameters()).dtype
+    sd = hf_model.state_dict()
+    if mt in ("vit", "t5", "whisper"):
+        from . import hf_io_encdec as ed
+        from .t5 import T5EncoderModel, T5ForConditionalGeneration, T5Model
+        from .vit import ViTForImageClassification, ViTModel
+        from .whisper import WhisperForConditionalGeneration, WhisperModel
+
+        name = type(hf_model).__name__
+        if mt == "vit":
+            cfg = ed.vit_config_from_hf(hf_cfg)
+            cls = ViTForImageClassification if "Classification" in name else ViTModel
+            if cls is ViTModel:
+                sd = {("vit." + k if not k.startswith("vit.") else k): v for k, v in sd.items()}
+                ours = cls(cfg, add_pooling_layer=any(k.startswith("vit.pooler") for k in sd))
+                conv = {k[len("vit."):]: v for k, v in ed.convert_vit(sd).items()}
+                ours.load_state_dict(conv, strict=False)
+                return ours.to(dtype)
+            ours = cls(cfg)
+        elif mt == "t5":
+            cfg = ed.t5_config_from_hf(hf_cfg)
+            cls = T5ForConditionalGeneration if "ConditionalGeneration" in name else (
+                T5EncoderModel if "Encoder" in name else T5Model)
+            ours = cls(cfg)
+        else:
+            cfg = ed.whisper_config_from_hf(hf_cfg)
+            if "ConditionalGeneration" in name:
+                ours = WhisperForConditionalGeneration(cfg)
+            else:
+                ours = WhisperModel(cfg)
+                sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in sd.items()}
+        return ed.load_hf_encdec(ours, sd, strict=False).to(dtype)
+    from . import build_model
+
+    cfg = config_from_hf(hf_cfg)
+    ours = build_model(cfg)
+    conv = convert_hf_state_dict(sd, cfg)
+    missing, unexpected = ours.load_state_dict(conv, strict=False)
+    bad = [m for m in missing if not (m == "lm_head.weight" and cfg.tie_word_embeddings) and not m.endswith("norm.bias")
+           and not m.endswith("layernorm.bias")]
+    if bad:
+        raise RuntimeError(f"from_hf_model({type(hf_model).__name__}): unmapped parameters {bad[:6]}")
+    return ours.to(dtype)

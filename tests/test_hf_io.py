@@ -211,3 +211,54 @@ def test_more_decoder_families_match_transformers():
     with torch.no_grad():
         torch.testing.assert_close(ours(input_ids=ids)["logits"].view(2, 12, -1)[..., :128], hf(input_ids=ids).logits,
                                    atol=1e-3, rtol=1e-3)
+
+
+def test_booster_accepts_hf_model_instances():
+    """Reference-style call: hand a transformers model to the Booster; it is converted to our implementation."""
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import LowLevelZeroPlugin
+    from colossalai_b200.models.hf_io import from_hf_model
+    from colossalai_b200.testing import spawn
+
+    torch.manual_seed(0)
+    hf = transformers.LlamaForCausalLM(transformers.LlamaConfig(
+        vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=64)).float().eval()
+    ids = torch.randint(3, 128, (2, 10))
+    ours = from_hf_model(hf)
+    with torch.no_grad():
+        torch.testing.assert_close(ours(input_ids=ids)["logits"].view(2, 10, -1)[..., :128], hf(input_ids=ids).logits,
+                                   atol=2e-4, rtol=1e-3)
+    for name, hf_m, kw in [
+        ("t5", transformers.T5ForConditionalGeneration(transformers.T5Config(
+            vocab_size=128, d_model=64, d_kv=16, d_ff=128, num_layers=1, num_heads=4, decoder_start_token_id=0)),
+         dict(input_ids=ids, decoder_input_ids=ids[:, :4])),
+        ("vit", transformers.ViTModel(transformers.ViTConfig(image_size=32, patch_size=8, hidden_size=64,
+                                                              num_hidden_layers=1, num_attention_heads=4,
+                                                              intermediate_size=128)),
+         dict(pixel_values=torch.randn(2, 3, 32, 32)))]:
+        hf_m = hf_m.float().eval()
+        conv = from_hf_model(hf_m).eval()
+        with torch.no_grad():
+            ref = hf_m(**kw)
+            got = conv(**kw)
+        r = ref.logits if hasattr(ref, "logits") else ref.last_hidden_state
+        g = got["logits"] if "logits" in got else got["last_hidden_state"]
+        torch.testing.assert_close(g, r, atol=3e-4, rtol=1e-3, msg=lambda m: f"{name}: {m}")
+
+    spawn(_hf_booster_worker, 1)
+
+
+def _hf_booster_worker(rank, world_size, port):
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import LowLevelZeroPlugin
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    hf = transformers.LlamaForCausalLM(transformers.LlamaConfig(
+        vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=1, num_attention_heads=4,
+        num_key_value_heads=2, max_position_embeddings=64)).float()
+    model, *_ = Booster(plugin=LowLevelZeroPlugin(stage=1, precision="fp32")).boost(hf)
+    inner = model.unwrap() if hasattr(model, "unwrap") else model
+    assert type(inner).__module__.startswith("colossalai_b200.models")
+    torch.distributed.destroy_process_group()
