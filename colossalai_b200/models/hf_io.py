@@ -22,7 +22,7 @@ import torch
 from .config import ModelConfig, MoEConfig
 
 __all__ = ["config_from_hf", "convert_hf_state_dict", "load_hf_checkpoint", "to_hf_state_dict", "iter_hf_shards",
-           "from_hf_model", "is_hf_model"]
+           "from_hf_model", "is_hf_model", "save_hf_checkpoint", "hf_config_dict"]
 
 _LLAMA_LIKE = ("llama", "mistral", "qwen2", "qwen3", "mixtral", "baichuan", "command")
 
@@ -464,3 +464,89 @@ def from_hf_model(hf_model, dtype: Optional[torch.dtype] = None):
     if bad:
         raise RuntimeError(f"from_hf_model({type(hf_model).__name__}): unmapped parameters {bad[:6]}")
     return ours.to(dtype)
+
+
+def hf_config_dict(cfg: ModelConfig) -> dict:
+    """`config.json` content for the llama-like families (enough for `AutoModelForCausalLM.from_pretrained`)."""
+    assert cfg.model_type in ("llama", "mistral", "qwen2", "qwen3", "mixtral"), cfg.model_type
+    arch = {"llama": "LlamaForCausalLM", "mistral": "MistralForCausalLM", "qwen2": "Qwen2ForCausalLM",
+            "qwen3": "Qwen3ForCausalLM", "mixtral": "MixtralForCausalLM"}[cfg.model_type]
+    d = {"architectures": [arch], "model_type": cfg.model_type, "vocab_size": cfg.vocab_size,
+         "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+         "num_hidden_layers": cfg.num_hidden_layers, "num_attention_heads": cfg.num_attention_heads,
+         "num_key_value_heads": cfg.num_key_value_heads, "head_dim": cfg.head_dim,
+         "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.norm_eps,
+         "rope_theta": cfg.rope_theta, "rope_scaling": cfg.rope_scaling, "hidden_act": cfg.hidden_act,
+         "tie_word_embeddings": cfg.tie_word_embeddings, "attention_bias": cfg.attention_bias,
+         "bos_token_id": cfg.bos_token_id, "eos_token_id": cfg.eos_token_id, "torch_dtype": "bfloat16"}
+    if cfg.sliding_window:
+        d["sliding_window"] = cfg.sliding_window
+    if cfg.moe is not None:
+        d.update(num_local_experts=cfg.moe.num_experts, num_experts_per_tok=cfg.moe.top_k)
+    return d
+
+
+def save_hf_checkpoint(model, path: str, max_shard_bytes: int = 5 * 2**30, safe_serialization: bool = True) -> None:
+    """Write a Hugging Face style directory (`config.json`, `model-0000x-of-0000N.safetensors`, index) from a —
+    possibly tensor-/expert-parallel sharded and wrapped — model: every rank takes part in gathering the shards,
+    rank 0 writes.  `transformers.AutoModelForCausalLM.from_pretrained(path)` loads the result."""
+    import torch.distributed as dist
+
+    from ..interface import ModelWrapper
+    from ..tensor.d_tensor import to_global
+
+    inner = model.unwrap() if isinstance(model, ModelWrapper) else model
+    cfg = inner.cfg
+    full: Dict[str, torch.Tensor] = {}
+    for name, p in inner.named_parameters():
+        t = to_global(p).detach()
+        if name.endswith(("embed_tokens.weight", "lm_head.weight")) and t.shape[0] > cfg.vocab_size:
+            t = t[: cfg.vocab_size]                       # drop the vocab padding added for tensor parallelism
+        full[name] = t.cpu()
+    if cfg.tie_word_embeddings and "lm_head.weight" not in full:
+        full["lm_head.weight"] = full["model.embed_tokens.weight"]
+    if dist.is_initialized() and dist.get_rank() != 0:
+        dist.barrier()
+        return
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.cfg = cfg
+    h.state_dict = lambda: full
+    sd = to_hf_state_dict(h, cfg)
+    if cfg.tie_word_embeddings:
+        sd.pop("lm_head.weight", None)
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        hf_cfg = hf_config_dict(cfg)
+        hf_cfg["torch_dtype"] = str(next(iter(sd.values())).dtype).replace("torch.", "")
+        json.dump(hf_cfg, f, indent=2)
+    shards, cur, size = [], {}, 0
+    for k, v in sd.items():
+        nb = v.numel() * v.element_size()
+        if cur and size + nb > max_shard_bytes:
+            shards.append(cur)
+            cur, size = {}, 0
+        cur[k] = v.contiguous()
+        size += nb
+    shards.append(cur)
+    weight_map = {}
+    ext = "safetensors" if safe_serialization else "bin"
+    for i, sh in enumerate(shards):
+        fname = f"model.{ext}" if len(shards) == 1 else f"model-{i + 1:05d}-of-{len(shards):05d}.{ext}"
+        if safe_serialization:
+            from safetensors.torch import save_file
+
+            save_file(sh, os.path.join(path, fname), metadata={"format": "pt"})
+        else:
+            torch.save(sh, os.path.join(path, fname))
+        weight_map.update({k: fname for k in sh})
+    if len(shards) > 1:
+        idx = "model.safetensors.index.json" if safe_serialization else "pytorch_model.bin.index.json"
+        with open(os.path.join(path, idx), "w") as f:
+            json.dump({"metadata": {"total_size": sum(v.numel() * v.element_size() for v in sd.values())},
+                       "weight_map": weight_map}, f, indent=2)
+    if dist.is_initialized():
+        dist.barrier()

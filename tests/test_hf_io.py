@@ -262,3 +262,36 @@ def _hf_booster_worker(rank, world_size, port):
     inner = model.unwrap() if hasattr(model, "unwrap") else model
     assert type(inner).__module__.startswith("colossalai_b200.models")
     torch.distributed.destroy_process_group()
+
+
+def _export_worker(rank, world_size, port, out_dir):
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.models import get_config
+    from colossalai_b200.models.hf_io import save_hf_checkpoint
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    torch.manual_seed(0)
+    model = build_model(get_config("llama-tiny", vocab_size=100))          # 100 -> padded to 128 under TP
+    model, *_ = Booster(plugin=HybridParallelPlugin(tp_size=2, pp_size=1, precision="fp32",
+                                                    parallel_output=False)).boost(model)
+    ids = torch.randint(0, 100, (2, 8), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = model(input_ids=ids)["logits"].view(2, 8, -1)[..., :100]
+    save_hf_checkpoint(model, out_dir, max_shard_bytes=200_000)
+    if rank == 0:
+        hf = transformers.AutoModelForCausalLM.from_pretrained(out_dir).float().eval()
+        with torch.no_grad():
+            torch.testing.assert_close(hf(input_ids=ids).logits, ref, atol=3e-4, rtol=1e-3)
+        assert os.path.exists(os.path.join(out_dir, "model.safetensors.index.json"))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.dist
+def test_export_tp_sharded_model_to_hf_directory():
+    from colossalai_b200.testing import spawn
+
+    with tempfile.TemporaryDirectory() as tmp:
+        spawn(_export_worker, 2, out_dir=tmp)
