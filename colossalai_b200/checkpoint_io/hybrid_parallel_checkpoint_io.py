@@ -362,6 +362,21 @@ class HybridParallelCheckpointIO(GeneralCheckpointIO):
             for _, st in sd.items():
                 all_states[st.get("__name__")] = st
         self._load_optim_states(optimizer, model, all_states)
+        pg_file = ckpt_index.get_param_group_filename()
+        if pg_file is not None and os.path.exists(pg_file):
+            self._load_param_group_hparams(optim, torch.load(pg_file, weights_only=False))
+
+    @staticmethod
+    def _load_param_group_hparams(optim, saved_groups) -> None:
+        """Restore the per-group hyper-parameters and counters (lr, betas, weight decay, the fused optimizers' shared
+        `step`) — everything of a param group except the parameter list, which belongs to the current layout.  The
+        number of groups is layout independent (PP stages and TP ranks all build the same groups)."""
+        if isinstance(saved_groups, dict):
+            saved_groups = saved_groups.get("param_groups", saved_groups)
+        for g, sg in zip(optim.param_groups, saved_groups):
+            for k, v in sg.items():
+                if k != "params":
+                    g[k] = v
 
     def _load_optim_states(self, optimizer, model, by_name: Dict[str, Dict]) -> None:
         optim = optimizer.unwrap()
@@ -409,3 +424,5 @@ class HybridParallelCheckpointIO(GeneralCheckpointIO):
         sd = load_state_dict(checkpoint)
         by_name = {st.get("__name__"): st for st in sd["state"].values()}
         self._load_optim_states(optimizer, optimizer.model.unwrap(), by_name)
+        if "param_groups" in sd:
+            self._load_param_group_hparams(optimizer.unwrap(), sd["param_groups"])
