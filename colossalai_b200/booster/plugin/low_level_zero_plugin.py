@@ -44,6 +44,13 @@ class LowLevelZeroModel(ModelWrapper, AMPModelMixin):
 
             convert_linear_to_fp8(self.module)
 
+    def update_master_params(self) -> None:
+        """Called by the checkpoint IO after weights were loaded: the optimizer's fp32 master shards follow."""
+        opt = getattr(self, "_zero_optimizer", None)
+        opt = opt() if opt is not None else None
+        if opt is not None:
+            opt.update_master_params(self.module)
+
     def forward(self, *args, **kwargs):
         if self.convert_fn is not None:
             args = _tree_map(self.convert_fn, args)
@@ -114,6 +121,8 @@ class LowLevelZeroCheckpointIO(GeneralCheckpointIO):
                            load_sub_module=True, low_cpu_mem_mode=True, num_threads=1):
         super().load_sharded_model(model, checkpoint_index_file, strict, use_safetensors, load_sub_module,
                                    low_cpu_mem_mode, num_threads)
+        if hasattr(model, "update_master_params"):      # the fp32 master shards must follow the loaded weights
+            model.update_master_params()
 
     def save_unsharded_model(self, model, checkpoint, gather_dtensor, use_safetensors, use_async=False):
         if dist.get_rank() == 0:
@@ -200,6 +209,9 @@ class LowLevelZeroPlugin(DPPluginBase):
             optimizer = LowLevelZeroOptimizer(optimizer, **self.zero_optim_kwargs, verbose=self.verbose,
                                               dp_process_group=self.dp_group, extra_dp_group=self.extra_dp_group)
             optimizer.model = model
+            import weakref
+
+            model._zero_optimizer = weakref.ref(optimizer)
         return model, optimizer, criterion, dataloader, lr_scheduler
 
     def control_checkpoint_io(self) -> bool:

@@ -214,51 +214,61 @@ class GeminiOptimizer(OptimizerWrapper):
         self.module.backward_by_grad(tensor, grad)
 
     # ------------------------------------------------------------------ checkpoint
-    def _gather_fake_state(self, fp: nn.Parameter, p: nn.Parameter, c16: Chunk, s: int, e: int) -> Dict:
-        """Full (un-sharded) optimizer state of one original parameter, gathered over the zero group."""
-        st = self.optim.state.get(fp, {})
-        info = c16.tensors_info[p]
-        out: Dict = {}
-        dev = get_accelerator().get_current_device()
-        ws = c16.pg_size
-        for k, v in st.items():
-            if torch.is_tensor(v) and v.dim() > 0 and v.numel() == e - s:
-                full = torch.zeros(info.end - info.offset, dtype=v.dtype, device=dev)
-                full[s - info.offset:e - info.offset] = v.to(dev)
-                if ws > 1 and not c16.keep_gathered:
-                    dist.all_reduce(full, group=c16.torch_pg)
-                out[k] = full.view(info.shape).cpu()
-            else:
-                out[k] = v.cpu() if torch.is_tensor(v) else v
-        return out
+    def _agreed_state_layout(self):
+        """(tensor keys -> dtype, scalar template) agreed over the zero group.  A rank whose chunk shards hold only
+        padding (tiny models, uneven tails) has no optimizer state at all, so the key list cannot be read locally —
+        every rank must still join the same sequence of collectives."""
+        tkeys: Dict[str, torch.dtype] = {}
+        scalars: Dict = {}
+        for st in self.optim.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v) and v.dim() > 0:
+                    tkeys.setdefault(k, v.dtype)
+                elif k not in scalars:
+                    scalars[k] = v.cpu() if torch.is_tensor(v) else v
+        # (`chunk16_set` only lists chunks this rank owns state for - ask the chunk manager, every rank has every chunk)
+        params = self.module.fp16_params
+        pg = self.chunk_manager.get_chunk(params[0]).torch_pg if params else None
+        ws = dist.get_world_size(pg) if dist.is_initialized() else 1       # pg None = the default (world) group
+        if ws > 1:
+            box = [None] * ws
+            dist.all_gather_object(box, (tkeys, scalars), group=pg)
+            merged_t: Dict[str, torch.dtype] = {}
+            merged_s: Dict = {}
+            for t, sc in box:
+                for k, v in t.items():
+                    merged_t.setdefault(k, v)
+                for k, v in sc.items():
+                    merged_s.setdefault(k, v)
+            tkeys, scalars = merged_t, merged_s
+        return dict(sorted(tkeys.items())), scalars
 
     def state_dict(self, only_rank_0: bool = True) -> dict:
-        """Gathered state keyed by the ORIGINAL parameter order.  Collective over the zero group."""
+        """Gathered state keyed by the ORIGINAL parameter order.  Collective over the zero group: for every parameter
+        and every tensor state key each rank contributes its slice (or zeros) to one all-reduce."""
         order = {id(p): i for i, p in enumerate(self.module.fp16_params)}
         by_param = {id(p): (fp, p, c, s, e) for fp, p, c, s, e in self._fake_info}
+        tkeys, scalars = self._agreed_state_layout()
         state: Dict[int, Dict] = {}
         dev = get_accelerator().get_current_device()
         for p in self.module.fp16_params:
             c16 = self.chunk_manager.get_chunk(p)
             info = c16.tensors_info[p]
             ent = by_param.get(id(p))
-            keys = None
-            if ent is not None:
-                keys = self._gather_fake_state(*ent)
-            else:
-                # this rank holds no slice: still take part in the collectives with zeros
-                some = next(iter(by_param.values()), None)
-                tmpl = self.optim.state.get(some[0], {}) if some else {}
-                keys = {}
-                for k, v in tmpl.items():
-                    if torch.is_tensor(v) and v.dim() > 0:
-                        full = torch.zeros(info.end - info.offset, dtype=v.dtype, device=dev)
-                        if c16.pg_size > 1 and not c16.keep_gathered:
-                            dist.all_reduce(full, group=c16.torch_pg)
-                        keys[k] = full.view(info.shape).cpu()
-                    else:
-                        keys[k] = v.cpu() if torch.is_tensor(v) else v
-            state[order[id(p)]] = keys
+            st = self.optim.state.get(ent[0], {}) if ent is not None else {}
+            out: Dict = {}
+            for k, dt in tkeys.items():
+                full = torch.zeros(info.end - info.offset, dtype=dt, device=dev)
+                if ent is not None and k in st:
+                    s, e = ent[3], ent[4]
+                    full[s - info.offset:e - info.offset] = st[k].to(dev).reshape(-1)
+                if c16.pg_size > 1 and not c16.keep_gathered:
+                    dist.all_reduce(full, group=c16.torch_pg)
+                out[k] = full.view(info.shape).cpu()
+            for k, v in scalars.items():
+                own = st.get(k, v)
+                out[k] = own.cpu() if torch.is_tensor(own) else own
+            state[order[id(p)]] = out
         groups = []
         for g in self.optim.param_groups:
             groups.append({**{k: v for k, v in g.items() if k != "params"},

@@ -325,6 +325,15 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             total = n if total is None else total + n
         return total if total is not None else torch.zeros(1)
 
+    @torch.no_grad()
+    def update_master_params(self, model: Optional[nn.Module] = None) -> None:
+        """Refresh the fp32 master shards from the working parameters (after weights were loaded into the model).
+        Parity: reference `LowLevelZeroOptimizer.update_master_params` (low_level_optim.py) called by the checkpoint
+        IO after `load_model`."""
+        for b in self.buckets:
+            if b.master.data.data_ptr() != b.working_shard().data_ptr():
+                b.master.data.copy_(b.working_shard().detach().to(b.master.device).float())
+
     def step(self, closure=None):
         assert closure is None, "closure is not supported by gemini/zero optimizers"
         if self._comm_stream is not None:
