@@ -88,7 +88,8 @@ def main():
     elif args.plugin in ("zero1", "zero2"):
         plugin = LowLevelZeroPlugin(stage=int(args.plugin[-1]), precision=precision, max_norm=1.0)
     elif args.plugin == "gemini":
-        plugin = GeminiPlugin(precision=precision if precision != "fp32" else "bf16", max_norm=1.0)
+        plugin = GeminiPlugin(precision=precision if precision != "fp32" else "bf16", max_norm=1.0,
+                              **(dict(min_chunk_size_m=1, search_range_m=1) if dev.type == "cpu" else {}))
     else:
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, precision=precision, max_norm=1.0,
                                       enable_sequence_parallelism=args.sp_mode is not None,
