@@ -183,8 +183,15 @@ def load_lora_adapters(model: nn.Module, checkpoint: str, prefix: str = "base_mo
         getattr(m, which).weight.data.copy_(v.to(getattr(m, which).weight.dtype))
 
 
-def merge_lora(model: nn.Module) -> nn.Module:
+def merge_lora(model: nn.Module, unload: bool = False) -> nn.Module:
+    """Fold every adapter into its base weight; with `unload` the `LoraLinear` wrappers are replaced by the plain
+    (now merged) base layers — peft's `merge_and_unload`."""
     for m in model.modules():
         if isinstance(m, LoraLinear):
             m.merge()
+    if unload:
+        for parent in list(model.modules()):
+            for name, child in list(parent.named_children()):
+                if isinstance(child, LoraLinear):
+                    setattr(parent, name, child.base_layer)
     return model
