@@ -9,6 +9,9 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import threading
+from contextlib import contextmanager
+
 import torch
 import torch.distributed as dist
 from torch.distributed import ProcessGroup
@@ -31,10 +34,38 @@ def group_rank(group: Optional[ProcessGroup]) -> int:
     return dist.get_rank(group)
 
 
+# ---- fp8 communication switch (reference: the `fp8_communication` flag threaded through every parallel layer).
+# Layers enter `fp8_communication(True)` around their forward; the autograd functions remember the flag for backward.
+_FP8_STATE = threading.local()
+
+
+def fp8_enabled() -> bool:
+    return getattr(_FP8_STATE, "on", False)
+
+
+@contextmanager
+def fp8_communication(enabled: bool = True):
+    prev = fp8_enabled()
+    _FP8_STATE.on = bool(enabled)
+    try:
+        yield
+    finally:
+        _FP8_STATE.on = prev
+
+
+def _fp8_ok(x: torch.Tensor) -> bool:
+    return fp8_enabled() and x.is_floating_point() and x.dtype in (torch.float16, torch.bfloat16, torch.float32)
+
+
 def all_reduce(x: torch.Tensor, group: Optional[ProcessGroup] = None, op=dist.ReduceOp.SUM,
                async_op: bool = False):
     if group_size(group) == 1:
         return None if async_op else x
+    if _fp8_ok(x) and op == dist.ReduceOp.SUM and not async_op:
+        from ..quantization.fp8 import all_reduce_fp8
+
+        all_reduce_fp8(x, "e4m3", group=group)
+        return x
     work = dist.all_reduce(x, op=op, group=group, async_op=async_op)
     return work if async_op else x
 
@@ -47,7 +78,12 @@ def all_gather(x: torch.Tensor, dim: int = 0, group: Optional[ProcessGroup] = No
     dim = dim % x.dim()
     x = x.contiguous()
     out = torch.empty((ws,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=group)
+    if _fp8_ok(x):
+        from ..quantization.fp8 import all_gather_fp8
+
+        all_gather_fp8(list(out.unbind(0)), x, group=group, fp8_format="e4m3")
+    else:
+        dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=group)
     if dim == 0:
         return out.view((ws * x.shape[0],) + tuple(x.shape[1:]))
     # [ws, d0, ..., ddim, ...] -> [d0, ..., ws*ddim, ...]
@@ -73,7 +109,12 @@ def reduce_scatter(x: torch.Tensor, dim: int = 0, group: Optional[ProcessGroup] 
         out_shape = [x.shape[0] // ws] + list(x.shape[1:])
     x = x.contiguous()
     out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
-    dist.reduce_scatter_tensor(out.view(-1), x.view(-1), group=group)
+    if _fp8_ok(x):
+        from ..quantization.fp8 import reduce_scatter_fp8
+
+        reduce_scatter_fp8(out, list(x.view((ws,) + tuple(out_shape)).unbind(0)), group=group, fp8_format="e5m2")
+    else:
+        dist.reduce_scatter_tensor(out.view(-1), x.view(-1), group=group)
     return out
 
 

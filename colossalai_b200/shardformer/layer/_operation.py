@@ -127,6 +127,7 @@ class _LinearWithAsyncComm(torch.autograd.Function):
     def forward(ctx, x, weight, bias, group, async_grad_allreduce, use_zbv):
         ctx.save_for_backward(x, weight)
         ctx.use_bias, ctx.group, ctx.async_ar, ctx.use_zbv = bias is not None, group, async_grad_allreduce, use_zbv
+        ctx.fp8 = comm.fp8_enabled()
         return ops.linear_forward(x, weight, bias)
 
     @staticmethod
@@ -136,7 +137,10 @@ class _LinearWithAsyncComm(torch.autograd.Function):
         dx = ops.matmul_nn(dy2, weight).view(x.shape)
         handle = None
         if comm.group_size(ctx.group) > 1:
-            if ctx.async_ar:
+            if ctx.fp8:                                  # fp8 payloads: quantise -> exchange -> reduce in fp32
+                with comm.fp8_communication(True):
+                    dx = comm.all_reduce(dx.contiguous(), ctx.group)
+            elif ctx.async_ar:
                 handle = dist.all_reduce(dx, group=ctx.group, async_op=True)
             else:
                 dist.all_reduce(dx, group=ctx.group)
@@ -182,7 +186,8 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
     def forward(ctx, x_local, weight, bias, group, dim, ring, use_zbv):
         ctx.group, ctx.dim, ctx.ring, ctx.use_zbv = group, dim, ring, use_zbv
         ctx.use_bias = bias is not None
-        ctx.fused = _use_fused(x_local, group) and dim == 0 and x_local.dim() == 2
+        ctx.fp8 = comm.fp8_enabled()
+        ctx.fused = _use_fused(x_local, group) and dim == 0 and x_local.dim() == 2 and not ctx.fp8
         ctx.saved_gathered = False
         if ctx.fused:
             from ...parallel import fused
@@ -230,6 +235,13 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
             db = dy2.sum(0) if ctx.use_bias else None
             if h_rs is not None:
                 h_rs.wait()
+            return dx_local, dw, db, None, None, None, None
+        if ctx.fp8 and ws > 1:
+            with comm.fp8_communication(True):
+                x_full = comm.all_gather(x_local.contiguous(), dim, group)
+                dx_local = comm.reduce_scatter(ops.matmul_nn(dy2, weight).view(x_full.shape), dim, group)
+            dw = _maybe_defer_wgrad(weight, dy2, x_full.reshape(-1, x_full.shape[-1]), ctx.use_zbv)
+            db = dy2.sum(0) if ctx.use_bias else None
             return dx_local, dw, db, None, None, None, None
         # re-gather X (async) while computing dX
         x_local_c = x_local.contiguous()
@@ -295,7 +307,8 @@ class _LinearReduceScatterFwdGatherBwd(torch.autograd.Function):
     def forward(ctx, x, weight, bias, group, dim, ring, use_zbv):
         ctx.group, ctx.dim, ctx.use_zbv = group, dim, use_zbv
         ctx.use_bias = bias is not None
-        ctx.fused = _use_fused(x, group) and dim == 0 and x.dim() == 2
+        ctx.fp8 = comm.fp8_enabled()
+        ctx.fused = _use_fused(x, group) and dim == 0 and x.dim() == 2 and not ctx.fp8
         ctx.save_for_backward(x, weight)
         if ctx.fused and _fused_rs_profitable(x.shape[1]):
             from ...parallel import fused
@@ -319,7 +332,8 @@ class _LinearReduceScatterFwdGatherBwd(torch.autograd.Function):
 
             dx, dy_full = fused.all_gather_gemm(dy_local.contiguous(), weight, group=ctx.group, transpose_b=False)
         else:
-            dy_full = comm.all_gather(dy_local.contiguous(), ctx.dim, ctx.group)
+            with comm.fp8_communication(ctx.fp8):
+                dy_full = comm.all_gather(dy_local.contiguous(), ctx.dim, ctx.group)
             dx = ops.matmul_nn(dy_full.reshape(-1, dy_full.shape[-1]), weight).view(x.shape)
         dy2 = dy_full.reshape(-1, dy_full.shape[-1])
         dw = _maybe_defer_wgrad(weight, dy2, x.reshape(-1, x.shape[-1]), ctx.use_zbv)
@@ -338,7 +352,7 @@ class _LinearAllReduceFwd(torch.autograd.Function):
     def forward(ctx, x, weight, group, use_zbv):
         ctx.save_for_backward(x, weight)
         ctx.use_zbv = use_zbv
-        if _use_fused(x, group) and x.dim() == 2:
+        if _use_fused(x, group) and x.dim() == 2 and not comm.fp8_enabled():
             from ...parallel import fused
 
             return fused.gemm_all_reduce(x, weight, group)

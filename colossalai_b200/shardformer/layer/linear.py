@@ -145,12 +145,13 @@ class Linear1D_Col(ParallelModule):
     def forward(self, x: Tensor):
         bias = self.bias if not self.skip_bias_add else None
         mode = self.seq_parallel_mode
-        if mode in ("split_gather", "ring"):
-            out = linear_gather_forward_reducescatter_backward(x, self.weight, bias, self.process_group,
-                                                               self.seq_parallel_dim, ring=(mode == "ring"),
-                                                               use_zbv=self.use_zbv)
-        else:
-            out = linear_with_async_comm(x, self.weight, bias, self.process_group, True, self.use_zbv)
+        with comm.fp8_communication(self.fp8_communication):
+            if mode in ("split_gather", "ring"):
+                out = linear_gather_forward_reducescatter_backward(x, self.weight, bias, self.process_group,
+                                                                   self.seq_parallel_dim, ring=(mode == "ring"),
+                                                                   use_zbv=self.use_zbv)
+            else:
+                out = linear_with_async_comm(x, self.weight, bias, self.process_group, True, self.use_zbv)
         if self.gather_output:
             out = gather_forward_split_backward(out, -1, self.process_group)
         return (out, self.bias) if self.skip_bias_add else out
@@ -224,14 +225,15 @@ class Linear1D_Row(ParallelModule):
             assert x.shape[-1] == self.weight.shape[-1], (
                 f"Linear1D_Row: input last dim {x.shape[-1]} != local in_features {self.weight.shape[-1]}")
         mode = self.seq_parallel_mode
-        if mode in ("split_gather", "ring"):
-            out = linear_reducescatter_forward_gather_backward(x, self.weight, None, self.process_group,
-                                                               self.seq_parallel_dim, ring=(mode == "ring"),
-                                                               use_zbv=self.use_zbv)
-        elif self.tp_size > 1:
-            out = linear_allreduce_forward(x, self.weight, self.process_group, self.use_zbv)
-        else:
-            out = linear_with_grad_accum(x, self.weight, None, self.use_zbv)
+        with comm.fp8_communication(self.fp8_communication):
+            if mode in ("split_gather", "ring"):
+                out = linear_reducescatter_forward_gather_backward(x, self.weight, None, self.process_group,
+                                                                   self.seq_parallel_dim, ring=(mode == "ring"),
+                                                                   use_zbv=self.use_zbv)
+            elif self.tp_size > 1:
+                out = linear_allreduce_forward(x, self.weight, self.process_group, self.use_zbv)
+            else:
+                out = linear_with_grad_accum(x, self.weight, None, self.use_zbv)
         if self.skip_bias_add:
             return out, self.bias
         return out if self.bias is None else out + self.bias
