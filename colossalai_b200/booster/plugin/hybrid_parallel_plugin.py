@@ -605,6 +605,8 @@ class HybridParallelPlugin(PipelinePluginBase):
                 optimizer.optim.setup_distributed(tp_group=self.tp_group, dp_group=self.mixed_dp_group,
                                                   shard_to_working_param=getattr(optimizer, "get_master_to_working_map", lambda: {})() or {},
                                                   padding_map=None, is_zero=self.zero_stage > 0)
+        if optimizer is not None and hasattr(model, "bind_optimizer"):
+            model.bind_optimizer(optimizer)          # load_model() must refresh the optimizer's fp32 masters
         return model, optimizer, criterion, dataloader, lr_scheduler
 
     # ------------------------------------------------------------------ training step helpers

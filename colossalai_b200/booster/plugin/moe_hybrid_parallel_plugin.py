@@ -124,6 +124,8 @@ class MoeHybridParallelPlugin(HybridParallelPlugin):
             pp_process_group=self.pp_group, verbose=False, clip_grad_norm=self.max_norm, **self.zero_config,
             **self.amp_config)
         optimizer.ep_pg = self.ep_group
+        if hasattr(model, "bind_optimizer"):
+            model.bind_optimizer(optimizer)
         return model, optimizer, criterion, dataloader, lr_scheduler
 
     def _tag(self, model: ModelWrapper) -> None:

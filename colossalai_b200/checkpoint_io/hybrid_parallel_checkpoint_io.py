@@ -285,6 +285,32 @@ class HybridParallelCheckpointIO(GeneralCheckpointIO):
         states: Dict[int, Dict] = {}
         pid = 0
         groups = []
+        if hasattr(optimizer, "working_params_in_state_order"):
+            # ZeRO: states live in dp-sharded flat buckets.  `state_dict()` gathers them over dp and splits them back
+            # per working parameter (still TP / EP local); globalise those exactly like the parameters themselves.
+            sd = optimizer.state_dict()
+            for i, wp in enumerate(optimizer.working_params_in_state_order()):
+                out = {}
+                for k, v in sd["state"].get(i, {}).items():
+                    if torch.is_tensor(v) and v.dim() > 0 and tuple(v.shape) == tuple(wp.shape):
+                        v = v.to(wp.device)
+                        for a in ("dist_shard", "shard_fn", "gather_fn", "dist_global_shape"):
+                            if hasattr(wp, a):
+                                try:
+                                    setattr(v, a, getattr(wp, a))
+                                except Exception:
+                                    pass
+                        full = to_global(v) if is_distributed_tensor(wp) else v.detach()
+                        mod = module_of.get(id(wp))
+                        old = getattr(mod, "old_num_embeddings", None) if mod is not None else None
+                        if old is not None and full.shape[0] > old:
+                            full = full[:old]
+                        out[k] = full.cpu()
+                    else:
+                        out[k] = v.detach().cpu() if torch.is_tensor(v) else v
+                out["__name__"] = name_of.get(id(wp), str(i))
+                states[i] = out
+            return states, sd["param_groups"]
         for g in optim.param_groups:
             ids = []
             for mp in g["params"]:
@@ -379,6 +405,26 @@ class HybridParallelCheckpointIO(GeneralCheckpointIO):
                     g[k] = v
 
     def _load_optim_states(self, optimizer, model, by_name: Dict[str, Dict]) -> None:
+        if hasattr(optimizer, "working_params_in_state_order"):          # ZeRO flat buckets
+            name_of = {id(p): n for n, p in model.named_parameters()}
+            local: Dict[int, Dict] = {}
+            for i, wp in enumerate(optimizer.working_params_in_state_order()):
+                st = by_name.get(name_of.get(id(wp)))
+                if st is None:
+                    continue
+                entry = {}
+                for k, v in st.items():
+                    if k == "__name__":
+                        continue
+                    if torch.is_tensor(v) and v.dim() > 0:
+                        v = _padded_like(wp, v)
+                        if is_distributed_tensor(wp) and tuple(v.shape) != tuple(wp.shape):
+                            v = distribute_tensor_with_spec(v, wp)
+                    entry[k] = v
+                local[i] = entry
+            groups = [{k: v for k, v in g.items() if k != "params"} for g in optimizer.unwrap().param_groups]
+            optimizer.load_state_dict({"state": local, "param_groups": groups})
+            return
         optim = optimizer.unwrap()
         m2w = getattr(optimizer, "master_to_working_map", {}) or {}
         name_of = {id(p): n for n, p in model.named_parameters()}

@@ -37,7 +37,17 @@ class AMPModelMixin:
     """Hook points used by mixed-precision optimizers."""
 
     def update_master_params(self) -> None:
-        pass
+        """Called by the checkpoint IO after weights were loaded into the model: a mixed-precision / ZeRO optimizer
+        registered through `bind_optimizer` re-derives its fp32 master copies from the new working weights."""
+        ref = getattr(self, "_bound_optimizer", None)
+        opt = ref() if ref is not None else None
+        if opt is not None and hasattr(opt, "update_master_params"):
+            opt.update_master_params(getattr(self, "module", self))
+
+    def bind_optimizer(self, optimizer) -> None:
+        import weakref
+
+        object.__setattr__(self, "_bound_optimizer", weakref.ref(optimizer))
 
 
 class PeftUnwrapMixin:

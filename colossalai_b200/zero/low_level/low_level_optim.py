@@ -325,15 +325,6 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             total = n if total is None else total + n
         return total if total is not None else torch.zeros(1)
 
-    @torch.no_grad()
-    def update_master_params(self, model: Optional[nn.Module] = None) -> None:
-        """Refresh the fp32 master shards from the working parameters (after weights were loaded into the model).
-        Parity: reference `LowLevelZeroOptimizer.update_master_params` (low_level_optim.py) called by the checkpoint
-        IO after `load_model`."""
-        for b in self.buckets:
-            if b.master.data.data_ptr() != b.working_shard().data_ptr():
-                b.master.data.copy_(b.working_shard().detach().to(b.master.device).float())
-
     def step(self, closure=None):
         assert closure is None, "closure is not supported by gemini/zero optimizers"
         if self._comm_stream is not None:
@@ -464,9 +455,21 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                 if k != "params":
                     group[k] = v
 
-    def update_master_params(self, model: nn.Module) -> None:
+    @torch.no_grad()
+    def update_master_params(self, model: Optional[nn.Module] = None) -> None:
+        """Refresh the fp32 master shards from the working parameters (after weights were loaded into the model);
+        reference: `LowLevelZeroOptimizer.update_master_params`, called by the checkpoint IO after `load_model`."""
         for b in self.buckets:
-            b.master.data.copy_(b.working_shard().to(b.master.device))
+            if b.master.data.data_ptr() != b.working_shard().data_ptr():
+                b.master.data.copy_(b.working_shard().detach().to(b.master.device).float())
+
+    def working_params_in_state_order(self) -> List[nn.Parameter]:
+        """Working parameters in the order `state_dict()` / `load_state_dict()` number them."""
+        out: List[nn.Parameter] = []
+        for gid, _ in enumerate(self.optim.param_groups):
+            for b in [bb for bb in self.buckets if bb.group_id == gid]:
+                out.extend(b.params)
+        return out
 
     def get_working_to_master_map(self) -> Dict[int, Tensor]:
         return {id(p): b.master for b in self.buckets for p in b.params}

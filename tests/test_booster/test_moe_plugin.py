@@ -87,6 +87,32 @@ def _run(rank, world, plugin_kw, tmp, max_norm=0.0, precision="fp32", tol=3e-4):
     for n, p in model.unwrap().named_parameters():
         torch.testing.assert_close(p.detach(), before[n], msg=lambda m: f"reload {n}: {m}")
     dist.barrier()
+    # optimizer states (expert moments sharded over ep, dense ones replicated / ZeRO-sharded) survive a round trip
+    opath = os.path.join(tmp, f"moe_optim_{plugin.ep_size}_{plugin.zero_stage}")
+    booster.save_optimizer(opt, opath, shard=True, size_per_shard=1)
+    dist.barrier()
+    inner = opt.unwrap() if hasattr(opt, "unwrap") else opt
+    getter = (lambda mp: opt.get_full_state(mp)) if hasattr(opt, "get_full_state") else (lambda mp: inner.state.get(mp, {}))
+    snap = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in getter(mp).items()}
+            for g in inner.param_groups for mp in g["params"]]
+    steps = [g.get("step") for g in inner.param_groups]
+    for g in inner.param_groups:
+        if "step" in g:
+            g["step"] = 0
+        for mp in g["params"]:
+            for v in inner.state.get(mp, {}).values():
+                if torch.is_tensor(v) and v.dim() > 0:
+                    v.add_(1.0)
+    booster.load_optimizer(opt, opath)
+    assert [g.get("step") for g in inner.param_groups] == steps
+    i = 0
+    for g in inner.param_groups:
+        for mp in g["params"]:
+            for k, v in getter(mp).items():
+                if torch.is_tensor(v) and v.dim() > 0:
+                    torch.testing.assert_close(v, snap[i][k], msg=lambda m: f"optimizer state {i}.{k}: {m}")
+            i += 1
+    dist.barrier()
 
 
 def _worker(rank, world_size, port, tmp):
