@@ -197,11 +197,18 @@ class HybridParallelModule(ModelWrapper, AMPModelMixin):
         return self.module
 
 
-def get_param_info(optim: Optimizer) -> Dict:
-    """Snapshot param ids/shapes before boosting (checkpoint IO needs the original layout to re-shard states)."""
+def get_param_info(optim: Optimizer, model: Optional[Module] = None) -> Dict:
+    """Snapshot param ids/shapes before boosting (checkpoint IO needs the original layout to re-shard states).  With
+    `model`, also the NAME of every optimizer parameter per group: sharding replaces the parameter tensors, and the
+    names are what ties a user's param groups (decay / no-decay, per-layer lr, ...) to the new tensors."""
     if optim is None:
         return {}
     info = {"param_groups": [], "param2id": {}, "id2param": {}, "param2shape": {}}
+    if model is not None:
+        inner = model.unwrap() if isinstance(model, ModelWrapper) else model
+        name_of = {id(p): n for n, p in inner.named_parameters()}
+        if all(id(p) in name_of for g in optim.param_groups for p in g["params"]):
+            info["group_names"] = [[name_of[id(p)] for p in g["params"]] for g in optim.param_groups]
     start = 0
     for group in optim.param_groups:
         packed = {k: v for k, v in group.items() if k != "params"}
@@ -216,8 +223,23 @@ def get_param_info(optim: Optimizer) -> Dict:
     return info
 
 
-def _reassign_params(optim: Optimizer, model: Module) -> None:
-    """After sharding, model parameters are NEW tensors: point the optimizer at them (keeps group order)."""
+def _reassign_params(optim: Optimizer, model: Module, param_info: Optional[Dict] = None) -> None:
+    """After sharding, model parameters are NEW tensors: point the optimizer at them, group by group."""
+    names = (param_info or {}).get("group_names")
+    if names is not None and len(names) == len(optim.param_groups):
+        inner = model.unwrap() if isinstance(model, ModelWrapper) else model
+        new = {n: p for n, p in inner.named_parameters() if p is not None}
+        taken = set()
+        for g, ns in zip(optim.param_groups, names):
+            g["params"] = [new[n] for n in ns if n in new and new[n].requires_grad]     # PP stages drop some names
+            taken.update(id(p) for p in g["params"])
+        rest = [p for p in inner.parameters() if p.requires_grad and id(p) not in taken]
+        # parameters the user left out of the optimizer stay out, except ones created by the sharding itself
+        created = [p for p in rest if id(p) not in {id(q) for q in new.values()}]
+        if created:
+            optim.param_groups[0]["params"].extend(created)
+        optim.state.clear()
+        return
     model_params = set(id(p) for p in model.parameters())
     new_groups = []
     # rebuild in model order; every group's hyper-params are preserved, params matched by position in the model
@@ -293,7 +315,7 @@ class HybridParallelNaiveOptimizer(OptimizerWrapper, _HybridNormMixin):
                  max_norm: float = 0, tp_process_group: Optional[ProcessGroup] = None,
                  pp_process_group: Optional[ProcessGroup] = None) -> None:
         self.param_info = param_info
-        _reassign_params(optim, model)
+        _reassign_params(optim, model, param_info)
         self.model = model
         self.stage_manager = model.stage_manager
         self.shared_params = model.shared_params
@@ -351,7 +373,7 @@ class HybridParallelAMPOptimizer(MixedPrecisionOptimizer, _HybridNormMixin):
         self.tp_pg, self.pp_pg = tp_process_group, pp_process_group
         self.tp_size = comm.group_size(tp_process_group) if tp_process_group is not None else 1
         self.pp_size = comm.group_size(pp_process_group) if pp_process_group is not None else 1
-        _reassign_params(optim, model)
+        _reassign_params(optim, model, param_info)
         super().__init__(optim, model, precision=precision, initial_scale=initial_scale, min_scale=min_scale,
                          growth_factor=growth_factor, backoff_factor=backoff_factor, growth_interval=growth_interval,
                          hysteresis=hysteresis, max_scale=max_scale, max_norm=max_norm)
@@ -565,7 +587,7 @@ class HybridParallelPlugin(PipelinePluginBase):
     # ------------------------------------------------------------------ configure
     def configure(self, model: Module, optimizer: Optional[Optimizer] = None, criterion: Optional[Callable] = None,
                   dataloader: Optional[DataLoader] = None, lr_scheduler: Optional[LRScheduler] = None):
-        param_info = get_param_info(optimizer)
+        param_info = get_param_info(optimizer, model)
         zbv = self.pp_style == "zbv" and self.pp_size > 1
         if not isinstance(model, ModelWrapper):
             use_ddp = False   # gradient averaging over dp is done explicitly (bucketed) so it composes with PP/SP

@@ -37,7 +37,7 @@ class HybridParallelZeroOptimizer(LowLevelZeroOptimizer):
         self.tp_pg, self.pp_pg = tp_process_group, pp_process_group
         self.tp_size = comm.group_size(tp_process_group) if tp_process_group is not None else 1
         self.pp_size = comm.group_size(pp_process_group) if pp_process_group is not None else 1
-        _reassign_params(optimizer, model)
+        _reassign_params(optimizer, model, param_info)
         super().__init__(optimizer=optimizer, pg_to_param_list=pg_to_param_list, initial_scale=initial_scale,
                          min_scale=min_scale, growth_factor=growth_factor, backoff_factor=backoff_factor,
                          growth_interval=growth_interval, hysteresis=hysteresis, max_scale=max_scale,

@@ -98,7 +98,7 @@ class MoeHybridParallelPlugin(HybridParallelPlugin):
             self._tag(model)
             return model, optimizer, criterion, dataloader, lr_scheduler
         # ZeRO: dense params are partitioned over dp (x sp), expert params over moe_dp
-        param_info = get_param_info(optimizer)
+        param_info = get_param_info(optimizer, model)
         if not isinstance(model, ModelWrapper):
             model = HybridParallelModule(model, precision=self.precision, shard_config=self.shard_config,
                                          dp_group=self.mixed_dp_group, tp_group=self.tp_group, sp_group=self.sp_group,
@@ -111,7 +111,7 @@ class MoeHybridParallelPlugin(HybridParallelPlugin):
         optimizer = cast_to_distributed(optimizer)
         from .hybrid_parallel_plugin import _reassign_params
 
-        _reassign_params(optimizer, model)
+        _reassign_params(optimizer, model, param_info)
         dense = [p for g in optimizer.param_groups for p in g["params"] if not is_moe_tensor(p)]
         moe = [p for g in optimizer.param_groups for p in g["params"] if is_moe_tensor(p)]
         pg_map = {self.mixed_dp_group: dense}

@@ -41,6 +41,8 @@ class DistributedAdaFactor(DistributedOptim):
     def _shard_dim(self, p) -> Optional[int]:
         wp = self.shard_to_working_param.get(id(p), p)
         sh = getattr(wp, "dist_shard", None)
+        if sh is None and hasattr(wp, "tp_shard_dim"):       # fused (customised) column / row parallel weights
+            sh = (wp.tp_shard_dim, None)
         if sh is not None and self.tp_size > 1:
             return sh[0]
         return None

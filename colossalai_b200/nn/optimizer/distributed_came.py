@@ -37,6 +37,8 @@ class DistributedCAME(DistributedOptim):
     def _shard_dim(self, p):
         wp = self.shard_to_working_param.get(id(p), p)
         sh = getattr(wp, "dist_shard", None)
+        if sh is None and hasattr(wp, "tp_shard_dim"):       # fused (customised) column / row parallel weights
+            sh = (wp.tp_shard_dim, None)
         return sh[0] if (sh is not None and self.tp_size > 1) else None
 
     def _rms(self, t, sharded):

@@ -40,6 +40,8 @@ class DistGaloreAwamW(DistributedOptim):
     def _shard(self, p):
         wp = self.shard_to_working_param.get(id(p), p)
         sh = getattr(wp, "dist_shard", None)
+        if sh is None and hasattr(wp, "tp_shard_dim"):       # fused (customised) column / row parallel weights
+            sh = (wp.tp_shard_dim, None)
         return sh if (sh is not None and self.tp_size > 1) else None
 
     @torch.no_grad()
@@ -56,7 +58,13 @@ class DistGaloreAwamW(DistributedOptim):
                 sh = self._shard(p)
                 projected = "rank" in group and grad.dim() == 2
                 if projected:
-                    full = comm.all_gather(grad, sh[0], sh[1]) if sh is not None else grad
+                    wp = self.shard_to_working_param.get(id(p), p)
+                    if sh is None:
+                        full = grad
+                    elif hasattr(wp, "gather_fn"):               # fused q|k|v / gate|up shards: block-aware gather
+                        full = wp.gather_fn(grad)
+                    else:
+                        full = comm.all_gather(grad, sh[0], sh[1] if sh[1] is not None else self.tp_group)
                     if "projector" not in st:
                         st["projector"] = GaLoreProjector(group["rank"], group.get("update_proj_gap", 200),
                                                           group.get("scale", 0.25), group.get("proj_type", "std"))
@@ -77,7 +85,9 @@ class DistGaloreAwamW(DistributedOptim):
                 if projected:
                     upd = st["projector"].project_back(upd)
                     if sh is not None:
-                        upd = comm.split_along(upd, sh[0], sh[1])
+                        wp = self.shard_to_working_param.get(id(p), p)
+                        upd = wp.shard_fn(upd) if hasattr(wp, "shard_fn") else \
+                            comm.split_along(upd, sh[0], sh[1] if sh[1] is not None else self.tp_group)
                 pf = p.float()
                 if group["weight_decay"] > 0:
                     pf = pf * (1 - group["lr"] * group["weight_decay"])

@@ -86,11 +86,13 @@ class FusedLinear1D_Col(Linear1D_Col):
                         lambda t: gather_fused_qkv_in_gpt2_style(t, ss, pg, False), gshape)
         if hasattr(self.weight, "dist_shard"):
             del self.weight.dist_shard
+        self.weight.tp_shard_dim = 0          # which dim the fused blocks are split on (TP-aware optimizers need it)
         if self.bias is not None:
             mark_customized(self.bias, lambda t: split_fused_qkv_in_gpt2_style(t, ss, pg, False),
                             lambda t: gather_fused_qkv_in_gpt2_style(t, ss, pg, False), (out_features,))
             if hasattr(self.bias, "dist_shard"):
                 del self.bias.dist_shard
+            self.bias.tp_shard_dim = 0
 
     @staticmethod
     def from_native_module(module: nn.Module, process_group=None, split_sizes: Sequence[int] = None, **kwargs):
@@ -124,6 +126,7 @@ class FusedLinear1D_Row(Linear1D_Row):
                         lambda t: gather_fused_qkv_in_gpt2_style(t, ss, pg, True), (out_features, in_features))
         if hasattr(self.weight, "dist_shard"):
             del self.weight.dist_shard
+        self.weight.tp_shard_dim = 1
 
     @staticmethod
     def from_native_module(module: nn.Module, process_group=None, split_sizes: Sequence[int] = None, **kwargs):

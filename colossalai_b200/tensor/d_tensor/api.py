@@ -60,7 +60,7 @@ def _hijack_detach_and_clone(t: torch.Tensor) -> torch.Tensor:
 
 
 def _copy_meta(src: torch.Tensor, dst: torch.Tensor) -> None:
-    for attr in ("dist_layout", "dist_shard", "shard_fn", "gather_fn", "dist_global_shape"):
+    for attr in ("dist_layout", "dist_shard", "shard_fn", "gather_fn", "dist_global_shape", "tp_shard_dim"):
         if hasattr(src, attr):
             setattr(dst, attr, getattr(src, attr))
 
