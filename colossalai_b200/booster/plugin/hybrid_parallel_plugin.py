@@ -209,6 +209,9 @@ def get_param_info(optim: Optimizer, model: Optional[Module] = None) -> Dict:
         name_of = {id(p): n for n, p in inner.named_parameters()}
         if all(id(p) in name_of for g in optim.param_groups for p in g["params"]):
             info["group_names"] = [[name_of[id(p)] for p in g["params"]] for g in optim.param_groups]
+            # tied parameters: every alias path -> the canonical name (a pipeline stage may only keep the alias, e.g. the
+            # last stage owns `lm_head.weight` of a model whose head is tied to the embedding)
+            info["alias_of"] = {n: name_of[id(p)] for n, p in inner.named_parameters(remove_duplicate=False)}
     start = 0
     for group in optim.param_groups:
         packed = {k: v for k, v in group.items() if k != "params"}
@@ -233,11 +236,17 @@ def _reassign_params(optim: Optimizer, model: Module, param_info: Optional[Dict]
         for g, ns in zip(optim.param_groups, names):
             g["params"] = [new[n] for n in ns if n in new and new[n].requires_grad]     # PP stages drop some names
             taken.update(id(p) for p in g["params"])
-        rest = [p for p in inner.parameters() if p.requires_grad and id(p) not in taken]
-        # parameters the user left out of the optimizer stay out, except ones created by the sharding itself
-        created = [p for p in rest if id(p) not in {id(q) for q in new.values()}]
-        if created:
-            optim.param_groups[0]["params"].extend(created)
+        # aliases of tied parameters that survive on this stage under their other name join their partner's group;
+        # parameters the user deliberately left out of the optimizer stay out
+        alias_of = (param_info or {}).get("alias_of", {})
+        group_of = {n: gi for gi, ns in enumerate(names) for n in ns}
+        for n, p in new.items():
+            if id(p) in taken or not p.requires_grad:
+                continue
+            canon = alias_of.get(n)
+            if canon is not None and canon in group_of:
+                optim.param_groups[group_of[canon]]["params"].append(p)
+                taken.add(id(p))
         optim.state.clear()
         return
     model_params = set(id(p) for p in model.parameters())
