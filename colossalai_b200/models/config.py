@@ -228,6 +228,28 @@ MODEL_ZOO: Dict[str, ModelConfig] = {
 }
 
 
+def _tiny(preset: str, **kw) -> ModelConfig:
+    """Test-size variant of a family preset (2 layers, hidden 64, 4 heads, vocab 512) keeping every family switch."""
+    base = dict(vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=None, max_position_embeddings=256)
+    base.update(kw)
+    return replace(MODEL_ZOO[preset], **base)
+
+
+MODEL_ZOO.update({
+    "mistral-tiny": _tiny("mistral-7b", sliding_window=None),
+    "qwen2-tiny": _tiny("qwen2-7b"),
+    "qwen3-tiny": _tiny("qwen3-8b", head_dim=16),
+    "opt-tiny": _tiny("opt-125m", num_key_value_heads=4),
+    "bloom-tiny": _tiny("bloom-560m", num_key_value_heads=4),
+    "falcon-tiny": _tiny("falcon-7b", num_key_value_heads=2),
+    "gptj-tiny": _tiny("gptj-6b", num_key_value_heads=4, partial_rotary_factor=0.5),
+    "chatglm-tiny": _tiny("chatglm2-6b"),
+    "command-tiny": _tiny("command-r", num_key_value_heads=4),
+    "bert-tiny": _tiny("bert-base", num_key_value_heads=4),
+})
+
+
 def get_config(name: str, **overrides) -> ModelConfig:
     if name not in MODEL_ZOO:
         raise KeyError(f"unknown model preset {name!r}; available: {sorted(MODEL_ZOO)}")

@@ -111,8 +111,8 @@ class Attention(nn.Module):
         T = qkv.shape[0]
         if cfg.qk_norm:
             q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
-            q = self.q_norm(q.reshape(T, hq, D)).reshape(T, hq * D)
-            k = self.k_norm(k.reshape(T, hkv, D)).reshape(T, hkv * D)
+            q = self._head_norm(self.q_norm, q.reshape(T, hq, D)).reshape(T, hq * D)
+            k = self._head_norm(self.k_norm, k.reshape(T, hkv, D)).reshape(T, hkv * D)
             qkv = torch.cat([q, k, v], dim=-1)
         if rope is not None:
             qkv = ops.rope_qkv(qkv, meta.positions, rope[0], rope[1], hq, hkv, D, rot_dim=cfg.rotary_dim,
@@ -139,6 +139,19 @@ class Attention(nn.Module):
             o = all_to_all_comm(o.reshape(B, S, hq, D), sp_group, scatter_dim=1, gather_dim=2)
             o = o.reshape(B * (S // sp), hq * sp * D)
         return self.o_proj(o)
+
+    def _head_norm(self, norm: nn.Module, t: torch.Tensor) -> torch.Tensor:
+        """Per-head q/k RMSNorm.  Its [head_dim] weight is replicated over TP while every rank only sees its own
+        heads, so the weight gradient is a partial sum: identity forward / all-reduce backward over the TP group."""
+        sc = self.shard_config
+        w = norm.weight
+        if sc is not None and sc.enable_tensor_parallelism and sc.tensor_parallel_size > 1:
+            from ..shardformer.layer._operation import reduce_backward
+
+            w = reduce_backward(w, sc.tp_group)
+        if w.dtype != t.dtype:
+            w = w.to(t.dtype)
+        return ops.rms_norm(t, w, norm.eps, None)
 
     def _local_alibi_slopes(self, device) -> torch.Tensor:
         sc = self.shard_config
@@ -451,9 +464,13 @@ class TransformerLMHeadModel(nn.Module):
         if sp_mode in ("all_to_all", "ring_attn") and not keep_sp_sharded and comm.group_size(sp_group) > 1:
             Sl = h.shape[0] // B
             h = gather_sp_output(h.view(B, Sl, -1), sp_group, sp_mode, sp_dim=1).reshape(B * S, -1)
-        if cfg.norm_head and isinstance(self.lm_head, nn.Linear):
-            logits = F.linear(h, F.normalize(self.lm_head.weight, dim=-1))
-        else:   # sharded heads: NormHead is folded into the weight at load time (inference) — see models/baichuan.py
+        if cfg.norm_head:
+            # Baichuan-2 NormHead: L2-normalised rows.  Rows are vocabulary entries, so the normalisation is local to
+            # a vocab-parallel shard too; run the (possibly parallel) head with the normalised weight swapped in.
+            w = F.normalize(self.lm_head.weight, dim=-1)
+            logits = F.linear(h, w) if isinstance(self.lm_head, nn.Linear) else \
+                torch.func.functional_call(self.lm_head, {"weight": w}, (h,))
+        else:
             logits = self.lm_head(h)
         if cfg.logit_scale != 1.0:
             logits = logits * cfg.logit_scale
