@@ -115,3 +115,42 @@ def test_vit_pipeline_stage_split():
 
 if __name__ == "__main__":
     test_shard_encdec_families_tp2()
+
+
+def _vit_pp_worker(rank, world_size, port):
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.nn.optimizer import FusedAdam
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    torch.manual_seed(7)
+    base = build_model("vit-tiny")
+    model = copy.deepcopy(base)
+    ref_opt = torch.optim.AdamW(base.parameters(), lr=1e-2, weight_decay=0.0)
+    opt = FusedAdam(model.parameters(), lr=1e-2, weight_decay=0.0)
+    booster = Booster(plugin=HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2))
+    model, opt, *_ = booster.boost(model, opt)
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    y = torch.tensor([1, 2, 3, 4])
+    out = booster.execute_pipeline(iter([{"pixel_values": x, "labels": y}]), model, lambda o, b: o["loss"], opt,
+                                   return_loss=True)
+    opt.step()
+    total = 0.0
+    for i in range(2):
+        l = base(pixel_values=x[2 * i: 2 * i + 2], labels=y[2 * i: 2 * i + 2])["loss"] / 2
+        l.backward()
+        total += l.item()
+    ref_opt.step()
+    if out["loss"] is not None:
+        assert abs(out["loss"].item() - total) < 1e-5
+    ref = dict(base.named_parameters())
+    for n, p in model.unwrap().named_parameters():
+        if p is not None:
+            torch.testing.assert_close(p.detach(), ref[n].detach(), atol=1e-5, rtol=1e-4, msg=lambda m: f"vit pp {n}: {m}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_vit_pipeline_parallel_matches_single_process():
+    spawn(_vit_pp_worker, 2)
