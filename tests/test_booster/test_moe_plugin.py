@@ -19,6 +19,8 @@ from colossalai_b200.testing import rerun_if_address_is_in_use, spawn
 
 
 def _gather(p):
+    if hasattr(p, "gather_fn"):
+        return p.gather_fn(p.detach())
     if hasattr(p, "dist_shard"):
         dim, group = p.dist_shard
         return comm.all_gather(p.detach(), dim, group)
@@ -132,6 +134,7 @@ def _worker4(rank, world_size, port, tmp):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     _run(rank, world_size, dict(tp_size=1, pp_size=1, ep_size=2), tmp, max_norm=0.5)          # moe_dp = 2
     _run(rank, world_size, dict(tp_size=1, pp_size=1, ep_size=2, zero_stage=1), tmp, precision="bf16", tol=3e-2)
+    _run(rank, world_size, dict(tp_size=2, pp_size=1, ep_size=2), tmp)                         # EP2 x TP2 (attention TP)
     dist.destroy_process_group()
 
 
