@@ -108,6 +108,10 @@ def _worker(rank, world_size, port):
                     sequence_parallelism_mode="all_to_all"), "ulysses2 x dp2")
     _run_pp(dict(tp_size=2, pp_size=2), "pp2xtp2")
     _run_pp(dict(tp_size=1, pp_size=2), "pp2xdp2")
+    _run_pp(dict(tp_size=2, pp_size=2, pp_style="interleaved", num_model_chunks=2), "interleaved pp2xtp2")
+    _run_pp(dict(tp_size=2, pp_size=2, pp_style="zbv", num_model_chunks=2), "zbv pp2xtp2")
+    _run_no_pp(dict(tp_size=2, pp_size=1, sp_size=2, enable_sequence_parallelism=True,
+                    sequence_parallelism_mode="ring_attn"), "ring_attn2 x tp2")
     dist.destroy_process_group()
 
 
