@@ -281,3 +281,41 @@ def test_attention_backends_agree_with_runtime_reference():
     md2 = AttentionMetaData(q[[4, 7]], None, None, kc, vc, bt, bs, sequence_lengths=torch.tensor(lens, dtype=torch.int32))
     dec = be.decode(md2)
     torch.testing.assert_close(dec, out[[4, 7]], atol=1e-5, rtol=1e-5)
+
+
+def test_streamingllm_window_eviction_bounds_kv_blocks():
+    """StreamingLLM (reference inference/config.py:enable_streamingllm, batch_bucket.py:streamingllm_update_batch):
+    once sink + generated window is full the oldest non-sink block is recycled, so a long generation holds a bounded
+    number of KV blocks; until the first eviction the tokens equal plain greedy decoding."""
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    kw = dict(max_batch_size=2, max_input_len=16, max_output_len=64, block_size=8, dtype="fp32", use_cuda_graph=False,
+              ignore_eos=True)
+    prompts = [[5, 9, 13, 200, 7], [11, 3, 8]]
+    gen = GenerationConfig(max_new_tokens=60)
+    _, plain = InferenceEngine(model, None, InferenceConfig(**kw)).generate(
+        prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    cfg = InferenceConfig(enable_streamingllm=True, start_token_size=4, generated_token_size=16, **kw)
+    assert cfg.start_token_size == 8                         # sinks are rounded up to one block
+    eng = InferenceEngine(model, None, cfg)
+    mgr = eng.request_handler.cache_manager
+    total = mgr.num_available_blocks
+    peak = []
+    orig = eng.request_handler.update
+
+    def spy():
+        out = orig()
+        peak.append(total - mgr.num_available_blocks)
+        return out
+
+    eng.request_handler.update = spy
+    _, ids = eng.generate(prompts_token_ids=prompts, return_token_ids=True, generation_config=gen)
+    window = cfg.start_token_size + cfg.generated_token_size + cfg.block_size        # eviction threshold (tokens)
+    for p, a, b in zip(prompts, plain, ids):
+        assert len(b) == len(p) + 60
+        n_same = window - 1
+        assert a[:n_same] == b[:n_same]
+    # two sequences, each at most window/block_size (+1 being filled) blocks
+    assert max(peak) <= 2 * (window // cfg.block_size + 1)
+    assert max(peak) < 2 * ((16 + 64) // cfg.block_size)
+    assert mgr.num_available_blocks == total
