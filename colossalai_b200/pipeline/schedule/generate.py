@@ -38,9 +38,6 @@ class DenseKVCache:
     def attend(self, layer_idx: int, q, k, v, meta, scale: float, alibi_slopes=None):
         from ... import ops
 
-        if alibi_slopes is not None:
-            raise NotImplementedError("pipeline generation with ALiBi models: use the paged inference engine")
-
         B = self.batch
         kb = k.view(B, -1, *k.shape[1:])
         vb = v.view(B, -1, *v.shape[1:])
@@ -48,6 +45,15 @@ class DenseKVCache:
             kb = torch.cat([self.k[layer_idx], kb], dim=1)
             vb = torch.cat([self.v[layer_idx], vb], dim=1)
         self.k[layer_idx], self.v[layer_idx] = kb, vb
+        if alibi_slopes is not None:
+            # queries are the last Sq positions of the Sk cached ones: bias = slope * (key_pos - query_pos), causal
+            Sq, Sk = q.shape[0] // B, kb.shape[1]
+            qpos = torch.arange(Sk - Sq, Sk, device=q.device)
+            rel = torch.arange(Sk, device=q.device)[None, :] - qpos[:, None]
+            bias = rel.clamp(max=0).float()[None, None] * alibi_slopes.float()[None, :, None, None]
+            bias = bias.masked_fill((rel > 0)[None, None], float("-inf")).to(q.dtype)
+            return ops.attention(q, kb.reshape(-1, *k.shape[1:]), vb.reshape(-1, *v.shape[1:]), batch=B, causal=False,
+                                 scale=scale, attn_mask=bias)
         return ops.attention(q, kb.reshape(-1, *k.shape[1:]), vb.reshape(-1, *v.shape[1:]), batch=B, causal=True,
                              scale=scale)
 

@@ -23,10 +23,10 @@ def _naive(model, ids, n_new):
     return out[:, ids.shape[1]:]
 
 
-def _worker(rank, world_size, port):
+def _worker(rank, world_size, port, family="llama-tiny"):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     torch.manual_seed(3)
-    full = build_model("llama-tiny").float().eval()
+    full = build_model(family).float().eval()
     mesh = DeviceMesh(pp=world_size)
     sm = PipelineStageManager(mesh, pipeline_axis=0)
     sc = ShardConfig(pipeline_stage_manager=sm, enable_tensor_parallelism=False)
@@ -49,3 +49,9 @@ def _worker(rank, world_size, port):
 @rerun_if_address_is_in_use()
 def test_pipeline_generate_pp2():
     spawn(_worker, 2)
+
+
+@rerun_if_address_is_in_use()
+def test_pipeline_generate_alibi_pp2():
+    """ALiBi family (bloom): the dense stage cache applies the per-head linear bias."""
+    spawn(_worker, 2, family="bloom-tiny")
