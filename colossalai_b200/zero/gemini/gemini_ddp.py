@@ -293,6 +293,10 @@ class GeminiDDP(ModelWrapper):
             self.chunk_manager.release_chunk(c)
         if not self._logged and self.gemini_manager.policy_name == "auto":
             self._logged = True
+        if self.enable_gradient_accumulation:
+            # from now on backward passes add into the reduced shards until the optimizer steps (reference
+            # gemini_ddp.py:341-342 turns the state on here, gemini_optimizer.py:293 turns it off after the step)
+            self.accumulating_grads = True
         self.gemini_manager.post_iter()
 
     def backward(self, loss: torch.Tensor) -> None:

@@ -167,11 +167,10 @@ class GeminiOptimizer(OptimizerWrapper):
     def zero_grad(self, *args, **kwargs):
         self.mix_precision_mixin.pre_zero_grad()
         self._clear_grads()
+        self.module.accumulating_grads = False
         return self.optim.zero_grad(set_to_none=True)
 
     def step(self, *args, **kwargs):
-        if self.module.accumulating_grads:
-            return
         if self.mix_precision_mixin.should_skip_step():
             if self.verbose:
                 self._logger.info("Found overflow. Skip step")
@@ -195,6 +194,7 @@ class GeminiOptimizer(OptimizerWrapper):
         self._update_fp16_params()
         self._clear_grads()
         self.module.overflow_counter.zero_()
+        self.module.accumulating_grads = False
         return ret
 
     def _update_fp16_params(self) -> None:

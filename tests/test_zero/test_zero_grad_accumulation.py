@@ -8,13 +8,17 @@ import torch.distributed as dist
 
 import colossalai_b200
 from colossalai_b200.booster import Booster
-from colossalai_b200.booster.plugin import HybridParallelPlugin, LowLevelZeroPlugin
+from colossalai_b200.booster.plugin import GeminiPlugin, HybridParallelPlugin, LowLevelZeroPlugin
 from colossalai_b200.models import build_model
 from colossalai_b200.nn.optimizer import HybridAdam
 from colossalai_b200.testing import rerun_if_address_is_in_use, spawn
 
 
 def _params(model):
+    from colossalai_b200.zero.gemini import GeminiDDP
+
+    if isinstance(model, GeminiDDP):
+        return {k: v.float() for k, v in model.state_dict(only_rank_0=False, dtype=torch.float32).items()}
     inner = model.unwrap() if hasattr(model, "unwrap") else model
     from colossalai_b200.tensor.d_tensor import to_global
 
@@ -53,6 +57,11 @@ def _worker(rank, world_size, port):
         ("zero1", lambda: LowLevelZeroPlugin(stage=1, precision="bf16"), False),
         ("zero2", lambda: LowLevelZeroPlugin(stage=2, precision="bf16"), False),
         ("hybrid zero1", lambda: HybridParallelPlugin(tp_size=1, pp_size=1, zero_stage=1, precision="bf16"), False),
+        ("gemini", lambda: GeminiPlugin(precision="bf16", min_chunk_size_m=0.01, search_range_m=1,
+                                        enable_gradient_accumulation=True), False),
+        ("gemini offload", lambda: GeminiPlugin(precision="bf16", min_chunk_size_m=0.01, search_range_m=1,
+                                                offload_optim_frac=1.0, offload_param_frac=1.0,
+                                                enable_gradient_accumulation=True), False),
     ]
     for tag, fn, ns in cases:
         whole = _train(fn, ids, accumulate=False, use_no_sync=False)
