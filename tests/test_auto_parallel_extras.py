@@ -124,3 +124,40 @@ def test_fx_split_and_checkpoint_passes():
     ck(xa).sum().backward()
     net(xb).sum().backward()
     torch.testing.assert_close(xa.grad, xb.grad)
+
+
+def test_analyzer_meta_tensor_flop_count_and_symbolic_profile():
+    """reference tests/test_analyzer/{test_subclasses,test_fx}: device-free tensors, fwd/bwd FLOPs, per-node MetaInfo."""
+    import torch.nn as nn
+
+    from colossalai_b200._analyzer import MeshConfig, MetaTensor, MetaTensorMode, flop_count
+    from colossalai_b200._analyzer.fx import symbolic_profile, symbolic_trace
+
+    class MLP(nn.Module):
+        def __init__(self, h=64, f=256):
+            super().__init__()
+            self.up, self.act, self.down = nn.Linear(h, f), nn.GELU(), nn.Linear(f, h)
+
+        def forward(self, x):
+            return self.down(self.act(self.up(x)))
+
+    m = MLP()
+    fwd, bwd = flop_count(m, torch.randn(8, 64))
+    gemm = 2 * 8 * 64 * 256 * 2
+    assert gemm <= fwd < 1.05 * gemm                      # GEMMs + a little pointwise work
+    assert 1.9 * gemm < bwd < 2.1 * gemm                  # dgrad + wgrad of both layers
+    with MetaTensorMode():
+        big = nn.Linear(8192, 4 * 8192)                   # 1 GiB of weights, nothing allocated
+        x = torch.randn(4, 8192, device="cuda:0")
+    assert isinstance(x, MetaTensor) and x.device == torch.device("cuda:0") and x._tensor.device.type == "meta"
+    y = big(x)
+    assert isinstance(y, MetaTensor) and tuple(y.shape) == (4, 4 * 8192)
+    t = MetaTensor(torch.randn(3, 4), device="cuda:1")
+    assert (t @ t.t()).device == torch.device("cuda:1") and t.to("cpu").device.type == "cpu"
+    gm = symbolic_profile(symbolic_trace(m), torch.randn(8, 64))
+    info = {n.name: n.meta["info"] for n in gm.graph.nodes}
+    assert info["up"].fwd_flop >= 2 * 8 * 64 * 256 and info["up"].bwd_flop >= 2 * info["up"].fwd_flop - 8 * 256 * 2
+    assert info["up"].param_bytes == (64 * 256 + 256) * 4 and info["act"].saved_bytes == 8 * 256 * 4
+    assert info["down"].outputs == ((8, 64), torch.float32)
+    cfg = MeshConfig()
+    assert cfg.TFLOPS > 1000 and cfg.HBM_BYTES == 180e9
