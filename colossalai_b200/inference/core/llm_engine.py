@@ -71,6 +71,7 @@ class LLMEngine(BaseEngine):
         self.request_handler = RequestHandler(self.inference_config, self.model_config)
         k_caches, v_caches = self.request_handler.get_kvcache()
         self.kv_runtime = PagedKVRuntime(k_caches, v_caches, self.inference_config.block_size)
+        self._init_decode_workspace(k_caches)
         self.counter = count()
         self.use_cuda_graph = self.inference_config.use_cuda_graph and torch.cuda.is_available()
         if self.use_cuda_graph and (self.model_config.head_dim not in (64, 128, 256)
@@ -128,6 +129,30 @@ class LLMEngine(BaseEngine):
     def _verify_args(self) -> None:
         assert isinstance(self.inference_config, InferenceConfig), "Invalid type of inference config provided."
         assert isinstance(self.model, nn.Module), f"the model type must be nn.Module, but got {type(self.model)}"
+
+    def _init_decode_workspace(self, k_caches) -> None:
+        """Size the persistent split-KV buffers of the paged decode kernel for the largest batch (reference
+        `flash_decoding_utils.FDIntermTensors.initialize` called from the request handler)."""
+        if not torch.cuda.is_available() or not k_caches or k_caches[0].device.type != "cuda":
+            return
+        import ctypes
+
+        from ...ops import inference as infer_ops
+        from ..flash_decoding_utils import FDIntermTensors
+
+        cfg = self.inference_config
+        hkv, d = k_caches[0].shape[2], k_caches[0].shape[3]
+        hq = hkv * (self.model_config.num_attention_heads // max(self.model_config.num_key_value_heads, 1))
+        max_len = cfg.max_input_len + cfg.max_output_len
+        max_len = (max_len + cfg.block_size - 1) // cfg.block_size * cfg.block_size
+        try:
+            lib = infer_ops._get_lib()
+            part = ctypes.c_int(0)
+            worst = max(n * lib.cb_decode_num_splits(n, hkv, max_len, ctypes.byref(part))
+                        for n in range(1, cfg.max_batch_size + 1))
+        except Exception:                     # extension not built: the op falls back and allocates on its own
+            return
+        FDIntermTensors().ensure(worst, hq, d, device=k_caches[0].device)
 
     def _model_forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         """input_ids: flattened tokens [T]; returns hidden->logits of the LAST token of every sequence."""

@@ -42,6 +42,16 @@ def kv_cache_write(k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_ca
     v_cache[blk, slot] = v.to(v_cache.dtype)
 
 
+def _decode_workspace(q: torch.Tensor, n: int, heads: int, splits: int, head_dim: int):
+    """Persistent split-KV buffers (`inference.flash_decoding_utils.FDIntermTensors`) when the engine set them up."""
+    from ..inference.flash_decoding_utils import FDIntermTensors
+
+    fd = FDIntermTensors()
+    if not fd.is_initialized or fd.mid_output.device != q.device or fd.mid_output.dtype != torch.float32:
+        return None
+    return fd.views(n, heads, splits, head_dim)
+
+
 def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_tables: torch.Tensor,
                            seq_lens: torch.Tensor, scale: Optional[float] = None,
                            alibi_slopes: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -56,8 +66,12 @@ def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torc
         part = ctypes.c_int(0)
         splits = lib.cb_decode_num_splits(n, Hkv, max_len, ctypes.byref(part))
         out = torch.empty_like(q)
-        o_part = torch.empty(n, Hq, splits, D, dtype=torch.float32, device=q.device)
-        ml_part = torch.empty(n, Hq, splits, 2, dtype=torch.float32, device=q.device)
+        ws = _decode_workspace(q, n, Hq, splits, D)
+        if ws is not None:
+            o_part, ml_part = ws
+        else:
+            o_part = torch.empty(n, Hq, splits, D, dtype=torch.float32, device=q.device)
+            ml_part = torch.empty(n, Hq, splits, 2, dtype=torch.float32, device=q.device)
         qc = q if q.stride(2) == 1 and q.stride(1) == D else q.contiguous()
         loader.check(lib.cb_paged_decode_attention(
             loader.ptr(qc), loader.ptr(k_cache), loader.ptr(v_cache), loader.ptr(block_tables), loader.ptr(seq_lens),

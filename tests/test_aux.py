@@ -54,3 +54,41 @@ def test_profilers_cpu():
     with prof:
         assert dist.all_reduce.__name__ == "wrapped"
     assert dist.all_reduce.__name__ != "wrapped" and "collective" in prof.result_str()
+
+
+def test_async_safetensors_seed_and_decode_workspace(tmp_path):
+    """utils.safetensors (reference utils/safetensors.py), testing.random.seed_all, FDIntermTensors workspace."""
+    import torch
+
+    from colossalai_b200.inference.flash_decoding_utils import FDIntermTensors
+    from colossalai_b200.testing.random import seed_all
+    from colossalai_b200.utils.safetensors import (create_pinned_state_dict, load_flat, move_and_save, save_nested)
+
+    seed_all(123)
+    a = torch.rand(3)
+    seed_all(123)
+    assert torch.equal(a, torch.rand(3))
+    sd = {"w": torch.randn(5, 7), "b": torch.arange(4, dtype=torch.int64), "h": torch.randn(3).bfloat16()}
+    pinned = create_pinned_state_dict(sd)
+    w = move_and_save(str(tmp_path / "m.safetensors"), sd, pinned)
+    w.synchronize()
+    from safetensors.torch import load_file
+
+    back = load_file(str(tmp_path / "m.safetensors"))
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    osd = {"state": {0: {"step": torch.tensor(3.0), "exp_avg": torch.randn(4), "flag": 7},
+                     1: {"step": torch.tensor(3.0), "exp_avg": torch.randn(2, 2)}},
+           "param_groups": [{"lr": 1e-3, "betas": [0.9, 0.95], "params": [0, 1]}]}
+    w = save_nested(str(tmp_path / "o.safetensors"), osd)
+    w.synchronize()
+    got = load_flat(str(tmp_path / "o.safetensors"))
+    assert got["param_groups"] == osd["param_groups"] and got["state"][0]["flag"] == 7
+    assert torch.equal(got["state"][1]["exp_avg"], osd["state"][1]["exp_avg"])
+    fd = FDIntermTensors()
+    fd._reset()
+    assert fd.views(2, 4, 3, 8) is None
+    fd.initialize(4, 4, 3, 8, device="cpu")
+    o, ml = fd.views(2, 4, 3, 8)
+    assert o.shape == (2, 4, 3, 8) and ml.shape == (2, 4, 3, 2) and o.data_ptr() == fd.mid_output.data_ptr()
+    assert fd.views(8, 4, 3, 8) is None and fd.exp_sums.shape == (4, 4, 3)
+    fd._reset()
