@@ -150,9 +150,9 @@ class LLMEngine(BaseEngine):
             part = ctypes.c_int(0)
             worst = max(n * lib.cb_decode_num_splits(n, hkv, max_len, ctypes.byref(part))
                         for n in range(1, cfg.max_batch_size + 1))
-        except Exception:                     # extension not built: the op falls back and allocates on its own
-            return
-        FDIntermTensors().ensure(worst, hq, d, device=k_caches[0].device)
+            FDIntermTensors().ensure(worst, hq, d, device=k_caches[0].device)
+        except Exception as e:                # extension not built / odd config: the op allocates per call instead
+            self.logger.warning(f"persistent decode workspace disabled: {e}", ranks=[0])
 
     def _model_forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         """input_ids: flattened tokens [T]; returns hidden->logits of the LAST token of every sequence."""
