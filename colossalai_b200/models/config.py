@@ -69,6 +69,12 @@ class ModelConfig:
     lm_head_bias: bool = False        # GPT-J
     norm_head: bool = False           # Baichuan-2 NormHead: L2-normalised LM-head rows
     moe: Optional[MoEConfig] = None
+    # multi-head latent attention (DeepSeek-V2 / V3): low-rank q and kv projections, decoupled rope key
+    q_lora_rank: Optional[int] = None
+    kv_lora_rank: Optional[int] = None
+    qk_nope_head_dim: int = 0
+    qk_rope_head_dim: int = 0
+    v_head_dim: int = 0
     pad_token_id: Optional[int] = None
     bos_token_id: int = 1
     eos_token_id: int = 2
@@ -76,6 +82,11 @@ class ModelConfig:
     def __post_init__(self) -> None:
         if self.num_key_value_heads is None:
             self.num_key_value_heads = self.num_attention_heads
+        if self.kv_lora_rank is not None:
+            # MLA: q / k heads are nope + rope wide (the KV cache stores that width; v is padded up to it)
+            self.head_dim = self.qk_nope_head_dim + self.qk_rope_head_dim
+            self.num_key_value_heads = self.num_attention_heads
+            self.v_head_dim = self.v_head_dim or self.head_dim
         if self.head_dim is None:
             self.head_dim = self.hidden_size // self.num_attention_heads
         if self.attention_out_bias is None:
@@ -92,7 +103,13 @@ class ModelConfig:
         return self.num_key_value_heads * self.head_dim
 
     @property
+    def use_mla(self) -> bool:
+        return self.kv_lora_rank is not None
+
+    @property
     def rotary_dim(self) -> int:
+        if self.use_mla:
+            return self.qk_rope_head_dim
         return int(self.head_dim * self.partial_rotary_factor)
 
     def num_params(self, include_embeddings: bool = True) -> int:
@@ -169,6 +186,21 @@ MODEL_ZOO: Dict[str, ModelConfig] = {
                                  num_hidden_layers=2, num_attention_heads=4, max_position_embeddings=256,
                                  moe=MoEConfig(num_experts=8, top_k=2, moe_intermediate_size=32, n_shared_experts=1,
                                                first_k_dense_replace=1, norm_topk_prob=False)),
+    # ---- DeepSeek-V3: MLA + sigmoid router with group-limited top-k, shared expert, first 3 layers dense
+    "deepseek-v3": ModelConfig(model_type="deepseek_v3", vocab_size=129280, hidden_size=7168, intermediate_size=18432,
+                               num_hidden_layers=61, num_attention_heads=128, max_position_embeddings=163840,
+                               norm_eps=1e-6, rope_theta=10000.0, rope_interleaved=True, q_lora_rank=1536,
+                               kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128,
+                               moe=MoEConfig(num_experts=256, top_k=8, moe_intermediate_size=2048, n_shared_experts=1,
+                                             first_k_dense_replace=3, norm_topk_prob=True, scoring_func="sigmoid",
+                                             n_group=8, topk_group=4, routed_scaling_factor=2.5)),
+    "deepseek_v3-tiny": ModelConfig(model_type="deepseek_v3", vocab_size=512, hidden_size=64, intermediate_size=128,
+                                    num_hidden_layers=3, num_attention_heads=4, max_position_embeddings=256,
+                                    norm_eps=1e-6, rope_interleaved=True, q_lora_rank=24, kv_lora_rank=16,
+                                    qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=12,
+                                    moe=MoEConfig(num_experts=8, top_k=2, moe_intermediate_size=32, n_shared_experts=1,
+                                                  first_k_dense_replace=1, norm_topk_prob=True, scoring_func="sigmoid",
+                                                  n_group=4, topk_group=2, routed_scaling_factor=2.5)),
     # ---- GPT-2 family (learned positions, LayerNorm, GELU, tied embeddings)
     "gpt2": ModelConfig(model_type="gpt2", vocab_size=50257, hidden_size=768, intermediate_size=3072,
                         num_hidden_layers=12, num_attention_heads=12, max_position_embeddings=1024, norm_type="layer",

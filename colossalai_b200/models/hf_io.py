@@ -95,6 +95,27 @@ def config_from_hf(hf: dict) -> ModelConfig:
                            hidden_act=hf.get("hidden_act", "gelu"), glu=False, attention_bias=True, mlp_bias=True,
                            pos_type="learned", causal=False, type_vocab_size=hf.get("type_vocab_size", 2), post_norm=True,
                            final_norm=False, embed_norm=True, norm_eps=hf.get("layer_norm_eps", 1e-12))
+    if mt == "deepseek_v3":
+        rp = hf.get("rope_parameters") or {}
+        scaling = hf.get("rope_scaling") or ({k: v for k, v in rp.items() if k != "rope_theta"}
+                                              if rp.get("rope_type", "default") != "default" else None)
+        return ModelConfig(
+            model_type="deepseek_v3", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+            intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
+            num_attention_heads=hf["num_attention_heads"], max_position_embeddings=hf.get("max_position_embeddings", 4096),
+            norm_eps=hf.get("rms_norm_eps", 1e-6), rope_theta=float(hf.get("rope_theta", rp.get("rope_theta", 10000.0))),
+            rope_scaling=scaling, rope_interleaved=hf.get("rope_interleave", True),
+            attention_bias=hf.get("attention_bias", False), tie_word_embeddings=hf.get("tie_word_embeddings", False),
+            q_lora_rank=hf.get("q_lora_rank"), kv_lora_rank=hf["kv_lora_rank"], qk_nope_head_dim=hf["qk_nope_head_dim"],
+            qk_rope_head_dim=hf["qk_rope_head_dim"], v_head_dim=hf["v_head_dim"],
+            bos_token_id=hf.get("bos_token_id", 0), eos_token_id=hf.get("eos_token_id", 1),
+            moe=MoEConfig(num_experts=hf["n_routed_experts"], top_k=hf["num_experts_per_tok"],
+                          moe_intermediate_size=hf["moe_intermediate_size"],
+                          n_shared_experts=hf.get("n_shared_experts") or 0,
+                          first_k_dense_replace=hf.get("first_k_dense_replace", 0),
+                          moe_layer_freq=hf.get("moe_layer_freq", 1), norm_topk_prob=hf.get("norm_topk_prob", True),
+                          scoring_func="sigmoid", n_group=hf.get("n_group", 1), topk_group=hf.get("topk_group", 1),
+                          routed_scaling_factor=hf.get("routed_scaling_factor", 1.0)))
     assert mt in _LLAMA_LIKE, f"unsupported HF model_type {mt!r}"
     kw = dict(model_type=mt, vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
               intermediate_size=hf["intermediate_size"], num_hidden_layers=hf["num_hidden_layers"],
@@ -353,12 +374,67 @@ def _convert_gptj(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str,
     return out
 
 
-_FAMILY_CONVERTERS = {"gptj": _convert_gptj, "opt": _convert_opt, "bloom": _convert_bloom, "falcon": _convert_falcon, "bert": _convert_bert}
+def _convert_deepseek_v3(hf_sd: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    """MLA projections keep their names; dense / shared-expert gate+up are fused; routed experts arrive either stacked
+    (`mlp.experts.gate_up_proj [E, 2I, H]`, transformers >= 5) or one module per expert (released checkpoints)."""
+    out: Dict[str, torch.Tensor] = {}
+    gu: Dict[str, Dict[str, torch.Tensor]] = {}
+    experts: Dict[str, Dict[int, Dict[str, torch.Tensor]]] = {}
+    for k, v in hf_sd.items():
+        m = re.match(r"(model\.layers\.\d+\.mlp\.)experts\.(\d+)\.(gate|up|down)_proj\.weight", k)
+        if m:
+            experts.setdefault(m.group(1), {}).setdefault(int(m.group(2)), {})[m.group(3)] = v
+            continue
+        m = re.match(r"(model\.layers\.\d+\.mlp\.(?:shared_experts\.)?)(gate|up)_proj\.weight", k)
+        if m:
+            gu.setdefault(m.group(1), {})[m.group(2)] = v
+            continue
+        if k.endswith("mlp.experts.gate_up_proj"):
+            out[k[: -len("gate_up_proj")] + "w_up"] = v
+        elif k.endswith("mlp.experts.down_proj"):
+            out[k[: -len("down_proj")] + "w_down"] = v
+        elif k.endswith("mlp.gate.weight"):
+            out[k[: -len("gate.weight")] + "router.gate.weight"] = v
+        elif k.endswith("mlp.gate.e_score_correction_bias"):
+            out[k[: -len("gate.e_score_correction_bias")] + "router.e_score_correction_bias"] = v
+        elif re.match(r"model\.layers\.(\d+)\.", k) and int(re.match(r"model\.layers\.(\d+)\.", k).group(1)) >= cfg.num_hidden_layers:
+            continue                                    # multi-token-prediction layers of the release are not used
+        else:
+            out[k] = v
+    for pre, parts in gu.items():
+        out[pre + "gate_up_proj.weight"] = torch.cat([parts["gate"], parts["up"]], dim=0)
+    for pre, ex in experts.items():
+        ids = sorted(ex)
+        out[pre + "experts.w_up"] = torch.stack([torch.cat([ex[i]["gate"], ex[i]["up"]], 0) for i in ids])
+        out[pre + "experts.w_down"] = torch.stack([ex[i]["down"] for i in ids])
+    return out
+
+
+_FAMILY_CONVERTERS = {"deepseek_v3": _convert_deepseek_v3, "gptj": _convert_gptj, "opt": _convert_opt, "bloom": _convert_bloom, "falcon": _convert_falcon, "bert": _convert_bert}
 
 
 def to_hf_state_dict(model, cfg: Optional[ModelConfig] = None) -> Dict[str, torch.Tensor]:
     """Inverse of `convert_hf_state_dict` for the llama-like families (un-fuses qkv / gate_up / experts)."""
     cfg = cfg or model.cfg
+    if cfg.model_type == "deepseek_v3":
+        out = {}
+        for k, v in model.state_dict().items():
+            v = v.detach()
+            if k.endswith("mlp.experts.w_up"):
+                out[k[: -len("w_up")] + "gate_up_proj"] = v
+            elif k.endswith("mlp.experts.w_down"):
+                out[k[: -len("w_down")] + "down_proj"] = v
+            elif k.endswith("gate_up_proj.weight"):
+                g, u = v.chunk(2, dim=0)
+                out[k[: -len("gate_up_proj.weight")] + "gate_proj.weight"] = g
+                out[k[: -len("gate_up_proj.weight")] + "up_proj.weight"] = u
+            elif k.endswith("mlp.router.gate.weight"):
+                out[k.replace("router.gate.weight", "gate.weight")] = v
+            elif k.endswith("mlp.router.e_score_correction_bias"):
+                out[k.replace("router.e_score_correction_bias", "gate.e_score_correction_bias")] = v
+            else:
+                out[k] = v
+        return out
     assert cfg.model_type in _LLAMA_LIKE, "export is implemented for the llama-like families"
     q, kv = cfg.num_attention_heads * cfg.head_dim, cfg.num_key_value_heads * cfg.head_dim
     out: Dict[str, torch.Tensor] = {}
@@ -468,6 +544,22 @@ def from_hf_model(hf_model, dtype: Optional[torch.dtype] = None):
 
 def hf_config_dict(cfg: ModelConfig) -> dict:
     """`config.json` content for the llama-like families (enough for `AutoModelForCausalLM.from_pretrained`)."""
+    if cfg.model_type == "deepseek_v3":
+        m = cfg.moe
+        return {"architectures": ["DeepseekV3ForCausalLM"], "model_type": "deepseek_v3", "vocab_size": cfg.vocab_size,
+                "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+                "moe_intermediate_size": m.moe_intermediate_size, "num_hidden_layers": cfg.num_hidden_layers,
+                "num_attention_heads": cfg.num_attention_heads, "num_key_value_heads": cfg.num_attention_heads,
+                "n_shared_experts": m.n_shared_experts, "n_routed_experts": m.num_experts,
+                "routed_scaling_factor": m.routed_scaling_factor, "kv_lora_rank": cfg.kv_lora_rank,
+                "q_lora_rank": cfg.q_lora_rank, "qk_rope_head_dim": cfg.qk_rope_head_dim, "v_head_dim": cfg.v_head_dim,
+                "qk_nope_head_dim": cfg.qk_nope_head_dim, "n_group": m.n_group, "topk_group": m.topk_group,
+                "num_experts_per_tok": m.top_k, "first_k_dense_replace": m.first_k_dense_replace,
+                "norm_topk_prob": m.norm_topk_prob, "hidden_act": cfg.hidden_act,
+                "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.norm_eps,
+                "rope_theta": cfg.rope_theta, "rope_scaling": cfg.rope_scaling, "rope_interleave": cfg.rope_interleaved,
+                "attention_bias": cfg.attention_bias, "tie_word_embeddings": cfg.tie_word_embeddings,
+                "bos_token_id": cfg.bos_token_id, "eos_token_id": cfg.eos_token_id, "torch_dtype": "bfloat16"}
     assert cfg.model_type in ("llama", "mistral", "qwen2", "qwen3", "mixtral"), cfg.model_type
     arch = {"llama": "LlamaForCausalLM", "mistral": "MistralForCausalLM", "qwen2": "Qwen2ForCausalLM",
             "qwen3": "Qwen3ForCausalLM", "mixtral": "MixtralForCausalLM"}[cfg.model_type]

@@ -180,6 +180,86 @@ class Attention(nn.Module):
         return bias.to(dtype)
 
 
+class MLAttention(nn.Module):
+    """Multi-head latent attention (DeepSeek-V2 / V3): queries through a low-rank bottleneck, keys / values rebuilt
+    from one shared `kv_lora_rank` latent per token plus a single rotary key shared by all heads.
+
+    Parity: reference `shardformer/policies/deepseek_v3.py` drives HF's `DeepseekV3Attention`
+    (transformers `modeling_deepseek_v3.py`), whose parameter names are kept so checkpoints map one to one.  Under
+    tensor parallelism the up-projections (`q_b_proj`, `kv_b_proj`) are column-split by heads and `o_proj` is
+    row-split; the small down-projections and their norms stay replicated.  With a KV cache the value heads are
+    zero-padded to the key width so one paged layout serves both."""
+
+    def __init__(self, cfg: ModelConfig, layer_idx: int = 0) -> None:
+        super().__init__()
+        self.cfg, self.layer_idx = cfg, layer_idx
+        self.num_heads = self.num_kv_heads = cfg.num_attention_heads
+        self.qk_nope, self.qk_rope, self.v_dim = cfg.qk_nope_head_dim, cfg.qk_rope_head_dim, cfg.v_head_dim
+        self.head_dim = self.qk_nope + self.qk_rope
+        H, hid = cfg.num_attention_heads, cfg.hidden_size
+        if cfg.q_lora_rank is None:
+            self.q_proj = nn.Linear(hid, H * self.head_dim, bias=False)
+        else:
+            self.q_a_proj = nn.Linear(hid, cfg.q_lora_rank, bias=cfg.attention_bias)
+            self.q_a_layernorm = FusedRMSNorm(cfg.q_lora_rank, eps=cfg.norm_eps)
+            self.q_b_proj = nn.Linear(cfg.q_lora_rank, H * self.head_dim, bias=False)
+        self.kv_a_proj_with_mqa = nn.Linear(hid, cfg.kv_lora_rank + self.qk_rope, bias=cfg.attention_bias)
+        self.kv_a_layernorm = FusedRMSNorm(cfg.kv_lora_rank, eps=cfg.norm_eps)
+        self.kv_b_proj = nn.Linear(cfg.kv_lora_rank, H * (self.qk_nope + self.v_dim), bias=False)
+        self.o_proj = nn.Linear(H * self.v_dim, hid, bias=cfg.attention_bias)
+        self.shard_config = None
+        self.scale = 1.0 / math.sqrt(self.head_dim)
+        rs = cfg.rope_scaling or {}
+        if rs.get("rope_type", rs.get("type", "default")) == "yarn" and rs.get("mscale_all_dim"):
+            f = rs.get("factor", 1.0)
+            m = 1.0 if f <= 1 else 0.1 * rs["mscale_all_dim"] * math.log(f) + 1.0
+            self.scale = self.scale * m * m
+
+    def _replicated_in_tp(self, t: torch.Tensor) -> torch.Tensor:
+        """The shared rotary key comes from a replicated projection but feeds this rank's heads only: its gradient is a
+        partial sum over the TP group (identity forward / all-reduce backward).  The latents entering `q_b_proj` /
+        `kv_b_proj` need nothing here, the column-parallel linears already all-reduce their input gradient."""
+        sc = self.shard_config
+        if sc is not None and sc.enable_tensor_parallelism and sc.tensor_parallel_size > 1 and t.requires_grad:
+            from ..shardformer.layer._operation import reduce_backward
+
+            return reduce_backward(t, sc.tp_group)
+        return t
+
+    def forward(self, x: torch.Tensor, meta: SeqMeta, rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                kv_cache=None) -> torch.Tensor:
+        cfg, sc = self.cfg, self.shard_config
+        if sc is not None and sc.sp_mode in ("all_to_all", "ring_attn") and comm.group_size(sc.sp_group) > 1:
+            raise NotImplementedError("multi-head latent attention supports tensor / pipeline / expert parallelism "
+                                      "and Megatron-style sequence parallelism is not wired for it yet")
+        T, Hl = x.shape[0], self.num_heads
+        if cfg.q_lora_rank is None:
+            q = self.q_proj(x)
+        else:
+            q = self.q_b_proj(self.q_a_layernorm(self.q_a_proj(x)))
+        q = q.view(T, Hl, self.head_dim)
+        ckv = self.kv_a_proj_with_mqa(x)
+        c, k_pe = ckv.split([cfg.kv_lora_rank, self.qk_rope], dim=-1)
+        kv = self.kv_b_proj(self.kv_a_layernorm(c)).view(T, Hl, self.qk_nope + self.v_dim)
+        k_nope, v = kv.split([self.qk_nope, self.v_dim], dim=-1)
+        q_nope, q_pe = q.split([self.qk_nope, self.qk_rope], dim=-1)
+        k_pe = self._replicated_in_tp(k_pe).reshape(T, 1, self.qk_rope)
+        if rope is not None:
+            q_pe = ops.rope_ref(q_pe, meta.positions, rope[0], rope[1], self.qk_rope, cfg.rope_interleaved)
+            k_pe = ops.rope_ref(k_pe, meta.positions, rope[0], rope[1], self.qk_rope, cfg.rope_interleaved)
+        q = torch.cat([q_nope, q_pe], dim=-1)
+        k = torch.cat([k_nope, k_pe.expand(T, Hl, self.qk_rope)], dim=-1)
+        if kv_cache is not None:
+            vp = F.pad(v, (0, self.head_dim - self.v_dim)) if self.v_dim < self.head_dim else v
+            o = kv_cache.attend(self.layer_idx, q.contiguous(), k.contiguous(), vp.contiguous(), meta, self.scale)
+            o = o.reshape(T, Hl, -1)[..., : self.v_dim]
+        else:
+            o = ops.attention(q, k, v.contiguous(), batch=meta.batch, causal=cfg.causal, scale=self.scale,
+                              cu_seqlens_q=meta.cu_seqlens, max_seqlen=meta.max_seqlen,
+                              dropout_p=cfg.attn_dropout if self.training else 0.0)
+        return self.o_proj(o.reshape(T, Hl * self.v_dim))
+
+
 class MLP(nn.Module):
     def __init__(self, cfg: ModelConfig, intermediate_size: Optional[int] = None) -> None:
         super().__init__()
@@ -212,7 +292,7 @@ class DecoderLayer(nn.Module):
         super().__init__()
         self.cfg, self.layer_idx = cfg, layer_idx
         self.input_layernorm = build_norm(cfg)
-        self.self_attn = Attention(cfg, layer_idx)
+        self.self_attn = MLAttention(cfg, layer_idx) if cfg.use_mla else Attention(cfg, layer_idx)
         if not cfg.parallel_block:
             self.post_attention_layernorm = build_norm(cfg)
         moe = cfg.moe

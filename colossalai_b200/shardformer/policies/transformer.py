@@ -45,7 +45,8 @@ class TransformerPolicy(Policy):
 
     def module_policy(self) -> Dict[Union[str, Type[nn.Module]], ModulePolicyDescription]:
         from ...models.moe import SparseMoE
-        from ...models.transformer import Attention, DecoderLayer, MLP, TransformerLMHeadModel, TransformerModel
+        from ...models.transformer import (Attention, DecoderLayer, MLAttention, MLP, TransformerLMHeadModel,
+                                           TransformerModel)
 
         sc = self.shard_config
         cfg = self.model.cfg
@@ -68,6 +69,17 @@ class TransformerPolicy(Policy):
                         kwargs=dict(split_sizes=[cfg.q_size, cfg.kv_size, cfg.kv_size], **common)),
                     SubModuleReplacementDescription("o_proj", Linear1D_Row, kwargs=dict(**common)),
                 ])
+            if cfg.use_mla:
+                assert lin_sp is None, "multi-head latent attention: sequence parallelism is not supported yet"
+                policy[MLAttention] = ModulePolicyDescription(
+                    attribute_replacement={"num_heads": cfg.num_attention_heads // tp,
+                                           "num_kv_heads": cfg.num_attention_heads // tp},
+                    sub_module_replacement=[
+                        SubModuleReplacementDescription("q_b_proj" if cfg.q_lora_rank is not None else "q_proj",
+                                                        Linear1D_Col, kwargs=dict(**common)),
+                        SubModuleReplacementDescription("kv_b_proj", Linear1D_Col, kwargs=dict(**common)),
+                        SubModuleReplacementDescription("o_proj", Linear1D_Row, kwargs=dict(**common)),
+                    ])
             mlp_subs = [SubModuleReplacementDescription("down_proj", Linear1D_Row, kwargs=dict(**common))]
             if cfg.glu:
                 mlp_subs.insert(0, SubModuleReplacementDescription(

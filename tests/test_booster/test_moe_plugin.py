@@ -27,8 +27,8 @@ def _gather(p):
     return p.detach()
 
 
-def _run(rank, world, plugin_kw, tmp, max_norm=0.0, precision="fp32", tol=3e-4):
-    cfg = get_config("mixtral-tiny", router_aux_loss=False) if False else get_config("mixtral-tiny")
+def _run(rank, world, plugin_kw, tmp, max_norm=0.0, precision="fp32", tol=3e-4, preset="mixtral-tiny"):
+    cfg = get_config(preset)
     torch.manual_seed(7)
     base = build_model(cfg)
     for m in base.modules():
@@ -121,6 +121,8 @@ def _worker(rank, world_size, port, tmp):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     _run(rank, world_size, dict(tp_size=1, pp_size=1, ep_size=2), tmp, max_norm=0.5)
     _run(rank, world_size, dict(tp_size=1, pp_size=1, ep_size=1), tmp)
+    # DeepSeek-V3: latent attention, sigmoid / group-limited routing, shared expert, one leading dense layer
+    _run(rank, world_size, dict(tp_size=1, pp_size=1, ep_size=2), tmp, preset="deepseek_v3-tiny")
     dist.destroy_process_group()
 
 

@@ -295,3 +295,31 @@ def test_export_tp_sharded_model_to_hf_directory():
 
     with tempfile.TemporaryDirectory() as tmp:
         spawn(_export_worker, 2, out_dir=tmp)
+
+
+def test_deepseek_v3_mla_matches_transformers():
+    """Multi-head latent attention + sigmoid / group-limited router + shared expert, weight for weight against HF's
+    `DeepseekV3ForCausalLM`; export maps back to the HF names."""
+    torch.manual_seed(0)
+    hf_cfg = transformers.DeepseekV3Config(
+        vocab_size=512, hidden_size=64, intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3,
+        num_attention_heads=4, num_key_value_heads=4, n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=2.5,
+        kv_lora_rank=16, q_lora_rank=24, qk_rope_head_dim=8, v_head_dim=12, qk_nope_head_dim=16, n_group=4,
+        topk_group=2, num_experts_per_tok=2, first_k_dense_replace=1, norm_topk_prob=True, max_position_embeddings=256,
+        rms_norm_eps=1e-6, tie_word_embeddings=False)
+    hf = transformers.DeepseekV3ForCausalLM(hf_cfg)
+    with torch.no_grad():                                    # a non-trivial routing bias and non-unit norm gains
+        for n, b in hf.named_buffers():
+            if n.endswith("e_score_correction_bias"):
+                b.copy_(torch.randn_like(b) * 0.1)
+        for n, p in hf.named_parameters():
+            if "layernorm" in n or n.endswith("norm.weight"):
+                p.add_(torch.randn_like(p) * 0.1)
+    ours, cfg = _check(hf, atol=3e-4)
+    assert cfg.use_mla and cfg.moe.scoring_func == "sigmoid" and cfg.head_dim == 24 and cfg.rotary_dim == 8
+    back = to_hf_state_dict(ours)
+    for k, v in hf.state_dict().items():
+        torch.testing.assert_close(back[k], v.float(), msg=lambda m: f"{k}: {m}")
+    # q without the low-rank bottleneck (DeepSeek-V2-Lite layout)
+    hf_cfg2 = transformers.DeepseekV3Config(**{**hf_cfg.to_dict(), "q_lora_rank": None})
+    _check(transformers.DeepseekV3ForCausalLM(hf_cfg2), atol=3e-4)

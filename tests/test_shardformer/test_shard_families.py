@@ -16,6 +16,7 @@ def _worker(rank, world_size, port):
     from test_shard_llama import _run_one
 
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    _run_one("deepseek_v3-tiny", dict(tp=2, sp_mode=None), atol=5e-5)     # MLA: head-split up-projections, shared rope key
     for name in FAMILIES:
         _run_one(name, dict(tp=2, sp_mode=None), atol=5e-5)
         if name not in ("bloom-tiny", "baichuan-tiny", "bert-tiny"):      # (ALiBi / padded-mask paths build full masks)
