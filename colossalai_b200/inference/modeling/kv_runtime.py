@@ -29,6 +29,7 @@ class PagedKVRuntime:
         self.cu_seqlens: Optional[torch.Tensor] = None
         self.max_seqlen: int = 0
         self.q_per_seq: int = 1                               # decode: tokens verified per sequence (spec-dec)
+        self.max_len_host: int = 0                            # longest sequence of the step (host side, no sync)
 
     def set_step(self, block_tables: torch.Tensor, seq_lens: torch.Tensor, is_prompt: bool, device,
                  q_per_seq: int = 1) -> torch.Tensor:
@@ -38,6 +39,7 @@ class PagedKVRuntime:
         self.is_prompt = is_prompt
         self.q_per_seq = q_per_seq
         lens = seq_lens.tolist()
+        self.max_len_host = max(lens) if lens else 0
         if is_prompt:
             seq = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens))
             pos = torch.cat([torch.arange(l) for l in lens])
@@ -54,9 +56,48 @@ class PagedKVRuntime:
         return pos.to(device=device, dtype=torch.int64)
 
     def attend(self, layer_idx: int, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, meta, scale: float,
-               alibi_slopes: Optional[torch.Tensor] = None) -> torch.Tensor:
+               alibi_slopes: Optional[torch.Tensor] = None, sliding_window: Optional[int] = None) -> torch.Tensor:
         kc, vc = self.k_caches[layer_idx], self.v_caches[layer_idx]
         iops.kv_cache_write(k, v, kc, vc, self.block_tables, self.token_seq, self.token_pos)
+        if sliding_window is not None and self.max_len_host > sliding_window:
+            return self._attend_windowed(q, k, v, kc, vc, scale, alibi_slopes, sliding_window)
+        return self._attend_full(q, k, v, kc, vc, scale, alibi_slopes)
+
+    def _attend_windowed(self, q, k, v, kc, vc, scale, alibi_slopes, window: int) -> torch.Tensor:
+        """Sliding-window attention (Mistral): a sequence longer than the window takes the banded reference path —
+        prefill with an explicit band mask per sequence, decode over the last `window` cached tokens."""
+        from ...ops.attention import attention_ref
+
+        if self.is_prompt:
+            cu = self.cu_seqlens.tolist()
+            outs = []
+            for i in range(len(cu) - 1):
+                a, b = cu[i], cu[i + 1]
+                S = b - a
+                pos = torch.arange(S, device=q.device)
+                rel = pos[None, :] - pos[:, None]
+                keep = (rel <= 0) & (rel > -window)
+                bias = torch.zeros(S, S, device=q.device, dtype=torch.float32)
+                if alibi_slopes is not None:
+                    bias = rel.clamp(max=0).float()[None] * alibi_slopes.float()[:, None, None]
+                bias = bias.expand(q.shape[1], S, S) if bias.dim() == 3 else bias[None].expand(q.shape[1], S, S)
+                bias = bias.masked_fill(~keep[None], float("-inf")).to(q.dtype)[None]
+                outs.append(attention_ref(q[a:b], k[a:b], v[a:b], batch=1, causal=False, scale=scale, attn_mask=bias))
+            return torch.cat(outs, 0)
+        n = self.q_per_seq
+        if n == 1:
+            return iops.paged_decode_attention(q, kc, vc, self.block_tables, self.seq_lens, scale,
+                                               alibi_slopes=alibi_slopes, window=window)
+        bsz = self.seq_lens.numel()
+        outs = []
+        for j in range(n):
+            qj = q.view(bsz, n, *q.shape[1:])[:, j]
+            outs.append(iops.paged_decode_attention(qj.contiguous(), kc, vc, self.block_tables,
+                                                    self.seq_lens - (n - 1 - j), scale, alibi_slopes=alibi_slopes,
+                                                    window=window))
+        return torch.stack(outs, 1).reshape(q.shape)
+
+    def _attend_full(self, q, k, v, kc, vc, scale, alibi_slopes) -> torch.Tensor:
         if alibi_slopes is not None:
             # ALiBi families (Baichuan-13B, BLOOM): biased varlen prefill through the reference backend, the paged
             # decode kernel takes the slopes natively

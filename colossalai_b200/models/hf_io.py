@@ -126,6 +126,8 @@ def config_from_hf(hf: dict) -> ModelConfig:
               tie_word_embeddings=hf.get("tie_word_embeddings", False), rope_scaling=hf.get("rope_scaling"))
     if hf.get("head_dim"):
         kw["head_dim"] = hf["head_dim"]
+    if hf.get("sliding_window") and (mt in ("mistral", "mixtral") or hf.get("use_sliding_window", False)):
+        kw["sliding_window"] = int(hf["sliding_window"])
     if mt == "qwen2":
         kw["attention_bias"], kw["attention_out_bias"] = True, False
     if mt == "qwen3":

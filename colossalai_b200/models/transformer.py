@@ -122,12 +122,18 @@ class Attention(nn.Module):
         if kv_cache is not None:
             slopes = self._local_alibi_slopes(q.device) if cfg.pos_type == "alibi" else None
             extra = {} if slopes is None else {"alibi_slopes": slopes}
+            if cfg.sliding_window:
+                extra["sliding_window"] = cfg.sliding_window
             o = kv_cache.attend(self.layer_idx, q, k, v, meta, self.scale, **extra)
         elif sp_mode == "ring_attn" and comm.group_size(sp_group) > 1:
             o = RingAttention.attention(q, k, v, sp_group, batch=meta.batch, scale=self.scale)
         else:
             mask = None
-            if cfg.pos_type == "alibi" or meta.attn_mask is not None:
+            windowed = bool(cfg.sliding_window) and (meta.max_seqlen or T // meta.batch) > cfg.sliding_window
+            if windowed and meta.cu_seqlens is not None:
+                raise NotImplementedError("sliding-window attention over packed (varlen) batches longer than the "
+                                          "window is not supported; pad to equal lengths")
+            if cfg.pos_type == "alibi" or meta.attn_mask is not None or windowed:
                 mask = self._build_mask(meta, T, hq, q.device, q.dtype)
             o = ops.attention(q, k, v, batch=meta.batch, causal=cfg.causal and mask is None, scale=self.scale,
                               cu_seqlens_q=meta.cu_seqlens, max_seqlen=meta.max_seqlen, attn_mask=mask,
@@ -168,6 +174,9 @@ class Attention(nn.Module):
             keep = keep & torch.ones(S, S, dtype=torch.bool, device=device).tril()
         if meta.attn_mask is not None:
             keep = keep & meta.attn_mask.bool()[:, None, None, :]
+        if self.cfg.sliding_window and S > self.cfg.sliding_window:       # Mistral: the last `window` keys only
+            idx = torch.arange(S, device=device)
+            keep = keep & ((idx[None, :] - idx[:, None]) > -self.cfg.sliding_window)
         if self.cfg.pos_type != "alibi":
             return keep
         sc = self.shard_config

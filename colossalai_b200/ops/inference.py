@@ -54,11 +54,15 @@ def _decode_workspace(q: torch.Tensor, n: int, heads: int, splits: int, head_dim
 
 def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_tables: torch.Tensor,
                            seq_lens: torch.Tensor, scale: Optional[float] = None,
-                           alibi_slopes: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q: [num_seqs, Hq, D] (one new token per sequence) -> [num_seqs, Hq, D]."""
+                           alibi_slopes: Optional[torch.Tensor] = None, window: Optional[int] = None) -> torch.Tensor:
+    """q: [num_seqs, Hq, D] (one new token per sequence) -> [num_seqs, Hq, D].  `window`: sliding-window attention
+    (only the last `window` cached tokens are visible) — served by the reference path; callers pass it only for
+    sequences that have actually outgrown the window."""
     n, Hq, D = q.shape
     nb, bs, Hkv, _ = k_cache.shape
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    if window is not None:
+        return paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale, alibi_slopes, window)
     if (use_native(q) and q.dtype in (torch.float16, torch.bfloat16) and k_cache.dtype == q.dtype
             and D in (64, 128, 256) and Hq // Hkv <= 8):
         lib = _get_lib()
@@ -83,7 +87,8 @@ def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torc
     return paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale, alibi_slopes)
 
 
-def paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale=None, alibi_slopes=None):
+def paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale=None, alibi_slopes=None,
+                               window=None):
     n, Hq, D = q.shape
     nb, bs, Hkv, _ = k_cache.shape
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
@@ -95,6 +100,8 @@ def paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scal
         blks = block_tables[i, :nblk].long()
         k = k_cache[blks].reshape(-1, Hkv, D)[:L].float()
         v = v_cache[blks].reshape(-1, Hkv, D)[:L].float()
+        if window is not None and L > window:
+            k, v, L = k[L - window:], v[L - window:], window
         k = k.repeat_interleave(G, dim=1)
         v = v.repeat_interleave(G, dim=1)
         s = torch.einsum("hd,lhd->hl", q[i].float(), k) * scale

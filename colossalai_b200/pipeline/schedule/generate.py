@@ -35,7 +35,7 @@ class DenseKVCache:
         self.k: Dict[int, torch.Tensor] = {}
         self.v: Dict[int, torch.Tensor] = {}
 
-    def attend(self, layer_idx: int, q, k, v, meta, scale: float, alibi_slopes=None):
+    def attend(self, layer_idx: int, q, k, v, meta, scale: float, alibi_slopes=None, sliding_window=None):
         from ... import ops
 
         B = self.batch
@@ -45,13 +45,18 @@ class DenseKVCache:
             kb = torch.cat([self.k[layer_idx], kb], dim=1)
             vb = torch.cat([self.v[layer_idx], vb], dim=1)
         self.k[layer_idx], self.v[layer_idx] = kb, vb
+        if sliding_window is not None and kb.shape[1] > sliding_window and alibi_slopes is None:
+            alibi_slopes = torch.zeros(q.shape[1], device=q.device)          # band mask through the bias path
         if alibi_slopes is not None:
             # queries are the last Sq positions of the Sk cached ones: bias = slope * (key_pos - query_pos), causal
             Sq, Sk = q.shape[0] // B, kb.shape[1]
             qpos = torch.arange(Sk - Sq, Sk, device=q.device)
             rel = torch.arange(Sk, device=q.device)[None, :] - qpos[:, None]
             bias = rel.clamp(max=0).float()[None, None] * alibi_slopes.float()[None, :, None, None]
-            bias = bias.masked_fill((rel > 0)[None, None], float("-inf")).to(q.dtype)
+            hidden = rel > 0
+            if sliding_window is not None:
+                hidden = hidden | (rel <= -sliding_window)
+            bias = bias.masked_fill(hidden[None, None], float("-inf")).to(q.dtype)
             return ops.attention(q, kb.reshape(-1, *k.shape[1:]), vb.reshape(-1, *v.shape[1:]), batch=B, causal=False,
                                  scale=scale, attn_mask=bias)
         return ops.attention(q, kb.reshape(-1, *k.shape[1:]), vb.reshape(-1, *v.shape[1:]), batch=B, causal=True,

@@ -323,3 +323,21 @@ def test_deepseek_v3_mla_matches_transformers():
     # q without the low-rank bottleneck (DeepSeek-V2-Lite layout)
     hf_cfg2 = transformers.DeepseekV3Config(**{**hf_cfg.to_dict(), "q_lora_rank": None})
     _check(transformers.DeepseekV3ForCausalLM(hf_cfg2), atol=3e-4)
+
+
+def test_mistral_sliding_window_matches_transformers():
+    """Sequences longer than `sliding_window` see only the last `window` keys (band mask), as in HF Mistral."""
+    torch.manual_seed(0)
+    hf_cfg = transformers.MistralConfig(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                        num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                                        sliding_window=5)
+    hf = transformers.MistralForCausalLM(hf_cfg)
+    ours, cfg = _check(hf)                                   # 12 tokens > window 5
+    assert cfg.sliding_window == 5
+    ids = torch.randint(0, 128, (2, 12))
+    full = build_model(cfg.replace(sliding_window=None)).float().eval()
+    full.load_state_dict(ours.state_dict())
+    with torch.no_grad():
+        a = ours(input_ids=ids)["logits"]
+        b = full(input_ids=ids)["logits"]
+    assert (a - b).abs().max() > 1e-3                        # the window really changes the result

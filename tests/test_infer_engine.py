@@ -319,3 +319,18 @@ def test_streamingllm_window_eviction_bounds_kv_blocks():
     assert max(peak) <= 2 * (window // cfg.block_size + 1)
     assert max(peak) < 2 * ((16 + 64) // cfg.block_size)
     assert mgr.num_available_blocks == total
+
+
+def test_engine_sliding_window_matches_naive_greedy():
+    """Mistral-style sliding window in the paged engine: prompts and generations that outgrow the window follow the
+    banded full-recompute oracle (prefill band mask, decode over the last `window` cached tokens)."""
+    torch.manual_seed(0)
+    model = build_model(get_config("mistral-tiny", sliding_window=6)).float().eval()
+    cfg = InferenceConfig(max_batch_size=2, max_input_len=16, max_output_len=10, block_size=8, dtype="fp32",
+                          use_cuda_graph=False, ignore_eos=True)
+    eng = InferenceEngine(model, None, cfg)
+    prompts = [[5, 9, 13, 200, 7, 21, 22, 23, 24, 25, 26], [11, 3, 8]]          # one prompt already beyond the window
+    _, ids = eng.generate(prompts_token_ids=prompts, return_token_ids=True,
+                          generation_config=GenerationConfig(max_new_tokens=10))
+    for p, got in zip(prompts, ids):
+        assert got == _naive_greedy(model, p, 10), (p, got)
