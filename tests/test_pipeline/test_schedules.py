@@ -28,14 +28,14 @@ def test_schedule_graphs_are_complete():
             assert sum(1 for n in sched[s] if n.type == "B") == 2 * n_micro
 
 
-def _run(pp_style, num_model_chunks, tied=False):
+def _run(pp_style, num_model_chunks, tied=False, **plugin_kw):
     torch.manual_seed(7)
     base = build_model("gpt2-tiny" if tied else "llama-tiny")
     model = copy.deepcopy(base)
     ref_opt = torch.optim.AdamW(base.parameters(), lr=1e-2, weight_decay=0.0)
     opt = FusedAdam(model.parameters(), lr=1e-2, weight_decay=0.0)
     plugin = HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=4, pp_style=pp_style,
-                                  num_model_chunks=num_model_chunks)
+                                  num_model_chunks=num_model_chunks, **plugin_kw)
     booster = Booster(plugin=plugin)
     model, opt, *_ = booster.boost(model, opt)
     torch.manual_seed(11)
@@ -65,6 +65,9 @@ def _run(pp_style, num_model_chunks, tied=False):
                                    msg=lambda m: f"{pp_style} {name}: {m}")
         n += 1
     assert n > 3
+    if "num_layers_per_stage" in plugin_kw:
+        held = sum(1 for name, _ in model.unwrap().named_parameters() if name.endswith("input_layernorm.weight"))
+        assert held == plugin_kw["num_layers_per_stage"][dist.get_rank()], (held, plugin_kw)
     del plugin
 
 
@@ -74,6 +77,12 @@ def _worker(rank, world_size, port):
     _run("1f1b", 1, tied=True)
     _run("interleaved", 2)
     _run("zbv", 2)
+    # uneven stages with per-stage activation checkpointing (the Llama-3-70B headline layout in miniature)
+    from colossalai_b200.shardformer import PipelineGradientCheckpointConfig
+
+    _run("1f1b", 1, num_layers_per_stage=[1, 3],
+         gradient_checkpoint_config=PipelineGradientCheckpointConfig(num_ckpt_layers_per_stage=[1, 2]))
+    _run("1f1b", 1, gradient_checkpoint_config=PipelineGradientCheckpointConfig(gradient_checkpointing_ratio=0.5))
     dist.destroy_process_group()
 
 
