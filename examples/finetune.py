@@ -65,7 +65,8 @@ def make_batch(model_type: str, cfg, batch: int, seq: int, device, gen: torch.Ge
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="llama-tiny")
-    ap.add_argument("--plugin", default="zero2", choices=["ddp", "zero1", "zero2", "gemini", "hybrid"])
+    ap.add_argument("--plugin", default="zero2", choices=["ddp", "zero1", "zero2", "gemini", "hybrid", "moe_hybrid"])
+    ap.add_argument("--ep", type=int, default=1, help="expert-parallel size (moe_hybrid)")
     ap.add_argument("--tp", type=int, default=1)
     ap.add_argument("--pp", type=int, default=1)
     ap.add_argument("--sp_mode", default=None)
@@ -90,6 +91,11 @@ def main():
     elif args.plugin == "gemini":
         plugin = GeminiPlugin(precision=precision if precision != "fp32" else "bf16", max_norm=1.0,
                               **(dict(min_chunk_size_m=1, search_range_m=1) if dev.type == "cpu" else {}))
+    elif args.plugin == "moe_hybrid":
+        from colossalai_b200.booster.plugin import MoeHybridParallelPlugin
+
+        plugin = MoeHybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, ep_size=args.ep, precision=precision,
+                                         max_norm=1.0, num_microbatches=args.batch if args.pp > 1 else None)
     else:
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, precision=precision, max_norm=1.0,
                                       enable_sequence_parallelism=args.sp_mode is not None,
@@ -103,12 +109,12 @@ def main():
     optimizer = HybridAdam(model.parameters(), lr=args.lr, weight_decay=0.01)
     sched = CosineAnnealingWarmupLR(optimizer, total_steps=args.steps, warmup_steps=max(1, args.steps // 10))
     model, optimizer, _, _, sched = booster.boost(model, optimizer, lr_scheduler=sched)
-    gen = torch.Generator().manual_seed(1234 + (dist.get_rank() if args.plugin != "hybrid" else 0))
+    gen = torch.Generator().manual_seed(1234 + (dist.get_rank() if args.plugin not in ("hybrid", "moe_hybrid") else 0))
     first = last = None
     t0 = time.perf_counter()
     for step in range(args.steps):
         batch = make_batch(mt, cfg, args.batch, args.seq, dev, gen)
-        if args.plugin == "hybrid" and args.pp > 1:
+        if args.plugin in ("hybrid", "moe_hybrid") and args.pp > 1:
             out = booster.execute_pipeline(iter([batch]), model, lambda o, b: o["loss"], optimizer, return_loss=True)
             loss = out["loss"]
         else:
