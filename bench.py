@@ -7,8 +7,17 @@
     python bench.py --impl reference ...                          # the UNMODIFIED reference from baseline/_ref
 
 Metric / config follow BASELINE.json: tokens/sec (whole box, device-timed, max over ranks), Llama-3-8B, bf16,
-synthetic tokens, random-init weights, TP = N (+ Megatron-style sequence parallelism) over NVSwitch, weak scaling
-(one 4096-token sequence per GPU per step).  Parity: reference `examples/language/llama/benchmark.py`.
+synthetic tokens, random-init weights, weak scaling (one 4096-token sequence per GPU per micro-step, 8 micro-steps per
+optimizer step).  Parity: reference `examples/language/llama/benchmark.py`.
+
+Parallelism (`--parallelism`, same flag and same spellings for both arms):
+    tp        the configuration BASELINE.json names: TP = N + Megatron sequence parallelism over NVSwitch (`tpN+sp`)
+    dp        pure data parallel with ZeRO-1 optimizer-state sharding (`zero1(dpN)`)
+    both      (default) the headline `value` is the `tp` row; the `dp` row is measured in the same process with the
+              same timing rules and reported under `rows` - for an 8B model on 180 GB GPUs plain data parallelism
+              scales better than TP=8, and the line says so instead of hiding it.
+At N = 1 the two coincide (`tp1`).  `config.parallelism` of the two arms is the same string whenever they ran the same
+thing, so the driver's same-config check compares like with like.
 """
 from __future__ import annotations
 
@@ -39,7 +48,9 @@ def parse_args():
     p.add_argument("--mbs", type=int, default=1, help="sequences per GPU per step (weak scaling)")
     p.add_argument("--accum", type=int, default=int(os.environ.get("CB200_BENCH_ACCUM", "8")),
                    help="gradient accumulation micro-steps per optimizer step (the reference headline uses batch/DP 128)")
-    p.add_argument("--tp", type=int, default=0, help="tensor parallel size (default: = gpus)")
+    p.add_argument("--parallelism", default=os.environ.get("CB200_BENCH_PARALLELISM", "both"),
+                   choices=["tp", "dp", "both"], help="see module docstring")
+    p.add_argument("--tp", type=int, default=0, help="tensor parallel size of the tp row (default: = gpus)")
     p.add_argument("--pp", type=int, default=1)
     p.add_argument("--sp-mode", default="split_gather")
     p.add_argument("--zero", type=int, default=0)
@@ -119,11 +130,37 @@ def _init_dist(args):
     return torch.distributed.get_rank(), torch.distributed.get_world_size()
 
 
-def run_ours(args) -> dict:
+METRIC = "tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B training step (fwd+bwd+AdamW)"
+L2_NOTE = "working set per step (>= 2 GB weights+activations per layer) >> 126 MB L2; no explicit flush"
+
+
+def row_label(kind: str, world: int, tp: int = 0, pp: int = 1, sp_mode: str = "split_gather", zero: int = 0) -> str:
+    """One spelling of a parallel layout for BOTH arms (the driver compares `config.parallelism` across arms)."""
+    if kind == "dp" and world > 1:
+        return f"zero1(dp{world})"
+    tp = tp or world
+    if world == 1:
+        return "tp1"
+    dp = world // (tp * pp)
+    return f"tp{tp}" + (f"+sp({sp_mode})" if tp > 1 else "") + (f"xpp{pp}" if pp > 1 else "") + \
+        (f"xdp{dp}" if dp > 1 else "") + (f"+zero{zero}" if zero else "")
+
+
+def shared_config(args, world: int, parallelism: str) -> dict:
+    """The part of `config` that must read the same in both arms."""
+    return {"model": args.model + (f"[layers={args.layers} DEBUG-INVALID]" if args.layers else ""),
+            "global_batch": args.mbs * world * args.accum, "seq_len": args.seq, "parallelism": parallelism,
+            "grad_accum": args.accum, "optimizer": "AdamW (fp32 master + moments, grad-norm clip 1.0)", "l2": L2_NOTE}
+
+
+def _measure_ours(args, kind: str, rank: int, world: int, steps: int, with_e2e: bool, profile_path: str = "") -> dict:
+    """Build the model under one parallel layout through the public API (Booster + HybridParallelPlugin), time
+    `steps` optimizer steps, tear everything down again."""
+    import gc
+
     import torch
     import torch.distributed as dist
 
-    import colossalai_b200
     from colossalai_b200.booster import Booster
     from colossalai_b200.booster.plugin import HybridParallelPlugin
     from colossalai_b200.kernel import launch_counter
@@ -132,11 +169,11 @@ def run_ours(args) -> dict:
     from colossalai_b200.nn.optimizer import FusedAdam
     from colossalai_b200.shardformer import GradientCheckpointConfig
 
-    rank, world = _init_dist(args)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dev = torch.device("cuda", torch.cuda.current_device())
-    tp = args.tp or world
-    pp = args.pp
+    if kind == "dp":
+        tp, pp, zero = 1, 1, (1 if world > 1 else 0)
+    else:
+        tp, pp, zero = (args.tp or world), args.pp, args.zero
     assert world % (tp * pp) == 0
     dp = world // (tp * pp)
     cfg = get_config(args.model)
@@ -154,7 +191,7 @@ def run_ours(args) -> dict:
                 comm_backend = "nccl"
     sp_on = tp > 1 and args.sp_mode in ("split_gather", "ring")
     plugin = HybridParallelPlugin(
-        tp_size=tp, pp_size=pp, precision="bf16", zero_stage=args.zero,
+        tp_size=tp, pp_size=pp, precision="bf16", zero_stage=zero,
         enable_sequence_parallelism=sp_on, sequence_parallelism_mode=args.sp_mode if sp_on else None,
         enable_fused_normalization=True, enable_flash_attention=True, parallel_output=True, max_norm=1.0,
         num_microbatches=(args.mbs * args.accum if pp > 1 else None),
@@ -168,7 +205,7 @@ def run_ours(args) -> dict:
     model, optimizer, _, _, _ = booster.boost(model, optimizer)
     model.train()
 
-    # ---- data: the TP/SP group consumes `tp * mbs` sequences per micro-step (one 4096-token sequence per GPU)
+    # ---- data: a TP/SP group consumes `tp * mbs` sequences per micro-step (one 4096-token sequence per GPU)
     B = args.mbs * tp
     S = args.seq
     global_batch = B * dp * args.accum
@@ -186,11 +223,10 @@ def run_ours(args) -> dict:
             ids = ids_dev[a]
             out = model(input_ids=ids, labels=ids, return_logits=False)
             loss = out["loss"] / args.accum
-            last = a == args.accum - 1
-            if last:
+            if a == args.accum - 1:
                 booster.backward(loss, optimizer)
             else:
-                with model.no_sync():
+                with booster.no_sync(model, optimizer):
                     optimizer.backward(loss)
             loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
         optimizer.step()
@@ -219,6 +255,7 @@ def run_ours(args) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
         return t[0].item(), t[1].item(), (last_loss if not torch.is_tensor(last_loss) else last_loss.item())
 
+    torch.cuda.reset_peak_memory_stats()
     for i in range(args.warmup):
         step(dev_ids[i % n_bufs])
     torch.cuda.synchronize()
@@ -226,40 +263,80 @@ def run_ours(args) -> dict:
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    ms, wall_ms, loss_val = timed(args.steps, e2e=False)
+    ms, wall_ms, loss_val = timed(steps, e2e=False)
     launches = launch_counter.count
+    by_name = dict(launch_counter.by_name)
     clocks = sampler.stop() if rank == 0 else {}
     e2e = None
-    if not args.no_e2e:
-        ms_e, wall_e, _ = timed(args.steps, e2e=True)
-        e2e = {"value": tokens_per_step * args.steps / (max(ms_e, wall_e) / 1e3), "unit": "tokens/s",
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": max(ms_e, wall_e) / args.steps}
-    value = tokens_per_step * args.steps / (ms / 1e3)
-    peak_mem = torch.cuda.max_memory_allocated() / 2**20
-    par = f"tp{tp}" + ("+sp(" + args.sp_mode + ")" if sp_on else "") + (f"xpp{pp}" if pp > 1 else "") + \
-        (f"xdp{dp}" if dp > 1 else "") + (f"+zero{args.zero}" if args.zero else "")
-    result = {
-        "metric": "tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B training step (fwd+bwd+AdamW)",
-        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": value / (BASELINE_TOKENS_PER_S_8GPU * world / 8.0), "dtype": "bf16",
-        "data": "synthetic tokens, random-init weights", "impl": "ours",
-        "config": {"model": args.model + (f"[layers={args.layers} DEBUG-INVALID]" if args.layers else ""),
-                   "global_batch": global_batch, "seq_len": S, "parallelism": par, "comm_backend": comm_backend,
-                   "optimizer": "AdamW (fp32 master+moments, fused single-launch, clip 1.0)",
-                   "grad_accum": args.accum, "grad_ckpt_ratio": args.grad_ckpt,
-                   "l2": "working set per step (>= 2 GB weights+activations per layer) >> 126 MB L2; no explicit flush",
-                   "baseline_note": "vs_baseline = value / (published 8xB200 7B number scaled to N GPUs)"},
-        "clocks": clocks, "gpu_launches": launches, "loss": loss_val, "peak_mem_mib": peak_mem,
-        "wall_ms_per_step": wall_ms / args.steps,
-        "tflops_per_gpu": cfg.flops_per_token(S) * tokens_per_step / (ms / args.steps / 1e3) / 1e12 / world,
-    }
+    if with_e2e:
+        ms_e, wall_e, _ = timed(steps, e2e=True)
+        e2e = {"value": tokens_per_step * steps / (max(ms_e, wall_e) / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": max(ms_e, wall_e) / steps}
+    value = tokens_per_step * steps / (ms / 1e3)
+    fused_stats = None
+    if comm_backend == "fused":
+        from colossalai_b200.parallel import fused
+
+        fused_stats = dict(fused.stats)
+    row = {"parallelism": row_label(kind, world, tp, pp, args.sp_mode, zero if kind != "dp" else 0),
+           "value": value, "unit": "tokens/s", "steps": steps, "ms_per_step": ms / steps,
+           "wall_ms_per_step": wall_ms / steps, "global_batch": global_batch, "comm_backend": comm_backend,
+           "gpu_launches": launches, "launches_by_kernel": by_name, "loss": loss_val,
+           "peak_mem_mib": torch.cuda.max_memory_allocated() / 2**20, "clocks": clocks,
+           "tflops_per_gpu": cfg.flops_per_token(S) * tokens_per_step / (ms / steps / 1e3) / 1e12 / world}
+    if fused_stats is not None:
+        row["fused_stats"] = fused_stats
     if e2e is not None:
-        result["e2e"] = e2e
+        row["e2e"] = e2e
+    if profile_path:
+        _profile_one_step(step, dev_ids[0], profile_path, rank)
+    # ---- tear down (a second layout may follow in this process)
+    del model, optimizer, booster, plugin, dev_ids, host_ids, step, timed
+    gc.collect()
+    torch.cuda.empty_cache()
+    return row
+
+
+def run_ours(args) -> dict:
+    import torch
+    import torch.distributed as dist
+
+    import colossalai_b200
+
+    rank, world = _init_dist(args)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    kinds = {"tp": ["tp"], "dp": ["dp"], "both": ["tp", "dp"]}[args.parallelism]
+    if world == 1 or (args.tp and args.tp == 1 and args.pp == 1):
+        kinds = kinds[:1]                           # tp1 == dp1
+    rows = []
+    for i, kind in enumerate(kinds):
+        # the headline row runs the K steps the driver asked for; the companion row at least 3 and half of K
+        steps = args.steps if i == 0 else max(3, args.steps // 2)
+        rows.append(_measure_ours(args, kind, rank, world, steps, with_e2e=not args.no_e2e,
+                                  profile_path=args.profile if i == 0 else ""))
+    head = rows[0]
+    result = {
+        "metric": METRIC, "value": head["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": head["value"] / (BASELINE_TOKENS_PER_S_8GPU * world / 8.0), "dtype": "bf16",
+        "data": "synthetic tokens, random-init weights", "impl": "ours",
+        "config": shared_config(args, world, head["parallelism"]),
+        "detail": {"comm_backend": head["comm_backend"], "grad_ckpt_ratio": args.grad_ckpt,
+                   "optimizer_impl": "one-launch multi-tensor AdamW over the flat fp32 master / moment arenas",
+                   "attention": os.environ.get("CB200_ATTN_BACKEND", "default"),
+                   "gemm": os.environ.get("CB200_GEMM_BACKEND", "default"),
+                   "baseline_note": "vs_baseline = value / (published 8xB200 7B number scaled to N GPUs)"},
+        "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "launches_by_kernel": head["launches_by_kernel"],
+        "loss": head["loss"], "peak_mem_mib": head["peak_mem_mib"], "wall_ms_per_step": head["wall_ms_per_step"],
+        "tflops_per_gpu": head["tflops_per_gpu"],
+        "rows": [{k: v for k, v in r.items() if k not in ("launches_by_kernel",)} for r in rows],
+    }
+    if "fused_stats" in head:
+        result["fused_stats"] = head["fused_stats"]
+    if "e2e" in head:
+        result["e2e"] = head["e2e"]
     if rank == 0:
         print(json.dumps(result), flush=True)
-    if args.profile:
-        _profile_one_step(step, dev_ids[0], args.profile, rank)
     dist.barrier()
     colossalai_b200.initialize.shutdown()
     return result

@@ -47,17 +47,51 @@ class HybridParallelZeroOptimizer(LowLevelZeroOptimizer):
                          forced_dtype=forced_dtype, overlap_allgather=overlap_allgather,
                          fp8_communication=fp8_communication)
 
-    def sync_grad(self) -> None:
-        # SP-partial grads live inside the flat bucket buffers: all-reduce those param slices over tp first
+    def _reduce_bucket(self, b) -> None:
+        """The dp reduce-scatter is the ONLY place a bucket's local gradient leaves `grad_full` (the grad hook calls it
+        directly for ZeRO-2 / overlapped ZeRO-1, `sync_grad` for the rest), so the two syncs that must precede it live
+        here (reference: `hybrid_parallel_plugin.py:88-137` + `layer/utils.py:75-127`, which run on `p.grad` before
+        the ZeRO reduction):
+          * tied parameters across pipeline stages: sum the tied slices over the shared-param group;
+          * split_gather / ring sequence parallelism: norm weights and row-linear biases only saw a sequence slice,
+            sum their slices over the tp group.
+        Every rank of a tp (resp. shared) group walks identical buckets in identical order, so the collectives match."""
+        if b.grad_full is None:
+            return
+        tied = self._tied_params()
+        if tied:
+            for p, o in zip(b.params, b.offsets):
+                group = tied.get(id(p))
+                if group is not None:
+                    dist.all_reduce(b.grad_full[o:o + p.numel()], group=group)
         sc = self.model.shard_config
         if sc.sp_mode in ("split_gather", "ring") and self.tp_size > 1:
-            for b in self.buckets:
-                if b.grad_full is None:
-                    continue
-                for p, o in zip(b.params, b.offsets):
-                    if getattr(p, "partial_derived", False):
-                        dist.all_reduce(b.grad_full[o:o + p.numel()], group=self.tp_pg)
-        super().sync_grad()
+            slices = [b.grad_full[o:o + p.numel()] for p, o in zip(b.params, b.offsets)
+                      if getattr(p, "partial_derived", False)]
+            if len(slices) == 1:
+                dist.all_reduce(slices[0], group=self.tp_pg)
+            elif slices:
+                flat = torch.cat(slices)
+                dist.all_reduce(flat, group=self.tp_pg)
+                off = 0
+                for s in slices:
+                    s.copy_(flat[off:off + s.numel()])
+                    off += s.numel()
+        super()._reduce_bucket(b)
+
+    def _tied_params(self) -> Dict[int, ProcessGroup]:
+        """id(param) -> process group of the pipeline stages that hold a copy of the same tied weight."""
+        cache = getattr(self, "_tied_cache", None)
+        if cache is None:
+            cache = {}
+            sm = self.stage_manager
+            groups = getattr(self.model, "shared_param_process_groups", [])
+            if sm is not None:
+                for shared, group in zip([s for s in self.shared_params if len(s) > 0], groups):
+                    if sm.stage in shared and comm.group_size(group) > 1:
+                        cache[id(shared[sm.stage])] = group
+            self._tied_cache = cache
+        return cache
 
     def _compute_grad_norm_sq(self) -> Tensor:
         """Bucket shards mix TP-sharded, replicated and expert-parallel params and may live on different dp groups

@@ -30,9 +30,10 @@ __all__ = ["MoeHybridParallelPlugin", "MoeHybridParallelZeroOptimizer"]
 
 
 def _scale_hook(scale: float):
-    def hook(p: torch.Tensor) -> None:
-        if p.grad is not None:
-            p.grad.mul_(scale)
+    """Tensor-level hook: scales only the INCOMING gradient of one backward.  (A post-accumulate hook that rescales
+    `p.grad` would rescale the contributions of earlier micro-batches again on every backward.)"""
+    def hook(grad: torch.Tensor) -> torch.Tensor:
+        return grad * scale
 
     return hook
 
@@ -137,7 +138,7 @@ class MoeHybridParallelPlugin(HybridParallelPlugin):
         if self.ep_size > 1:
             for p in model.unwrap().parameters():
                 if is_moe_tensor(p) and p.requires_grad:
-                    p.register_post_accumulate_grad_hook(_scale_hook(1.0 / self.ep_size))
+                    p.register_hook(_scale_hook(1.0 / self.ep_size))
 
     def get_checkpoint_io(self) -> CheckpointIO:
         from ...checkpoint_io import MoECheckpointIO

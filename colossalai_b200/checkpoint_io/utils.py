@@ -250,13 +250,26 @@ def clean_folder(checkpoint_path: str, weights_name: str, shard_filenames: List[
 
 
 # ---------------------------------------------------------------------------------------- load
-def load_state_dict(checkpoint_file_path: Union[str, Path]) -> Dict:
+def load_state_dict(checkpoint_file_path: Union[str, Path], trusted: Optional[bool] = None) -> Dict:
+    """Load one checkpoint file.  Pickle (`.bin`) files are read with `weights_only=True` (tensors and plain
+    containers only - a checkpoint from an untrusted source cannot run code).  Files this framework wrote itself that
+    hold richer python objects (param-group files, scheduler state) can opt in with `trusted=True` or
+    `CB200_TRUSTED_CHECKPOINTS=1`."""
     p = str(checkpoint_file_path)
     if is_safetensor_checkpoint(p):
         from safetensors.torch import load_file
 
         return load_file(p)
-    return torch.load(p, map_location="cpu", weights_only=False)
+    if trusted is None:
+        trusted = os.environ.get("CB200_TRUSTED_CHECKPOINTS", "0") == "1"
+    if trusted:
+        return torch.load(p, map_location="cpu", weights_only=False)
+    try:
+        return torch.load(p, map_location="cpu", weights_only=True)
+    except Exception as e:   # pickle.UnpicklingError on non-tensor payloads
+        raise RuntimeError(
+            f"{p} holds objects that `weights_only=True` refuses to unpickle ({type(e).__name__}: {e}). If the file "
+            "comes from a source you trust, pass trusted=True or set CB200_TRUSTED_CHECKPOINTS=1.") from e
 
 
 def load_shard_state_dict(checkpoint_file: Union[str, Path], use_safetensors: bool = False) -> Dict:

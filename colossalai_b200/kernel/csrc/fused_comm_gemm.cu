@@ -42,7 +42,9 @@ constexpr int MAX_RANKS = 16;
 constexpr int SLOT_IN_READY = 0;                 // [MAX_RANKS]  peer p wrote: "my input buffer holds epoch e"
 constexpr int SLOT_PULL_DONE = MAX_RANKS;        // [MAX_RANKS]  peer p wrote: "I finished reading your buffer (epoch e)"
 constexpr int SLOT_CHUNK_DONE = 2 * MAX_RANKS;   // [MAX_RANKS]  peer p wrote: "my partial of YOUR chunk is complete"
-constexpr int SLOT_LOCAL = 3 * MAX_RANKS;        // local scratch counters (never written by peers)
+constexpr int SLOT_LOCAL = 3 * MAX_RANKS;        // local scratch counters (never written by peers): [0..3]
+constexpr int SLOT_AR_DONE = 3 * MAX_RANKS + 4;  // [MAX_RANKS]  peer p wrote: "my chunk of the all-reduced output has
+                                                 // been broadcast into your copy (epoch e)"; page = 5 * MAX_RANKS words
 
 template <int BLOCK_N> struct Cfg {
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
@@ -78,6 +80,7 @@ struct CommParams {
   uint32_t* reduce_ticket;               // local work-queue head of the tile-granular reduction
   uint32_t* rs_progress;                 // local per-slice progress words ((epoch << 5) | steps accumulated)
   int rs_stream;                         // 1: uniform interleaved tile order + streamed in-switch reduction (below)
+  void* ar_out_mc;                       // GEMM+all-reduce: multicast address of the symmetric [T, N] output (or null)
 };
 
 struct GemmParams {
@@ -139,6 +142,12 @@ SM100_DEVICE uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
   asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc_addr) : "memory");
   return r;
+}
+
+// 16-byte store through the multicast mapping: the NVSwitch replicates it into every rank's copy of the buffer
+SM100_DEVICE void multimem_st_16B(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 SM100_DEVICE void tile_coords_rot(int tile, int m_blocks, int n_blocks, int m_rot, int& m_blk, int& n_blk) {
@@ -431,6 +440,10 @@ SM100_DEVICE void rs_reduce_tiles_stream(const GemmParams& p, const CommParams& 
   const size_t ldc_vec = p.ldc / 8;
   const size_t ldo_vec = c.ld_out / 8;
   const uint4* mc = reinterpret_cast<const uint4*>(c.mc_part);
+  // GEMM + ALL-REDUCE: the reduced tile is not kept for this rank only but stored through the multicast mapping of the
+  // symmetric [T, N] output, i.e. the switch broadcasts every reduced value to all ranks (reduce and broadcast both
+  // happen inside the NVSwitch; each output byte leaves this GPU once).
+  uint4* ar_mc = reinterpret_cast<uint4*>(c.ar_out_mc);
   while (true) {
     int t = 0;
     if (lane == 0) t = (int)atomicAdd(c.reduce_ticket, 1u);
@@ -460,23 +473,36 @@ SM100_DEVICE void rs_reduce_tiles_stream(const GemmParams& p, const CommParams& 
         doff[q] = (size_t)-1;
         if (i >= nvec) continue;
         const int r = i / vec_per_row, cv = i - r * vec_per_row;
-        doff[q] = (size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv;
+        doff[q] = ar_mc ? ((size_t)(row0 + r) * ldo_vec + (col0 / 8) + cv)
+                        : ((size_t)(out_row0 + r) * ldo_vec + (col0 / 8) + cv);
         v[q] = multimem_ld_reduce_bf16x8(mc + (size_t)(row0 + r) * ldc_vec + (col0 / 8) + cv);
       }
 #pragma unroll
-      for (int q = 0; q < RU; ++q)
-        if (doff[q] != (size_t)-1) reinterpret_cast<uint4*>(c.out)[doff[q]] = v[q];
+      for (int q = 0; q < RU; ++q) {
+        if (doff[q] == (size_t)-1) continue;
+        if (ar_mc) multimem_st_16B(ar_mc + doff[q], v[q]);
+        else reinterpret_cast<uint4*>(c.out)[doff[q]] = v[q];
+      }
     }
   }
   __syncwarp();
   if (lane == 0) {
+    if (ar_mc) __threadfence_system();                            // my broadcast stores are performed everywhere
     const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 1, 1u) + 1;
     if (done == (uint32_t)total_warps) {
       my_flags[SLOT_LOCAL + 1] = 0;
       *c.reduce_ticket = 0;
       __threadfence_system();
-      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+      for (int r = 0; r < c.world; ++r) {
+        st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+        if (ar_mc) st_release_sys(c.peer_flags[r] + SLOT_AR_DONE + c.rank, c.epoch);
+      }
     }
+  }
+  if (ar_mc) {
+    // the kernel may only retire once EVERY rank's chunk has landed in this rank's copy of the output
+    if (lane < c.world) wait_epoch<true>(my_flags + SLOT_AR_DONE + lane, c.epoch);
+    __syncwarp();
   }
 }
 
@@ -1048,7 +1074,7 @@ int launch_fused(const void* A, const void* B, int M, int N, int K, int lda, int
 extern "C" {
 
 int cb_fused_max_ranks() { return MAX_RANKS; }
-int cb_fused_flag_words() { return 4 * MAX_RANKS; }
+int cb_fused_flag_words() { return 5 * MAX_RANKS; }
 
 // Y[T, N] = gather(x)[T, K] (x) B.   peer_in[r] = rank r's symmetric x_local buffer; `gathered` is a local [T, ld_in]
 // buffer (returned to the caller for the backward pass); `ready` is a local uint32[T/128] array.
@@ -1078,7 +1104,8 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
                uint32_t* const* peer_flags, uint32_t* chunk_counter, void* out, int T, int N, int K, int lda, int ldb,
                int ld_out, int a_mn_major, int b_mn_major, int in_dtype, int rank, int world, uint32_t epoch,
                int block_n, uint32_t* const* peer_tile_flags, int tile_flag_stride, uint32_t* tile_counter,
-               int tile_counter_len, uint32_t* rs_progress, int rs_progress_len, cudaStream_t stream) {
+               int tile_counter_len, uint32_t* rs_progress, int rs_progress_len, int rs_variant, void* ar_out_mc,
+               cudaStream_t stream) {
   if (world > MAX_RANKS || T % (world * BLOCK_M) != 0 || N % 8 != 0) return (int)cudaErrorInvalidValue;
   CommParams c{};
   c.rank = rank; c.world = world; c.epoch = epoch; c.rows_per_chunk = T / world;
@@ -1098,14 +1125,20 @@ int cb_gemm_rs(const void* A, const void* B, void* part, const void* const* peer
     c.reduce_ticket = tile_counter + (tile_counter_len - 1);
     c.rs_progress = rs_progress;
     // CB200_RS_STREAM=1: uniform tile order + streamed in-switch reduction (bf16 partials, multicast mapping needed)
-    static int rs_stream = -1;
-    if (rs_stream < 0) {
+    // rs_variant: 0 = env default (CB200_RS_STREAM), 1 = staggered P2P pull-accumulate, 2 = streamed in-switch reduce
+    static int rs_stream_env = -1;
+    if (rs_stream_env < 0) {
       const char* e = getenv("CB200_RS_STREAM");
-      rs_stream = e ? atoi(e) : 0;
+      rs_stream_env = e ? atoi(e) : 0;
     }
-    c.rs_stream = (rs_stream && mc_part != nullptr && in_dtype == CB_BF16 && N % 256 == 0) ? 1 : 0;
+    const bool want_stream = rs_variant == 2 || (rs_variant == 0 && rs_stream_env);
+    const bool can_stream = mc_part != nullptr && in_dtype == CB_BF16 && N % 256 == 0;
+    if ((rs_variant == 2 || ar_out_mc) && !can_stream) return (int)cudaErrorInvalidValue;
+    c.rs_stream = (want_stream || ar_out_mc) ? 1 : 0;
+    c.ar_out_mc = ar_out_mc;
     return launch_fused_2cta<1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);
   }
+  if (rs_variant == 2 || ar_out_mc) return (int)cudaErrorInvalidValue;   // only the CTA-pair kernel streams
   if (block_n == 0 || block_n == 512) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
   if (block_n == 256)
     return launch_fused<256, 1>(A, B, T, N, K, lda, ldb, a_mn_major, b_mn_major, in_dtype, p, c, stream);

@@ -55,15 +55,14 @@ def _use_fused(x: torch.Tensor, group) -> bool:
     return fused.available(group)
 
 
-_FUSED_RS_MIN_K = int(os.environ.get("CB200_FUSED_RS_MIN_K", "2048"))
+def _fused_rs_variant(a: torch.Tensor, weight: torch.Tensor, group, transpose_b: bool) -> str:
+    """Implementation of GEMM->reduce-scatter for this shape: 'stream' / 'stagger' (one fused sm_100a kernel) or 'lib'
+    (GEMM + NCCL reduce-scatter).  Measured once per shape on the live tensors by `parallel.fused.rs_variant` - round 1
+    used a fixed reduction-depth threshold (K >= 2048) taken from the TP=8 timings, which was wrong at other TP
+    degrees and froze the library fallback in place."""
+    from ...parallel import fused
 
-
-def _fused_rs_profitable(k_local: int) -> bool:
-    """GEMM->reduce-scatter as ONE kernel pays when the GEMM (2*M*N*K flops) is long enough to hide the M*N
-    partial-sum traffic; below ~2k of reduction depth the op is pure communication and the in-switch NCCL
-    reduce-scatter behind a cuBLAS GEMM is faster (measured at TP=4 and TP=8: profiles/fused_comm_n{4,8}_timing_v3.log:
-    K=512..1792 -> 0.53-0.72 ms NCCL vs 0.93-0.98 ms fused; K>=3584 -> fused wins)."""
-    return k_local >= _FUSED_RS_MIN_K
+    return fused.rs_variant(a, weight, group, transpose_b)
 
 
 def _accumulate_wgrad(weight: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor) -> Optional[torch.Tensor]:
@@ -223,8 +222,9 @@ class _LinearGatherFwdReduceScatterBwd(torch.autograd.Function):
             # dX = dY @ W fused with the reduce-scatter; X comes from forward (saved) or is re-gathered over NVLink
             x_full = x_local if ctx.saved_gathered else fused.all_gather(x_local, group)
             h_rs = None
-            if _fused_rs_profitable(dy2.shape[1]):
-                dx_local = fused.gemm_reduce_scatter(dy2, weight, group, transpose_b=False)
+            variant = _fused_rs_variant(dy2, weight, group, False)
+            if variant != "lib":
+                dx_local = fused.gemm_reduce_scatter(dy2, weight, group, transpose_b=False, variant=variant)
             else:
                 # communication-bound shape: cuBLAS dgrad, NCCL reduce-scatter in flight under the wgrad GEMM
                 dx_full = ops.matmul_nn(dy2, weight)
@@ -310,12 +310,10 @@ class _LinearReduceScatterFwdGatherBwd(torch.autograd.Function):
         ctx.fp8 = comm.fp8_enabled()
         ctx.fused = _use_fused(x, group) and dim == 0 and x.dim() == 2 and not ctx.fp8
         ctx.save_for_backward(x, weight)
-        if ctx.fused and _fused_rs_profitable(x.shape[1]):
+        if ctx.fused:
             from ...parallel import fused
 
-            y = fused.gemm_reduce_scatter(x, weight, group, transpose_b=True)
-        elif ctx.fused:
-            y = comm.reduce_scatter(ops.linear_forward(x, weight), dim, group)
+            y = fused.gemm_reduce_scatter(x, weight, group, transpose_b=True)      # autotuned variant per shape
         elif ring and comm.group_size(group) > 1:
             y = _ring_gemm_reducescatter(x, weight, group, dim)
         else:

@@ -222,7 +222,6 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             return
         ws = b.ws
         full = b.grad_full
-        shard = torch.empty(b.shard_size, dtype=full.dtype, device=full.device)
         stream = self._comm_stream
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream())
@@ -232,6 +231,9 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
 
             ctx = nullcontext()
         with ctx:
+            # allocated on the stream that writes and consumes it (a temporary allocated on the compute stream could be
+            # handed out again there while the comm stream still reads it)
+            shard = torch.empty(b.shard_size, dtype=full.dtype, device=full.device)
             if ws > 1:
                 full.div_(ws)
                 if self._fp8_communication:

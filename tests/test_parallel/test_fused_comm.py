@@ -62,44 +62,58 @@ def _worker(rank, world_size, port, timing=False):
         # ---- GEMM + RS: every rank holds a different A (a K-shard of the activations)
         a = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
         ref = comm.reduce_scatter((a.float() @ w.float().t()), 0, group)
+        ref2 = comm.reduce_scatter((a.float() @ w2.float()), 0, group)
+        variants = ["stagger"] + (["stream"] if (N % 256 == 0 and t % 256 == 0) else [])
+        for v in variants:      # staggered P2P pull-accumulate / streamed in-switch (multimem) reduction
+            got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True, variant=v)
+            torch.testing.assert_close(got.float(), ref, atol=0.15, rtol=3e-2, msg=lambda m: f"{v} NT {(t, K, N)}: {m}")
+            got2 = fused.gemm_reduce_scatter(a, w2, group, transpose_b=False, variant=v)
+            torch.testing.assert_close(got2.float(), ref2, atol=0.15, rtol=3e-2, msg=lambda m: f"{v} NN {(t, K, N)}: {m}")
+        # autotuned dispatch (measures every candidate once on these tensors, then sticks to the fastest)
         got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True)
         torch.testing.assert_close(got.float(), ref, atol=0.15, rtol=3e-2)
-        got2 = fused.gemm_reduce_scatter(a, w2, group, transpose_b=False)
-        ref2 = comm.reduce_scatter((a.float() @ w2.float()), 0, group)
-        torch.testing.assert_close(got2.float(), ref2, atol=0.15, rtol=3e-2)
+        # ---- GEMM + all-reduce in one kernel (in-switch reduce + multicast broadcast)
+        ref_ar = (a.float() @ w.float().t())
+        dist.all_reduce(ref_ar, group=group)
+        got_ar = fused.gemm_all_reduce(a, w, group)
+        torch.testing.assert_close(got_ar.float(), ref_ar, atol=0.15, rtol=3e-2, msg=lambda m: f"AR {(t, K, N)}: {m}")
         # the 1-CTA (128x256 tile) kernels stay available behind block_n=256; block_n=0 picks the CTA-pair kernels
         y1, _ = fused.all_gather_gemm(x_local, w, group, transpose_b=True, block_n=256)
         torch.testing.assert_close(y1.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
         got1 = fused.gemm_reduce_scatter(a, w, group, transpose_b=True, block_n=256)
         torch.testing.assert_close(got1.float(), ref, atol=0.15, rtol=3e-2)
         # repeated calls exercise buffer reuse / epoch guards
-        for _ in range(5):
-            got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True)
+        for i in range(6):
+            got = fused.gemm_reduce_scatter(a, w, group, transpose_b=True, variant=variants[i % len(variants)])
             y, _ = fused.all_gather_gemm(x_local, w, group, transpose_b=True)
+            got_ar = fused.gemm_all_reduce(a, w, group)
         torch.testing.assert_close(got.float(), ref, atol=0.15, rtol=3e-2)
+        torch.testing.assert_close(got_ar.float(), ref_ar, atol=0.15, rtol=3e-2)
         torch.testing.assert_close(y.float(), ref_full.float() @ w.float().t(), atol=0.08, rtol=2e-2)
         if timing and t >= 1024:
-            t_f = _time(lambda: fused.all_gather_gemm(x_local, w, group))
-            t_f1 = _time(lambda: fused.all_gather_gemm(x_local, w, group, block_n=256))
-            t_n = _time(lambda: torch.nn.functional.linear(comm.all_gather(x_local, 0, group), w))
-            t_f2 = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
-            t_f21 = _time(lambda: fused.gemm_reduce_scatter(a, w, group, block_n=256))
-            os.environ["CB200_NO_MULTIMEM"] = "1"          # reduction by P2P loads instead of the in-switch reduction
-            got_p2p = fused.gemm_reduce_scatter(a, w, group)
-            torch.testing.assert_close(got_p2p.float(), comm.reduce_scatter((a.float() @ w.float().t()), 0, group),
-                                       atol=0.15, rtol=3e-2)
-            t_f2p = _time(lambda: fused.gemm_reduce_scatter(a, w, group))
-            os.environ["CB200_NO_MULTIMEM"] = "0"
-            t_n2 = _time(lambda: comm.reduce_scatter(torch.nn.functional.linear(a, w), 0, group))
-            results.append({"world": world_size, "t_local": t, "K": K, "N": N, "ag_gemm_fused_ms": t_f,
-                            "ag_gemm_fused_1cta_ms": t_f1, "ag_gemm_nccl_cublas_ms": t_n, "gemm_rs_fused_ms": t_f2,
-                            "gemm_rs_fused_1cta_ms": t_f21, "gemm_rs_fused_p2p_ms": t_f2p,
-                            "gemm_rs_nccl_cublas_ms": t_n2})
+            def ar_lib():
+                y_ = torch.nn.functional.linear(a, w)
+                dist.all_reduce(y_, group=group)
+                return y_
+
+            r = {"world": world_size, "t_local": t, "K": K, "N": N,
+                 "ag_gemm_fused_ms": _time(lambda: fused.all_gather_gemm(x_local, w, group)),
+                 "ag_gemm_nccl_cublas_ms": _time(lambda: torch.nn.functional.linear(comm.all_gather(x_local, 0, group), w)),
+                 "gemm_rs_stagger_ms": _time(lambda: fused.gemm_reduce_scatter(a, w, group, variant="stagger")),
+                 "gemm_rs_nccl_cublas_ms": _time(lambda: fused.gemm_reduce_scatter(a, w, group, variant="lib")),
+                 "gemm_ar_fused_ms": _time(lambda: fused.gemm_all_reduce(a, w, group)),
+                 "gemm_ar_nccl_cublas_ms": _time(ar_lib)}
+            if "stream" in variants:
+                r["gemm_rs_stream_ms"] = _time(lambda: fused.gemm_reduce_scatter(a, w, group, variant="stream"))
+            r["rs_autotuned"] = fused.rs_variant(a, w, group, True)
+            results.append(r)
     assert fused.stats["ag_gemm"] > 0 and fused.stats["gemm_rs"] > 0, fused.stats
     if rank == 0:
         for r in results:
             print("FUSED_TIMING " + json.dumps(r), flush=True)
         print("FUSED_STATS " + json.dumps(fused.stats), flush=True)
+        for r in fused.rs_tuning_log:
+            print("RS_TUNING " + json.dumps(r), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
