@@ -102,7 +102,11 @@ def install_transformers_shims() -> None:
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
-        kwargs.pop("past_key_values", None)
+        if "past_key_values" in kwargs:
+            # a call in the installed transformers' own convention (its stock `LlamaModel.forward`, used by the
+            # reference's DDP / ZeRO plugins which do not replace the model forward): pass through untouched
+            return orig(self, hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                        use_cache=use_cache, position_embeddings=position_embeddings, **kwargs)
         out = orig(self, hidden_states, attention_mask=attention_mask, position_ids=position_ids,
                    past_key_values=past_key_value, use_cache=use_cache, position_embeddings=position_embeddings,
                    cache_position=cache_position, output_attentions=output_attentions, **kwargs)

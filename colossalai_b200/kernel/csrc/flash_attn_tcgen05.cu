@@ -360,6 +360,437 @@ int launch_flash_fwd(const void* q, const void* k, const void* v, void* out, flo
   return (int)cudaGetLastError();
 }
 
+
+// =====================================================================================================================
+// Flash attention BACKWARD on tcgen05 / TMEM.
+//
+//   P = exp(scale * Q K^T - LSE),  dP = dO V^T,  dS = P o (dP - delta),  delta = rowsum(dO o O)
+//   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K
+//
+// One CTA owns ONE key tile (128 keys) of ONE kv head and walks over every query tile (64 rows) of every query head of
+// its GQA group that can see it.  dK / dV therefore accumulate in TMEM across the whole walk - over the query tiles AND
+// over the query heads of the group - and are written exactly once (no atomics, no KV expansion); dQ leaves the CTA as
+// fp32 `red.global.add` into an accumulator that a cast kernel turns into bf16/fp16 afterwards.
+//
+// Everything is computed TRANSPOSED so that every MMA has M = 128 (full TMEM lanes) and the softmax threads own KEY
+// rows:   S^T = K Q^T and dP^T = V dO^T are [128 keys x 64 q] accumulators; thread k of the softmax warps reads key row k,
+// forms P^T and dS^T, and stores them as bf16 [keys x q] K-major swizzled tiles.  Those two tiles feed
+//   dV  += P^T  (A, K-major)  x dO (B, MN-major: the SAME smem bytes that were the K-major B of dP^T = V dO^T)
+//   dK  += dS^T (A, K-major)  x Q  (B, MN-major: the same bytes as the B of S^T = K Q^T)
+//   dQ^T = K^T  (A, MN-major view of the resident K tile) x dS (B, MN-major view of the dS^T tile)      [128 d x 64 q]
+// i.e. five tensor-core GEMMs per (key tile, query tile) pair out of four smem operands, no transposition pass.
+//
+// Warps (10): 0 TMA producer (K, V once; Q_i / dO_i through a 2-stage ring), 1 MMA issuer, 2..5 softmax (thread = key
+// row), 6..9 dQ drain (thread = head-dim lane; 128-byte coalesced fp32 reductions per query row).
+// The issuer runs S^T / dP^T of tile i+1 BEFORE the three accumulation GEMMs of tile i, so the tensor pipe works while
+// the softmax warps are busy (same trick as the forward kernel).
+// TMEM (512 columns): [0,64) S^T, [64,128) dP^T, [128,192) dQ^T, [256,384) dV, [384,512) dK.
+// Shared memory: K 32 KB + V 32 KB + 2 x (Q 16 KB + dO 16 KB) + P^T 16 KB + dS^T 16 KB + lse/delta = 161 KB (D = 128).
+constexpr int BWD_BLOCK_KV = 128;
+constexpr int BWD_BLOCK_Q = 64;
+constexpr int BWD_THREADS = 320;
+constexpr int BWD_QSTAGES = 2;
+
+template <int D> struct FaBwdCfg {
+  static constexpr int K_BYTES = BWD_BLOCK_KV * D * 2;
+  static constexpr int V_BYTES = BWD_BLOCK_KV * D * 2;
+  static constexpr int Q_BYTES = BWD_BLOCK_Q * D * 2;
+  static constexpr int DO_BYTES = BWD_BLOCK_Q * D * 2;
+  static constexpr int QDO_STAGE_BYTES = Q_BYTES + DO_BYTES;
+  static constexpr int PT_BYTES = BWD_BLOCK_KV * BWD_BLOCK_Q * 2;
+  static constexpr int SMEM_BYTES = K_BYTES + V_BYTES + BWD_QSTAGES * QDO_STAGE_BYTES + 2 * PT_BYTES +
+                                    2 * BWD_BLOCK_Q * 4 /*lse, delta*/ + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int COL_ST = 0, COL_DPT = 64, COL_DQT = 128, COL_DV = 256, COL_DK = 384;
+};
+
+struct FaBwdParams {
+  int batch, seqlen;                 // equal-length sequences, seqlen_q == seqlen_k (self attention)
+  int hq, hkv;
+  int causal;
+  float scale, scale_log2;
+  const float* lse;                  // [batch * seqlen, hq] natural log
+  const float* delta;                // [batch * seqlen, hq] rowsum(dO o O)
+  float* dq_acc;                     // [batch * seqlen, hq * D] fp32, zero-initialised
+  void* dk;                          // [batch * seqlen, hkv * D]
+  void* dv;
+  int out_dtype;
+  uint32_t idesc_st, idesc_dv, idesc_dqt;
+};
+
+template <int D>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                 const FaBwdParams p) {
+  using C = FaBwdCfg<D>;
+  static_assert(D == 128, "head_dim 128");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem_k + C::K_BYTES;
+  uint8_t* smem_qdo = smem_v + C::V_BYTES;
+  uint8_t* smem_pt = smem_qdo + BWD_QSTAGES * C::QDO_STAGE_BYTES;
+  uint8_t* smem_dst = smem_pt + C::PT_BYTES;
+  float* smem_lse = reinterpret_cast<float*>(smem_dst + C::PT_BYTES);     // [64] lse * log2(e)
+  float* smem_delta = smem_lse + BWD_BLOCK_Q;                             // [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_delta + BWD_BLOCK_Q);
+  uint64_t* kv_full = bars;                // [1]
+  uint64_t* qdo_full = bars + 1;           // [2]
+  uint64_t* qdo_empty = bars + 3;          // [2]
+  uint64_t* sp_full = bars + 5;            // [1]  S^T and dP^T are in TMEM
+  uint64_t* sp_empty = bars + 6;           // [1]  4 softmax warps have read them
+  uint64_t* pds_full = bars + 7;           // [1]  4 softmax warps wrote P^T / dS^T to smem
+  uint64_t* pds_empty = bars + 8;          // [1]  the three accumulation GEMMs that read them retired
+  uint64_t* dq_full = bars + 9;            // [1]  dQ^T is in TMEM
+  uint64_t* dq_empty = bars + 10;          // [1]  4 drain warps have read it
+  uint64_t* acc_full = bars + 11;          // [1]  final dK / dV complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kv_tile = blockIdx.x;
+  const int kv_head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int group = p.hq / p.hkv;
+  const int q_tiles = p.seqlen / BWD_BLOCK_Q;
+  // causal: query tile i (rows 64 i ..) sees key tile j (keys 128 j ..) iff 64 i + 63 >= 128 j  <=>  i >= 2 j
+  const int i_start = p.causal ? 2 * kv_tile : 0;
+  const int n_i = q_tiles - i_start;
+  const int n_iter = n_i * group;                                  // (query head of the group, query tile) pairs
+  const int kv_row0 = b * p.seqlen + kv_tile * BWD_BLOCK_KV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_k);
+    prefetch_tensormap(&tmap_v);
+    prefetch_tensormap(&tmap_do);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(sp_empty, 4);
+    mbar_init(pds_full, 4);
+    mbar_init(pds_empty, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, C::K_BYTES + C::V_BYTES);
+#pragma unroll
+      for (int h = 0; h < D / 64; ++h) {
+        tma_load_2d(&tmap_k, kv_full, smem_k + h * (BWD_BLOCK_KV * 128), kv_head * D + h * 64, kv_row0);
+        tma_load_2d(&tmap_v, kv_full, smem_v + h * (BWD_BLOCK_KV * 128), kv_head * D + h * 64, kv_row0);
+      }
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = kv_head * group + it / n_i;
+      const int q_row0 = b * p.seqlen + (i_start + it % n_i) * BWD_BLOCK_Q;
+      mbar_wait(&qdo_empty[stage], phase ^ 1);
+      if (lane == 0) {
+        uint8_t* sq = smem_qdo + stage * C::QDO_STAGE_BYTES;
+        uint8_t* sdo = sq + C::Q_BYTES;
+        mbar_arrive_expect_tx(&qdo_full[stage], C::QDO_STAGE_BYTES);
+#pragma unroll
+        for (int h = 0; h < D / 64; ++h) {               // boxes [64 rows, 64 d]
+          tma_load_2d(&tmap_q, &qdo_full[stage], sq + h * (BWD_BLOCK_Q * 128), hq * D + h * 64, q_row0);
+          tma_load_2d(&tmap_do, &qdo_full[stage], sdo + h * (BWD_BLOCK_Q * 128), hq * D + h * 64, q_row0);
+        }
+      }
+      __syncwarp();
+      if (++stage == BWD_QSTAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t sk = smem_u32(smem_k), sv = smem_u32(smem_v);
+    const uint64_t dk_kmaj = make_smem_desc_sw128(sk, 16, 1024);                        // A of S^T: [keys x d] K-major
+    const uint64_t dv_kmaj = make_smem_desc_sw128(sv, 16, 1024);                        // A of dP^T
+    const uint64_t dk_mnmaj = make_smem_desc_sw128(sk, BWD_BLOCK_KV * 128, 1024);       // A of dQ^T: K^T, M = d contiguous
+    const uint64_t d_pt = make_smem_desc_sw128(smem_u32(smem_pt), 16, 1024);            // A of dV: [keys x q] K-major
+    const uint64_t d_dst = make_smem_desc_sw128(smem_u32(smem_dst), 16, 1024);          // A of dK
+    const uint64_t d_ds_mn = make_smem_desc_sw128(smem_u32(smem_dst), BWD_BLOCK_KV * 128, 1024);   // B of dQ^T (N = q)
+    auto issue_sp = [&](int it) {
+      const int stage = it % BWD_QSTAGES;
+      mbar_wait(&qdo_full[stage], (uint32_t)((it / BWD_QSTAGES) & 1));
+      mbar_wait(sp_empty, (uint32_t)((it & 1) ^ 1));          // softmax of iteration it-1 has read S^T / dP^T
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sq = smem_u32(smem_qdo + stage * C::QDO_STAGE_BYTES);
+        const uint64_t dq_b = make_smem_desc_sw128(sq, 16, 1024);                       // B: [q x d] K-major
+        const uint64_t ddo_b = make_smem_desc_sw128(sq + C::Q_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < D / UMMA_K; ++k) {
+          const uint32_t ao = (k >> 2) * (BWD_BLOCK_KV * 128) + (k & 3) * (UMMA_K * 2);
+          const uint32_t bo = (k >> 2) * (BWD_BLOCK_Q * 128) + (k & 3) * (UMMA_K * 2);
+          umma_f16_ss(tmem_base + C::COL_ST, advance_desc(dk_kmaj, ao), advance_desc(dq_b, bo), p.idesc_st,
+                      k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < D / UMMA_K; ++k) {
+          const uint32_t ao = (k >> 2) * (BWD_BLOCK_KV * 128) + (k & 3) * (UMMA_K * 2);
+          const uint32_t bo = (k >> 2) * (BWD_BLOCK_Q * 128) + (k & 3) * (UMMA_K * 2);
+          umma_f16_ss(tmem_base + C::COL_DPT, advance_desc(dv_kmaj, ao), advance_desc(ddo_b, bo), p.idesc_st,
+                      k > 0 ? 1u : 0u);
+        }
+        umma_commit(sp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    tc_fence_after();
+    if (n_iter > 0) issue_sp(0);
+    for (int it = 0; it < n_iter; ++it) {
+      if (it + 1 < n_iter) issue_sp(it + 1);                 // tensor pipe stays busy during softmax(it)
+      const int stage = it % BWD_QSTAGES;
+      mbar_wait(pds_full, (uint32_t)(it & 1));
+      mbar_wait(dq_empty, (uint32_t)((it & 1) ^ 1));         // dQ^T of iteration it-1 has been drained
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sq = smem_u32(smem_qdo + stage * C::QDO_STAGE_BYTES);
+        // B operands, MN-major views of the Q / dO tiles: rows = q (the reduction dim), N = d contiguous,
+        // 64-element N chunks are BWD_BLOCK_Q * 128 bytes apart
+        const uint64_t dq_mn = make_smem_desc_sw128(sq, BWD_BLOCK_Q * 128, 1024);
+        const uint64_t ddo_mn = make_smem_desc_sw128(sq + C::Q_BYTES, BWD_BLOCK_Q * 128, 1024);
+        const uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < BWD_BLOCK_Q / UMMA_K; ++k)      // dV += P^T dO      (reduction over the 64 query rows)
+          umma_f16_ss(tmem_base + C::COL_DV, advance_desc(d_pt, k * (UMMA_K * 2)),
+                      advance_desc(ddo_mn, k * (UMMA_K * 128)), p.idesc_dv, (acc | (k > 0)) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BWD_BLOCK_Q / UMMA_K; ++k)      // dK += dS^T Q
+          umma_f16_ss(tmem_base + C::COL_DK, advance_desc(d_dst, k * (UMMA_K * 2)),
+                      advance_desc(dq_mn, k * (UMMA_K * 128)), p.idesc_dv, (acc | (k > 0)) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BWD_BLOCK_KV / UMMA_K; ++k)     // dQ^T = K^T dS     (reduction over the 128 keys)
+          umma_f16_ss(tmem_base + C::COL_DQT, advance_desc(dk_mnmaj, k * (UMMA_K * 128)),
+                      advance_desc(d_ds_mn, k * (UMMA_K * 128)), p.idesc_dqt, k > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        umma_commit(pds_empty);                              // P^T / dS^T smem may be overwritten
+        umma_commit(&qdo_empty[stage]);                      // Q_i / dO_i consumed
+        if (it == n_iter - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ================================================================ softmax warps: thread = key row
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // key row inside the tile
+    const int key_pos = kv_tile * BWD_BLOCK_KV + r;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int sm_tid = threadIdx.x - 64;                     // 0..127 among the softmax warps
+    uint8_t* pt_row = smem_pt + r * 128;
+    uint8_t* dst_row = smem_dst + r * 128;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = kv_head * group + it / n_i;
+      const int q_tile = i_start + it % n_i;
+      const int q_row0 = b * p.seqlen + q_tile * BWD_BLOCK_Q;
+      // per-query-row statistics of this tile (64 lse + 64 delta values, read by every softmax thread)
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // previous iteration's readers are done
+      if (sm_tid < BWD_BLOCK_Q) smem_lse[sm_tid] = p.lse[(size_t)(q_row0 + sm_tid) * p.hq + hq] * 1.4426950408889634f;
+      else smem_delta[sm_tid - BWD_BLOCK_Q] = p.delta[(size_t)(q_row0 + sm_tid - BWD_BLOCK_Q) * p.hq + hq];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sp_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      const bool diag = p.causal && (q_tile <= 2 * kv_tile + 1);
+      const int q_base = q_tile * BWD_BLOCK_Q;
+      uint32_t p_packed[BWD_BLOCK_Q / 2], ds_packed[BWD_BLOCK_Q / 2];
+#pragma unroll
+      for (int c = 0; c < BWD_BLOCK_Q; c += 32) {
+        uint32_t sv_[32], dpv[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + C::COL_ST + c, sv_);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + C::COL_DPT + c, dpv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c + i + e;
+            float pe = fast_exp2(__uint_as_float(sv_[i + e]) * p.scale_log2 - smem_lse[col]);
+            if (diag && key_pos > q_base + col) pe = 0.f;
+            pv[e] = pe;
+            dsv[e] = pe * (__uint_as_float(dpv[i + e]) - smem_delta[col]);
+          }
+          if (p.out_dtype == CB_BF16) {
+            __nv_bfloat162 hp = __floats2bfloat162_rn(pv[0], pv[1]);
+            __nv_bfloat162 hd = __floats2bfloat162_rn(dsv[0], dsv[1]);
+            p_packed[(c + i) >> 1] = *reinterpret_cast<uint32_t*>(&hp);
+            ds_packed[(c + i) >> 1] = *reinterpret_cast<uint32_t*>(&hd);
+          } else {
+            __half2 hp = __floats2half2_rn(pv[0], pv[1]);
+            __half2 hd = __floats2half2_rn(dsv[0], dsv[1]);
+            p_packed[(c + i) >> 1] = *reinterpret_cast<uint32_t*>(&hp);
+            ds_packed[(c + i) >> 1] = *reinterpret_cast<uint32_t*>(&hd);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sp_empty);                  // S^T / dP^T may be overwritten by iteration it+1
+      // the accumulation GEMMs of iteration it-1 must have retired before their smem operands are replaced
+      mbar_wait(pds_empty, (uint32_t)((it & 1) ^ 1));
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {                       // 64 q = 128 bytes = 8 chunks of 16 B, SWIZZLE_128B
+        const int pos = (ch ^ (r & 7)) * 16;
+        *reinterpret_cast<uint4*>(pt_row + pos) =
+            make_uint4(p_packed[ch * 4], p_packed[ch * 4 + 1], p_packed[ch * 4 + 2], p_packed[ch * 4 + 3]);
+        *reinterpret_cast<uint4*>(dst_row + pos) =
+            make_uint4(ds_packed[ch * 4], ds_packed[ch * 4 + 1], ds_packed[ch * 4 + 2], ds_packed[ch * 4 + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // ---- epilogue: dV and scale * dK rows of this thread's key
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const size_t row = (size_t)kv_row0 + r;
+    const size_t ld = (size_t)p.hkv * D;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t col0 = which == 0 ? C::COL_DV : C::COL_DK;
+      const float mul = which == 0 ? 1.f : p.scale;
+      uint8_t* base = reinterpret_cast<uint8_t*>(which == 0 ? p.dv : p.dk) + (row * ld + (size_t)kv_head * D) * 2;
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + col0 + c, v);
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = n_iter > 0 ? __uint_as_float(v[2 * i]) * mul : 0.f;
+          const float a1 = n_iter > 0 ? __uint_as_float(v[2 * i + 1]) * mul : 0.f;
+          if (p.out_dtype == CB_BF16) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __half2 h = __floats2half2_rn(a0, a1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(base + (c + i * 8) * 2) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+  } else {
+    // ================================================================ dQ drain warps: thread = head-dim lane
+    const int quarter = warp & 3;
+    const int dlane = quarter * 32 + lane;                   // d index (row of dQ^T)
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int it = 0; it < n_iter; ++it) {
+      const int hq = kv_head * group + it / n_i;
+      const int q_row0 = b * p.seqlen + (i_start + it % n_i) * BWD_BLOCK_Q;
+      mbar_wait(dq_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      float* dst = p.dq_acc + ((size_t)q_row0 * p.hq + hq) * D + dlane;
+      const size_t row_stride = (size_t)p.hq * D;
+#pragma unroll
+      for (int c = 0; c < BWD_BLOCK_Q; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + C::COL_DQT + c, v);
+        tmem_ld_wait();
+        if (dlane < D) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)                      // one 128-byte coalesced fp32 reduction per warp and row
+            atomicAdd(dst + (size_t)(c + i) * row_stride, __uint_as_float(v[i]) * p.scale);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// delta[t, h] = sum_d dO[t, h, d] * O[t, h, d]   (one warp per (token, head) row)
+template <typename T>
+__global__ void flash_bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
+                                       long long rows, int D) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* o = out + row * D;
+  const T* g = dout + row * D;
+  float acc = 0.f;
+  for (int i = lane * 8; i < D; i += 32 * 8) {
+    Vec16<T> a, b2;
+    a.load(o + i);
+    b2.load(g + i);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += a.get(e) * b2.get(e);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[row] = acc;
+}
+
+template <typename T>
+__global__ void flash_bwd_cast_dq_kernel(const float* __restrict__ acc, T* __restrict__ dq, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const float4 a = *reinterpret_cast<const float4*>(acc + i);
+  const float4 b2 = *reinterpret_cast<const float4*>(acc + i + 4);
+  Vec16<T> o;
+  o.set(0, a.x); o.set(1, a.y); o.set(2, a.z); o.set(3, a.w);
+  o.set(4, b2.x); o.set(5, b2.y); o.set(6, b2.z); o.set(7, b2.w);
+  o.store(dq + i);
+}
+
+template <int D>
+int launch_flash_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+                     float* dq_acc, void* dk, void* dv, int batch, int seqlen, int hq, int hkv, int causal, float scale,
+                     int dtype, cudaStream_t stream) {
+  using C = FaBwdCfg<D>;
+  const bool bf16 = dtype == CB_BF16;
+  CUtensorMap tq, tk, tv, tdo;
+  const uint64_t T = (uint64_t)batch * seqlen;
+  int r = make_tmap_2d_16b(&tq, q, T, (uint64_t)hq * D, (uint64_t)hq * D, BWD_BLOCK_Q, 64, bf16);
+  if (r) return 1000 + r;
+  r = make_tmap_2d_16b(&tdo, dout, T, (uint64_t)hq * D, (uint64_t)hq * D, BWD_BLOCK_Q, 64, bf16);
+  if (r) return 4000 + r;
+  r = make_tmap_2d_16b(&tk, k, T, (uint64_t)hkv * D, (uint64_t)hkv * D, BWD_BLOCK_KV, 64, bf16);
+  if (r) return 2000 + r;
+  r = make_tmap_2d_16b(&tv, v, T, (uint64_t)hkv * D, (uint64_t)hkv * D, BWD_BLOCK_KV, 64, bf16);
+  if (r) return 3000 + r;
+  FaBwdParams p;
+  p.batch = batch; p.seqlen = seqlen; p.hq = hq; p.hkv = hkv; p.causal = causal;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = dk; p.dv = dv; p.out_dtype = dtype;
+  const int f = bf16 ? 1 : 0;
+  p.idesc_st = make_idesc_f16(BWD_BLOCK_KV, BWD_BLOCK_Q, f, 0, 0);     // [128 keys x 64 q]  = K-major x K-major
+  p.idesc_dv = make_idesc_f16(BWD_BLOCK_KV, D, f, 0, 1);                // [128 keys x D]     = K-major x MN-major
+  p.idesc_dqt = make_idesc_f16(D, BWD_BLOCK_Q, f, 1, 1);                // [D x 64 q]         = MN-major x MN-major
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(seqlen / BWD_BLOCK_KV, hkv, batch);
+  flash_bwd_kernel<D><<<grid, BWD_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -379,6 +810,36 @@ int cb_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   if (head_dim == 64)
     return launch_flash_fwd<64>(q, k, v, out, lse, batch, seqlen_q, seqlen_k, hq, hkv, causal, scale, dtype, stream);
   return (int)cudaErrorInvalidValue;
+}
+
+// Backward of cb_flash_attn_fwd for self attention (seqlen_q == seqlen_k).  q / out / dout / dq [T, hq, D], k / v / dk /
+// dv [T, hkv, D], lse [T, hq] fp32 from the forward.  Workspaces: delta [T, hq] fp32 and dq_acc [T, hq, D] fp32 (this
+// function zeroes dq_acc).  Requirements as the forward; head_dim 128 (64 also instantiated).
+int cb_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                      void* dq, void* dk, void* dv, float* delta, float* dq_acc, int batch, int seqlen, int hq, int hkv,
+                      int head_dim, int causal, float scale, int dtype, cudaStream_t stream) {
+  if (batch <= 0 || seqlen <= 0) return 0;
+  // head_dim 64 would make dQ^T an M = 64 MMA (different TMEM lane layout): not wired up yet
+  if (seqlen % BWD_BLOCK_KV || hq % hkv || head_dim != 128) return (int)cudaErrorInvalidValue;
+  if (dtype != CB_BF16 && dtype != CB_F16) return (int)cudaErrorInvalidValue;
+  const long long rows = (long long)batch * seqlen * hq;
+  const long long n = rows * head_dim;
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)n * sizeof(float), stream);
+  if (e != cudaSuccess) return (int)e;
+  const int wpb = 8;
+  if (dtype == CB_BF16)
+    flash_bwd_delta_kernel<__nv_bfloat16><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows, head_dim);
+  else
+    flash_bwd_delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        (const __half*)out, (const __half*)dout, delta, rows, head_dim);
+  int rc = launch_flash_bwd<128>(q, k, v, dout, lse, delta, dq_acc, dk, dv, batch, seqlen, hq, hkv, causal, scale, dtype,
+                                 stream);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((n / 8 + 255) / 256);
+  if (dtype == CB_BF16) flash_bwd_cast_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(dq_acc, (__nv_bfloat16*)dq, n);
+  else flash_bwd_cast_dq_kernel<__half><<<blocks, 256, 0, stream>>>(dq_acc, (__half*)dq, n);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -50,7 +50,59 @@ struct GemmParams {
   void* C;
   const float* scale_a = nullptr;   // fp8 path: per-tensor dequantisation scales (device pointers, may be null)
   const float* scale_b = nullptr;
+  // tail-wave split (CTA-pair kernel): the tiles of the last, partial wave are cut along K into `tail_split` work
+  // units each so that all CTA pairs stay busy; units j < tail_split - 1 park their fp32 partial tile in `ws_part` and
+  // raise `ws_flag`, the last unit folds them in before its epilogue store (stream-K style fix-up, no atomics on C).
+  int tail_split = 1;
+  // tail-wave N halving (CTA-pair kernel): the tiles of the partial last wave are cut into two 256 x 128 halves
+  // (UMMA 256 x 128 x 16, 64 B columns per CTA) when that fills more CTA pairs; no fix-up needed.  `idesc_half` is the
+  // instruction descriptor with N = 128.
+  int tail_half = 0;
+  uint32_t idesc_half = 0;
+  float* ws_part = nullptr;         // [tail tiles][tail_split - 1][256][256] fp32
+  uint32_t* ws_flag = nullptr;      // [tail tiles][tail_split - 1][2 CTAs][4 epilogue warps]
 };
+
+// Work unit -> (tile, k-block range) of the CTA-pair kernel.  Units [0, full) are whole tiles of the complete waves;
+// the rest enumerates (tail tile, split index) pairs, split index fastest, so the units of one tile run on
+// neighbouring pairs in the same (last) wave.
+struct WorkUnit {
+  int tile, kb_begin, kb_end, split, nsplit, tail_idx;
+  int half;      // -1: whole 256 x 256 tile; 0 / 1: left / right 256 x 128 half of a tail tile
+};
+SM100_DEVICE WorkUnit get_unit(int unit, int full, int tail_split, int k_blocks, int tail_half) {
+  WorkUnit w;
+  w.half = -1;
+  if (unit < full) {
+    w.tile = unit; w.kb_begin = 0; w.kb_end = k_blocks; w.split = 0; w.nsplit = 1; w.tail_idx = 0;
+  } else if (tail_half) {
+    const int u = unit - full;
+    w.tail_idx = u >> 1;
+    w.half = u & 1;
+    w.tile = full + w.tail_idx;
+    w.kb_begin = 0; w.kb_end = k_blocks; w.split = 0; w.nsplit = 1;
+  } else {
+    const int u = unit - full;
+    w.tail_idx = u / tail_split;
+    w.split = u - w.tail_idx * tail_split;
+    w.nsplit = tail_split;
+    w.tile = full + w.tail_idx;
+    // uneven K ranges: the last unit (the one that folds the partials in) gets 1.5 shares, so the writers' epilogues
+    // (fp32 partial -> workspace) and their flags are done while the reader is still in its main loop
+    const int share = (2 * k_blocks) / (2 * tail_split + 1);
+    w.kb_begin = share * w.split;
+    w.kb_end = (w.split == tail_split - 1) ? k_blocks : share * (w.split + 1);
+  }
+  return w;
+}
+SM100_DEVICE void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+SM100_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 SM100_DEVICE void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
   const int tiles_per_group = GROUP_M * n_blocks;
@@ -299,7 +351,7 @@ template <int BK_, int STAGES_> struct Cfg2 {
 template <int BK, int STAGES, bool F8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_bh, const GemmParams p) {
   using C = Cfg2<BK, STAGES>;
   constexpr int KE = F8 ? 2 * BK : BK;      // K elements per stage
   constexpr int SUB = F8 ? 128 : 64;        // K elements per 128-byte swizzled sub-tile
@@ -324,10 +376,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int n_blocks = (p.N + PAIR_N - 1) / PAIR_N;
   const int num_tiles = m_blocks * n_blocks;
   const int k_blocks = (p.K + KE - 1) / KE;
+  const int tail_half = p.tail_half;
+  const int tail_split = (!tail_half && p.tail_split > 1) ? p.tail_split : 1;
+  // tiles of the complete waves; the rest are "tail" tiles cut in N halves or K ranges
+  const int full = (tail_half || tail_split > 1) ? (num_tiles / num_pairs) * num_pairs : num_tiles;
+  const int num_units = full + (num_tiles - full) * (tail_half ? 2 : tail_split);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_bh);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -351,15 +409,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ================================================================ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    for (int unit = pair_id; unit < num_units; unit += num_pairs) {
+      const WorkUnit wu = get_unit(unit, full, tail_split, k_blocks, tail_half);
       int m_blk, n_blk;
-      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+      tile_coords(wu.tile, m_blocks, n_blocks, m_blk, n_blk);
       const int m0 = m_blk * PAIR_M + (int)cta_rank * 128;
-      const int n0 = n_blk * PAIR_N + (int)cta_rank * 128;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const bool halfw = wu.half >= 0;                 // 256 x 128 half tile: this CTA stages 64 columns of B
+      const int n0 = halfw ? n_blk * PAIR_N + wu.half * 128 + (int)cta_rank * 64 : n_blk * PAIR_N + (int)cta_rank * 128;
+      for (int kb = wu.kb_begin; kb < wu.kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], halfw ? 2 * (C::A_BYTES + C::B_BYTES / 2) : 2 * C::STAGE_BYTES);
           const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
@@ -372,8 +432,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_a, fb, sa + j * (BK * 128), m0 + j * 64, k0);
           }
           if (!p.b_mn_major) {
+            // K-major B: 64-k sub-tiles of 128 rows (16 KB apart); a half tile fills the first 64 rows of each
 #pragma unroll
-            for (int j = 0; j < BK / 64; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (128 * 128), k0 + j * SUB, n0);
+            for (int j = 0; j < BK / 64; ++j)
+              tma_load_2d_2sm(halfw ? &tmap_bh : &tmap_b, fb, sb + j * (128 * 128), k0 + j * SUB, n0);
+          } else if (halfw) {
+            tma_load_2d_2sm(&tmap_b, fb, sb, n0, k0);           // MN-major B: one 64-column chunk instead of two
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d_2sm(&tmap_b, fb, sb + j * (BK * 128), n0 + j * 64, k0);
@@ -392,11 +456,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t acc_phase = 0;
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : UMMA_K * 2;
       const uint32_t b_kstep = p.b_mn_major ? UMMA_K * 128 : UMMA_K * 2;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      for (int unit = pair_id; unit < num_units; unit += num_pairs) {
+        const WorkUnit wu = get_unit(unit, full, tail_split, k_blocks, tail_half);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * PAIR_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = wu.kb_begin; kb < wu.kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (lane == 0) {
@@ -412,20 +477,21 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               // MN-major: one 16-k-row slab (2 KB) per step
               const uint32_t ao = p.a_mn_major ? k * a_kstep : (k >> 2) * (128 * 128) + (k & 3) * a_kstep;
               const uint32_t bo = p.b_mn_major ? k * b_kstep : (k >> 2) * (128 * 128) + (k & 3) * b_kstep;
+              const uint32_t idesc = wu.half >= 0 ? p.idesc_half : p.idesc;
               if constexpr (F8)
-                umma_f8_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
-                                (kb > 0 || k > 0) ? 1u : 0u);
+                umma_f8_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), idesc,
+                                (kb > wu.kb_begin || k > 0) ? 1u : 0u);
               else
-                umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), p.idesc,
-                                 (kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ss_2cta(tmem_d, advance_desc(da, ao), advance_desc(db, bo), idesc,
+                                 (kb > wu.kb_begin || k > 0) ? 1u : 0u);
             }
             umma_commit_2cta(&empty_bar[stage], 3);
-            if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[acc], 3);
+            if (kb == wu.kb_end - 1) umma_commit_2cta(&tmem_full[acc], 3);
           }
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (k_blocks == 0 && lane == 0) umma_commit_2cta(&tmem_full[acc], 3);
+        if (wu.kb_end <= wu.kb_begin && lane == 0) umma_commit_2cta(&tmem_full[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -440,21 +506,67 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (p.scale_a) alpha *= __ldg(p.scale_a);
       if (p.scale_b) alpha *= __ldg(p.scale_b);
     }
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    for (int unit = pair_id; unit < num_units; unit += num_pairs) {
+      const WorkUnit wu = get_unit(unit, full, tail_split, k_blocks, tail_half);
       int m_blk, n_blk;
-      tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+      tile_coords(wu.tile, m_blocks, n_blocks, m_blk, n_blk);
       const int row = m_blk * PAIR_M + (int)cta_rank * 128 + quarter * 32 + lane;
-      const int n0 = n_blk * PAIR_N;
+      const int n0 = n_blk * PAIR_N + (wu.half > 0 ? 128 : 0);
+      const int tile_n = wu.half >= 0 ? 128 : PAIR_N;
+      // split tail tile: this warp's 32 x 256 slice of the fp32 partial of split j lives at part_base(j), its flag at
+      // flag_base[j * 8]; writer and reader of a slice are the SAME (cta, quarter) warp position of two different pairs
+      const int nparts = wu.nsplit - 1;
+      float* part_row = nullptr;
+      uint32_t* flag_base = nullptr;
+      if (nparts > 0) {
+        part_row = p.ws_part + ((size_t)wu.tail_idx * nparts * PAIR_M + (size_t)cta_rank * 128 + quarter * 32 + lane) * PAIR_N;
+        flag_base = p.ws_flag + (size_t)wu.tail_idx * nparts * 8 + cta_rank * 4 + quarter;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * PAIR_N + ((uint32_t)(quarter * 32) << 16);
+      const bool reader = wu.split == nparts;   // the LAST unit of a tile folds the partials in (its writers have lower
+                                                // block indices, i.e. were dispatched no later than it)
+      if (nparts > 0 && reader) {
+        // partial sums of the other K ranges must have landed before they are folded in
+        for (int j = 0; j < nparts; ++j)
+          while (ld_acquire_gpu_u32(flag_base + j * 8) == 0u) __nanosleep(64);
+      }
 #pragma unroll 1
-      for (int c = 0; c < PAIR_N; c += 64) {
+      for (int c = 0; c < tile_n; c += 64) {
         // two 32-column TMEM loads in flight per wait: halves the exposed tcgen05.ld latency of the epilogue
         uint32_t v0[32], v1[32];
         tmem_ld_32x32b_x32(taddr + c, v0);
         tmem_ld_32x32b_x32(taddr + c + 32, v1);
         tmem_ld_wait();
+        if (nparts > 0) {
+          if (!reader) {
+            // park this K range's partial (fp32, this thread's row, 64 columns) and move on: no store to C
+            float* dst = part_row + (size_t)wu.split * PAIR_M * PAIR_N + c;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              *reinterpret_cast<uint4*>(dst + i) = make_uint4(v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
+              *reinterpret_cast<uint4*>(dst + 32 + i) = make_uint4(v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
+            }
+            continue;
+          }
+          for (int j = 0; j < nparts; ++j) {
+            const float* src = part_row + (size_t)j * PAIR_M * PAIR_N + c;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 a0 = __ldcg(reinterpret_cast<const float4*>(src + i));
+              const float4 a1 = __ldcg(reinterpret_cast<const float4*>(src + 32 + i));
+              v0[i] = __float_as_uint(__uint_as_float(v0[i]) + a0.x);
+              v0[i + 1] = __float_as_uint(__uint_as_float(v0[i + 1]) + a0.y);
+              v0[i + 2] = __float_as_uint(__uint_as_float(v0[i + 2]) + a0.z);
+              v0[i + 3] = __float_as_uint(__uint_as_float(v0[i + 3]) + a0.w);
+              v1[i] = __float_as_uint(__uint_as_float(v1[i]) + a1.x);
+              v1[i + 1] = __float_as_uint(__uint_as_float(v1[i + 1]) + a1.y);
+              v1[i + 2] = __float_as_uint(__uint_as_float(v1[i + 2]) + a1.z);
+              v1[i + 3] = __float_as_uint(__uint_as_float(v1[i + 3]) + a1.w);
+            }
+          }
+        }
         if constexpr (F8) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -485,6 +597,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
       }
+      if (nparts > 0) {
+        if (!reader) {
+          __threadfence();             // every lane's partial rows are visible device-wide before the flag
+          __syncwarp();
+          if (lane == 0) st_release_gpu_u32(flag_base + wu.split * 8, 1u);
+        } else {
+          __syncwarp();                // all lanes are done reading the partials: re-arm the flags for the next launch
+          if (lane < nparts) flag_base[lane * 8] = 0u;
+        }
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -492,6 +614,46 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_before();
   cluster_sync();                      // the leader's MMAs read the peer's shared memory: nobody leaves early
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+}
+
+// Split-K workspace of the tail wave: one per stream that launches GEMMs (kernels on one stream are serialised, so a
+// workspace is never shared by two running kernels).  74 fp32 tiles of 256 x 256 + their flags = 19.4 MB.
+struct TailWorkspace {
+  cudaStream_t stream;
+  float* part;
+  uint32_t* flag;
+};
+constexpr int MAX_TAIL_UNITS = 80;
+inline TailWorkspace* get_tail_workspace(cudaStream_t stream) {
+  static TailWorkspace slots[8] = {};
+  static int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (slots[i].stream == stream) return &slots[i];
+  if (used == 8) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+  TailWorkspace w{stream, nullptr, nullptr};
+  if (cudaMalloc(&w.part, (size_t)MAX_TAIL_UNITS * PAIR_M * PAIR_N * sizeof(float)) != cudaSuccess) return nullptr;
+  if (cudaMalloc(&w.flag, (size_t)MAX_TAIL_UNITS * 8 * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+  cudaMemset(w.flag, 0, (size_t)MAX_TAIL_UNITS * 8 * sizeof(uint32_t));
+  slots[used] = w;
+  return &slots[used++];
+}
+
+// How many K ranges the tiles of the partial last wave are cut into (1 = no split).
+inline int pick_tail_split(int tiles, int pairs, int k_blocks) {
+  // CB200_GEMM_TAIL_SPLIT: 0 = off (default until it is a measured win), n > 0 = at most n K ranges per tail tile.
+  // Read on every launch so one process can A/B the two schedules.
+  const char* e = getenv("CB200_GEMM_TAIL_SPLIT");
+  const int max_split = e ? atoi(e) : 0;
+  if (max_split < 2 || tiles <= pairs) return 1;
+  const int tail = tiles % pairs;
+  if (tail == 0) return 1;
+  int s = pairs / tail;                    // all units of the tail wave run concurrently on distinct pairs
+  if (s > max_split) s = max_split;
+  while (s > 1 && (2 * k_blocks) / (2 * s + 1) < 4) --s;   // keep >= 4 k-blocks (512 deep) per writer
+  if (tail * s > MAX_TAIL_UNITS) return 1;
+  return s < 2 ? 1 : s;
 }
 
 template <int BK, int STAGES>
@@ -520,7 +682,30 @@ int launch_2cta(const void* A, const void* B, void* Cp, int M, int N, int K, int
   int pairs = cb_num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
   if (pairs <= 0) return 0;
-  gemm_tcgen05_2cta_kernel<BK, STAGES><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  // tail wave: N halves (default) when the partial last wave fills at most half of the CTA pairs; K ranges on request
+  CUtensorMap tbh = tb;
+  {
+    const char* e = getenv("CB200_GEMM_TAIL_HALF");
+    const int want_half = e ? atoi(e) : 1;
+    const int tail = tiles > pairs ? tiles % pairs : 0;
+    if (want_half && tail > 0 && 2 * tail <= pairs) {
+      if (!b_mn) {
+        r = make_tmap_2d_16b(&tbh, B, N, K, ldb, 64, 64, bf16);      // K-major B: boxes of 64 rows for a half tile
+        if (r) return 3000 + r;
+      }
+      p.tail_half = 1;
+      p.idesc_half = make_idesc_f16(PAIR_M, 128, bf16 ? 1 : 0, a_mn, b_mn);
+    }
+  }
+  if (!p.tail_half) {
+    const int split = pick_tail_split(tiles, pairs, (K + BK - 1) / BK);
+    if (split > 1) {
+      if (TailWorkspace* w = get_tail_workspace(stream)) {
+        p.tail_split = split; p.ws_part = w->part; p.ws_flag = w->flag;
+      }
+    }
+  }
+  gemm_tcgen05_2cta_kernel<BK, STAGES><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tbh, p);
   return (int)cudaGetLastError();
 }
 
@@ -553,7 +738,7 @@ int launch_2cta_f8(const void* A, const void* B, void* Cp, int M, int N, int K, 
   int pairs = cb_num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
   if (pairs <= 0) return 0;
-  gemm_tcgen05_2cta_kernel<BK, STAGES, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_2cta_kernel<BK, STAGES, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tb, p);
   return (int)cudaGetLastError();
 }
 

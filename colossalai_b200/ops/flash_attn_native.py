@@ -1,9 +1,11 @@
-"""ctypes face of the sm_100a flash-attention forward kernel (`kernel/csrc/flash_attn_tcgen05.cu`).
+"""ctypes face of the sm_100a flash-attention kernels (`kernel/csrc/flash_attn_tcgen05.cu`): tcgen05 forward (validated
+on a B200 in round 2: 17/17 numerics cases) and tcgen05 backward (dK / dV accumulated in TMEM per key tile over the whole
+GQA group, dQ through fp32 reductions).
 
-The kernel has been compiled and reviewed but not yet executed on hardware, so it is OFF unless
-`CB200_FLASH_NATIVE=1`; with the flag on, `ops.attention` and the ring-attention block functions route equal-length
-bf16 / fp16 batches (head_dim 64 / 128, sequence length a multiple of 128) through it.  The backward pass reuses the
-library flash backward (it only needs q, k, v, out and the log-sum-exp we return).
+`CB200_FLASH_NATIVE=1` (or `enable(True)`) routes `ops.attention` and the ring-attention block functions through them
+for equal-length bf16 / fp16 batches (head_dim 64 / 128 forward, 128 backward; sequence length a multiple of 128);
+everything else, and the default until the kernels match the library's speed, goes to SDPA.  `CB200_FLASH_BWD=lib`
+keeps the native forward but uses the library backward (which only needs q, k, v, out and our log-sum-exp).
 """
 from __future__ import annotations
 
@@ -69,6 +71,30 @@ def flash_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, cau
     return out, lse
 
 
+def bwd_supported(q: torch.Tensor, k: torch.Tensor, batch: int) -> bool:
+    return (os.environ.get("CB200_FLASH_BWD", "native") == "native" and q.shape[-1] == 128 and q.shape[0] == k.shape[0]
+            and (q.shape[0] // batch) % 128 == 0)
+
+
+def flash_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, dout: torch.Tensor,
+              lse: torch.Tensor, batch: int, causal: bool, scale: Optional[float]):
+    """Gradients of `flash_fwd` for self attention: returns (dq, dk, dv) in the input dtype."""
+    T, Hq, D = q.shape
+    Hkv = k.shape[1]
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    dout = dout.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty(T, Hq, D, dtype=torch.float32, device=q.device)
+    rc = _get_lib().cb_flash_attn_bwd(loader.ptr(q), loader.ptr(k), loader.ptr(v), loader.ptr(out), loader.ptr(dout),
+                                      loader.ptr(lse), loader.ptr(dq), loader.ptr(dk), loader.ptr(dv), loader.ptr(delta),
+                                      loader.ptr(dq_acc), batch, T // batch, Hq, Hkv, D, int(causal),
+                                      ctypes.c_float(scale), code(q.dtype), loader.stream_ptr())
+    loader.check(rc, "flash_attn_bwd")
+    loader.launch_counter.add("flash_attn_bwd")
+    return dq, dk, dv
+
+
 class _FlashFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, batch, causal, scale):
@@ -83,7 +109,10 @@ class _FlashFn(torch.autograd.Function):
 
         q, k, v, out, lse = ctx.saved_tensors
         scale = ctx.scale if ctx.scale is not None else 1.0 / math.sqrt(q.shape[-1])
-        dq, dk, dv = _block_bwd(dout.contiguous(), q, k, v, out, lse, ctx.batch, ctx.causal, scale)
+        if bwd_supported(q, k, ctx.batch):
+            dq, dk, dv = flash_bwd(q, k, v, out, dout, lse, ctx.batch, ctx.causal, scale)
+        else:
+            dq, dk, dv = _block_bwd(dout.contiguous(), q, k, v, out, lse, ctx.batch, ctx.causal, scale)
         return dq, dk, dv, None, None, None
 
 

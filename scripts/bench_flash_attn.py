@@ -30,3 +30,14 @@ for (B, S, Hq, Hkv, D) in [(1, 4096, 32, 8, 128), (4, 4096, 32, 8, 128), (1, 163
     fl = 4.0 * B * Hq * S * S * D / 2
     print("FLASH_FWD " + json.dumps({"B": B, "S": S, "Hq": Hq, "Hkv": Hkv, "D": D, "native_ms": t_nat, "sdpa_ms": t_lib,
                                      "native_tflops": fl / t_nat / 1e9, "sdpa_tflops": fl / t_lib / 1e9}), flush=True)
+    # backward: ours = one launch chain (delta, tcgen05 bwd, dq cast); library = autograd through SDPA (cuDNN bprop)
+    out, lse = fa.flash_fwd(q, k, v, B, True, None)
+    dout = torch.randn_like(out)
+    t_nat_b = timeit(lambda: fa.flash_bwd(q, k, v, out, dout, lse, B, True, None))
+    ql, kl, vl = (t.detach().clone().requires_grad_(True) for t in (qb, kb, vb))
+    ol = F.scaled_dot_product_attention(ql, kl, vl, is_causal=True, enable_gqa=True)
+    gl = torch.randn_like(ol)
+    t_lib_b = timeit(lambda: torch.autograd.grad(ol, (ql, kl, vl), gl, retain_graph=True))
+    print("FLASH_BWD " + json.dumps({"B": B, "S": S, "Hq": Hq, "Hkv": Hkv, "D": D, "native_ms": t_nat_b,
+                                     "sdpa_ms": t_lib_b, "native_tflops": 2.5 * fl / t_nat_b / 1e9,
+                                     "sdpa_tflops": 2.5 * fl / t_lib_b / 1e9}), flush=True)

@@ -35,8 +35,9 @@ def main():
     except Exception:
         pass
     peak = peaks.get("bf16_tflops", 1590.0)
-    shapes = [(8192, 6144, 4096, "qkv fwd"), (8192, 4096, 4096, "o_proj fwd"), (8192, 28672, 4096, "gate_up fwd"),
-              (8192, 4096, 14336, "down fwd"), (4096, 128256, 4096, "lm_head fwd"), (8192, 8192, 8192, "square")]
+    M0 = int(os.environ.get("CB200_GEMM_BENCH_M", "8192"))     # tokens per micro-batch (4096 = the N=1 bench step)
+    shapes = [(M0, 6144, 4096, "qkv fwd"), (M0, 4096, 4096, "o_proj fwd"), (M0, 28672, 4096, "gate_up fwd"),
+              (M0, 4096, 14336, "down fwd"), (4096, 128256, 4096, "lm_head fwd"), (8192, 8192, 8192, "square")]
     out = []
     for M, N, K, name in shapes:
         x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
