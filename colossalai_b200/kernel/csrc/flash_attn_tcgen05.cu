@@ -47,12 +47,20 @@ template <int D> struct FaCfg {
 };
 
 struct FaParams {
+  // packed / variable-length batches: cu_seqlens[b] .. cu_seqlens[b + 1] are the token rows of sequence b (self
+  // attention, the same boundaries for queries and keys); null = `batch` equal-length sequences
+  const int* cu_seqlens;
   int batch, seqlen_q, seqlen_k;     // equal-length sequences, token-major tensors [batch * seqlen, heads * D]
   int hq, hkv;
   int causal;
   float scale_log2;                  // softmax scale * log2(e)
   void* out;                         // [batch * seqlen_q, hq * D]
   float* lse;                        // [batch * seqlen_q, hq] natural-log LSE
+  // ring / blockwise attention: the online-softmax state of every query row lives in (o_state, lse) between launches.
+  // has_prev: start from that state (m = lse, l = 1, acc = o_state) instead of (-inf, 0, 0); the result - the merge of
+  // the previous partial result with this launch's keys - is written back in fp32.  No separate rescale / merge pass.
+  float* o_state;                    // [rows, hq * D] fp32, or null (plain attention: `out` in the input dtype)
+  int has_prev;
   int out_dtype;
   uint32_t idesc_qk, idesc_pv;
 };
@@ -86,16 +94,35 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // heaviest (longest causal) query tiles first
-  const int q_tiles = p.seqlen_q / BLOCK_Q;
-  const int q_tile = p.causal ? (q_tiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;
   const int head = blockIdx.y;
-  const int b = blockIdx.z;
   const int kv_head = head / (p.hq / p.hkv);
-  const int q_row0 = b * p.seqlen_q + q_tile * BLOCK_Q;            // row in the token-major Q / O tensors
-  const int kv_row0 = b * p.seqlen_k;
+  int q_tile, seq_row0, len_q, len_k;
+  if (p.cu_seqlens != nullptr) {
+    // packed batch: blockIdx.x enumerates (sequence, query tile) pairs in order; surplus CTAs (the grid is sized for
+    // the worst case without knowing the lengths on the host) leave at once
+    int t = (int)blockIdx.x, bsel = -1, start = 0, len = 0;
+    for (int bb = 0; bb < p.batch; ++bb) {
+      start = p.cu_seqlens[bb];
+      len = p.cu_seqlens[bb + 1] - start;
+      const int nt = (len + BLOCK_Q - 1) / BLOCK_Q;
+      if (t < nt) { bsel = bb; break; }
+      t -= nt;
+    }
+    if (bsel < 0) return;                      // uniform across the CTA: nothing has been allocated yet
+    q_tile = t; seq_row0 = start; len_q = len; len_k = len;
+  } else {
+    // heaviest (longest causal) query tiles first
+    const int q_tiles = (p.seqlen_q + BLOCK_Q - 1) / BLOCK_Q;
+    q_tile = p.causal ? (q_tiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+    seq_row0 = -1; len_q = p.seqlen_q; len_k = p.seqlen_k;
+  }
+  const int b = blockIdx.z;
+  const int q_row0 = (seq_row0 >= 0 ? seq_row0 : b * p.seqlen_q) + q_tile * BLOCK_Q;   // row in the token-major Q / O
+  const int kv_row0 = seq_row0 >= 0 ? seq_row0 : b * p.seqlen_k;
+  const int kv_tiles_all = (len_k + BLOCK_KV - 1) / BLOCK_KV;
   // causal with seqlen_q == seqlen_k: key tiles 0..q_tile; otherwise all of them
-  const int kv_tiles = p.causal ? (q_tile + 1) : (p.seqlen_k / BLOCK_KV);
+  const int kv_tiles = p.causal ? min(q_tile + 1, kv_tiles_all) : kv_tiles_all;
+  const bool ragged_k = (len_k % BLOCK_KV) != 0;   // the last key tile runs past the end of the sequence
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_q);
@@ -206,13 +233,31 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY;                             // running max in the exp2 domain
     float l_run = 0.f;
+    if (p.o_state != nullptr && p.has_prev && q_pos < len_q) {
+      // resume from the merged result of the key blocks processed by earlier launches (normalised output + LSE)
+      const size_t row_ = (size_t)q_row0 + r;
+      const float lse_prev = p.lse[row_ * p.hq + head];
+      if (lse_prev > -INFINITY) {
+        m_run = lse_prev * 1.4426950408889634f;
+        l_run = 1.f;
+        const float4* src = reinterpret_cast<const float4*>(p.o_state + row_ * ((size_t)p.hq * D) + (size_t)head * D);
+#pragma unroll
+        for (int i = 0; i < D / 4; ++i) {
+          const float4 t4 = src[i];
+          o_acc[4 * i] = t4.x; o_acc[4 * i + 1] = t4.y; o_acc[4 * i + 2] = t4.z; o_acc[4 * i + 3] = t4.w;
+        }
+      }
+    }
     uint8_t* p_row = smem_p + r * 128;
     for (int j = 0; j < kv_tiles; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_addr + sb * BLOCK_KV;
-      const bool diag = p.causal && (j == kv_tiles - 1);
+      const bool diag = p.causal && (j == q_tile);
+      const bool tail_k = ragged_k && (j == kv_tiles_all - 1);
+      const bool masked = diag || tail_k;
+      const int k_lim = diag ? min(q_pos, len_k - 1) : (len_k - 1);      // last visible key position of this row
       const int k_base = j * BLOCK_KV;
       // ---- pass 1: row max
       float m_tile = -INFINITY;
@@ -224,7 +269,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (diag && (k_base + c + i) > q_pos) s = -INFINITY;
+          if (masked && (k_base + c + i) > k_lim) s = -INFINITY;
           m_tile = fmaxf(m_tile, s);
         }
       }
@@ -247,8 +292,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < 32; i += 2) {
           float s0 = __uint_as_float(v[i]) * p.scale_log2;
           float s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-          if (diag && (k_base + c + i) > q_pos) s0 = -INFINITY;
-          if (diag && (k_base + c + i + 1) > q_pos) s1 = -INFINITY;
+          if (masked && (k_base + c + i) > k_lim) s0 = -INFINITY;
+          if (masked && (k_base + c + i + 1) > k_lim) s1 = -INFINITY;
           const float p0 = fast_exp2(s0 - m_safe);
           const float p1 = fast_exp2(s1 - m_safe);
           l_tile += p0 + p1;
@@ -298,7 +343,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- epilogue: normalise and store this thread's row
     const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
     const size_t row = (size_t)q_row0 + r;
-    if (p.out_dtype == CB_BF16) {
+    if (q_pos >= len_q) {
+      // a row past the end of its (packed) sequence: computed on garbage, never stored
+    } else if (p.o_state != nullptr) {
+      float4* dst = reinterpret_cast<float4*>(p.o_state + row * ((size_t)p.hq * D) + (size_t)head * D);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i)
+        dst[i] = make_float4(o_acc[4 * i] * inv_l, o_acc[4 * i + 1] * inv_l, o_acc[4 * i + 2] * inv_l,
+                             o_acc[4 * i + 3] * inv_l);
+    } else if (p.out_dtype == CB_BF16) {
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * ((size_t)p.hq * D) + (size_t)head * D;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
@@ -323,7 +376,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    if (p.lse) p.lse[row * p.hq + head] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    if (p.lse && q_pos < len_q)
+      p.lse[row * p.hq + head] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -332,17 +386,23 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
 template <int D>
 int launch_flash_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int seqlen_q,
-                     int seqlen_k, int hq, int hkv, int causal, float scale, int dtype, cudaStream_t stream) {
+                     int seqlen_k, int hq, int hkv, int causal, float scale, int dtype, cudaStream_t stream,
+                     const int* cu_seqlens = nullptr, long long total_tokens = 0, float* o_state = nullptr,
+                     int has_prev = 0) {
   using C = FaCfg<D>;
   const bool bf16 = dtype == CB_BF16;
   CUtensorMap tq, tk, tv;
-  int r = make_tmap_2d_16b(&tq, q, (uint64_t)batch * seqlen_q, (uint64_t)hq * D, (uint64_t)hq * D, BLOCK_Q, 64, bf16);
+  const uint64_t rows_q = cu_seqlens ? (uint64_t)total_tokens : (uint64_t)batch * seqlen_q;
+  const uint64_t rows_k = cu_seqlens ? (uint64_t)total_tokens : (uint64_t)batch * seqlen_k;
+  int r = make_tmap_2d_16b(&tq, q, rows_q, (uint64_t)hq * D, (uint64_t)hq * D, BLOCK_Q, 64, bf16);
   if (r) return 1000 + r;
-  r = make_tmap_2d_16b(&tk, k, (uint64_t)batch * seqlen_k, (uint64_t)hkv * D, (uint64_t)hkv * D, BLOCK_KV, 64, bf16);
+  r = make_tmap_2d_16b(&tk, k, rows_k, (uint64_t)hkv * D, (uint64_t)hkv * D, BLOCK_KV, 64, bf16);
   if (r) return 2000 + r;
-  r = make_tmap_2d_16b(&tv, v, (uint64_t)batch * seqlen_k, (uint64_t)hkv * D, (uint64_t)hkv * D, BLOCK_KV, 64, bf16);
+  r = make_tmap_2d_16b(&tv, v, rows_k, (uint64_t)hkv * D, (uint64_t)hkv * D, BLOCK_KV, 64, bf16);
   if (r) return 3000 + r;
   FaParams p;
+  p.cu_seqlens = cu_seqlens;
+  p.o_state = o_state; p.has_prev = has_prev;
   p.batch = batch; p.seqlen_q = seqlen_q; p.seqlen_k = seqlen_k; p.hq = hq; p.hkv = hkv; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.lse = lse; p.out_dtype = dtype;
@@ -355,7 +415,9 @@ int launch_flash_fwd(const void* q, const void* k, const void* v, void* out, flo
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(seqlen_q / BLOCK_Q, hq, batch);
+  // packed: at most total/128 + batch query tiles exist; uniform: ceil(seqlen / 128) per sequence
+  dim3 grid(cu_seqlens ? (unsigned)(total_tokens / BLOCK_Q + batch) : (unsigned)((seqlen_q + BLOCK_Q - 1) / BLOCK_Q), hq,
+            cu_seqlens ? 1 : batch);
   flash_fwd_kernel<D><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return (int)cudaGetLastError();
 }
@@ -405,6 +467,7 @@ template <int D> struct FaBwdCfg {
 };
 
 struct FaBwdParams {
+  const int* cu_seqlens;             // packed batch boundaries (see FaParams) or null
   int batch, seqlen;                 // equal-length sequences, seqlen_q == seqlen_k (self attention)
   int hq, hkv;
   int causal;
@@ -414,6 +477,10 @@ struct FaBwdParams {
   float* dq_acc;                     // [batch * seqlen, hq * D] fp32, zero-initialised
   void* dk;                          // [batch * seqlen, hkv * D]
   void* dv;
+  // ring attention: dK / dV of this key block are ADDED (fp32 vector reductions) into accumulators that may live in
+  // the block owner's memory (peer-mapped symmetric buffer: the reduction crosses NVLink) instead of being stored
+  float* dk_acc;                     // [rows, hkv * D] fp32 or null
+  float* dv_acc;
   int out_dtype;
   uint32_t idesc_st, idesc_dv, idesc_dqt;
 };
@@ -449,16 +516,31 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kv_tile = blockIdx.x;
   const int kv_head = blockIdx.y;
-  const int b = blockIdx.z;
   const int group = p.hq / p.hkv;
-  const int q_tiles = p.seqlen / BWD_BLOCK_Q;
+  int kv_tile, seq_row0, len;
+  if (p.cu_seqlens != nullptr) {
+    int t = (int)blockIdx.x, bsel = -1, start = 0;
+    len = 0;
+    for (int bb = 0; bb < p.batch; ++bb) {
+      start = p.cu_seqlens[bb];
+      len = p.cu_seqlens[bb + 1] - start;
+      const int nt = (len + BWD_BLOCK_KV - 1) / BWD_BLOCK_KV;
+      if (t < nt) { bsel = bb; break; }
+      t -= nt;
+    }
+    if (bsel < 0) return;
+    kv_tile = t; seq_row0 = start;
+  } else {
+    kv_tile = blockIdx.x; seq_row0 = (int)blockIdx.z * p.seqlen; len = p.seqlen;
+  }
+  const int q_tiles = (len + BWD_BLOCK_Q - 1) / BWD_BLOCK_Q;
   // causal: query tile i (rows 64 i ..) sees key tile j (keys 128 j ..) iff 64 i + 63 >= 128 j  <=>  i >= 2 j
   const int i_start = p.causal ? 2 * kv_tile : 0;
-  const int n_i = q_tiles - i_start;
+  const int n_i = max(q_tiles - i_start, 0);
   const int n_iter = n_i * group;                                  // (query head of the group, query tile) pairs
-  const int kv_row0 = b * p.seqlen + kv_tile * BWD_BLOCK_KV;
+  const int kv_row0 = seq_row0 + kv_tile * BWD_BLOCK_KV;
+  const bool ragged = (len % BWD_BLOCK_KV) != 0;                    // partial last key tile and / or query tile
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_q);
@@ -501,7 +583,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t phase = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int hq = kv_head * group + it / n_i;
-      const int q_row0 = b * p.seqlen + (i_start + it % n_i) * BWD_BLOCK_Q;
+      const int q_row0 = seq_row0 + (i_start + it % n_i) * BWD_BLOCK_Q;
       mbar_wait(&qdo_empty[stage], phase ^ 1);
       if (lane == 0) {
         uint8_t* sq = smem_qdo + stage * C::QDO_STAGE_BYTES;
@@ -599,16 +681,26 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int it = 0; it < n_iter; ++it) {
       const int hq = kv_head * group + it / n_i;
       const int q_tile = i_start + it % n_i;
-      const int q_row0 = b * p.seqlen + q_tile * BWD_BLOCK_Q;
-      // per-query-row statistics of this tile (64 lse + 64 delta values, read by every softmax thread)
+      const int q_row0 = seq_row0 + q_tile * BWD_BLOCK_Q;
+      // per-query-row statistics of this tile (64 lse + 64 delta values, read by every softmax thread); rows past the
+      // end of the sequence read as 0 (their P / dS are forced to 0 below)
       asm volatile("bar.sync 1, 128;" ::: "memory");         // previous iteration's readers are done
-      if (sm_tid < BWD_BLOCK_Q) smem_lse[sm_tid] = p.lse[(size_t)(q_row0 + sm_tid) * p.hq + hq] * 1.4426950408889634f;
-      else smem_delta[sm_tid - BWD_BLOCK_Q] = p.delta[(size_t)(q_row0 + sm_tid - BWD_BLOCK_Q) * p.hq + hq];
+      {
+        const int qr = sm_tid < BWD_BLOCK_Q ? sm_tid : sm_tid - BWD_BLOCK_Q;
+        const bool live = q_tile * BWD_BLOCK_Q + qr < len;
+        if (sm_tid < BWD_BLOCK_Q)
+          smem_lse[qr] = live ? p.lse[(size_t)(q_row0 + qr) * p.hq + hq] * 1.4426950408889634f : 0.f;
+        else
+          smem_delta[qr] = live ? p.delta[(size_t)(q_row0 + qr) * p.hq + hq] : 0.f;
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(sp_full, (uint32_t)(it & 1));
       tc_fence_after();
-      const bool diag = p.causal && (q_tile <= 2 * kv_tile + 1);
+      const bool diag = (p.causal && (q_tile <= 2 * kv_tile + 1)) ||
+                        (ragged && (kv_tile == (len - 1) / BWD_BLOCK_KV || q_tile == q_tiles - 1));
       const int q_base = q_tile * BWD_BLOCK_Q;
+      const int q_lo = p.causal ? key_pos : 0;               // this key is visible to query positions [q_lo, len)
+      const bool key_live = key_pos < len;
       uint32_t p_packed[BWD_BLOCK_Q / 2], ds_packed[BWD_BLOCK_Q / 2];
 #pragma unroll
       for (int c = 0; c < BWD_BLOCK_Q; c += 32) {
@@ -623,9 +715,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int e = 0; e < 2; ++e) {
             const int col = c + i + e;
             float pe = fast_exp2(__uint_as_float(sv_[i + e]) * p.scale_log2 - smem_lse[col]);
-            if (diag && key_pos > q_base + col) pe = 0.f;
+            float de = pe * (__uint_as_float(dpv[i + e]) - smem_delta[col]);
+            if (diag && !(key_live && q_base + col >= q_lo && q_base + col < len)) { pe = 0.f; de = 0.f; }
             pv[e] = pe;
-            dsv[e] = pe * (__uint_as_float(dpv[i + e]) - smem_delta[col]);
+            dsv[e] = de;
           }
           if (p.out_dtype == CB_BF16) {
             __nv_bfloat162 hp = __floats2bfloat162_rn(pv[0], pv[1]);
@@ -658,14 +751,31 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane == 0) mbar_arrive(pds_full);
     }
     // ---- epilogue: dV and scale * dK rows of this thread's key
-    mbar_wait(acc_full, 0);
+    if (n_iter > 0) mbar_wait(acc_full, 0);
     tc_fence_after();
     const size_t row = (size_t)kv_row0 + r;
     const size_t ld = (size_t)p.hkv * D;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < 2 && key_pos < len; ++which) {
       const uint32_t col0 = which == 0 ? C::COL_DV : C::COL_DK;
       const float mul = which == 0 ? 1.f : p.scale;
+      if (p.dk_acc != nullptr) {
+        float* acc_row = (which == 0 ? p.dv_acc : p.dk_acc) + (row * ld + (size_t)kv_head * D);
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + col0 + c, v);
+          tmem_ld_wait();
+          if (n_iter > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                           :: "l"(acc_row + c + i), "f"(__uint_as_float(v[i]) * mul), "f"(__uint_as_float(v[i + 1]) * mul),
+                              "f"(__uint_as_float(v[i + 2]) * mul), "f"(__uint_as_float(v[i + 3]) * mul) : "memory");
+          }
+        }
+        continue;
+      }
       uint8_t* base = reinterpret_cast<uint8_t*>(which == 0 ? p.dv : p.dk) + (row * ld + (size_t)kv_head * D) * 2;
 #pragma unroll 1
       for (int c = 0; c < D; c += 32) {
@@ -697,7 +807,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     for (int it = 0; it < n_iter; ++it) {
       const int hq = kv_head * group + it / n_i;
-      const int q_row0 = b * p.seqlen + (i_start + it % n_i) * BWD_BLOCK_Q;
+      const int q_tile = i_start + it % n_i;
+      const int q_row0 = seq_row0 + q_tile * BWD_BLOCK_Q;
+      const int q_live = len - q_tile * BWD_BLOCK_Q;         // rows of this tile that belong to the sequence
       mbar_wait(dq_full, (uint32_t)(it & 1));
       tc_fence_after();
       float* dst = p.dq_acc + ((size_t)q_row0 * p.hq + hq) * D + dlane;
@@ -710,7 +822,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (dlane < D) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)                      // one 128-byte coalesced fp32 reduction per warp and row
-            atomicAdd(dst + (size_t)(c + i) * row_stride, __uint_as_float(v[i]) * p.scale);
+            if (c + i < q_live) atomicAdd(dst + (size_t)(c + i) * row_stride, __uint_as_float(v[i]) * p.scale);
         }
       }
       tc_fence_before();
@@ -759,11 +871,12 @@ __global__ void flash_bwd_cast_dq_kernel(const float* __restrict__ acc, T* __res
 template <int D>
 int launch_flash_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
                      float* dq_acc, void* dk, void* dv, int batch, int seqlen, int hq, int hkv, int causal, float scale,
-                     int dtype, cudaStream_t stream) {
+                     int dtype, cudaStream_t stream, const int* cu_seqlens = nullptr, long long total_tokens = 0,
+                     float* dk_acc = nullptr, float* dv_acc = nullptr) {
   using C = FaBwdCfg<D>;
   const bool bf16 = dtype == CB_BF16;
   CUtensorMap tq, tk, tv, tdo;
-  const uint64_t T = (uint64_t)batch * seqlen;
+  const uint64_t T = cu_seqlens ? (uint64_t)total_tokens : (uint64_t)batch * seqlen;
   int r = make_tmap_2d_16b(&tq, q, T, (uint64_t)hq * D, (uint64_t)hq * D, BWD_BLOCK_Q, 64, bf16);
   if (r) return 1000 + r;
   r = make_tmap_2d_16b(&tdo, dout, T, (uint64_t)hq * D, (uint64_t)hq * D, BWD_BLOCK_Q, 64, bf16);
@@ -773,9 +886,11 @@ int launch_flash_bwd(const void* q, const void* k, const void* v, const void* do
   r = make_tmap_2d_16b(&tv, v, T, (uint64_t)hkv * D, (uint64_t)hkv * D, BWD_BLOCK_KV, 64, bf16);
   if (r) return 3000 + r;
   FaBwdParams p;
+  p.cu_seqlens = cu_seqlens;
   p.batch = batch; p.seqlen = seqlen; p.hq = hq; p.hkv = hkv; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = dk; p.dv = dv; p.out_dtype = dtype;
+  p.dk_acc = dk_acc; p.dv_acc = dv_acc;
   const int f = bf16 ? 1 : 0;
   p.idesc_st = make_idesc_f16(BWD_BLOCK_KV, BWD_BLOCK_Q, f, 0, 0);     // [128 keys x 64 q]  = K-major x K-major
   p.idesc_dv = make_idesc_f16(BWD_BLOCK_KV, D, f, 0, 1);                // [128 keys x D]     = K-major x MN-major
@@ -786,7 +901,8 @@ int launch_flash_bwd(const void* q, const void* k, const void* v, const void* do
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(seqlen / BWD_BLOCK_KV, hkv, batch);
+  dim3 grid(cu_seqlens ? (unsigned)(total_tokens / BWD_BLOCK_KV + batch) : (unsigned)((seqlen + BWD_BLOCK_KV - 1) / BWD_BLOCK_KV),
+            hkv, cu_seqlens ? 1 : batch);
   flash_bwd_kernel<D><<<grid, BWD_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
   return (int)cudaGetLastError();
 }
@@ -802,8 +918,8 @@ int cb_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
                       int seqlen_k, int hq, int hkv, int head_dim, int causal, float scale, int dtype,
                       cudaStream_t stream) {
   if (batch <= 0 || seqlen_q <= 0) return 0;
-  if (seqlen_q % BLOCK_Q || seqlen_k % BLOCK_KV || hq % hkv || (causal && seqlen_q != seqlen_k))
-    return (int)cudaErrorInvalidValue;
+  if (hq % hkv || (causal && seqlen_q != seqlen_k)) return (int)cudaErrorInvalidValue;
+  // sequence lengths need not be multiples of the tile: partial tiles are masked (keys) / not stored (queries)
   if (dtype != CB_BF16 && dtype != CB_F16) return (int)cudaErrorInvalidValue;
   if (head_dim == 128)
     return launch_flash_fwd<128>(q, k, v, out, lse, batch, seqlen_q, seqlen_k, hq, hkv, causal, scale, dtype, stream);
@@ -812,17 +928,34 @@ int cb_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, fl
   return (int)cudaErrorInvalidValue;
 }
 
+// Packed (variable-length) self attention: q / k / v [total_tokens, heads, D]; cu_seqlens int32[batch + 1] ON THE DEVICE
+// (never read by the host: the grid is sized for the worst case and surplus CTAs exit).  Reference counterpart:
+// `flash_attn_varlen_kvpacked_func` behind `extensions/pybind/flash_attention/flash_attention_dao_cuda.py:37-96`.
+int cb_flash_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* cu_seqlens,
+                             int batch, long long total_tokens, int hq, int hkv, int head_dim, int causal, float scale,
+                             int dtype, cudaStream_t stream) {
+  if (batch <= 0 || total_tokens <= 0) return 0;
+  if (hq % hkv || (dtype != CB_BF16 && dtype != CB_F16) || cu_seqlens == nullptr) return (int)cudaErrorInvalidValue;
+  if (head_dim == 128)
+    return launch_flash_fwd<128>(q, k, v, out, lse, batch, 0, 0, hq, hkv, causal, scale, dtype, stream, cu_seqlens, total_tokens);
+  if (head_dim == 64)
+    return launch_flash_fwd<64>(q, k, v, out, lse, batch, 0, 0, hq, hkv, causal, scale, dtype, stream, cu_seqlens, total_tokens);
+  return (int)cudaErrorInvalidValue;
+}
+
 // Backward of cb_flash_attn_fwd for self attention (seqlen_q == seqlen_k).  q / out / dout / dq [T, hq, D], k / v / dk /
 // dv [T, hkv, D], lse [T, hq] fp32 from the forward.  Workspaces: delta [T, hq] fp32 and dq_acc [T, hq, D] fp32 (this
 // function zeroes dq_acc).  Requirements as the forward; head_dim 128 (64 also instantiated).
 int cb_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                       void* dq, void* dk, void* dv, float* delta, float* dq_acc, int batch, int seqlen, int hq, int hkv,
-                      int head_dim, int causal, float scale, int dtype, cudaStream_t stream) {
-  if (batch <= 0 || seqlen <= 0) return 0;
+                      int head_dim, int causal, float scale, int dtype, const int* cu_seqlens, long long total_tokens,
+                      cudaStream_t stream) {
+  // cu_seqlens != null: packed batch of `total_tokens` rows (seqlen ignored); else `batch` sequences of `seqlen`
+  if (batch <= 0 || (cu_seqlens ? total_tokens <= 0 : seqlen <= 0)) return 0;
   // head_dim 64 would make dQ^T an M = 64 MMA (different TMEM lane layout): not wired up yet
-  if (seqlen % BWD_BLOCK_KV || hq % hkv || head_dim != 128) return (int)cudaErrorInvalidValue;
+  if (hq % hkv || head_dim != 128) return (int)cudaErrorInvalidValue;
   if (dtype != CB_BF16 && dtype != CB_F16) return (int)cudaErrorInvalidValue;
-  const long long rows = (long long)batch * seqlen * hq;
+  const long long rows = (cu_seqlens ? total_tokens : (long long)batch * seqlen) * hq;
   const long long n = rows * head_dim;
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)n * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
@@ -834,11 +967,60 @@ int cb_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o
     flash_bwd_delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
         (const __half*)out, (const __half*)dout, delta, rows, head_dim);
   int rc = launch_flash_bwd<128>(q, k, v, dout, lse, delta, dq_acc, dk, dv, batch, seqlen, hq, hkv, causal, scale, dtype,
-                                 stream);
+                                 stream, cu_seqlens, total_tokens);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((n / 8 + 255) / 256);
   if (dtype == CB_BF16) flash_bwd_cast_dq_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(dq_acc, (__nv_bfloat16*)dq, n);
   else flash_bwd_cast_dq_kernel<__half><<<blocks, 256, 0, stream>>>(dq_acc, (__half*)dq, n);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Blockwise entry points for fused ring (context-parallel) attention.  One launch = the queries of this rank against ONE
+// key/value block that may live in a PEER's memory (k / v are then peer-mapped symmetric-buffer addresses: the TMA
+// loads of the main loop pull the tiles over NVLink, GQA heads only, no staging copy).
+//   forward : the online-softmax state (o_state fp32, lse) is carried from launch to launch inside the kernel
+//             (`has_prev`), which replaces the reference's per-hop `_rescale_out_lse` pass (`layer/attn.py:376-403`);
+//   backward: dQ accumulates in the local fp32 `dq_acc` (not zeroed here), dK / dV are reduced straight into the block
+//             owner's fp32 accumulators (`dk_acc` / `dv_acc`, peer pointers) - the reference circulates fp32 dKV
+//             buffers around the ring instead (`layer/attn.py:1066-1163`).  `delta` = rowsum(dO o O) is an input.
+int cb_flash_attn_block_fwd(const void* q, const void* k, const void* v, float* o_state, float* lse, int rows, int hq,
+                            int hkv, int head_dim, int causal, int has_prev, float scale, int dtype, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (hq % hkv || (dtype != CB_BF16 && dtype != CB_F16) || o_state == nullptr || lse == nullptr)
+    return (int)cudaErrorInvalidValue;
+  if (head_dim == 128)
+    return launch_flash_fwd<128>(q, k, v, nullptr, lse, 1, rows, rows, hq, hkv, causal, scale, dtype, stream, nullptr, 0,
+                                 o_state, has_prev);
+  if (head_dim == 64)
+    return launch_flash_fwd<64>(q, k, v, nullptr, lse, 1, rows, rows, hq, hkv, causal, scale, dtype, stream, nullptr, 0,
+                                o_state, has_prev);
+  return (int)cudaErrorInvalidValue;
+}
+
+int cb_flash_attn_block_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                            const float* delta, float* dq_acc, float* dk_acc, float* dv_acc, int rows, int hq, int hkv,
+                            int head_dim, int causal, float scale, int dtype, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (hq % hkv || head_dim != 128 || (dtype != CB_BF16 && dtype != CB_F16) || !dq_acc || !dk_acc || !dv_acc)
+    return (int)cudaErrorInvalidValue;
+  return launch_flash_bwd<128>(q, k, v, dout, lse, delta, dq_acc, nullptr, nullptr, 1, rows, hq, hkv, causal, scale, dtype,
+                               stream, nullptr, 0, dk_acc, dv_acc);
+}
+
+// delta[t, h] = sum_d dO o O for `rows` (token, head) rows of width head_dim
+int cb_flash_attn_delta(const void* out, const void* dout, float* delta, long long rows, int head_dim, int dtype,
+                        cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  const int wpb = 8;
+  if (dtype == CB_BF16)
+    flash_bwd_delta_kernel<__nv_bfloat16><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows, head_dim);
+  else if (dtype == CB_F16)
+    flash_bwd_delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+        (const __half*)out, (const __half*)dout, delta, rows, head_dim);
+  else
+    return (int)cudaErrorInvalidValue;
   return (int)cudaGetLastError();
 }
 

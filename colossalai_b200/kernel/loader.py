@@ -44,6 +44,7 @@ LIBS: Dict[str, dict] = {
     "cb200_softmax": {"sources": ["softmax.cu"], "kind": "cuda"},
     "cb200_loss": {"sources": ["cross_entropy.cu"], "kind": "cuda"},
     "cb200_gemm": {"sources": ["gemm_tcgen05.cu"], "kind": "cuda"},
+    "cb200_grouped_gemm": {"sources": ["grouped_gemm_tcgen05.cu"], "kind": "cuda"},
     "cb200_attn": {"sources": ["flash_attn_tcgen05.cu"], "kind": "cuda"},
     "cb200_comm": {"sources": ["fused_comm_gemm.cu"], "kind": "cuda"},
     "cb200_moe": {"sources": ["moe.cu"], "kind": "cuda"},

@@ -107,7 +107,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int = 1,
     if use_native(q) and attn_mask is None and dropout_p == 0.0:
         from . import flash_attn_native as fa
 
-        if fa.supported(q, k, v, cu_seqlens_q):
-            return fa.flash_attention(q, k, v, batch=batch, causal=causal, scale=scale, cu_seqlens_q=cu_seqlens_q,
-                                      cu_seqlens_k=cu_seqlens_k, max_seqlen=max_seqlen)
+        # packed (cu_seqlens) batches always take the native kernels when they can: the boundaries stay on the device and
+        # one launch covers the whole batch (the library path below loops over sequences after a `.tolist()` host sync)
+        packed = cu_seqlens_q is not None and q.shape[-1] == 128
+        if fa.supported(q, k, v, cu_seqlens_q, cu_seqlens_k, force=packed):
+            return fa.flash_attention(q, k, v, batch=batch, causal=causal, scale=scale, cu_seqlens_q=cu_seqlens_q)
     return attention_ref(q, k, v, batch, causal, scale, cu_seqlens_q, cu_seqlens_k, attn_mask)

@@ -386,4 +386,10 @@ class RingAttention(torch.autograd.Function):
         """Entry point used by the model forwards."""
         if comm.group_size(sp_group) == 1:
             return ops.attention(q, k, v, batch=batch, causal=True, scale=scale)
+        from . import ring_attn_fused as rf
+
+        if rf.available(q, k, sp_group, batch):
+            # sm_100a path: KV tiles are TMA-loaded from the owner's HBM inside the attention main loop, the softmax
+            # state is merged in registers, dK / dV are reduced into the owner's accumulators (ring_attn_fused.py)
+            return rf.ring_attention_fused(q, k, v, sp_group, batch, scale)
         return RingAttention.apply(q, k, v, sp_group, batch, scale)

@@ -75,3 +75,90 @@ def test_flash_bwd_matches_reference(B, S, Hq, Hkv, causal, dtype):
         assert err <= 2e-2 * scale + 1e-3, f"{name}: max err {err:.4g} vs max |ref| {scale:.4g}"
         # no systematic bias: the mean signed error is tiny compared with the mean magnitude
         assert (got.float() - ref).mean().abs().item() <= 2e-3 * ref.abs().mean().item() + 1e-5, name
+
+
+def _packed_reference(q, k, v, dout, lens, causal):
+    """Per-sequence fp32 oracle for a packed batch: returns out, lse, dq, dk, dv."""
+    from colossalai_b200.ops.attention import attention_with_lse_ref
+
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    outs, lses, s = [], [], 0
+    for n in lens:
+        o, l = attention_with_lse_ref(qf[s:s + n], kf[s:s + n], vf[s:s + n], batch=1, causal=causal)
+        outs.append(o)
+        lses.append(l)
+        s += n
+    out = torch.cat(outs, 0)
+    out.backward(dout.float())
+    return out.detach(), torch.cat(lses, 0).detach(), qf.grad, kf.grad, vf.grad
+
+
+@pytest.mark.parametrize("lens", [[128, 256], [100, 128, 333, 1000], [1, 7, 64, 65, 129], [2048, 77]])
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("Hq,Hkv", [(4, 4), (8, 2)])
+def test_flash_varlen_fwd_bwd(lens, causal, Hq, Hkv):
+    """Packed variable-length batch: cu_seqlens stays on the device, lengths are not multiples of the tile."""
+    from colossalai_b200.ops import flash_attn_native as fa
+
+    D, dtype = 128, torch.bfloat16
+    T = sum(lens)
+    torch.manual_seed(2)
+    q = torch.randn(T, Hq, D, device="cuda", dtype=dtype)
+    k = torch.randn(T, Hkv, D, device="cuda", dtype=dtype)
+    v = torch.randn(T, Hkv, D, device="cuda", dtype=dtype)
+    dout = torch.randn(T, Hq, D, device="cuda", dtype=dtype)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    out, lse = fa.flash_fwd(q, k, v, 1, causal, None, cu_seqlens=cu)
+    dq, dk, dv = fa.flash_bwd(q, k, v, out, dout, lse, 1, causal, None, cu_seqlens=cu)
+    ref_o, ref_lse, rdq, rdk, rdv = _packed_reference(q, k, v, dout, lens, causal)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(out.float(), ref_o, atol=2e-2, rtol=2e-2)
+    for name, got, ref in (("dq", dq, rdq), ("dk", dk, rdk), ("dv", dv, rdv)):
+        err = (got.float() - ref).abs().max().item()
+        assert err <= 2e-2 * ref.abs().max().item() + 1e-3, f"{name}: max err {err:.4g}"
+
+
+@pytest.mark.parametrize("B,S", [(2, 200), (3, 64), (1, 1000)])
+def test_flash_ragged_uniform_lengths(B, S):
+    """Equal-length batches whose length is not a multiple of 128."""
+    from colossalai_b200.ops import flash_attn_native as fa
+    from colossalai_b200.ops.attention import attention_with_lse_ref
+
+    Hq, Hkv, D = 8, 2, 128
+    torch.manual_seed(3)
+    q = torch.randn(B * S, Hq, D, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(B * S, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(B * S, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    dout = torch.randn_like(q)
+    out, lse = fa.flash_fwd(q, k, v, B, True, None)
+    dq, dk, dv = fa.flash_bwd(q, k, v, out, dout, lse, B, True, None)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref_o, ref_lse = attention_with_lse_ref(qf, kf, vf, batch=B, causal=True)
+    ref_o.backward(dout.float())
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(out.float(), ref_o.detach(), atol=2e-2, rtol=2e-2)
+    for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        assert (got.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3, name
+
+
+def test_attention_frontend_packed_uses_native_kernels():
+    """`ops.attention` with cu_seqlens: one native launch for the whole packed batch, autograd included."""
+    from colossalai_b200.kernel import loader
+    from colossalai_b200.ops.attention import attention
+
+    lens = [300, 212, 512]
+    T, Hq, Hkv, D = sum(lens), 8, 2, 128
+    torch.manual_seed(4)
+    q, k, v = (torch.randn(T, h, D, device="cuda", dtype=torch.bfloat16, requires_grad=True) for h in (Hq, Hkv, Hkv))
+    cu = torch.tensor([0, 300, 512, 1024], device="cuda", dtype=torch.int32)
+    before = dict(loader.launch_counter.by_name)
+    out = attention(q, k, v, causal=True, cu_seqlens_q=cu, cu_seqlens_k=cu)
+    out.float().pow(2).mean().backward()
+    after = loader.launch_counter.by_name
+    assert after.get("flash_attn_varlen_fwd", 0) == before.get("flash_attn_varlen_fwd", 0) + 1
+    assert after.get("flash_attn_bwd", 0) == before.get("flash_attn_bwd", 0) + 1
+    dout = (2.0 / out.numel()) * out.detach().float()
+    _, _, rdq, rdk, rdv = _packed_reference(q.detach(), k.detach(), v.detach(), dout, lens, True)
+    for got, ref in ((q.grad, rdq), (k.grad, rdk), (v.grad, rdv)):
+        assert (got.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item() + 1e-6

@@ -57,7 +57,16 @@ def _gpu_worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="nccl", verbose=False)
     from colossalai_b200.parallel import fused
 
+    from colossalai_b200.shardformer.layer import ring_attn_fused as rf
+
     tol = dict(rtol=3e-2, atol=3e-2)
+    # fused ring attention (default on sm_100a): KV tiles TMA-loaded from the owner's HBM inside the kernel, in-kernel
+    # softmax-state merge, dK / dV reduced into the owner's accumulators.  GQA, batch > 1, repeated layers (buffer reuse)
+    for (B, S, Hq, Hkv) in [(2, 1024, 8, 2), (1, 2048 * world_size, 8, 2), (1, 512, 4, 4)]:
+        for _ in range(2):
+            _check("cuda", torch.bfloat16, B=B, S=S, Hq=Hq, Hkv=Hkv, D=128, tol=tol)
+    assert rf.stats["layers_fwd"] >= 6 and rf.stats["layers_bwd"] >= 6, rf.stats
+    os.environ["CB200_RING_ATTN"] = "python"
     _check("cuda", torch.bfloat16, B=2, S=1024, Hq=8, Hkv=2, D=128, tol=tol)      # P2P gather + fused RS path
     assert fused.stats.get("reduce_scatter", 0) > 0 and fused.stats["all_gather"] > 0, fused.stats
     os.environ["CB200_RING_ATTN_P2P"] = "0"
@@ -71,9 +80,54 @@ def _gpu_worker(rank, world_size, port):
         got = fused.reduce_scatter(x, dist.group.WORLD)
         torch.testing.assert_close(got.float(), ref[rank * 300:(rank + 1) * 300], rtol=2e-2, atol=2e-2)
     dist.barrier()
+    if os.environ.get("CB200_RING_ATTN_TIMING", "0") == "1":
+        _timing(rank, world_size)
     if rank == 0:
         print("RING_ATTN_GPU_OK", flush=True)
     dist.destroy_process_group()
+
+
+def _timing(rank, world_size):
+    """Device-timed fwd+bwd of one attention layer (Llama-3-8B heads) at 16k local tokens per rank (= 128k context at
+    sp = 8): fused ring vs the python ring of library flash calls (P2P gather) vs NCCL ring."""
+    import json
+
+    from colossalai_b200.shardformer.layer import ring_attn_fused as rf
+
+    Sl = int(os.environ.get("CB200_RING_LOCAL_TOKENS", "16384"))
+    Hq, Hkv, D = 32, 8, 128
+    torch.manual_seed(rank)
+    q, k, v = (torch.randn(Sl, h, D, device="cuda", dtype=torch.bfloat16, requires_grad=True) for h in (Hq, Hkv, Hkv))
+    do = torch.randn(Sl, Hq, D, device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        out = RingAttention.attention(q, k, v, dist.group.WORLD, batch=1)
+        out.backward(do)
+        q.grad = k.grad = v.grad = None
+
+    res = {"world": world_size, "local_tokens": Sl, "context": Sl * world_size}
+    for mode, env in (("fused", dict(CB200_RING_ATTN="fused")),
+                      ("python_p2p_gather", dict(CB200_RING_ATTN="python", CB200_RING_ATTN_P2P="1")),
+                      ("python_nccl_ring", dict(CB200_RING_ATTN="python", CB200_RING_ATTN_P2P="0"))):
+        os.environ.update(env)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            run()
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / 3], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[mode + "_ms"] = t.item()
+    # causal attention FLOPs of this rank's share: fwd 4 S^2 H D / 2 / sp, bwd 2.5x
+    S = Sl * world_size
+    res["fused_tflops_per_gpu"] = 3.5 * 4.0 * S * S * Hq * D / 2 / world_size / res["fused_ms"] / 1e9
+    if rank == 0:
+        print("RING_TIMING " + json.dumps(res), flush=True)
 
 
 @pytest.mark.gpu
