@@ -85,6 +85,86 @@ __global__ void __launch_bounds__(256) rope_kv_cache_write_kernel(T* __restrict_
   }
 }
 
+// 16-byte vectorised variants (the hot ones): one thread moves one 16-byte vector, grid = all vectors of the step, so a
+// prefill of thousands of tokens is a single HBM-rate streaming kernel instead of one small CTA per token.
+template <typename T>
+__global__ void __launch_bounds__(256) kv_cache_write_vec_kernel(const T* __restrict__ k, const T* __restrict__ v,
+                                                                 T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                                                 const int* __restrict__ block_tables,
+                                                                 const int* __restrict__ token_seq,
+                                                                 const int* __restrict__ token_pos, int tokens,
+                                                                 int vec_per_tok, int block_size, int max_blocks_per_seq,
+                                                                 int64_t k_stride, int64_t v_stride) {
+  // vec_per_tok = kv_heads * D / 8 (16-bit elements); work items = tokens * 2 (K, V) * vec_per_tok
+  const int64_t total = (int64_t)tokens * 2 * vec_per_tok;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(w / (2 * vec_per_tok));
+    const int r = (int)(w - (int64_t)t * 2 * vec_per_tok);
+    const bool is_v = r >= vec_per_tok;
+    const int i = is_v ? r - vec_per_tok : r;
+    const int seq = __ldg(token_seq + t), pos = __ldg(token_pos + t);
+    const int blk = __ldg(block_tables + seq * max_blocks_per_seq + pos / block_size);
+    const int64_t dst = ((int64_t)blk * block_size + pos % block_size) * vec_per_tok + i;       // in 16-byte units
+    const uint4 val = is_v ? __ldg(reinterpret_cast<const uint4*>(v + (int64_t)t * v_stride) + i)
+                           : __ldg(reinterpret_cast<const uint4*>(k + (int64_t)t * k_stride) + i);
+    reinterpret_cast<uint4*>(is_v ? v_cache : k_cache)[dst] = val;
+  }
+}
+
+// RoPE (half rotation, rot == D) on q and k in place + rotated K and V into the paged cache, 16-byte vectors: a work
+// item is one (token, head, 8-element group of the FIRST half) - it owns the matching group of the second half too -
+// or one V vector.  K is written to the cache from registers (no second pass, no block barrier).
+template <typename T>
+__global__ void __launch_bounds__(256) rope_kv_cache_write_vec_kernel(
+    T* __restrict__ q, T* __restrict__ k, const T* __restrict__ v, T* __restrict__ k_cache, T* __restrict__ v_cache,
+    const float* __restrict__ cos_c, const float* __restrict__ sin_c, const int* __restrict__ block_tables,
+    const int* __restrict__ token_seq, const int* __restrict__ token_pos, int tokens, int Hq, int Hkv, int D,
+    int block_size, int max_blocks_per_seq, int64_t q_stride, int64_t k_stride, int64_t v_stride) {
+  const int half = D / 2;
+  const int gph = half / 8;                          // 8-element groups per half head
+  const int rope_items = (Hq + Hkv) * gph;
+  const int v_items = Hkv * D / 8;
+  const int per_tok = rope_items + v_items;
+  const int64_t total = (int64_t)tokens * per_tok;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(w / per_tok);
+    const int r = (int)(w - (int64_t)t * per_tok);
+    const int seq = __ldg(token_seq + t), pos = __ldg(token_pos + t);
+    const int blk = __ldg(block_tables + seq * max_blocks_per_seq + pos / block_size);
+    const int64_t slot = ((int64_t)blk * block_size + pos % block_size) * Hkv * D;              // in elements
+    if (r >= rope_items) {
+      const int i = r - rope_items;
+      reinterpret_cast<uint4*>(v_cache + slot)[i] = __ldg(reinterpret_cast<const uint4*>(v + (int64_t)t * v_stride) + i);
+      continue;
+    }
+    const int h = r / gph, g = r - h * gph;
+    T* base = h < Hq ? q + (int64_t)t * q_stride + (int64_t)h * D : k + (int64_t)t * k_stride + (int64_t)(h - Hq) * D;
+    Vec16<T> a, b2;
+    a.load(base + g * 8);
+    b2.load(base + half + g * 8);
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cos_c + (int64_t)pos * half + g * 8));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(cos_c + (int64_t)pos * half + g * 8 + 4));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sin_c + (int64_t)pos * half + g * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sin_c + (int64_t)pos * half + g * 8 + 4));
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    Vec16<T> oa, ob;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = a.get(e), y = b2.get(e);
+      oa.set(e, x * cs[e] - y * sn[e]);
+      ob.set(e, y * cs[e] + x * sn[e]);
+    }
+    oa.store(base + g * 8);
+    ob.store(base + half + g * 8);
+    if (h >= Hq) {
+      T* kc = k_cache + slot + (int64_t)(h - Hq) * D;
+      oa.store(kc + g * 8);
+      ob.store(kc + half + g * 8);
+    }
+  }
+}
+
 // One CTA: sequence `seq`, kv head `kvh`, KV partition `split`.  q: [num_seqs, Hq, D].
 // partial outputs: o_part [num_seqs, Hq, splits, D] fp32, ml_part [num_seqs, Hq, splits, 2] (max, sumexp)
 template <typename T, typename TC, int D>
@@ -250,6 +330,18 @@ int cb_kv_cache_write(const void* k, const void* v, void* k_cache, void* v_cache
                       const int* token_seq, const int* token_pos, int tokens, int kv_heads, int D, int block_size,
                       int max_blocks_per_seq, int64_t k_stride, int64_t v_stride, int dtype, cudaStream_t s) {
   if (tokens == 0) return 0;
+  const int n = kv_heads * D;
+  if (n % 8 == 0 && k_stride % 8 == 0 && v_stride % 8 == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+      ((uintptr_t)k_cache % 16) == 0 && ((uintptr_t)v_cache % 16) == 0) {
+    const int64_t total = (int64_t)tokens * 2 * (n / 8);
+    const int grid = (int)((total + 255) / 256 < 16 * cb_num_sms() ? (total + 255) / 256 : 16 * cb_num_sms());
+    CB_DISPATCH_HALF(dtype, T, {
+      kv_cache_write_vec_kernel<T><<<grid, 256, 0, s>>>((const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_tables,
+                                                       token_seq, token_pos, tokens, n / 8, block_size,
+                                                       max_blocks_per_seq, k_stride, v_stride);
+    });
+    return CB_LAUNCH_CHECK();
+  }
   CB_DISPATCH_HALF(dtype, T, {
     kv_cache_write_kernel<T, T><<<tokens, 256, 0, s>>>((const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_tables,
                                                       token_seq, token_pos, tokens, kv_heads, D, block_size,
@@ -263,6 +355,19 @@ int cb_rope_kv_cache_write(void* q, void* k, const void* v, void* k_cache, void*
                            int tokens, int Hq, int Hkv, int D, int rot, int block_size, int max_blocks_per_seq,
                            int64_t q_stride, int64_t k_stride, int64_t v_stride, int dtype, cudaStream_t s) {
   if (tokens == 0) return 0;
+  if (rot == D && D % 16 == 0 && q_stride % 8 == 0 && k_stride % 8 == 0 && v_stride % 8 == 0 &&
+      ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+      ((uintptr_t)k_cache % 16) == 0 && ((uintptr_t)v_cache % 16) == 0 && ((uintptr_t)cos_c % 16) == 0 &&
+      ((uintptr_t)sin_c % 16) == 0) {
+    const int64_t total = (int64_t)tokens * ((Hq + Hkv) * (D / 16) + Hkv * D / 8);
+    const int grid = (int)((total + 255) / 256 < 16 * cb_num_sms() ? (total + 255) / 256 : 16 * cb_num_sms());
+    CB_DISPATCH_HALF(dtype, T, {
+      rope_kv_cache_write_vec_kernel<T><<<grid, 256, 0, s>>>((T*)q, (T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, cos_c,
+                                                            sin_c, block_tables, token_seq, token_pos, tokens, Hq, Hkv, D,
+                                                            block_size, max_blocks_per_seq, q_stride, k_stride, v_stride);
+    });
+    return CB_LAUNCH_CHECK();
+  }
   CB_DISPATCH_HALF(dtype, T, {
     rope_kv_cache_write_kernel<T><<<tokens, 256, 0, s>>>((T*)q, (T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, cos_c,
                                                         sin_c, block_tables, token_seq, token_pos, tokens, Hq, Hkv, D,

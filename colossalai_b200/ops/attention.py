@@ -109,7 +109,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int = 1,
 
         # packed (cu_seqlens) batches always take the native kernels when they can: the boundaries stay on the device and
         # one launch covers the whole batch (the library path below loops over sequences after a `.tolist()` host sync)
-        packed = cu_seqlens_q is not None and q.shape[-1] == 128
+        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        packed = cu_seqlens_q is not None and (q.shape[-1] == 128 or (q.shape[-1] == 64 and not needs_grad))
         if fa.supported(q, k, v, cu_seqlens_q, cu_seqlens_k, force=packed):
             return fa.flash_attention(q, k, v, batch=batch, causal=causal, scale=scale, cu_seqlens_q=cu_seqlens_q)
     return attention_ref(q, k, v, batch, causal, scale, cu_seqlens_q, cu_seqlens_k, attn_mask)
