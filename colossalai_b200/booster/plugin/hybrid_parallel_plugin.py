@@ -421,7 +421,8 @@ class HybridParallelPlugin(PipelinePluginBase):
                  hysteresis: int = 2, max_scale: float = 2**32, max_norm: float = 0, broadcast_buffers: bool = True,
                  ddp_bucket_cap_mb: int = 25, find_unused_parameters: bool = False, check_reduction: bool = False,
                  gradient_as_bucket_view: bool = False, static_graph: bool = False, zero_bucket_size_in_m: int = 12,
-                 cpu_offload: bool = False, communication_dtype: Optional[torch.dtype] = None,
+                 cpu_offload: bool = False, offload_optim_frac: float = 1.0,
+                 communication_dtype: Optional[torch.dtype] = None,
                  overlap_communication: bool = True, custom_policy: Policy = None, pp_style: str = "1f1b",
                  num_model_chunks: int = 1, scheduler_nodes: List = None, num_layers_per_stage: Optional[List[int]] = None,
                  gradient_checkpoint_config: Optional[GradientCheckpointConfig] = None,
@@ -463,6 +464,10 @@ class HybridParallelPlugin(PipelinePluginBase):
         self.tp_size, self.pp_size = tp_size, pp_size
         self.precision, self.zero_stage = precision, zero_stage
         self.cpu_offload = cpu_offload
+        # with cpu_offload: fraction of the optimizer state kept in pinned host memory (tiering between 180 GB HBM and
+        # DRAM that composes with TP x PP - the reference only has Gemini's tiering without PP, or all-or-nothing ZeRO
+        # offload: `hybrid_parallel_plugin.py:666-719`)
+        self.offload_optim_frac = offload_optim_frac
         self.enable_all_optimization = enable_all_optimization
         self.enable_fused_normalization = enable_fused_normalization
         self.enable_flash_attention = enable_flash_attention
@@ -556,7 +561,8 @@ class HybridParallelPlugin(PipelinePluginBase):
                                gradient_as_bucket_view=gradient_as_bucket_view, static_graph=static_graph)
         self.zero_config = dict(reduce_bucket_size=zero_bucket_size_in_m * 1024 * 1024,
                                 communication_dtype=communication_dtype, overlap_communication=overlap_communication,
-                                cpu_offload=cpu_offload, partition_grad=(self.zero_stage == 2), forced_dtype=PRECISION_TORCH_TYPE[precision],
+                                cpu_offload=cpu_offload, offload_optim_frac=offload_optim_frac,
+                                partition_grad=(self.zero_stage == 2), forced_dtype=PRECISION_TORCH_TYPE[precision],
                                 overlap_allgather=overlap_allgather, fp8_communication=fp8_communication)
         self.max_norm = max_norm
         set_comm_backend(comm_backend)

@@ -27,7 +27,8 @@ class HybridParallelZeroOptimizer(LowLevelZeroOptimizer):
                  overlap_communication: bool = True, partition_grad: bool = False, cpu_offload: bool = False,
                  dp_process_group: Optional[ProcessGroup] = None, tp_process_group: Optional[ProcessGroup] = None,
                  pp_process_group: Optional[ProcessGroup] = None, forced_dtype: Optional[torch.dtype] = None,
-                 overlap_allgather: bool = False, fp8_communication: bool = False, **unused) -> None:
+                 overlap_allgather: bool = False, fp8_communication: bool = False, offload_optim_frac: float = 1.0,
+                 **unused) -> None:
         from .hybrid_parallel_plugin import _reassign_params
 
         self.model = model
@@ -45,7 +46,7 @@ class HybridParallelZeroOptimizer(LowLevelZeroOptimizer):
                          communication_dtype=communication_dtype, overlap_communication=overlap_communication,
                          partition_grad=partition_grad, cpu_offload=cpu_offload, dp_process_group=dp_process_group,
                          forced_dtype=forced_dtype, overlap_allgather=overlap_allgather,
-                         fp8_communication=fp8_communication)
+                         fp8_communication=fp8_communication, offload_optim_frac=offload_optim_frac)
 
     def _reduce_bucket(self, b) -> None:
         """The dp reduce-scatter is the ONLY place a bucket's local gradient leaves `grad_full` (the grad hook calls it

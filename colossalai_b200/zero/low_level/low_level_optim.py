@@ -93,8 +93,16 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                  overlap_communication: bool = False, partition_grad: bool = False, cpu_offload: bool = False,
                  dp_process_group: Optional[ProcessGroup] = None, extra_dp_group: Optional[ProcessGroup] = None,
                  forced_dtype: Optional[torch.dtype] = None, master_weights: bool = True,
-                 overlap_allgather: bool = False, fp8_communication: bool = False, backward_context=None) -> None:
+                 overlap_allgather: bool = False, fp8_communication: bool = False, backward_context=None,
+                 offload_optim_frac: float = 1.0) -> None:
         super().__init__(optim=optimizer)
+        # cpu_offload: fraction of the optimizer state (fp32 master + moments, by element count) that lives in pinned
+        # host memory and is stepped by the AVX-512 CPU Adam; the rest stays in HBM on the fused multi-tensor path.
+        # 1.0 = everything (the reference's `cpu_offload=True`), smaller values tier the state between HBM and DRAM.
+        self._offload_frac = float(offload_optim_frac)
+        self._offload_numel_seen = 0
+        self._offload_total = sum(p.numel() for g in optimizer.param_groups for p in g["params"] if p.requires_grad)
+        self._offload_stream = None
         self._dtype = self.optim.param_groups[0]["params"][0].dtype
         self._logger = get_dist_logger()
         self._verbose = verbose
@@ -178,8 +186,11 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             master = shard.detach().clone().float()
         else:
             master = shard.detach()
-        if self._cpu_offload:
+        b.offloaded = False
+        if self._cpu_offload and self._offload_numel_seen < self._offload_frac * self._offload_total:
             master = master.cpu().pin_memory() if torch.cuda.is_available() else master.cpu()
+            b.offloaded = True
+        self._offload_numel_seen += b.numel
         mp = nn.Parameter(master, requires_grad=True)
         b.master = mp
         self._master_of_bucket[id(b)] = mp
@@ -343,8 +354,16 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             self._grad_norm_dev = norm
             clip_coef = (self._clip_grad_norm / (norm + 1e-6)).clamp(max=1.0).float().reshape(1)
         live = [b for b in self.buckets if b.grad_shard is not None]
-        fused = (live and use_native(live[0].grad_shard) and not self._cpu_offload and self._is_adam())
-        if fused:
+        self._stepped_groups = set()
+        fused = (live and use_native(live[0].grad_shard) and self._is_adam())
+        if fused and self._cpu_offload:
+            # tiered optimizer state: HBM-resident buckets on the fused GPU kernel (asynchronous), host-resident
+            # buckets through the pipelined D2H -> CPU Adam -> H2D path, which overlaps with it
+            on_gpu = [b for b in live if not b.offloaded]
+            if on_gpu:
+                self._fused_adam(on_gpu, div_scale, clip_coef)
+            self._offload_adam([b for b in live if b.offloaded], div_scale, clip_coef)
+        elif fused:
             self._fused_adam(live, div_scale, clip_coef)
         else:
             coef = 1.0 / div_scale
@@ -371,6 +390,12 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                 else:
                     dist.all_gather_into_tensor(b.flat, b.working_shard().clone(), group=b.pg)
 
+    def _bump_step(self, gid: int, group: dict) -> None:
+        """Advance a param group's Adam step counter once per optimizer step (both state tiers share it)."""
+        if gid not in self._stepped_groups:
+            group["step"] = group.get("step", 0) + 1
+            self._stepped_groups.add(gid)
+
     def _is_adam(self) -> bool:
         from ...nn.optimizer.cpu_adam import CPUAdam
         from ...nn.optimizer.fused_adam import FusedAdam
@@ -395,11 +420,59 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
                 lps.append(b.working_shard() if b.working_shard().data_ptr() != b.master.data.data_ptr() else None)
-            group["step"] = group.get("step", 0) + 1
+            self._bump_step(gid, group)
             tbl = mt.TensorTable(ps, gs, ms, vs, lps)     # grad shards are fresh tensors every step
             beta1, beta2 = group["betas"]
             mt.adam(tbl, group["lr"], beta1, beta2, group["eps"], group["weight_decay"], group["step"], adamw,
                     group.get("bias_correction", True), inv_scale=1.0 / div_scale, inv_scale_dev=clip_coef)
+
+    def _offload_adam(self, live: List[_Bucket], div_scale: float, clip_coef: Optional[Tensor]) -> None:
+        """Adam on host-resident optimizer state, pipelined over buckets:
+            copy stream : D2H grad shard(b0) | D2H(b1) | D2H(b2) ...        H2D bf16 params(b0) | H2D(b1) ...
+            host (OpenMP): . . . . . . . . . | AdamW(b0) | AdamW(b1) | ...
+        All D2H copies are queued up front into pinned staging buffers; the host steps bucket i as soon as its copy has
+        landed (event), writing the updated low-precision working copy into a pinned buffer whose H2D copy is queued
+        at once - so PCIe traffic in both directions overlaps the CPU arithmetic.  (Reference: ZeRO `cpu_offload` of
+        `HybridParallelPlugin`, `hybrid_parallel_plugin.py:666-719`, which copies, steps and copies back serially.)"""
+        if not live:
+            return
+        from ...nn.optimizer.cpu_adam import cpu_adam_step
+
+        if self._offload_stream is None:
+            self._offload_stream = torch.cuda.Stream()
+        st_copy = self._offload_stream
+        st_copy.wait_stream(torch.cuda.current_stream())
+        inv = 1.0 / div_scale
+        if clip_coef is not None:
+            inv *= float(clip_coef.item())            # the only host sync of the step (the global norm is a scalar)
+        events = []
+        with torch.cuda.stream(st_copy):
+            for b in live:
+                if getattr(b, "host_grad", None) is None or b.host_grad.dtype != b.grad_shard.dtype:
+                    b.host_grad = torch.empty(b.shard_size, dtype=b.grad_shard.dtype).pin_memory()
+                    b.host_lp = torch.empty(b.shard_size, dtype=b.flat.dtype).pin_memory()
+                b.host_grad.copy_(b.grad_shard, non_blocking=True)
+                b.grad_shard.record_stream(st_copy)
+                ev = torch.cuda.Event()
+                ev.record(st_copy)
+                events.append(ev)
+        adamw = getattr(self.optim, "adamw_mode", isinstance(self.optim, torch.optim.AdamW))
+        for b, ev in zip(live, events):
+            group = self.optim.param_groups[b.group_id]
+            self._bump_step(b.group_id, group)
+            stt = self.optim.state[b.master]
+            if "exp_avg" not in stt:
+                stt["exp_avg"] = torch.zeros_like(b.master.data)
+                stt["exp_avg_sq"] = torch.zeros_like(b.master.data)
+            beta1, beta2 = group["betas"]
+            ev.synchronize()
+            same = b.flat.dtype == torch.float32
+            cpu_adam_step(b.master.data, b.host_grad, stt["exp_avg"], stt["exp_avg_sq"], group["lr"], beta1, beta2,
+                          group["eps"], group["weight_decay"], group["step"], group.get("bias_correction", True), adamw,
+                          inv_scale=inv, lp=None if same else b.host_lp)
+            with torch.cuda.stream(st_copy):
+                b.working_shard().copy_(b.master.data if same else b.host_lp, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(st_copy)
 
     def get_grad_norm(self, norm_type=2.0, **kwargs) -> Optional[float]:
         g = getattr(self, "_grad_norm_dev", None)
