@@ -66,6 +66,12 @@ for _fam, _classes in _FAMILIES.items():
         register_policy(f"colossalai_b200.models.{_fam}.{_c}", _fam, f"{_c}Policy")
 
 
+# user-supplied HuggingFace modules (sharded in place by sub-module / method replacement)
+for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3")):
+    for _suffix in ("Model", "ForCausalLM"):
+        register_policy(f"transformers.models.{_mod}.modeling_{_mod}.{_pre}{_suffix}", "hf_decoder", "HFDecoderPolicy")
+
+
 def import_policy(loc: PolicyLocation) -> type:
     module = importlib.import_module(f"{_P}.{loc.file_name}")
     return getattr(module, loc.class_name)

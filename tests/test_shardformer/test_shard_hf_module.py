@@ -1,0 +1,85 @@
+"""Sharding a user's HuggingFace module in place (sub-module + method replacement through the generic ModelSharder):
+a `transformers` Llama / Mistral / Qwen2 built by the USER is tensor-parallelised over 2 ranks and must reproduce the
+single-process logits, loss and (gathered) gradients.  Reference pattern: tests/test_shardformer/test_model/
+test_shard_llama.py:29-170 (org model vs sharded model)."""
+import copy
+
+import pytest
+import torch
+import torch.distributed as dist
+
+import colossalai_b200
+from colossalai_b200.parallel import comm
+from colossalai_b200.shardformer import ShardConfig, ShardFormer
+from colossalai_b200.testing import rerun_if_address_is_in_use, spawn
+
+
+def _build(family):
+    import transformers
+
+    kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+              num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=False)
+    cfg_cls = {"llama": transformers.LlamaConfig, "mistral": transformers.MistralConfig, "qwen2": transformers.Qwen2Config}[family]
+    model_cls = {"llama": transformers.LlamaForCausalLM, "mistral": transformers.MistralForCausalLM,
+                 "qwen2": transformers.Qwen2ForCausalLM}[family]
+    cfg = cfg_cls(**kw)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    return model_cls(cfg).float()
+
+
+def _gather_grad(p):
+    """Full gradient of a (possibly sharded) parameter, using the parameter's own sharding annotation."""
+    g = p.grad.detach()
+    if hasattr(p, "dist_shard"):
+        dim, group = p.dist_shard
+        return comm.all_gather(g, dim, group)
+    if hasattr(p, "gather_fn"):
+        return p.gather_fn(g)
+    return g
+
+
+def _check(family):
+    org = _build(family)
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True,
+                     enable_fused_normalization=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)          # auto policy: looked up by the HF class's qualified name
+    # the policy really rewrote the user's module
+    layer = sharded.model.layers[0]
+    assert type(layer.self_attn.q_proj).__name__ == "Linear1D_Col" and type(layer.mlp.down_proj).__name__ == "Linear1D_Row"
+    assert layer.self_attn.q_proj.weight.shape[0] == org.model.layers[0].self_attn.q_proj.weight.shape[0] // 2
+    assert type(sharded.model.embed_tokens).__name__ == "VocabParallelEmbedding1D"
+    assert layer.input_layernorm.forward.__func__.__name__ == "_fused_rmsnorm_forward"      # method replacement
+    torch.manual_seed(5)
+    ids = torch.randint(0, 320, (2, 16))
+    ref = org(input_ids=ids, labels=ids)
+    out = sharded(input_ids=ids, labels=ids)
+    torch.testing.assert_close(out.logits, ref.logits, atol=2e-4, rtol=2e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        full = _gather_grad(p)
+        r = ref_grads[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        torch.testing.assert_close(full, r, atol=2e-4, rtol=2e-3, msg=lambda m: f"{family} {name}: {m}")
+        n += 1
+    assert n > 10
+
+
+def _worker(rank, world_size, port):
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    for family in ("llama", "mistral", "qwen2"):
+        _check(family)
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_shard_user_hf_modules_tp2():
+    pytest.importorskip("transformers")
+    spawn(_worker, 2)
