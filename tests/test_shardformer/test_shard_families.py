@@ -32,3 +32,87 @@ def test_all_families_tp2():
 
     sys.path.insert(0, os.path.dirname(__file__))
     spawn(_worker, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# second tier: the sequence-parallel modes that have their own attention path (Ulysses all-to-all, ring attention) and
+# the families missing above (GPT-2 fused QKV Conv1D layout, the MoE families under TP), plus pipeline stages of five
+# families through the plugin (held layers, stage-aware forward, tied / untied heads)
+ROTARY_FAMILIES = ["mistral-tiny", "qwen2-tiny", "qwen3-tiny", "command-tiny", "gptj-tiny", "falcon-tiny"]
+EXTRA_TP = ["gpt2-tiny", "mixtral-tiny", "deepseek-tiny"]
+PP_FAMILIES = ["mistral-tiny", "qwen3-tiny", "gpt2-tiny", "opt-tiny", "falcon-tiny"]
+
+
+def _sp_worker(rank, world_size, port):
+    from test_shard_llama import _run_one
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    for name in ROTARY_FAMILIES:
+        _run_one(name, dict(tp=1, sp=2, sp_mode="all_to_all"), atol=5e-5)
+        _run_one(name, dict(tp=1, sp=2, sp_mode="ring_attn"), atol=5e-5)
+    for name in EXTRA_TP:
+        _run_one(name, dict(tp=2, sp_mode=None), atol=1e-4)
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_families_ulysses_ring_attn_and_moe_tp():
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    spawn(_sp_worker, 2)
+
+
+def _pp_worker(rank, world_size, port):
+    import copy
+
+    import torch
+
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.models import build_model
+    from colossalai_b200.nn.optimizer import FusedAdam
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    for name in PP_FAMILIES:
+        torch.manual_seed(3)
+        base = build_model(name)
+        model = copy.deepcopy(base)
+        ref_opt = torch.optim.AdamW(base.parameters(), lr=1e-2, weight_decay=0.0)
+        opt = FusedAdam(model.parameters(), lr=1e-2, weight_decay=0.0)
+        plugin = HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2)
+        booster = Booster(plugin=plugin)
+        model, opt, *_ = booster.boost(model, opt)
+        torch.manual_seed(9)
+        ids = torch.randint(0, base.cfg.vocab_size, (2, 16))
+        out = booster.execute_pipeline(iter([{"input_ids": ids, "labels": ids}]), model, lambda o, b: o["loss"], opt,
+                                       return_loss=True)
+        opt.step()
+        total = 0.0
+        for i in range(2):
+            l = base(input_ids=ids[i:i + 1], labels=ids[i:i + 1])["loss"] / 2
+            l.backward()
+            total += l.item()
+        ref_opt.step()
+        if out["loss"] is not None:
+            assert abs(out["loss"].item() - total) < 2e-4, (name, out["loss"].item(), total)
+        ref_params = dict(base.named_parameters())
+        n = 0
+        for pname, p in model.unwrap().named_parameters():
+            if p is None:
+                continue
+            rn = pname if pname in ref_params else "model.embed_tokens.weight"     # tied head on the last stage
+            torch.testing.assert_close(p.detach(), ref_params[rn].detach(), atol=3e-4, rtol=3e-3,
+                                       msg=lambda m: f"pp2 {name} {pname}: {m}")
+            n += 1
+        assert n > 3, name
+        del plugin
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+@rerun_if_address_is_in_use()
+def test_families_pipeline_stages():
+    spawn(_pp_worker, 2)
