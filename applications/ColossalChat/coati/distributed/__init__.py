@@ -1,7 +1,13 @@
+from .comm import RolloutBuffer, WeightMailbox, deserialize_rollout, serialize_rollout
 from .consumer import GRPOConsumer
 from .launch import launch_distributed
+from .launch_zero_bubble import launch_zero_bubble
 from .producer import EngineRolloutBackend, ModelRolloutBackend, Producer
-from .reward import boxed_math_reward, extract_boxed, format_reward, make_reward_fn
+from .profiling_utils import StepProfiler
+from .reward import (boxed_math_reward, code_reward, combine_rewards, extract_boxed, format_reward, length_penalty,
+                     make_reward_fn)
 
 __all__ = ["Producer", "ModelRolloutBackend", "EngineRolloutBackend", "GRPOConsumer", "launch_distributed",
-           "boxed_math_reward", "format_reward", "extract_boxed", "make_reward_fn"]
+           "launch_zero_bubble", "RolloutBuffer", "WeightMailbox", "serialize_rollout", "deserialize_rollout",
+           "StepProfiler", "boxed_math_reward", "format_reward", "extract_boxed", "make_reward_fn", "length_penalty",
+           "code_reward", "combine_rewards"]

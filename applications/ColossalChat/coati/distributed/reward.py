@@ -69,3 +69,57 @@ def make_reward_fn(decode: Callable[[List[int]], str], scorer: Callable[..., flo
         return torch.tensor(out, dtype=torch.float32)
 
     return fn
+
+
+def length_penalty(num_tokens: int, max_new_tokens: int, soft_cache: int = 0, penalty: float = 1.0) -> float:
+    """DAPO "soft overlong punishment": 0 inside `max_new_tokens - soft_cache`, linearly down to `-penalty` at the
+    generation limit (an answer truncated by the limit is penalised whatever its content)."""
+    if soft_cache <= 0:
+        return -penalty if num_tokens >= max_new_tokens else 0.0
+    start = max_new_tokens - soft_cache
+    if num_tokens <= start:
+        return 0.0
+    return -penalty * min(1.0, (num_tokens - start) / soft_cache)
+
+
+def code_reward(response: str, tests: str, timeout_s: float = 5.0) -> float:
+    """1.0 when the LAST fenced python block of the response passes `tests` (python source with asserts) in a fresh
+    interpreter with a wall-clock limit; 0.0 otherwise (no block, exception, timeout)."""
+    import subprocess
+    import sys
+    import tempfile
+
+    blocks = re.findall(r"```(?:python)?\n(.*?)```", response, flags=re.S)
+    if not blocks:
+        return 0.0
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(blocks[-1] + "\n\n" + tests + "\n")
+        path = f.name
+    try:
+        r = subprocess.run([sys.executable, "-I", path], capture_output=True, timeout=timeout_s)
+        return 1.0 if r.returncode == 0 else 0.0
+    except subprocess.TimeoutExpired:
+        return 0.0
+    finally:
+        import os
+
+        os.unlink(path)
+
+
+def combine_rewards(*scorers_and_weights) -> Callable[..., float]:
+    """`combine_rewards((boxed_math_reward, 1.0), (format_reward, 0.1))` -> scorer(text, gt) = weighted sum; scorers
+    that do not take a ground truth are called with the text only."""
+    import inspect
+
+    items = []
+    for fn, w in scorers_and_weights:
+        n = len([p for p in inspect.signature(fn).parameters.values() if p.default is inspect._empty])
+        items.append((fn, float(w), n))
+
+    def scorer(text: str, gt: Optional[str] = None) -> float:
+        total = 0.0
+        for fn, w, n in items:
+            total += w * (fn(text, gt) if n >= 2 else fn(text))
+        return total
+
+    return scorer

@@ -163,6 +163,51 @@ def test_grpo_trainer_and_producer_consumer_loop():
         assert a.shape == b.shape
 
 
+def test_zero_bubble_loop_buffer_and_rewards(tmp_path):
+    """Producer thread + bounded buffer + latest-wins weight mailbox; rollout (de)serialisation; extra verifiers."""
+    from coati.distributed import (RolloutBuffer, StepProfiler, WeightMailbox, code_reward, combine_rewards,
+                                   deserialize_rollout, launch_zero_bubble, length_penalty, serialize_rollout)
+
+    policy, sampler = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    prod = Producer(ModelRolloutBackend(sampler, dict(max_new_tokens=6)), _prompt_loader(), num_generations=8)
+    cons = GRPOConsumer(policy, torch.optim.AdamW(policy.parameters(), lr=3e-3), _count_reward, num_generations=8,
+                        minibatch_size=16)
+    prof = StepProfiler(log_file=str(tmp_path / "prof.log"))
+    torch.manual_seed(0)
+    h = launch_zero_bubble(prod, cons, num_steps=16, sync_every=1, buffer_capacity=2, max_staleness=3, profiler=prof)
+    assert len(h) == 16 and cons.version == 16
+    assert sum(x["reward"] for x in h[-4:]) / 4 > sum(x["reward"] for x in h[:4]) / 4 + 0.03
+    assert max(x["staleness"] for x in h) <= 3 and prod.model_version >= 10       # weights kept flowing to the producer
+    s = prof.summary()
+    assert s["rollout"]["calls"] >= 16 and s["train"]["calls"] == 16 and 0.0 <= prof.overlap_fraction() <= 1.0
+    assert (tmp_path / "prof.log").read_text().count("train") == 16
+    # staleness filter + back-pressure
+    buf = RolloutBuffer(capacity=2, max_staleness=1)
+    assert buf.push({"model_version": 0}) and buf.push({"model_version": 3})
+    assert buf.push({"model_version": 9}, timeout=0.05) is False                  # full
+    assert buf.pop(current_version=4)["model_version"] == 3 and buf.stats["dropped_stale"] == 1
+    buf.close()
+    assert buf.pop(0) is None
+    box = WeightMailbox()
+    box.publish({"w": torch.ones(2)}, 1)
+    box.publish({"w": torch.full((2,), 2.0)}, 2)
+    sd, ver = box.take()
+    assert ver == 2 and float(sd["w"][0]) == 2.0 and box.take() is None
+    r = {"sequences": torch.arange(12).view(3, 4), "mask": torch.ones(3, 4, dtype=torch.bool), "prompt_len": 2,
+         "gt_answer": ["1", "2", "3"], "model_version": 7, "lp": torch.randn(3, 2).bfloat16()}
+    back = deserialize_rollout(serialize_rollout(r))
+    assert back["gt_answer"] == r["gt_answer"] and back["prompt_len"] == 2 and back["lp"].dtype == torch.bfloat16
+    for k in ("sequences", "mask", "lp"):
+        assert torch.equal(back[k], r[k])
+    assert length_penalty(90, 100, soft_cache=20) == -0.5 and length_penalty(50, 100, soft_cache=20) == 0.0
+    assert length_penalty(100, 100) == -1.0
+    good = "Here:\n```python\ndef add(a, b):\n    return a + b\n```"
+    assert code_reward(good, "assert add(2, 3) == 5") == 1.0
+    assert code_reward(good, "assert add(2, 3) == 6") == 0.0 and code_reward("no code", "assert True") == 0.0
+    sc = combine_rewards((boxed_math_reward, 1.0), (format_reward, 0.5))
+    assert sc("<think>x</think><answer>\\boxed{4}</answer>", "4") == 1.5
+
+
 def test_colossal_llama_eval_and_qa_utilities(tmp_path):
     for sub in ("Colossal-LLaMA", "ColossalEval", "ColossalQA"):
         sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", sub))
