@@ -756,7 +756,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const size_t row = (size_t)kv_row0 + r;
     const size_t ld = (size_t)p.hkv * D;
 #pragma unroll 1
-    for (int which = 0; which < 2 && key_pos < len; ++which) {
+    // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every lane runs the loads, only the STORES are predicated on
+    // the key being inside the sequence (a ragged last tile leaves some lanes of a warp without a row)
+    const bool key_ok = key_pos < len;
+    for (int which = 0; which < 2; ++which) {
       const uint32_t col0 = which == 0 ? C::COL_DV : C::COL_DK;
       const float mul = which == 0 ? 1.f : p.scale;
       if (p.dk_acc != nullptr) {
@@ -766,7 +769,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + lane_addr + col0 + c, v);
           tmem_ld_wait();
-          if (n_iter > 0) {
+          if (n_iter > 0 && key_ok) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -795,9 +798,11 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             w[i] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
+        if (key_ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(base + (c + i * 8) * 2) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(base + (c + i * 8) * 2) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
       }
     }
   } else {

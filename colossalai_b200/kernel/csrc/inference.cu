@@ -172,13 +172,16 @@ __global__ void __launch_bounds__(DEC_THREADS) paged_decode_kernel(
     const T* __restrict__ q, const TC* __restrict__ k_cache, const TC* __restrict__ v_cache,
     const int* __restrict__ block_tables, const int* __restrict__ seq_lens, float* __restrict__ o_part,
     float* __restrict__ ml_part, int Hq, int Hkv, int block_size, int max_blocks_per_seq, int splits, int part_len,
-    float scale, const float* __restrict__ alibi_slopes, int64_t q_stride) {
+    float scale, const float* __restrict__ alibi_slopes, int64_t q_stride, int window) {
   constexpr int VEC = 16 / sizeof(TC);          // cache elements per 16-byte load
   constexpr int DV = D / 32;                    // output dims owned by a lane
   const int seq = blockIdx.x, kvh = blockIdx.y, split = blockIdx.z;
   const int G = Hq / Hkv;
   const int len = seq_lens[seq];
-  const int t0 = split * part_len, t1 = min(len, t0 + part_len);
+  // sliding-window attention (Mistral): only the last `window` cached tokens are visible - partitions that lie before
+  // the window start contribute nothing (m = -inf, l = 0) and are skipped by the merge
+  const int window_start = window > 0 ? max(0, len - window) : 0;
+  const int t0 = max(split * part_len, window_start), t1 = min(len, split * part_len + part_len);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = DEC_THREADS / 32;
   __shared__ float q_s[MAX_GROUP][D];
   __shared__ float red_m[DEC_THREADS / 32][MAX_GROUP], red_l[DEC_THREADS / 32][MAX_GROUP];
@@ -397,14 +400,14 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
                               const int* seq_lens, void* out, float* o_part, float* ml_part, int num_seqs, int Hq,
                               int Hkv, int D, int block_size, int max_blocks_per_seq, int splits, int part_len,
                               float scale, const float* alibi_slopes, int64_t q_stride, int64_t out_stride, int dtype,
-                              cudaStream_t s) {
+                              int window, cudaStream_t s) {
   if (num_seqs == 0) return 0;
   if (Hq % Hkv != 0 || Hq / Hkv > MAX_GROUP) return (int)cudaErrorInvalidValue;
   dim3 grid(num_seqs, Hkv, splits);
 #define LAUNCH_DEC(T, DD)                                                                                           \
   paged_decode_kernel<T, T, DD><<<grid, DEC_THREADS, 0, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache,      \
       block_tables, seq_lens, o_part, ml_part, Hq, Hkv, block_size, max_blocks_per_seq, splits, part_len, scale,     \
-      alibi_slopes, q_stride);                                                                                       \
+      alibi_slopes, q_stride, window);                                                                               \
   decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride)
   CB_DISPATCH_HALF(dtype, T, {
     if (D == 128) { LAUNCH_DEC(T, 128); }

@@ -252,6 +252,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline PFN_encodeTiled get_encode_fn() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  Autograd runs backward
+  // on its own thread, where no runtime call may have happened yet when every tensor came out of the caching allocator
+  // (seen as CUDA_ERROR_INVALID_CONTEXT = 201 on the first grouped-GEMM backward); cudaFree(0) binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;

@@ -56,13 +56,10 @@ def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torc
                            seq_lens: torch.Tensor, scale: Optional[float] = None,
                            alibi_slopes: Optional[torch.Tensor] = None, window: Optional[int] = None) -> torch.Tensor:
     """q: [num_seqs, Hq, D] (one new token per sequence) -> [num_seqs, Hq, D].  `window`: sliding-window attention
-    (only the last `window` cached tokens are visible) — served by the reference path; callers pass it only for
-    sequences that have actually outgrown the window."""
+    (only the last `window` cached tokens are visible), handled inside the split-KV kernel (`window_start`)."""
     n, Hq, D = q.shape
     nb, bs, Hkv, _ = k_cache.shape
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
-    if window is not None:
-        return paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale, alibi_slopes, window)
     if (use_native(q) and q.dtype in (torch.float16, torch.bfloat16) and k_cache.dtype == q.dtype
             and D in (64, 128, 256) and Hq // Hkv <= 8):
         lib = _get_lib()
@@ -81,10 +78,11 @@ def paged_decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torc
             loader.ptr(qc), loader.ptr(k_cache), loader.ptr(v_cache), loader.ptr(block_tables), loader.ptr(seq_lens),
             loader.ptr(out), loader.ptr(o_part), loader.ptr(ml_part), n, Hq, Hkv, D, bs, block_tables.shape[1], splits,
             part.value, ctypes.c_float(scale), loader.ptr(alibi_slopes), ctypes.c_int64(qc.stride(0)),
-            ctypes.c_int64(out.stride(0)), code(q.dtype), loader.stream_ptr()), "paged_decode_attention")
+            ctypes.c_int64(out.stride(0)), code(q.dtype), int(window or 0), loader.stream_ptr()),
+            "paged_decode_attention")
         loader.launch_counter.add("paged_decode_attention", 2)
         return out
-    return paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale, alibi_slopes)
+    return paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale, alibi_slopes, window)
 
 
 def paged_decode_attention_ref(q, k_cache, v_cache, block_tables, seq_lens, scale=None, alibi_slopes=None,

@@ -69,6 +69,22 @@ def main():
            "decode_tokens_per_s": args.batch_size * (steps - 1) / (t_decode / 1e3),
            "our_kernel_launches": loader.launch_counter.count,
            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
+    # decode is HBM-bound: every step streams all weights once plus the live KV cache; roofline = bytes / measured
+    # copy bandwidth (MEASURED_PEAKS.json, 6555.8 GB/s on this pool's B200s)
+    hbm_gbs = 6555.8
+    try:
+        hbm_gbs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..",
+                                              "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    n_params = sum(p.numel() for p in model.parameters())
+    w_bytes = n_params * 2
+    ctx = args.in_len + args.out_len / 2
+    kv_bytes = args.batch_size * ctx * 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * cfg.head_dim * 2
+    roof_ms = (w_bytes + kv_bytes) / (hbm_gbs * 1e9) * 1e3
+    out.update({"params": n_params, "decode_hbm_roofline_ms": roof_ms,
+                "decode_frac_of_measured_hbm_roofline": roof_ms / out["decode_ms_per_step"],
+                "prefill_tflops": 2.0 * n_params * args.batch_size * args.in_len / (t_prefill / 1e3) / 1e12})
     print(json.dumps(out), flush=True)
 
 

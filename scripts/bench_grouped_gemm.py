@@ -63,8 +63,11 @@ def main():
                 y = gg.grouped_linear(xg, wg, c)
                 y.backward(dy)
                 xg.grad = wg.grad = None
-            row["native_fwd_bwd_ms"] = timeit(fb, 5)
-            row["native_fwd_bwd_tflops"] = 3 * fl / row["native_fwd_bwd_ms"] / 1e9
+            try:
+                row["native_fwd_bwd_ms"] = timeit(fb, 5)
+                row["native_fwd_bwd_tflops"] = 3 * fl / row["native_fwd_bwd_ms"] / 1e9
+            except Exception as e:
+                row["native_fwd_bwd_error"] = f"{type(e).__name__}: {str(e)[:160]}"
         print("GROUPED_GEMM " + json.dumps(row), flush=True)
 
 

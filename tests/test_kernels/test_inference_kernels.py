@@ -57,6 +57,67 @@ def test_paged_decode_alibi():
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
 
 
+# wider grid in the spirit of the reference's flash-decoding test
+# (tests/test_infer/test_kernels/cuda/test_flash_decoding_attention.py:59-66: batch x block size x context x group size x
+#  head dim x same / mixed context lengths, with and without ALiBi)
+@pytest.mark.parametrize("bsz", [1, 7, 32])
+@pytest.mark.parametrize("bs", [8, 16, 32])
+@pytest.mark.parametrize("max_blocks", [1, 8, 67])
+@pytest.mark.parametrize("group", [1, 4, 8])
+@pytest.mark.parametrize("D", [64, 128, 256])
+@pytest.mark.parametrize("same_len", [True, False])
+def test_paged_decode_grid(bsz, bs, max_blocks, group, D, same_len):
+    dev = torch.device("cuda")
+    torch.manual_seed(bsz * 131 + bs * 17 + max_blocks + group + D)
+    Hkv = 2
+    Hq = Hkv * group
+    max_len = bs * max_blocks
+    kc, vc, tables = _mk_cache(bsz, max_len, bs, Hkv, D, torch.bfloat16, dev)
+    lens = torch.full((bsz,), max_len, dtype=torch.int32) if same_len else torch.randint(1, max_len + 1, (bsz,)).int()
+    lens = lens.to(dev)
+    q = torch.randn(bsz, Hq, D, device=dev, dtype=torch.bfloat16)
+    out = iops.paged_decode_attention(q, kc, vc, tables, lens)
+    ref = iops.paged_decode_attention_ref(q.float(), kc.float(), vc.float(), tables, lens)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("window", [1, 16, 100, 4096])
+@pytest.mark.parametrize("alibi", [False, True])
+def test_paged_decode_sliding_window(window, alibi):
+    """`window_start` inside the split-KV kernel: only the last `window` cached tokens are visible."""
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    kc, vc, tables = _mk_cache(5, 3000, 16, 4, 128, torch.bfloat16, dev)
+    lens = torch.tensor([1, 15, 100, 1025, 3000], device=dev, dtype=torch.int32)
+    q = torch.randn(5, 16, 128, device=dev, dtype=torch.bfloat16)
+    slopes = torch.tensor([2 ** (-(i + 1) / 2) for i in range(16)], device=dev, dtype=torch.float32) if alibi else None
+    out = iops.paged_decode_attention(q, kc, vc, tables, lens, alibi_slopes=slopes, window=window)
+    ref = iops.paged_decode_attention_ref(q.float(), kc.float(), vc.float(), tables, lens, alibi_slopes=slopes,
+                                          window=window)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("tokens,Hkv,D", [(1, 8, 128), (33, 2, 64), (4096, 8, 128), (515, 4, 256)])
+def test_kv_cache_write_vectorised_shapes(tokens, Hkv, D):
+    """The 16-byte path of `cb_kv_cache_write` over prefill-sized token counts and strided (fused-QKV view) inputs."""
+    dev = torch.device("cuda")
+    torch.manual_seed(tokens)
+    bs = 16
+    n_seqs = max(1, tokens // 100)
+    per = (tokens + n_seqs - 1) // n_seqs
+    seq = (torch.arange(tokens, device=dev) // per).int()
+    pos = (torch.arange(tokens, device=dev) % per).int()
+    kc, vc, tables = _mk_cache(n_seqs, per, bs, Hkv, D, torch.bfloat16, dev)
+    fused = torch.randn(tokens, 3 * Hkv * D, device=dev, dtype=torch.bfloat16)
+    k = fused[:, Hkv * D: 2 * Hkv * D].view(tokens, Hkv, D)          # row stride 3 * Hkv * D
+    v = fused[:, 2 * Hkv * D:].view(tokens, Hkv, D)
+    kc.zero_(); vc.zero_()
+    iops.kv_cache_write(k, v, kc, vc, tables, seq, pos)
+    blk = tables[seq.long(), (pos // bs).long()].long()
+    torch.testing.assert_close(kc[blk, (pos % bs).long()], k, atol=0, rtol=0)
+    torch.testing.assert_close(vc[blk, (pos % bs).long()], v, atol=0, rtol=0)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_kv_cache_write(dtype):
     dev = torch.device("cuda")
