@@ -353,17 +353,23 @@ class TransformerModel(nn.Module):
         self._rope_cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ helpers
-    def rope_cache(self, device) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    def rope_cache(self, device, min_len: int = 0) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        """cos / sin tables [positions, rotary_dim / 2].  Sized by the config, but never shorter than the sequence in
+        flight (`min_len`, rounded up to a power of two): a 128k-token context on a checkpoint configured for 8k must
+        not index past the table."""
         cfg = self.cfg
         if cfg.pos_type != "rope":
             return None
-        key = (str(device), cfg.max_position_embeddings)
+        n_pos = cfg.max_position_embeddings
+        if min_len > n_pos:
+            n_pos = 1 << (min_len - 1).bit_length()
+        key = (str(device), n_pos)
         if key not in self._rope_cache:
             llama3 = cfg.rope_scaling if (cfg.rope_scaling and cfg.rope_scaling.get("rope_type") == "llama3") else None
             factor = 1.0
             if cfg.rope_scaling and cfg.rope_scaling.get("rope_type", cfg.rope_scaling.get("type")) == "linear":
                 factor = cfg.rope_scaling.get("factor", 1.0)
-            self._rope_cache[key] = ops.build_rope_cache(cfg.max_position_embeddings, cfg.rotary_dim, cfg.rope_theta,
+            self._rope_cache[key] = ops.build_rope_cache(n_pos, cfg.rotary_dim, cfg.rope_theta,
                                                          device=device, scaling_factor=factor, llama3_scaling=llama3)
         return self._rope_cache[key]
 
@@ -474,7 +480,7 @@ class TransformerModel(nn.Module):
                 pass
         else:
             x = hidden_states
-        rope = self.rope_cache(device)
+        rope = self.rope_cache(device, min_len=int(getattr(meta, "seqlen", 0) or 0))
         start, end = self.layer_range()
         n_ckpt = self._num_ckpt_layers(end - start) if self.training else 0
         for i in range(start, end):
