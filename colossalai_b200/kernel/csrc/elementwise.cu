@@ -35,8 +35,11 @@ template <int ACT> CB_DEVICE float act_grad_f(float x) {
 
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ gu, T* __restrict__ out, int64_t rows,
-                                                      int I) {
+                                                      int I, const int64_t* __restrict__ row_limit) {
   constexpr int VEC = Vec16<T>::N;
+  // row_limit (device scalar, optional): only the first *row_limit rows hold data - expert-parallel receive buffers are
+  // sized for the worst case and the number of rows that actually arrived is only known on the device
+  if (row_limit != nullptr) rows = min(rows, *row_limit);
   const int64_t vec_per_row = I / VEC, total = rows * vec_per_row;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -53,8 +56,10 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ gu, 
 
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ gu,
-                                                      T* __restrict__ dgu, int64_t rows, int I) {
+                                                      T* __restrict__ dgu, int64_t rows, int I,
+                                                      const int64_t* __restrict__ row_limit) {
   constexpr int VEC = Vec16<T>::N;
+  if (row_limit != nullptr) rows = min(rows, *row_limit);
   const int64_t vec_per_row = I / VEC, total = rows * vec_per_row;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -194,29 +199,37 @@ static inline int ew_grid(int64_t items, int block) {
 
 extern "C" {
 
-int cb_glu_fwd(const void* gu, void* out, int64_t rows, int I, int act, int dtype, cudaStream_t s) {
+int cb_glu_fwd_bounded(const void* gu, void* out, int64_t rows, int I, int act, int dtype, const int64_t* row_limit, cudaStream_t s) {
   if (rows == 0) return 0;
   CB_DISPATCH_FLOAT(dtype, T, {
     const int64_t items = rows * (I / Vec16<T>::N);
     const int g = ew_grid(items, 256);
-    if (act == 0) glu_fwd_kernel<T, 0><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I);
-    else if (act == 1) glu_fwd_kernel<T, 1><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I);
-    else glu_fwd_kernel<T, 2><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I);
+    if (act == 0) glu_fwd_kernel<T, 0><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I, row_limit);
+    else if (act == 1) glu_fwd_kernel<T, 1><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I, row_limit);
+    else glu_fwd_kernel<T, 2><<<g, 256, 0, s>>>((const T*)gu, (T*)out, rows, I, row_limit);
   });
   return CB_LAUNCH_CHECK();
 }
 
-int cb_glu_bwd(const void* dout, const void* gu, void* dgu, int64_t rows, int I, int act, int dtype,
-               cudaStream_t s) {
+int cb_glu_bwd_bounded(const void* dout, const void* gu, void* dgu, int64_t rows, int I, int act, int dtype,
+               const int64_t* row_limit, cudaStream_t s) {
   if (rows == 0) return 0;
   CB_DISPATCH_FLOAT(dtype, T, {
     const int64_t items = rows * (I / Vec16<T>::N);
     const int g = ew_grid(items, 256);
-    if (act == 0) glu_bwd_kernel<T, 0><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I);
-    else if (act == 1) glu_bwd_kernel<T, 1><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I);
-    else glu_bwd_kernel<T, 2><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I);
+    if (act == 0) glu_bwd_kernel<T, 0><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I, row_limit);
+    else if (act == 1) glu_bwd_kernel<T, 1><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I, row_limit);
+    else glu_bwd_kernel<T, 2><<<g, 256, 0, s>>>((const T*)dout, (const T*)gu, (T*)dgu, rows, I, row_limit);
   });
   return CB_LAUNCH_CHECK();
+}
+
+int cb_glu_fwd(const void* gu, void* out, int64_t rows, int I, int act, int dtype, cudaStream_t s) {
+  return cb_glu_fwd_bounded(gu, out, rows, I, act, dtype, nullptr, s);
+}
+
+int cb_glu_bwd(const void* dout, const void* gu, void* dgu, int64_t rows, int I, int act, int dtype, cudaStream_t s) {
+  return cb_glu_bwd_bounded(dout, gu, dgu, rows, I, act, dtype, nullptr, s);
 }
 
 int cb_rope(void* qkv, const int64_t* pos, const float* cos_c, const float* sin_c, int64_t tokens,

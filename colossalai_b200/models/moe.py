@@ -80,7 +80,10 @@ class GroupedExperts(nn.Module):
         from ..moe.grouped_gemm import grouped_linear
 
         h = grouped_linear(x_sorted, self.w_up, counts)
-        h = ops.glu(h, self.cfg.hidden_act) if self.cfg.glu else ops.get_activation(self.cfg.hidden_act)(h)
+        # rows past sum(counts) are padding of an over-allocated receive buffer: the activation skips them (the count
+        # stays on the device)
+        h = ops.glu(h, self.cfg.hidden_act, valid_rows=counts.sum()) if self.cfg.glu \
+            else ops.get_activation(self.cfg.hidden_act)(h)
         return grouped_linear(h, self.w_down, counts)
 
 

@@ -41,38 +41,44 @@ def glu_ref(gate_up: torch.Tensor, act: str = "silu") -> torch.Tensor:
 
 class _GLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gate_up, act):
+    def forward(ctx, gate_up, act, valid_rows=None):
         lib = _get_lib()
         shape = gate_up.shape
         I = shape[-1] // 2
         gu = gate_up.contiguous().view(-1, 2 * I)
         out = torch.empty(gu.shape[0], I, dtype=gu.dtype, device=gu.device)
-        loader.check(lib.cb_glu_fwd(loader.ptr(gu), loader.ptr(out), ctypes.c_int64(gu.shape[0]), I, act,
-                                    code(gu.dtype), loader.stream_ptr()), "glu_fwd")
+        loader.check(lib.cb_glu_fwd_bounded(loader.ptr(gu), loader.ptr(out), ctypes.c_int64(gu.shape[0]), I, act,
+                                            code(gu.dtype), loader.ptr(valid_rows), loader.stream_ptr()), "glu_fwd")
         loader.launch_counter.add("glu_fwd")
-        ctx.save_for_backward(gu)
+        ctx.save_for_backward(gu, valid_rows if valid_rows is not None else torch.empty(0))
         ctx.act, ctx.shape = act, shape
         return out.view(shape[:-1] + (I,))
 
     @staticmethod
     def backward(ctx, dout):
         lib = _get_lib()
-        (gu,) = ctx.saved_tensors
+        gu, vr = ctx.saved_tensors
+        vr = vr if vr.numel() else None
         I = gu.shape[1] // 2
         d = dout.contiguous().view(-1, I)
         dgu = torch.empty_like(gu)
-        loader.check(lib.cb_glu_bwd(loader.ptr(d), loader.ptr(gu), loader.ptr(dgu), ctypes.c_int64(gu.shape[0]), I,
-                                    ctx.act, code(gu.dtype), loader.stream_ptr()), "glu_bwd")
+        loader.check(lib.cb_glu_bwd_bounded(loader.ptr(d), loader.ptr(gu), loader.ptr(dgu), ctypes.c_int64(gu.shape[0]),
+                                            I, ctx.act, code(gu.dtype), loader.ptr(vr), loader.stream_ptr()), "glu_bwd")
         loader.launch_counter.add("glu_bwd")
-        return dgu.view(ctx.shape), None
+        return dgu.view(ctx.shape), None, None
 
 
-def glu(gate_up: torch.Tensor, act: str = "silu") -> torch.Tensor:
-    """out = act(gate) * up where gate = gate_up[..., :I], up = gate_up[..., I:]."""
+def glu(gate_up: torch.Tensor, act: str = "silu", valid_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(gate) * up where gate = gate_up[..., :I], up = gate_up[..., I:].
+    `valid_rows` (int64 device scalar, optional): only the first `valid_rows` rows are computed (expert-parallel
+    receive buffers are over-allocated and the number of rows that arrived is only known on the device); the rest of
+    the output is left uninitialised."""
     I = gate_up.shape[-1] // 2
     vec = 4 if gate_up.dtype == torch.float32 else 8
     if use_native(gate_up) and gate_up.dtype in (torch.float32, torch.float16, torch.bfloat16) and I % vec == 0:
-        return _GLUFn.apply(gate_up, _ACT[act])
+        if valid_rows is not None:
+            valid_rows = valid_rows.to(device=gate_up.device, dtype=torch.int64).reshape(1).contiguous()
+        return _GLUFn.apply(gate_up, _ACT[act], valid_rows)
     return glu_ref(gate_up, act)
 
 

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--grouped_gemm", default="native", choices=["native", "lib"])
     args = ap.parse_args()
     os.environ["CB200_GROUPED_GEMM"] = args.grouped_gemm
+    os.environ.setdefault("CB200_EP_CAPACITY_FACTOR", "2")      # receive buffers: 2x the balanced load (overflow raises)
     colossalai_b200.launch_from_torch(verbose=False)
     rank, world = dist.get_rank(), dist.get_world_size()
     dc.set_moe_backend(args.moe_backend)

@@ -151,3 +151,22 @@ def test_dist_cross_entropy_matches_torch():
     ref.backward()
     torch.testing.assert_close(loss, ref, atol=2e-3, rtol=1e-3)
     torch.testing.assert_close(logits.grad.float(), lr.grad, atol=1e-5, rtol=5e-2)
+
+
+def test_glu_row_limit():
+    """`valid_rows`: rows past the device-side limit are neither read nor written, forward and backward."""
+    import torch
+
+    from colossalai_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(512, 2 * 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    n = torch.tensor(300, device="cuda")
+    y = ops.glu(x, "silu", valid_rows=n)
+    ref = ops.glu(x.detach()[:300], "silu")
+    torch.testing.assert_close(y[:300], ref, atol=0, rtol=0)
+    dy = torch.randn(512, 256, device="cuda", dtype=torch.bfloat16)
+    (g,) = torch.autograd.grad(y, x, dy)
+    xr = x.detach()[:300].clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad(ops.glu(xr, "silu"), xr, dy[:300])
+    torch.testing.assert_close(g[:300], gr, atol=0, rtol=0)
