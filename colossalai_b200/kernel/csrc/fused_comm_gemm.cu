@@ -1039,6 +1039,67 @@ __global__ void __launch_bounds__(256) reduce_scatter_kernel(const CommParams c,
   }
 }
 
+// Ulysses (DeepSpeed sequence-parallel) layout switch as ONE pull kernel over peer memory, q / k / v segments together:
+//   mode 0 "gather sequence, scatter heads":  in  [B * Sl, ld_in]  (all heads of my sequence shard)
+//                                             out [B * sp * Sl, ld_out] (my head slice of the whole sequence); for segment s
+//                                             out[(b * sp + src) * Sl + t, out_base[s] + c] = in_src[b * Sl + t, in_base[s] + me * ncols[s] + c]
+//   mode 1 "scatter sequence, gather heads":  in  [B * sp * Sl, ld_in], out [B * Sl, ld_out];
+//                                             out[b * Sl + t, out_base[s] + src * ncols[s] + c] = in_src[(b * sp + me) * Sl + t, in_base[s] + c]
+// Replaces the reference's three `all_to_all` calls before attention and the one after it
+// (`shardformer/modeling/llama.py:522-526,595-600`, `layer/_operation.py:1082-1153`) plus their chunk / cat copies.
+struct A2ASeg {
+  int in_base, out_base, ncols;          // in 16-byte vectors
+};
+struct A2AParams {
+  int mode, B, Sl, n_seg, ld_in, ld_out; // leading dimensions in 16-byte vectors
+  A2ASeg seg[3];
+  void* out;
+};
+
+__global__ void __launch_bounds__(256) ulysses_a2a_kernel(const CommParams c, const A2AParams a) {
+  uint32_t* my_flags = c.peer_flags[c.rank];
+  if (blockIdx.x == 0 && threadIdx.x < c.world)
+    st_release_sys(c.peer_flags[threadIdx.x] + SLOT_IN_READY + c.rank, c.epoch);
+  const int sp = c.world, me = c.rank;
+  uint4* out = reinterpret_cast<uint4*>(a.out);
+  for (int step = 0; step < sp; ++step) {
+    const int src = (me + step) % sp;
+    if (step > 0) {
+      if (threadIdx.x == 0) wait_epoch<true>(my_flags + SLOT_IN_READY + src, c.epoch);
+      __syncthreads();
+    }
+    const uint4* in = reinterpret_cast<const uint4*>(c.peer_in[src]);
+    for (int s = 0; s < a.n_seg; ++s) {
+      const A2ASeg sg = a.seg[s];
+      const size_t per_b = (size_t)a.Sl * sg.ncols;
+      const size_t total = (size_t)a.B * per_b;
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_b);
+        const size_t r = i - (size_t)b * per_b;
+        const int t = (int)(r / sg.ncols), cv = (int)(r - (size_t)t * sg.ncols);
+        size_t in_off, out_off;
+        if (a.mode == 0) {
+          in_off = ((size_t)b * a.Sl + t) * a.ld_in + sg.in_base + (size_t)me * sg.ncols + cv;
+          out_off = (((size_t)b * sp + src) * a.Sl + t) * a.ld_out + sg.out_base + cv;
+        } else {
+          in_off = (((size_t)b * sp + me) * a.Sl + t) * a.ld_in + sg.in_base + cv;
+          out_off = ((size_t)b * a.Sl + t) * a.ld_out + sg.out_base + (size_t)src * sg.ncols + cv;
+        }
+        out[out_off] = ld_peer_16B(in + in_off);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(my_flags + SLOT_LOCAL + 3, 1u) + 1;
+    if (done == gridDim.x) {
+      my_flags[SLOT_LOCAL + 3] = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(c.peer_flags[r] + SLOT_PULL_DONE + c.rank, c.epoch);
+    }
+  }
+}
+
 // Wait until every peer has finished reading this rank's symmetric buffers of `epoch` (buffer-reuse guard).
 __global__ void wait_pull_done_kernel(uint32_t* my_flags, int world, uint32_t epoch) {
   if (threadIdx.x < world)
@@ -1171,6 +1232,27 @@ int cb_reduce_scatter(const void* const* peer_part, const void* mc_part, uint32_
   return (int)cudaGetLastError();
 }
 
+// Ulysses layout switch (see ulysses_a2a_kernel).  Column quantities are in ELEMENTS of `elem_bytes` and must be multiples
+// of 16 bytes; peer_in[r] = rank r's symmetric input buffer.
+int cb_ulysses_a2a(const void* const* peer_in, uint32_t* const* peer_flags, void* out, int mode, int B, int Sl, int n_seg,
+                   const int* in_base, const int* out_base, const int* ncols, int ld_in, int ld_out, int elem_bytes,
+                   int rank, int world, uint32_t epoch, int n_ctas, cudaStream_t stream) {
+  if (world > MAX_RANKS || n_seg < 1 || n_seg > 3 || (mode != 0 && mode != 1)) return (int)cudaErrorInvalidValue;
+  const int per = 16 / elem_bytes;
+  CommParams c{};
+  c.rank = rank; c.world = world; c.epoch = epoch;
+  for (int r = 0; r < world; ++r) { c.peer_in[r] = peer_in[r]; c.peer_flags[r] = peer_flags[r]; }
+  A2AParams a{};
+  a.mode = mode; a.B = B; a.Sl = Sl; a.n_seg = n_seg; a.out = out;
+  if (ld_in % per || ld_out % per) return (int)cudaErrorInvalidValue;
+  a.ld_in = ld_in / per; a.ld_out = ld_out / per;
+  for (int s = 0; s < n_seg; ++s) {
+    if (in_base[s] % per || out_base[s] % per || ncols[s] % per) return (int)cudaErrorInvalidValue;
+    a.seg[s].in_base = in_base[s] / per; a.seg[s].out_base = out_base[s] / per; a.seg[s].ncols = ncols[s] / per;
+  }
+  ulysses_a2a_kernel<<<n_ctas, 256, 0, stream>>>(c, a);
+  return (int)cudaGetLastError();
+}
 int cb_wait_pull_done(uint32_t* my_flags, int world, uint32_t epoch, cudaStream_t stream) {
   wait_pull_done_kernel<<<1, 32, 0, stream>>>(my_flags, world, epoch);
   return (int)cudaGetLastError();

@@ -53,6 +53,17 @@ class SeqMeta:
     local_seqlen: Optional[int] = None          # per-sequence tokens held by this rank under a2a / ring_attn
 
 
+def _use_fused_a2a(x: torch.Tensor, sp_group) -> bool:
+    """Ulysses all-to-all through the sm_100a pull kernel: CUDA tensors under the `fused` comm backend."""
+    from ..shardformer.layer._operation import get_comm_backend
+
+    if not x.is_cuda or get_comm_backend() != "fused" or comm.group_size(sp_group) == 1:
+        return False
+    from ..parallel import fused
+
+    return fused.available(sp_group)
+
+
 def build_norm(cfg: ModelConfig, hidden: Optional[int] = None) -> nn.Module:
     h = hidden or cfg.hidden_size
     if cfg.norm_type == "rms":
@@ -101,13 +112,24 @@ class Attention(nn.Module):
             # Ulysses: [B*S/sp, heads*D] -> [B*S, (heads/sp)*D]: scatter heads, gather sequence
             sp = comm.group_size(sp_group)
             B, Sl = meta.batch, qkv.shape[0] // meta.batch
-            q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
-            def a2a(t, nh):
-                t = t.reshape(B, Sl, nh, D)
-                t = all_to_all_comm(t, sp_group, scatter_dim=2, gather_dim=1)
-                return t.reshape(B * Sl * sp, (nh // sp) * D)
-            hq, hkv = hq // sp, hkv // sp
-            qkv = torch.cat([a2a(q, hq * sp), a2a(k, hkv * sp), a2a(v, hkv * sp)], dim=-1)
+            fused_qkv = None
+            if _use_fused_a2a(qkv, sp_group):
+                # ONE pull kernel over peer memory moves q, k and v together (no chunk / stack / cat copies)
+                from ..parallel import fused
+
+                fused_qkv = fused.ulysses_all_to_all(qkv, sp_group, True, B, Sl,
+                                                     [hq // sp * D, hkv // sp * D, hkv // sp * D])
+            if fused_qkv is not None:
+                hq, hkv = hq // sp, hkv // sp
+                qkv = fused_qkv
+            else:
+                q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
+                def a2a(t, nh):
+                    t = t.reshape(B, Sl, nh, D)
+                    t = all_to_all_comm(t, sp_group, scatter_dim=2, gather_dim=1)
+                    return t.reshape(B * Sl * sp, (nh // sp) * D)
+                hq, hkv = hq // sp, hkv // sp
+                qkv = torch.cat([a2a(q, hq * sp), a2a(k, hkv * sp), a2a(v, hkv * sp)], dim=-1)
         T = qkv.shape[0]
         if cfg.qk_norm:
             q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
@@ -142,8 +164,16 @@ class Attention(nn.Module):
         if sp_mode == "all_to_all" and comm.group_size(sp_group) > 1:
             sp = comm.group_size(sp_group)
             B, S = meta.batch, T // meta.batch
-            o = all_to_all_comm(o.reshape(B, S, hq, D), sp_group, scatter_dim=1, gather_dim=2)
-            o = o.reshape(B * (S // sp), hq * sp * D)
+            fused_o = None
+            if _use_fused_a2a(o, sp_group):
+                from ..parallel import fused
+
+                fused_o = fused.ulysses_all_to_all(o, sp_group, False, B, S // sp, [hq * D])
+            if fused_o is not None:
+                o = fused_o
+            else:
+                o = all_to_all_comm(o.reshape(B, S, hq, D), sp_group, scatter_dim=1, gather_dim=2)
+                o = o.reshape(B * (S // sp), hq * sp * D)
         return self.o_proj(o)
 
     def _head_norm(self, norm: nn.Module, t: torch.Tensor) -> torch.Tensor:

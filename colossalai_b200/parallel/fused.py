@@ -28,7 +28,7 @@ from ..ops._dtypes import code
 from . import comm
 
 __all__ = ["available", "build_available", "all_gather_gemm", "gemm_reduce_scatter", "gemm_all_reduce", "all_gather",
-           "reduce_scatter",
+           "reduce_scatter", "ulysses_all_to_all",
            "FusedWorkspace", "stats"]
 
 _lib = None
@@ -419,3 +419,68 @@ def gemm_all_reduce(a: torch.Tensor, w: torch.Tensor, group: Optional[ProcessGro
             # hand out a private copy: the symmetric buffer is reused by the call after next
             return out_buf.tensor[:nbytes].view(a.dtype).view(T, N).clone()
     return all_gather(gemm_reduce_scatter(a, w, group, transpose_b=True), group)
+
+
+# ------------------------------------------------------------------------------------------------ Ulysses all-to-all
+def _ulysses_launch(x: torch.Tensor, group, mode: int, B: int, Sl: int, segs, out_cols: int) -> torch.Tensor:
+    """One pull kernel for a sequence <-> head layout switch.  `segs`: [(in_base, out_base, ncols)] in elements."""
+    ws = workspace(group)
+    lib = _get_lib()
+    world = ws.world
+    nbytes = x.numel() * x.element_size()
+    buf = ws.in_buffer(nbytes)
+    buf.tensor[:nbytes].view(x.dtype).view(x.shape).copy_(x)
+    epoch = ws.next_epoch()
+    rows_out = B * Sl * world if mode == 0 else B * Sl
+    out = torch.empty(rows_out, out_cols, dtype=x.dtype, device=x.device)
+    n = len(segs)
+    arr = lambda i: (ctypes.c_int * n)(*[int(sg[i]) for sg in segs])
+    n_ctas = 2 * torch.cuda.get_device_properties(x.device).multi_processor_count
+    loader.check(lib.cb_ulysses_a2a(buf.ptr_array(world), ws.flags.ptr_array(world), loader.ptr(out), mode, B, Sl, n,
+                                    arr(0), arr(1), arr(2), x.shape[1], out_cols, x.element_size(), ws.rank, world,
+                                    ctypes.c_uint32(epoch), n_ctas, loader.stream_ptr()), "ulysses_a2a")
+    buf.last_epoch = epoch
+    loader.launch_counter.add("fused_ulysses_a2a")
+    stats["ulysses_a2a"] = stats.get("ulysses_a2a", 0) + 1
+    return out
+
+
+class _UlyssesA2A(torch.autograd.Function):
+    """mode 0: [B*Sl, sum_s sp*w_s] -> [B*sp*Sl, sum_s w_s] (gather sequence, scatter the heads of every segment);
+    mode 1: the inverse.  The backward of one mode is the other mode on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group, mode, B, Sl, widths):
+        world = comm.group_size(group)
+        ctx.group, ctx.mode, ctx.B, ctx.Sl, ctx.widths = group, mode, B, Sl, widths
+        return _UlyssesA2A._run(x.contiguous(), group, mode, B, Sl, widths, world)
+
+    @staticmethod
+    def _run(x, group, mode, B, Sl, widths, world):
+        segs, full, local = [], 0, 0
+        for w in widths:                      # w = columns of ONE rank's head slice of this segment
+            segs.append((full, local, w) if mode == 0 else (local, full, w))
+            full += w * world
+            local += w
+        return _ulysses_launch(x, group, mode, B, Sl, segs, local if mode == 0 else full)
+
+    @staticmethod
+    def backward(ctx, dy):
+        world = comm.group_size(ctx.group)
+        dx = _UlyssesA2A._run(dy.contiguous(), ctx.group, 1 - ctx.mode, ctx.B, ctx.Sl, ctx.widths, world)
+        return dx, None, None, None, None, None
+
+
+def ulysses_all_to_all(x: torch.Tensor, group: Optional[ProcessGroup], gather_sequence: bool, batch: int,
+                       local_seqlen: int, widths) -> Optional[torch.Tensor]:
+    """Fused Ulysses layout switch of a token-major 2-D tensor made of column segments (e.g. q | k | v).
+    gather_sequence=True : x [B*Sl, sum(sp * w)] -> [B*sp*Sl, sum(w)]   (before attention: all tokens, my heads)
+    gather_sequence=False: x [B*sp*Sl, sum(w)]   -> [B*Sl, sum(sp * w)] (after attention: my tokens, all heads)
+    `widths`: per segment, the column count of one rank's head slice.  Returns None when the shape cannot take the
+    kernel (caller falls back to the NCCL all_to_all)."""
+    ws = workspace(group)
+    per = 16 // x.element_size()
+    if ws is None or x.dim() != 2 or not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16, torch.float32) \
+            or any(w % per for w in widths) or len(widths) > 3:
+        return None
+    return _UlyssesA2A.apply(x, group, 0 if gather_sequence else 1, batch, local_seqlen, tuple(int(w) for w in widths))

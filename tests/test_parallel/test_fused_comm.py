@@ -107,6 +107,44 @@ def _worker(rank, world_size, port, timing=False):
                 r["gemm_rs_stream_ms"] = _time(lambda: fused.gemm_reduce_scatter(a, w, group, variant="stream"))
             r["rs_autotuned"] = fused.rs_variant(a, w, group, True)
             results.append(r)
+    # ---- Ulysses layout switch (q | k | v segments in one pull kernel) vs the NCCL all_to_all composition
+    B, Sl, hq, hkv, D = 2, 192, 4 * world_size, 2 * world_size, 128
+    torch.manual_seed(300 + rank)
+    qkv = torch.randn(B * Sl, (hq + 2 * hkv) * D, device="cuda").bfloat16().requires_grad_(True)
+    got = fused.ulysses_all_to_all(qkv, group, True, B, Sl, [hq // world_size * D, hkv // world_size * D, hkv // world_size * D])
+    parts = []
+    for t, nh in zip(qkv.detach().split([hq * D, hkv * D, hkv * D], dim=-1), (hq, hkv, hkv)):
+        r = comm.all_to_all_single(t.reshape(B, Sl, nh, D), 2, 1, group)
+        parts.append(r.reshape(B * Sl * world_size, nh // world_size * D))
+    ref = torch.cat(parts, -1)
+    torch.testing.assert_close(got, ref, atol=0, rtol=0)
+    gw = torch.randn_like(got)
+    got.backward(gw)                                       # backward = the inverse switch of the gradient
+    back = []
+    off = 0
+    for nh in (hq, hkv, hkv):
+        w = nh // world_size * D
+        g = comm.all_to_all_single(gw[:, off:off + w].reshape(B, Sl * world_size, nh // world_size, D), 1, 2, group)
+        back.append(g.reshape(B * Sl, nh * D))
+        off += w
+    torch.testing.assert_close(qkv.grad, torch.cat(back, -1), atol=0, rtol=0)
+    o = torch.randn(B * Sl * world_size, hq // world_size * D, device="cuda").bfloat16()
+    got_o = fused.ulysses_all_to_all(o, group, False, B, Sl, [hq // world_size * D])
+    ref_o = comm.all_to_all_single(o.reshape(B, Sl * world_size, hq // world_size, D), 1, 2, group).reshape(B * Sl, hq * D)
+    torch.testing.assert_close(got_o, ref_o, atol=0, rtol=0)
+    if timing:
+        Bt, St = 1, 16384 // world_size
+        x = torch.randn(Bt * St, (32 + 16) * 128, device="cuda").bfloat16()
+        t_f = _time(lambda: fused.ulysses_all_to_all(x, group, True, Bt, St, [32 // world_size * 128] + [8 // world_size * 128] * 2)) \
+            if 8 % world_size == 0 else None
+
+        def lib():
+            outs = []
+            for t, nh in zip(x.split([32 * 128, 8 * 128, 8 * 128], dim=-1), (32, 8, 8)):
+                outs.append(comm.all_to_all_single(t.reshape(Bt, St, nh, 128), 2, 1, group).reshape(Bt * St * world_size, -1))
+            return torch.cat(outs, -1)
+        t_n = _time(lib) if 8 % world_size == 0 else None
+        results.append({"world": world_size, "op": "ulysses_qkv_a2a", "tokens_local": St, "fused_ms": t_f, "nccl_ms": t_n})
     assert fused.stats["ag_gemm"] > 0 and fused.stats["gemm_rs"] > 0, fused.stats
     if rank == 0:
         for r in results:
