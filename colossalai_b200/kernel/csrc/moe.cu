@@ -200,6 +200,7 @@ struct EpParams {
   uint32_t* flags[MAX_PEERS];   // symmetric flag pages
   int* counts[MAX_PEERS];       // symmetric count matrices [world][E]
   int rank, world, E, n_local, capacity;
+  int align;                    // every (owner, expert) segment starts on a multiple of this many rows (1 = packed)
   uint32_t epoch;
 };
 
@@ -246,12 +247,13 @@ __global__ void ep_histogram_kernel(const int* __restrict__ topk_idx, int n, int
 
 // one block: publish my histogram row to every peer, wait for all rows, derive offsets.
 //   send_off[e]      : first row (in the owner's buffer) of MY segment for global expert e
-//   local_counts[el] : rows received for local expert el (int64, feeds the grouped GEMM offsets)
+//   local_counts[el] : rows of local expert el's segment, rounded up to p.align (int64, feeds the grouped GEMM offsets)
 //   local_offs[el]   : inclusive cumsum (int32) of local_counts
-//   meta[0] = total rows received, meta[1] = overflow flag
+//   real_counts[el]  : rows actually received for local expert el (the rest of the segment is padding)
+//   meta[0] = total rows of the local layout (padding included), meta[1] = overflow flag
 __global__ void ep_exchange_counts_kernel(EpParams p, const int* __restrict__ my_counts, int* __restrict__ send_off,
                                           int64_t* __restrict__ local_counts, int* __restrict__ local_offs,
-                                          int* __restrict__ meta) {
+                                          int* __restrict__ real_counts, int* __restrict__ meta) {
   const int E = p.E, W = p.world, R = p.rank;
   for (int peer = 0; peer < W; ++peer) {
     int* dst = p.counts[peer] + (int64_t)R * E;
@@ -281,15 +283,17 @@ __global__ void ep_exchange_counts_kernel(EpParams p, const int* __restrict__ my
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int owner_first = (e / p.n_local) * p.n_local;
     int base = 0;
-    for (int e2 = owner_first; e2 < e; ++e2) base += tot[e2];
+    for (int e2 = owner_first; e2 < e; ++e2) base += (tot[e2] + p.align - 1) / p.align * p.align;
     send_off[e] = base + pre[e];
   }
   if (threadIdx.x == 0) {
     int run = 0;
     for (int el = 0; el < p.n_local; ++el) {
       const int c = tot[R * p.n_local + el];
-      local_counts[el] = c;
-      run += c;
+      const int pc = (c + p.align - 1) / p.align * p.align;
+      real_counts[el] = c;
+      local_counts[el] = pc;
+      run += pc;
       local_offs[el] = run;
     }
     meta[0] = run;
@@ -298,7 +302,7 @@ __global__ void ep_exchange_counts_kernel(EpParams p, const int* __restrict__ my
   // overflow on ANY owner must stop every sender that targets it: check all owners
   for (int o = threadIdx.x; o < W; o += blockDim.x) {
     int run = 0;
-    for (int el = 0; el < p.n_local; ++el) run += tot[o * p.n_local + el];
+    for (int el = 0; el < p.n_local; ++el) run += (tot[o * p.n_local + el] + p.align - 1) / p.align * p.align;
     if (run > p.capacity) atomicExch(&meta[1], 1);
   }
 }
@@ -412,10 +416,39 @@ inline EpParams make_ep(const void* const* rows, const void* const* flags, const
     p.counts[i] = i < world && counts ? (int*)counts[i] : nullptr;
   }
   p.rank = rank; p.world = world; p.E = E; p.n_local = E / world; p.capacity = capacity; p.epoch = epoch;
+  p.align = 1;
   return p;
 }
 
 }  // namespace
+
+// Copy the live part of a receive buffer into an autograd-owned tensor: rows of the padded local layout that hold a
+// received row are copied, padding rows are zero-filled, nothing beyond the layout (the over-allocated rest of the
+// buffer) is touched.  One warp per row, 16-byte chunks.
+__global__ void __launch_bounds__(256) ep_take_rows_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                            int row_vecs, const int* __restrict__ local_offs,
+                                                            const int* __restrict__ real_counts, int n_local,
+                                                            int max_rows) {
+  const int total = min(local_offs[n_local - 1], max_rows);   // (an overflowing dispatch is reported by meta[1])
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < total; r += warps) {
+    int lo = 0, hi = n_local - 1;            // first segment whose end is beyond r
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (local_offs[mid] > r) hi = mid; else lo = mid + 1;
+    }
+    const int start = lo ? local_offs[lo - 1] : 0;
+    const bool live = r - start < real_counts[lo];
+    uint4* d = dst + (int64_t)r * row_vecs;
+    const uint4* s = src + (int64_t)r * row_vecs;
+    if (live) {
+      for (int i = lane; i < row_vecs; i += 32) d[i] = s[i];
+    } else {
+      for (int i = lane; i < row_vecs; i += 32) d[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
 
 extern "C" {
 
@@ -479,11 +512,12 @@ int cb_moe_router_topk(const void* logits, float* w_out, int* idx_out, float* pr
 // meta int[2]; pos int[T*K] (output)
 int cb_moe_ep_dispatch(const void* x, const int* topk_idx, const void* const* rows, const void* const* flags,
                        const void* const* counts, int* counts_local, int* cursor, int* send_off, int64_t* local_counts,
-                       int* local_offs, int* meta, int* pos, unsigned int* done_ctr, int tokens, int K, int H,
-                       int64_t x_stride, int E, int capacity, int rank, int world, uint32_t epoch, int dtype,
-                       cudaStream_t st) {
-  if (world > MAX_PEERS || E % world != 0 || H % 8 != 0) return (int)cudaErrorInvalidValue;
+                       int* local_offs, int* real_counts, int* meta, int* pos, unsigned int* done_ctr, int tokens, int K,
+                       int H, int64_t x_stride, int E, int capacity, int align, int rank, int world, uint32_t epoch,
+                       int dtype, cudaStream_t st) {
+  if (world > MAX_PEERS || E % world != 0 || H % 8 != 0 || align < 1) return (int)cudaErrorInvalidValue;
   EpParams p = make_ep(rows, flags, counts, rank, world, E, capacity, epoch);
+  p.align = align;
   const int n = tokens * K;
   cudaMemsetAsync(counts_local, 0, sizeof(int) * E, st);
   cudaMemsetAsync(cursor, 0, sizeof(int) * E, st);
@@ -492,7 +526,8 @@ int cb_moe_ep_dispatch(const void* x, const int* topk_idx, const void* const* ro
     if (g > 148) g = 148;
     ep_histogram_kernel<<<g, 256, E * sizeof(int), st>>>(topk_idx, n, E, counts_local);
   }
-  ep_exchange_counts_kernel<<<1, 256, 2 * E * sizeof(int), st>>>(p, counts_local, send_off, local_counts, local_offs, meta);
+  ep_exchange_counts_kernel<<<1, 256, 2 * E * sizeof(int), st>>>(p, counts_local, send_off, local_counts, local_offs,
+                                                                 real_counts, meta);
   int grid = (n + 7) / 8;
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
@@ -501,6 +536,15 @@ int cb_moe_ep_dispatch(const void* x, const int* topk_idx, const void* const* ro
                                                  x_stride, 1, meta, done_ctr);
   });
   ep_wait_kernel<<<1, 32, 0, st>>>(p, SLOT_ROWS);
+  return CB_LAUNCH_CHECK();
+}
+
+// dst[r] = live row ? src[r] : 0 over the rows of the padded local layout (see ep_take_rows_kernel); row_bytes % 16 == 0
+int cb_moe_ep_take_rows(void* dst, const void* src, int64_t row_bytes, const int* local_offs, const int* real_counts,
+                        int n_local, int max_rows, cudaStream_t st) {
+  if (row_bytes % 16 != 0 || n_local < 1) return (int)cudaErrorInvalidValue;
+  ep_take_rows_kernel<<<148 * 4, 256, 0, st>>>((uint4*)dst, (const uint4*)src, (int)(row_bytes / 16), local_offs,
+                                               real_counts, n_local, max_rows);
   return CB_LAUNCH_CHECK();
 }
 

@@ -25,6 +25,7 @@ from ..parallel import comm
 __all__ = ["EPWorkspace", "ep_workspace", "available", "dispatch", "combine", "moe_forward_fused"]
 
 _lib = None
+ALIGN = 128     # row alignment of every local expert's segment in the receive layout (k-block of the grouped wgrad GEMM)
 _workspaces: Dict[Tuple[int, int, int], "EPWorkspace"] = {}
 
 
@@ -125,7 +126,7 @@ def ep_workspace(group, hidden: int, dtype: torch.dtype, num_experts: int, rows_
     factor = float(os.environ.get("CB200_EP_CAPACITY_FACTOR", "0"))
     worst = rows_per_rank * world
     cap = worst if factor <= 0 else min(worst, int(rows_per_rank * factor))
-    cap = (cap + 127) // 128 * 128
+    cap = (cap + 127) // 128 * 128 + (num_experts // world) * ALIGN      # every local expert's segment is ALIGN-padded
     if world > 1:
         # symmetric allocations must have the same size on every rank: agree on the largest request
         t = torch.tensor([cap], device="cuda", dtype=torch.int64)
@@ -145,8 +146,9 @@ class EPContext:
     topk_idx: torch.Tensor      # int32 [T, K]
     pos: torch.Tensor           # int32 [T*K] row of (t,k) in the owner's buffer
     meta: torch.Tensor          # int32 [2]
-    local_counts: torch.Tensor  # int64 [n_local]
-    local_offs: torch.Tensor    # int32 [n_local]
+    local_counts: torch.Tensor  # int64 [n_local] rows per local expert segment, padded to ALIGN
+    local_offs: torch.Tensor    # int32 [n_local] inclusive cumsum of local_counts
+    real_counts: torch.Tensor   # int32 [n_local] rows actually received per local expert
     tokens: int
     K: int
 
@@ -160,6 +162,8 @@ def _push_assign(ws: EPWorkspace, x: torch.Tensor, idx32: torch.Tensor) -> EPCon
     send_off = torch.empty(ws.E, dtype=torch.int32, device=dev)
     local_counts = torch.empty(n_local, dtype=torch.int64, device=dev)
     local_offs = torch.empty(n_local, dtype=torch.int32, device=dev)
+    real_counts = torch.empty(n_local, dtype=torch.int32, device=dev)
+    local_counts.cb200_aligned = True       # grouped_linear: segments start / end on multiples of 128, padding is zero
     meta = torch.zeros(2, dtype=torch.int32, device=dev)
     pos = torch.empty(T * K, dtype=torch.int32, device=dev)
     ws.check_overflow()
@@ -167,8 +171,9 @@ def _push_assign(ws: EPWorkspace, x: torch.Tensor, idx32: torch.Tensor) -> EPCon
     loader.check(lib.cb_moe_ep_dispatch(
         loader.ptr(x), loader.ptr(idx32), ws.rows_in.ptr_array(ws.world), ws.flags.ptr_array(ws.world),
         ws.counts.ptr_array(ws.world), loader.ptr(ws.counts_local), loader.ptr(ws.cursor), loader.ptr(send_off),
-        loader.ptr(local_counts), loader.ptr(local_offs), loader.ptr(meta), loader.ptr(pos), loader.ptr(ws.done_ctr),
-        T, K, H, ctypes.c_int64(x.stride(0)), ws.E, ws.capacity, ws.rank, ws.world, ctypes.c_uint32(epoch),
+        loader.ptr(local_counts), loader.ptr(local_offs), loader.ptr(real_counts), loader.ptr(meta), loader.ptr(pos),
+        loader.ptr(ws.done_ctr), T, K, H, ctypes.c_int64(x.stride(0)), ws.E, ws.capacity, ALIGN, ws.rank, ws.world,
+        ctypes.c_uint32(epoch),
         code(x.dtype), loader.stream_ptr()), "moe_ep_dispatch")
     loader.launch_counter.add("moe_ep_dispatch", 5)
     host = torch.empty(2, dtype=torch.int32, pin_memory=True)
@@ -176,7 +181,21 @@ def _push_assign(ws: EPWorkspace, x: torch.Tensor, idx32: torch.Tensor) -> EPCon
     ev = torch.cuda.Event()
     ev.record()
     ws._pending_meta = (host, ev)
-    return EPContext(ws, idx32, pos, meta, local_counts, local_offs, T, K)
+    return EPContext(ws, idx32, pos, meta, local_counts, local_offs, real_counts, T, K)
+
+
+def _take_rows(ctx: EPContext, src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Copy the rows of the local receive layout out of (or into) a symmetric buffer: live rows are copied, the padding
+    of every expert segment is zero-filled, the over-allocated tail of the buffer is not touched (no traffic that
+    scales with the worst-case capacity, no host sync on the row count)."""
+    if dst is None:
+        dst = torch.empty_like(src)
+    n_local = ctx.local_offs.numel()
+    loader.check(_get_lib().cb_moe_ep_take_rows(
+        loader.ptr(dst), loader.ptr(src), ctypes.c_int64(src.shape[1] * src.element_size()), loader.ptr(ctx.local_offs),
+        loader.ptr(ctx.real_counts), n_local, min(src.shape[0], dst.shape[0]), loader.stream_ptr()), "moe_ep_take_rows")
+    loader.launch_counter.add("moe_ep_take_rows")
+    return dst
 
 
 def _push_known(ctx: EPContext, x: torch.Tensor, scale: Optional[torch.Tensor]) -> torch.Tensor:
@@ -199,7 +218,7 @@ def _pull(ctx: EPContext, y_rows: torch.Tensor, w: Optional[torch.Tensor], keep:
     H = ws.hidden
     out_view = ws.view(ws.rows_out)
     if y_rows.data_ptr() != out_view.data_ptr():
-        out_view[: y_rows.shape[0]].copy_(y_rows)
+        _take_rows(ctx, y_rows, out_view[: y_rows.shape[0]])
     out = torch.empty(ctx.tokens, H, dtype=ws.dtype, device=y_rows.device)
     ys = torch.empty(ctx.tokens * ctx.K, H, dtype=ws.dtype, device=y_rows.device) if keep else None
     epoch = ws.next_epoch()
@@ -217,7 +236,7 @@ class FusedEPDispatch(torch.autograd.Function):
         ep = _push_assign(ws, x.contiguous() if x.stride(1) != 1 else x, idx32)
         ep_ctx_holder.append(ep)
         ctx.ep = ep
-        rows = ws.view(ws.rows_in).clone()       # autograd-owned copy (the symmetric buffer is recycled per layer)
+        rows = _take_rows(ep, ws.view(ws.rows_in))   # autograd-owned copy (the symmetric buffer is recycled per layer)
         ctx.mark_non_differentiable(ep.local_counts)
         return rows, ep.local_counts
 
@@ -242,7 +261,7 @@ class FusedEPCombine(torch.autograd.Function):
         w, ys = ctx.saved_tensors
         ep = ctx.ep
         dout = dout.contiguous()
-        d_rows = _push_known(ep, dout, w)[: ctx.rows].clone()
+        d_rows = _take_rows(ep, _push_known(ep, dout, w)[: ctx.rows])
         dw = None
         if ys.numel():
             dw = (ys.view(ep.tokens, ep.K, -1).float() * dout.float()[:, None, :]).sum(-1).to(ctx.w_dtype)
@@ -255,6 +274,7 @@ def dispatch(x: torch.Tensor, topk_idx: torch.Tensor, num_experts: int, group) -
     ws = ep_workspace(group, H, x.dtype, num_experts, T * K)
     holder: list = []
     rows, local_counts = FusedEPDispatch.apply(x, holder, ws, topk_idx.to(torch.int32).contiguous())
+    local_counts.cb200_aligned = True
     return rows, local_counts, holder[0]
 
 

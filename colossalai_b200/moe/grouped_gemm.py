@@ -84,9 +84,10 @@ def _pad_groups(counts: torch.Tensor, rows: int, device) -> Tuple[torch.Tensor, 
     pends = torch.cumsum(pc, 0)
     pstarts = pends - pc
     row = torch.arange(rows, device=device)
-    g = torch.searchsorted(ends, row, right=True).clamp_(max=E - 1)
-    dest = row + (pstarts - starts)[g]
+    g = torch.searchsorted(ends, row, right=True)
     bound = (rows + E * (ALIGN - 1) + ALIGN - 1) // ALIGN * ALIGN
+    # rows past the last group (a caller's over-allocated buffer) go to a dump row behind the padded layout
+    dest = torch.where(g < E, row + (pstarts - starts)[g.clamp(max=E - 1)], torch.full_like(row, bound))
     return dest, pends.to(torch.int32), bound
 
 
@@ -115,9 +116,9 @@ class _GroupedLinearNative(torch.autograd.Function):
                 dw = _native_wgrad(dy, x, offs, w.shape[0], w.dtype)
             else:
                 dest, poffs, bound = _pad_groups(counts, x.shape[0], x.device)
-                xp = torch.zeros(bound, x.shape[1], dtype=x.dtype, device=x.device).index_copy_(0, dest, x)
-                dyp = torch.zeros(bound, dy.shape[1], dtype=dy.dtype, device=x.device).index_copy_(0, dest, dy)
-                dw = _native_wgrad(dyp, xp, poffs, w.shape[0], w.dtype)
+                xp = torch.zeros(bound + 1, x.shape[1], dtype=x.dtype, device=x.device).index_copy_(0, dest, x)
+                dyp = torch.zeros(bound + 1, dy.shape[1], dtype=dy.dtype, device=x.device).index_copy_(0, dest, dy)
+                dw = _native_wgrad(dyp[:bound], xp[:bound], poffs, w.shape[0], w.dtype)
         return dx, dw, None, None
 
 
@@ -154,7 +155,7 @@ def grouped_linear(x: torch.Tensor, w: torch.Tensor, counts: torch.Tensor, align
     range starts and ends on a multiple of 128 (zero rows as padding) - the weight-gradient GEMM then runs without the
     re-layout pass."""
     if native_ok(x, w):
-        return _GroupedLinearNative.apply(x, w, counts, aligned)
+        return _GroupedLinearNative.apply(x, w, counts, aligned or getattr(counts, "cb200_aligned", False))
     if x.is_cuda and hasattr(torch, "_grouped_mm") and x.dtype == torch.bfloat16 and x.shape[0] > 0 \
             and x.shape[1] % 8 == 0 and w.shape[1] % 8 == 0:
         offs = _offs(counts, x.device)

@@ -169,6 +169,14 @@ class Chunk:
             t = self.cuda_global_chunk[: self.utilized_size]
         return bool(t is not None and (not torch.isfinite(t).all()))
 
+    def nonfinite_flag(self) -> Optional[torch.Tensor]:
+        """Device-side 0/1 int32 tensor version of `has_inf_or_nan` (no host sync: the backward pass adds it into the
+        overflow counter and keeps launching)."""
+        t = self.cuda_shard if self.cuda_shard is not None else self.cpu_shard
+        if self.is_gathered and self.cuda_global_chunk is not None:
+            t = self.cuda_global_chunk[: self.utilized_size]
+        return None if t is None else (~torch.isfinite(t).all()).to(torch.int32)
+
     @property
     def num_tensors(self) -> int:
         return len(self.tensors_info)
@@ -177,7 +185,8 @@ class Chunk:
         t = self.cuda_shard if self.cuda_shard is not None else self.cpu_shard
         if self.is_gathered and self.cuda_global_chunk is not None:
             t = self.cuda_global_chunk[: self.utilized_size]
-        self.l2_norm = float(torch.sum(t.float() ** 2).item()) if t is not None else 0.0
+        # kept as a tensor on the shard's device: the optimizer sums the per-chunk values and reads them back once
+        self.l2_norm = torch.sum(t.float() ** 2) if t is not None else 0.0
 
     # ------------------------------------------------------------------ construction
     def append_tensor(self, tensor: torch.Tensor) -> None:

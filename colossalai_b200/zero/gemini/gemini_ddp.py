@@ -251,8 +251,9 @@ class GeminiDDP(ModelWrapper):
         cm.trans_tensor_state(p, TensorState.HOLD_AFTER_BWD)
         if gchunk.can_reduce:
             cm.reduce_chunk(gchunk)
-            if gchunk.has_inf_or_nan:
-                self.overflow_counter += 1
+            flag = gchunk.nonfinite_flag()
+            if flag is not None:
+                self.overflow_counter += flag.to(self.overflow_counter.device)
             gchunk.set_l2_norm()
             tgt = self.grads_device[p]
             if tgt.type == "cpu" and get_accelerator().name != "cpu":

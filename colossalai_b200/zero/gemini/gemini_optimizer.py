@@ -141,12 +141,12 @@ class GeminiOptimizer(OptimizerWrapper):
             c.grad_chunk = None
 
     def _calc_global_norm(self) -> float:
-        total = 0.0
+        dev = get_accelerator().get_current_device()
+        t = torch.zeros(1, dtype=torch.float64, device=dev)
         for c in self.chunk16_set:
             g = c.grad_chunk
             if g is not None and g.l2_norm is not None:
-                total += g.l2_norm
-        t = torch.tensor([total], dtype=torch.float64, device=get_accelerator().get_current_device())
+                t += g.l2_norm.to(device=dev, dtype=torch.float64) if torch.is_tensor(g.l2_norm) else g.l2_norm
         if dist.is_initialized():
             dist.all_reduce(t, group=self.module.zero_group)
             if self.tp_size > 1:

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count")
     ap.add_argument("--cuda_graph", action="store_true")
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--profile", default="", help="write a per-kernel breakdown of 8 decode steps to this file")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "this benchmark needs a GPU"
     cfg = get_config(args.model, **({"num_hidden_layers": args.layers} if args.layers else {}))
@@ -86,6 +87,29 @@ def main():
                 "decode_frac_of_measured_hbm_roofline": roof_ms / out["decode_ms_per_step"],
                 "prefill_tflops": 2.0 * n_params * args.batch_size * args.in_len / (t_prefill / 1e3) / 1e12})
     print(json.dumps(out), flush=True)
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        eng.add_request(prompts_token_ids=prompts, generation_config=gen)
+        eng.step()
+        for _ in range(4):
+            eng.step()
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(8):
+                eng.step()
+            torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 8 * 1e3
+        while eng.request_handler.check_unfinished_reqs():
+            eng.step()
+        evs = [e for e in prof.key_averages() if e.device_time_total > 0 and str(e.device_type).endswith("CUDA")]
+        tot = sum(e.device_time_total for e in evs) / 8 / 1e3
+        with open(args.profile, "w") as f:
+            f.write(f"# decode step: wall {wall:.3f} ms (under profiler), sum of GPU kernel time {tot:.3f} ms/step\n")
+            for e in sorted(evs, key=lambda e: -e.device_time_total)[:25]:
+                f.write(f"{e.device_time_total / 8 / 1e3:9.4f} ms/step  x{e.count / 8:7.1f}  {e.key[:110]}\n")
 
 
 if __name__ == "__main__":

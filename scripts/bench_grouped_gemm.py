@@ -68,6 +68,28 @@ def main():
                 row["native_fwd_bwd_tflops"] = 3 * fl / row["native_fwd_bwd_ms"] / 1e9
             except Exception as e:
                 row["native_fwd_bwd_error"] = f"{type(e).__name__}: {str(e)[:160]}"
+            # the three GEMMs separately, on a 128-aligned group layout (what the fused EP dispatch produces)
+            ca = (counts // 128 * 128)
+            ca[0] += rows - ca.sum()
+            offa = torch.cumsum(ca.cuda(), 0).int()
+            try:
+                row["native_dgrad_ms"] = timeit(lambda: gg._native_fwd(dy, w, offa, False))
+                row["native_wgrad_ms"] = timeit(lambda: gg._native_wgrad(dy, x, offa, E, torch.bfloat16))
+                row["native_wgrad_tflops"] = fl / row["native_wgrad_ms"] / 1e9
+                row["native_wgrad_unaligned_ms"] = timeit(lambda: gg._GroupedLinearNative.backward(
+                    type("C", (), {"saved_tensors": (x, w, c, offs), "aligned": False,
+                                   "needs_input_grad": (False, True, False, False)})(), dy))
+            except Exception as e:
+                row["native_split_error"] = f"{type(e).__name__}: {str(e)[:160]}"
+            if hasattr(torch, "_grouped_mm"):
+                def fb_lib():
+                    y = torch._grouped_mm(xg, wg.transpose(-2, -1), offs=offs)
+                    y.backward(dy)
+                    xg.grad = wg.grad = None
+                try:
+                    row["grouped_mm_fwd_bwd_ms"] = timeit(fb_lib, 5)
+                except Exception as e:
+                    row["grouped_mm_fwd_bwd_error"] = f"{type(e).__name__}: {str(e)[:160]}"
         print("GROUPED_GEMM " + json.dumps(row), flush=True)
 
 
