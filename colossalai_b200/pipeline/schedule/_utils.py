@@ -91,3 +91,8 @@ def merge_batch(data: List[Any], batch_size_dim: int = 0) -> Any:
         else:
             merged.append(list(leaves))
     return tree_unflatten(merged, spec)
+
+
+def default_criterion(outputs: Any, inputs: Any) -> torch.Tensor:
+    """Loss of a model that computes it itself (dict with a "loss" entry, or an object with `.loss`)."""
+    return outputs["loss"] if isinstance(outputs, dict) else outputs.loss

@@ -12,7 +12,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
-__all__ = ["ScheduledNode", "PipelineGraph", "interleaved_1f1b_schedule", "COMM_TYPES"]
+__all__ = ["ScheduledNode", "PipelineGraph", "interleaved_1f1b_schedule", "one_f_one_b_schedule", "COMM_TYPES"]
 
 COMM_TYPES = ("SEND_FORWARD", "RECV_FORWARD", "SEND_BACKWARD", "RECV_BACKWARD")
 
@@ -220,3 +220,11 @@ def interleaved_1f1b_schedule(n_stage: int, n_micro: int, n_chunk: int) -> List[
     compute = _list_schedule(n_stage, n_micro, n_chunk, False, False, 2, 2, 2, 0, 1.0, -1.0, 0.0, None,
                              warmup_cap=[max(c, 1) for c in cap])
     return _insert_comm(compute, n_stage, n_chunk, False)
+
+
+def one_f_one_b_schedule(n_stage: int, n_micro: int) -> List[List[ScheduledNode]]:
+    """Plain 1F1B as a node list: one chunk per stage, backward preferred over forward, at most `n_stage - stage`
+    forwards in flight on a stage (its warm-up depth plus the one of the steady 1F1B pair)."""
+    compute = _list_schedule(n_stage, n_micro, 1, False, False, 2, 2, 2, 0, 1.0, -1.0, 0.0, None,
+                             warmup_cap=[n_stage - s for s in range(n_stage)])
+    return _insert_comm(compute, n_stage, 1, False)

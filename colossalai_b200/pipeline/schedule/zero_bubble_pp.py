@@ -24,9 +24,9 @@ from ...interface import OptimizerWrapper
 from ..p2p import P2PMetadata, create_send_metadata
 from ..stage_manager import PipelineStageManager
 from ..weight_grad_store import WeightGradStore
-from ._utils import detach, get_batch_size, get_micro_batch, merge_batch, model_forward, retain_grad
+from ._utils import (default_criterion, detach, get_batch_size, get_micro_batch, merge_batch, model_forward,
+                     retain_grad)
 from .base import PipelineSchedule
-from .one_f_one_b import default_criterion
 from .v_schedule import PipelineGraph, ScheduledNode, _locate, _stage_of
 
 __all__ = ["ZeroBubbleVPipeScheduler", "NodeListScheduler"]
@@ -72,9 +72,12 @@ def _dev(group) -> torch.device:
 
 
 class NodeListScheduler(PipelineSchedule):
-    """Executes per-stage `ScheduledNode` lists."""
+    """Executes per-stage `ScheduledNode` lists.  `schedule` is the list itself or a function `n_micro -> list` (the
+    list is then built as soon as the number of micro-batches is known, and rebuilt when it changes)."""
 
-    def __init__(self, stage_manager: PipelineStageManager, schedule: List[List[ScheduledNode]], num_model_chunks: int,
+    def __init__(self, stage_manager: PipelineStageManager,
+                 schedule: Union[List[List[ScheduledNode]], Callable[[int], List[List[ScheduledNode]]]],
+                 num_model_chunks: int,
                  num_microbatch: Optional[int] = None, microbatch_size: Optional[int] = None, v_shape: bool = True,
                  split_w: bool = True, enable_metadata_cache: bool = True, overlap_p2p: bool = True,
                  recv_lookahead: int = 1) -> None:
@@ -87,6 +90,12 @@ class NodeListScheduler(PipelineSchedule):
         self.last_batch_size = None
         self.enable_metadata_cache = enable_metadata_cache
         self.recv_lookahead = recv_lookahead
+        self._schedule_fn = schedule if callable(schedule) else None
+        self._built_for: Optional[int] = None
+        if self._schedule_fn is not None:
+            self._built_for = num_microbatch
+            schedule = self._schedule_fn(num_microbatch) if num_microbatch is not None \
+                else [[] for _ in range(stage_manager.num_stages)]
         self.full_schedule = schedule
         self.channels = _Channels(stage_manager) if stage_manager.num_stages > 1 else None
         self._meta_cache: Dict[Tuple, P2PMetadata] = {}
@@ -115,6 +124,13 @@ class NodeListScheduler(PipelineSchedule):
                 if ds == sm.stage:
                     self.incoming[s].append(key)
         self._incoming_template = {k: list(v) for k, v in self.incoming.items()}
+
+    def load_batch(self, data_iter, device=None) -> None:
+        super().load_batch(data_iter, device)
+        if self._schedule_fn is not None and self._built_for != self.num_microbatch:
+            self.full_schedule = self._schedule_fn(self.num_microbatch)
+            self._prepare(self.full_schedule)
+            self._built_for = self.num_microbatch
 
     def reset_metadata_cache(self) -> None:
         self._meta_cache.clear()
