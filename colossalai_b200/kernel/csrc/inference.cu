@@ -15,8 +15,8 @@
 // Capability parity: reference inference_ops_cuda (extensions/csrc/kernel/cuda/{flash_decoding_attention,
 // decode_kv_cache_memcpy,context_kv_cache_memcpy,fused_rotary_emb_and_cache,get_cos_and_sin,convert_fp8}_kernel.cu,
 // N12-N19) and the Triton twins (kernel/triton/{flash_decoding,kvcache_copy,no_pad_rotary_embedding}.py).
-// Decode attention is HBM-bound (every K/V byte is read once): the design goal is full-sector 16-byte loads and enough
-// CTAs (seqs x kv_heads x splits >= 2 waves of 148 SMs) rather than tensor cores.
+// Decode attention is HBM-bound (every K/V byte is read once): the design goal is full-sector 16-byte loads, many of them
+// in flight per SM, and enough CTAs (seqs x kv_heads x splits >= 2 waves of 2 x 148) rather than tensor cores.
 #include "common.cuh"
 
 namespace {
@@ -167,14 +167,33 @@ __global__ void __launch_bounds__(256) rope_kv_cache_write_vec_kernel(
 
 // One CTA: sequence `seq`, kv head `kvh`, KV partition `split`.  q: [num_seqs, Hq, D].
 // partial outputs: o_part [num_seqs, Hq, splits, D] fp32, ml_part [num_seqs, Hq, splits, 2] (max, sumexp)
+//
+// Work mapping (the kernel is HBM-bound: every K/V byte is read once, so the job is to keep many full-sector loads in
+// flight per SM and to spend few instructions per byte):
+//   * a K or V row of one (token, kv head) is D contiguous elements; LPT = D/16 adjacent lanes cover one row with two
+//     16-byte loads each, so a warp reads 32/LPT whole rows per pass (fully used 32-byte sectors, 128-byte lines);
+//   * DEC_U passes are issued back to back before anything is consumed: 4 x (K + V) x 32 lanes x 32 B = 8 KB in flight
+//     per warp, all through registers (no shared-memory staging, no block-wide barrier in the main loop);
+//   * the query rows live in registers (GH = 4 query heads per warp, the lane's 16 dims of each); a GQA group wider
+//     than 4 is split over the CTA's warps (the second read of a K/V row by the sibling warp set is an L1/L2 hit);
+//   * every lane group keeps its OWN online-softmax state (m, l, o) for the tokens it sees - no cross-lane traffic in
+//     the loop except the log2(LPT) shuffles that finish a dot product; the 32/LPT states of a warp are merged once at
+//     the end, then the warps through shared memory.
+constexpr int DEC_U = 4;    // passes in flight
+constexpr int DEC_GH = 4;   // query heads per warp
+
 template <typename T, typename TC, int D>
-__global__ void __launch_bounds__(DEC_THREADS) paged_decode_kernel(
+__global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
     const T* __restrict__ q, const TC* __restrict__ k_cache, const TC* __restrict__ v_cache,
     const int* __restrict__ block_tables, const int* __restrict__ seq_lens, float* __restrict__ o_part,
     float* __restrict__ ml_part, int Hq, int Hkv, int block_size, int max_blocks_per_seq, int splits, int part_len,
     float scale, const float* __restrict__ alibi_slopes, int64_t q_stride, int window) {
-  constexpr int VEC = 16 / sizeof(TC);          // cache elements per 16-byte load
-  constexpr int DV = D / 32;                    // output dims owned by a lane
+  static_assert(sizeof(TC) == 2, "the paged cache is read as 16-byte vectors of 16-bit elements");
+  constexpr int EPL = 16;                       // elements of a row owned by a lane
+  constexpr int LPT = D / EPL;                  // lanes per token row: 4 / 8 / 16
+  constexpr int TPW = 32 / LPT;                 // token rows per warp pass
+  constexpr int NW = DEC_THREADS / 32;
+  constexpr int GH = DEC_GH, U = DEC_U;
   const int seq = blockIdx.x, kvh = blockIdx.y, split = blockIdx.z;
   const int G = Hq / Hkv;
   const int len = seq_lens[seq];
@@ -182,101 +201,126 @@ __global__ void __launch_bounds__(DEC_THREADS) paged_decode_kernel(
   // the window start contribute nothing (m = -inf, l = 0) and are skipped by the merge
   const int window_start = window > 0 ? max(0, len - window) : 0;
   const int t0 = max(split * part_len, window_start), t1 = min(len, split * part_len + part_len);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = DEC_THREADS / 32;
-  __shared__ float q_s[MAX_GROUP][D];
-  __shared__ float red_m[DEC_THREADS / 32][MAX_GROUP], red_l[DEC_THREADS / 32][MAX_GROUP];
-  __shared__ float red_o[DEC_THREADS / 32][MAX_GROUP][D];
-  for (int i = threadIdx.x; i < G * D; i += DEC_THREADS) {
-    const int g = i / D, d = i - g * D;
-    q_s[g][d] = to_f32<T>(q[(int64_t)seq * q_stride + (int64_t)(kvh * G + g) * D + d]) * scale;
-  }
-  __syncthreads();
-  float m[MAX_GROUP], l[MAX_GROUP], o[MAX_GROUP][DV];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsets = (G + GH - 1) / GH;          // sets of <= 4 query heads; each set is served by NW / nsets warps
+  const int wps = NW / nsets;
+  const int set = warp / wps, wi = warp - set * wps;
+  const int g0 = set * GH;
+  const int ng = set < nsets ? min(GH, G - g0) : 0;
+  const int grp = lane / LPT, sub = lane - grp * LPT;
+  __shared__ float red_m[NW][GH], red_l[NW][GH];
+  __shared__ float red_o[NW][GH][D];
+
+  float qr[GH][EPL];
 #pragma unroll
-  for (int g = 0; g < MAX_GROUP; ++g) {
+  for (int g = 0; g < GH; ++g) {
+    const T* qp = q + (int64_t)seq * q_stride + (int64_t)(kvh * G + g0 + (g < ng ? g : 0)) * D + sub * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) qr[g][e] = g < ng ? to_f32<T>(qp[e]) * scale : 0.f;
+  }
+  float slope[GH];
+#pragma unroll
+  for (int g = 0; g < GH; ++g) slope[g] = (alibi_slopes && g < ng) ? alibi_slopes[kvh * G + g0 + g] : 0.f;
+  float m[GH], l[GH], o[GH][EPL];
+#pragma unroll
+  for (int g = 0; g < GH; ++g) {
     m[g] = -INFINITY; l[g] = 0.f;
 #pragma unroll
-    for (int j = 0; j < DV; ++j) o[g][j] = 0.f;
+    for (int e = 0; e < EPL; ++e) o[g][e] = 0.f;
   }
   const int* bt = block_tables + seq * max_blocks_per_seq;
-  // each warp walks chunks of 32 tokens: lane i scores token (base + i) against all G query heads
-  for (int base = t0 + warp * 32; base < t1; base += nwarps * 32) {
-    const int t = base + lane;
-    float s[MAX_GROUP];
+  if (ng > 0) {
+    for (int base = t0 + wi * (TPW * U); base < t1; base += wps * (TPW * U)) {
+      Vec16<TC> kk[U][2], vv[U][2];
+      bool ok[U];
 #pragma unroll
-    for (int g = 0; g < MAX_GROUP; ++g) s[g] = -INFINITY;
-    if (t < t1) {
-      const int blk = bt[t / block_size];
-      const TC* kr = k_cache + (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D;
-#pragma unroll
-      for (int g = 0; g < MAX_GROUP; ++g) if (g < G) s[g] = 0.f;
-#pragma unroll 4
-      for (int d = 0; d < D; d += VEC) {
-        Vec16<TC> kv;
-        kv.load_nc(kr + d);
-#pragma unroll
-        for (int g = 0; g < MAX_GROUP; ++g) {
-          if (g < G) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) s[g] += q_s[g][d + e] * kv.get(e);
-          }
+      for (int u = 0; u < U; ++u) {
+        const int t = base + u * TPW + grp;
+        ok[u] = t < t1;
+        if (ok[u]) {
+          const int blk = bt[t / block_size];
+          const int64_t row = (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D + sub * EPL;
+          kk[u][0].load_nc(k_cache + row); kk[u][1].load_nc(k_cache + row + 8);
+          vv[u][0].load_nc(v_cache + row); vv[u][1].load_nc(v_cache + row + 8);
+        } else {
+          kk[u][0].raw = kk[u][1].raw = vv[u][0].raw = vv[u][1].raw = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      if (alibi_slopes) {
+      float sc[U][GH];
 #pragma unroll
-        for (int g = 0; g < MAX_GROUP; ++g) if (g < G) s[g] += alibi_slopes[kvh * G + g] * (float)(t - (len - 1));
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int g = 0; g < GH; ++g) {
+          float acc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc += qr[g][e] * kk[u][0].get(e);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * kk[u][1].get(e);
+#pragma unroll
+          for (int off = LPT / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          const int t = base + u * TPW + grp;
+          acc += slope[g] * (float)(t - (len - 1));
+          sc[u][g] = ok[u] ? acc : -INFINITY;
+        }
       }
-    }
-    // online softmax across the 32 tokens of this chunk
-    float p[MAX_GROUP];
 #pragma unroll
-    for (int g = 0; g < MAX_GROUP; ++g) {
-      if (g < G) {
-        const float cm = warp_max(s[g]);
-        const float nm = fmaxf(m[g], cm);
-        const float corr = __expf(m[g] - nm);
-        p[g] = (t < t1) ? __expf(s[g] - nm) : 0.f;
-        l[g] = l[g] * corr + warp_sum(p[g]);
+      for (int g = 0; g < GH; ++g) {
+        float nm = m[g];
+#pragma unroll
+        for (int u = 0; u < U; ++u) nm = fmaxf(nm, sc[u][g]);
+        const float corr = (nm == -INFINITY) ? 1.f : __expf(m[g] - nm);
+        l[g] *= corr;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float p = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
+          l[g] += p;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[g][e] += p * vv[u][0].get(e);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[g][8 + e] += p * vv[u][1].get(e);
+        }
         m[g] = nm;
-#pragma unroll
-        for (int j = 0; j < DV; ++j) o[g][j] *= corr;
-      }
-    }
-    // V accumulation: every lane owns DV output dims; token probabilities are broadcast by shuffle
-    const int n_tok = min(32, t1 - base);
-    for (int tt = 0; tt < n_tok; ++tt) {
-      const int tok = base + tt;
-      const int blk = bt[tok / block_size];
-      const TC* vr = v_cache + (((int64_t)blk * block_size + tok % block_size) * Hkv + kvh) * D + lane * DV;
-      float vv[DV];
-#pragma unroll
-      for (int j = 0; j < DV; ++j) vv[j] = kv_to_f32<TC>(vr[j]);
-#pragma unroll
-      for (int g = 0; g < MAX_GROUP; ++g) {
-        if (g < G) {
-          const float pg = __shfl_sync(0xffffffffu, p[g], tt);
-#pragma unroll
-          for (int j = 0; j < DV; ++j) o[g][j] += pg * vv[j];
-        }
       }
     }
   }
-  // merge the warps of this CTA
-  for (int g = 0; g < G; ++g) {
-    if (lane == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
+  // merge the TPW lane-group states of the warp (butterfly over the group index)
 #pragma unroll
-    for (int j = 0; j < DV; ++j) red_o[warp][g][lane * DV + j] = o[g][j];
+  for (int off = LPT; off < 32; off <<= 1) {
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m[g], off);
+      const float lo = __shfl_xor_sync(0xffffffffu, l[g], off);
+      const float nm = fmaxf(m[g], mo);
+      const float c1 = (m[g] == -INFINITY) ? 0.f : __expf(m[g] - nm);
+      const float c2 = (mo == -INFINITY) ? 0.f : __expf(mo - nm);
+      l[g] = l[g] * c1 + lo * c2;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o[g][e] = o[g][e] * c1 + __shfl_xor_sync(0xffffffffu, o[g][e], off) * c2;
+      m[g] = nm;
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+      if (sub == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) red_o[warp][g][sub * EPL + e] = o[g][e];
+    }
   }
   __syncthreads();
+  // merge the warps of each query-head set
   for (int i = threadIdx.x; i < G * D; i += DEC_THREADS) {
     const int g = i / D, d = i - g * D;
+    const int st = g / GH, gl = g - st * GH;
     float gm = -INFINITY;
-    for (int w = 0; w < nwarps; ++w) gm = fmaxf(gm, red_m[w][g]);
+    for (int w = st * wps; w < (st + 1) * wps; ++w) gm = fmaxf(gm, red_m[w][gl]);
     float acc = 0.f, ls = 0.f;
-    for (int w = 0; w < nwarps; ++w) {
-      const float c = (red_m[w][g] == -INFINITY) ? 0.f : __expf(red_m[w][g] - gm);
-      acc += red_o[w][g][d] * c;
-      ls += red_l[w][g] * c;
+    for (int w = st * wps; w < (st + 1) * wps; ++w) {
+      const float c = (red_m[w][gl] == -INFINITY) ? 0.f : __expf(red_m[w][gl] - gm);
+      acc += red_o[w][gl][d] * c;
+      ls += red_l[w][gl] * c;
     }
     const int64_t oi = (((int64_t)seq * Hq + kvh * G + g) * splits + split);
     o_part[oi * D + d] = acc;
@@ -381,10 +425,10 @@ int cb_rope_kv_cache_write(void* q, void* k, const void* v, void* k_cache, void*
 }
 
 int cb_decode_num_splits(int num_seqs, int kv_heads, int max_len, int* part_len_out) {
-  // enough CTAs for >= 2 waves, partitions of >= 256 tokens
-  const int target = 2 * cb_num_sms();
+  // two CTAs are resident per SM: aim at >= 2 waves of 2 x SMs CTAs, partitions of >= 128 tokens
+  const int target = 4 * cb_num_sms();
   int splits = (target + num_seqs * kv_heads - 1) / (num_seqs * kv_heads);
-  const int max_splits = (max_len + 255) / 256;
+  const int max_splits = (max_len + 127) / 128;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int part = (max_len + splits - 1) / splits;
