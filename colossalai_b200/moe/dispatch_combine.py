@@ -45,6 +45,22 @@ def _use_fused(x: torch.Tensor, num_experts: int, ep_group) -> bool:
     return ok and ((ep_group is not None and comm.group_size(ep_group) > 1) or _BACKEND == "fused")
 
 
+def _aligned_rows(x: torch.Tensor) -> bool:
+    """Lay the expert-grouped rows out with every expert's range padded to 128 rows (zero rows): the native grouped
+    weight-gradient GEMM then needs no re-layout pass (moe/grouped_gemm.py)."""
+    return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16)
+            and os.environ.get("CB200_GROUPED_GEMM", "native") == "native"
+            and torch.cuda.get_device_capability(x.device)[0] == 10)
+
+
+def _padded_counts(counts: torch.Tensor) -> torch.Tensor:
+    from .grouped_gemm import ALIGN
+
+    pc = (counts + ALIGN - 1) // ALIGN * ALIGN
+    pc.cb200_aligned = True
+    return pc
+
+
 def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, experts, num_experts: int,
                 ep_group: Optional[dist.ProcessGroup]) -> torch.Tensor:
     """x [T, H]; topk_w [T, k] fp32; topk_idx [T, k] -> [T, H]."""
@@ -59,9 +75,9 @@ def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, e
     flat_idx = topk_idx.reshape(-1)                                    # [T*k]
     order = torch.argsort(flat_idx, stable=True)                       # rows grouped by global expert id
     token_of = order // k
-    xs = x.index_select(0, token_of)                                   # [T*k, H]  (autograd: index_add in bwd)
     counts = torch.bincount(flat_idx, minlength=num_experts)           # rows per global expert
     if ep > 1:
+        xs = x.index_select(0, token_of)                               # [T*k, H]  (autograd: index_add in bwd)
         # exchange per-expert counts: recv_counts[src, e_local]
         recv_counts = torch.empty_like(counts)
         dist.all_to_all_single(recv_counts, counts, group=ep_group)
@@ -76,15 +92,37 @@ def moe_forward(x: torch.Tensor, topk_w: torch.Tensor, topk_idx: torch.Tensor, e
         seg_len = rc.reshape(-1)
         row_expert = torch.repeat_interleave(seg_expert, seg_len, output_size=n_rows)
         perm = torch.argsort(row_expert, stable=True)
-        grouped = recv.index_select(0, perm)
         local_counts = rc.sum(0)
-        y = experts(grouped, local_counts)
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(n_rows, device=x.device)
-        y = y.index_select(0, inv)
+        if _aligned_rows(x):
+            from .grouped_gemm import _pad_groups
+
+            slot_sorted, _, bound = _pad_groups(local_counts, n_rows, x.device)   # slot of the i-th row in expert order
+            slot = torch.empty_like(perm)
+            slot[perm] = slot_sorted                                              # slot of every received row
+            grouped = recv.new_zeros(bound, H).index_copy(0, slot, recv)
+            y = experts(grouped, _padded_counts(local_counts)).index_select(0, slot)
+        else:
+            grouped = recv.index_select(0, perm)
+            y = experts(grouped, local_counts)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(n_rows, device=x.device)
+            y = y.index_select(0, inv)
         ys = AllToAllUneven.apply(y, recv_splits, send_splits, ep_group)
+    elif _aligned_rows(x):
+        # no expert parallelism: gather the token rows straight into the padded layout (padding slots read a zero row
+        # appended to x and are combined with weight 0 into a scratch row) - no host sync, same number of passes
+        from .grouped_gemm import _pad_groups
+
+        slot, _, bound = _pad_groups(counts, T * k, x.device)
+        src = torch.full((bound,), T, dtype=torch.int64, device=x.device).index_copy_(0, slot, token_of)
+        x_ext = torch.cat([x, x.new_zeros(1, H)])
+        ys = experts(x_ext.index_select(0, src), _padded_counts(counts))
+        w_pad = torch.zeros(bound, dtype=ys.dtype, device=x.device).index_copy(
+            0, slot, topk_w.reshape(-1).index_select(0, order).to(ys.dtype))
+        out = torch.zeros(T + 1, H, dtype=ys.dtype, device=x.device).index_add(0, src, ys * w_pad.unsqueeze(-1))
+        return out[:T]
     else:
-        ys = experts(xs, counts)
+        ys = experts(x.index_select(0, token_of), counts)
     # weighted combine back to token order
     wsorted = topk_w.reshape(-1).index_select(0, order).to(ys.dtype).unsqueeze(-1)
     out = torch.zeros(T, H, dtype=ys.dtype, device=x.device)
