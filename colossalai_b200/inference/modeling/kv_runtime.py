@@ -63,12 +63,25 @@ class PagedKVRuntime:
             return self._attend_windowed(q, k, v, kc, vc, scale, alibi_slopes, sliding_window)
         return self._attend_full(q, k, v, kc, vc, scale, alibi_slopes)
 
+    def _native_prefill(self, q, k, v, scale, window: int, alibi_slopes) -> Optional[torch.Tensor]:
+        """Sliding-window / ALiBi prefill inside the tcgen05 flash kernel (packed batch, device-resident boundaries);
+        None when the tensors are outside the kernel's envelope (CPU tests, head_dim other than 64 / 128, fp32)."""
+        from ...ops import flash_attn_native as fan
+
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        if not fan.supported(q, k, v, self.cu_seqlens, self.cu_seqlens, force=True):
+            return None
+        return fan.flash_prefill(q, k, v, self.cu_seqlens, scale, window=window, alibi_slopes=alibi_slopes)
+
     def _attend_windowed(self, q, k, v, kc, vc, scale, alibi_slopes, window: int) -> torch.Tensor:
         """Sliding-window attention (Mistral): a sequence longer than the window takes the banded reference path —
         prefill with an explicit band mask per sequence, decode over the last `window` cached tokens."""
         from ...ops.attention import attention_ref
 
         if self.is_prompt:
+            native = self._native_prefill(q, k, v, scale, window, alibi_slopes)
+            if native is not None:
+                return native
             cu = self.cu_seqlens.tolist()
             outs = []
             for i in range(len(cu) - 1):
@@ -104,6 +117,9 @@ class PagedKVRuntime:
             from .backends.attention_backend import AttentionMetaData, ReferenceAttentionBackend
 
             if self.is_prompt:
+                native = self._native_prefill(q, k, v, scale, 0, alibi_slopes)
+                if native is not None:
+                    return native
                 md = AttentionMetaData(q, k, v, kc, vc, self.block_tables, self.block_size, cu_seqlens=self.cu_seqlens,
                                        sm_scale=scale, alibi_slopes=alibi_slopes)
                 return ReferenceAttentionBackend().prefill(md)

@@ -63,6 +63,9 @@ struct FaParams {
   int has_prev;
   int out_dtype;
   uint32_t idesc_qk, idesc_pv;
+  // EXTRA variant of the kernel only (inference prefill of sliding-window / ALiBi models):
+  int window;                        // > 0: query q sees keys (q - window, q]; key tiles left of every window are skipped
+  const float* alibi;                // [hq] slopes (score += slope * (key - query)), or null
 };
 
 SM100_DEVICE float fast_exp2(float x) {
@@ -71,7 +74,7 @@ SM100_DEVICE float fast_exp2(float x) {
   return y;
 }
 
-template <int D>
+template <int D, bool EXTRA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const FaParams p) {
@@ -121,7 +124,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int kv_row0 = seq_row0 >= 0 ? seq_row0 : b * p.seqlen_k;
   const int kv_tiles_all = (len_k + BLOCK_KV - 1) / BLOCK_KV;
   // causal with seqlen_q == seqlen_k: key tiles 0..q_tile; otherwise all of them
-  const int kv_tiles = p.causal ? min(q_tile + 1, kv_tiles_all) : kv_tiles_all;
+  const int kv_last = p.causal ? min(q_tile + 1, kv_tiles_all) : kv_tiles_all;   // one past the last visible key tile
+  // sliding window: the lowest key any row of this query tile can see is (q_tile * BLOCK_Q - window + 1)
+  const int kv_first = (EXTRA && p.window > 0) ? max(0, q_tile * BLOCK_Q - p.window + 1) / BLOCK_KV : 0;
+  const int kv_tiles = kv_last - kv_first;         // tiles walked; loop index j <-> key tile kv_first + j
   const bool ragged_k = (len_k % BLOCK_KV) != 0;   // the last key tile runs past the end of the sequence
 
   if (warp == 0 && lane == 0) {
@@ -164,7 +170,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint8_t* sk = smem_kv + stage * C::KV_STAGE_BYTES;
         uint8_t* sv = sk + C::K_BYTES;
         mbar_arrive_expect_tx(&kv_full[stage], C::KV_STAGE_BYTES);
-        const int row = kv_row0 + j * BLOCK_KV;
+        const int row = kv_row0 + (kv_first + j) * BLOCK_KV;
 #pragma unroll
         for (int h = 0; h < D / 64; ++h) {
           tma_load_2d(&tmap_k, &kv_full[stage], sk + h * (BLOCK_KV * 128), kv_head * D + h * 64, row);   // K-major B
@@ -249,16 +255,20 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
     uint8_t* p_row = smem_p + r * 128;
+    const float slope2 = (EXTRA && p.alibi != nullptr) ? p.alibi[head] * 1.4426950408889634f : 0.f;
+    (void)slope2;
     for (int j = 0; j < kv_tiles; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_addr + sb * BLOCK_KV;
-      const bool diag = p.causal && (j == q_tile);
-      const bool tail_k = ragged_k && (j == kv_tiles_all - 1);
-      const bool masked = diag || tail_k;
+      const int kt = kv_first + j;                                       // key tile of this step
+      const bool diag = p.causal && (kt == q_tile);
+      const bool tail_k = ragged_k && (kt == kv_tiles_all - 1);
+      const bool masked = diag || tail_k || (EXTRA && p.window > 0);
       const int k_lim = diag ? min(q_pos, len_k - 1) : (len_k - 1);      // last visible key position of this row
-      const int k_base = j * BLOCK_KV;
+      const int k_low = (EXTRA && p.window > 0) ? q_pos - p.window + 1 : 0;   // first visible key position
+      const int k_base = kt * BLOCK_KV;
       // ---- pass 1: row max
       float m_tile = -INFINITY;
 #pragma unroll 1
@@ -269,7 +279,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (masked && (k_base + c + i) > k_lim) s = -INFINITY;
+          if (EXTRA) s = fmaf(slope2, (float)(k_base + c + i - q_pos), s);
+          if (masked && ((k_base + c + i) > k_lim || (EXTRA && (k_base + c + i) < k_low))) s = -INFINITY;
           m_tile = fmaxf(m_tile, s);
         }
       }
@@ -292,8 +303,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < 32; i += 2) {
           float s0 = __uint_as_float(v[i]) * p.scale_log2;
           float s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-          if (masked && (k_base + c + i) > k_lim) s0 = -INFINITY;
-          if (masked && (k_base + c + i + 1) > k_lim) s1 = -INFINITY;
+          if (EXTRA) {
+            s0 = fmaf(slope2, (float)(k_base + c + i - q_pos), s0);
+            s1 = fmaf(slope2, (float)(k_base + c + i + 1 - q_pos), s1);
+          }
+          if (masked && ((k_base + c + i) > k_lim || (EXTRA && (k_base + c + i) < k_low))) s0 = -INFINITY;
+          if (masked && ((k_base + c + i + 1) > k_lim || (EXTRA && (k_base + c + i + 1) < k_low))) s1 = -INFINITY;
           const float p0 = fast_exp2(s0 - m_safe);
           const float p1 = fast_exp2(s1 - m_safe);
           l_tile += p0 + p1;
@@ -388,7 +403,7 @@ template <int D>
 int launch_flash_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int seqlen_q,
                      int seqlen_k, int hq, int hkv, int causal, float scale, int dtype, cudaStream_t stream,
                      const int* cu_seqlens = nullptr, long long total_tokens = 0, float* o_state = nullptr,
-                     int has_prev = 0) {
+                     int has_prev = 0, int window = 0, const float* alibi = nullptr) {
   using C = FaCfg<D>;
   const bool bf16 = dtype == CB_BF16;
   CUtensorMap tq, tk, tv;
@@ -406,19 +421,25 @@ int launch_flash_fwd(const void* q, const void* k, const void* v, void* out, flo
   p.batch = batch; p.seqlen_q = seqlen_q; p.seqlen_k = seqlen_k; p.hq = hq; p.hkv = hkv; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.lse = lse; p.out_dtype = dtype;
+  p.window = window; p.alibi = alibi;
   p.idesc_qk = make_idesc_f16(BLOCK_Q, BLOCK_KV, bf16 ? 1 : 0, 0, 0);      // S[128 x 128] = Q (K-major) x K (K-major)
   p.idesc_pv = make_idesc_f16(BLOCK_Q, D, bf16 ? 1 : 0, 0, 1);              // O[128 x D]  = P (K-major) x V (MN-major)
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(flash_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   // packed: at most total/128 + batch query tiles exist; uniform: ceil(seqlen / 128) per sequence
   dim3 grid(cu_seqlens ? (unsigned)(total_tokens / BLOCK_Q + batch) : (unsigned)((seqlen_q + BLOCK_Q - 1) / BLOCK_Q), hq,
             cu_seqlens ? 1 : batch);
-  flash_fwd_kernel<D><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  if (window > 0 || alibi != nullptr)
+    flash_fwd_kernel<D, true><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  else
+    flash_fwd_kernel<D, false><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   return (int)cudaGetLastError();
 }
 
@@ -945,6 +966,23 @@ int cb_flash_attn_varlen_fwd(const void* q, const void* k, const void* v, void* 
     return launch_flash_fwd<128>(q, k, v, out, lse, batch, 0, 0, hq, hkv, causal, scale, dtype, stream, cu_seqlens, total_tokens);
   if (head_dim == 64)
     return launch_flash_fwd<64>(q, k, v, out, lse, batch, 0, 0, hq, hkv, causal, scale, dtype, stream, cu_seqlens, total_tokens);
+  return (int)cudaErrorInvalidValue;
+}
+
+// Packed causal forward for inference prefill with a sliding window (Mistral: query q sees keys (q - window, q]) and /
+// or ALiBi slopes ([hq] fp32: score += slope * (key - query); BLOOM, Baichuan-13B).  Forward only.
+int cb_flash_attn_varlen_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse,
+                                const int* cu_seqlens, int batch, long long total_tokens, int hq, int hkv, int head_dim,
+                                float scale, int window, const float* alibi_slopes, int dtype, cudaStream_t stream) {
+  if (batch <= 0 || total_tokens <= 0) return 0;
+  if (hq % hkv || (dtype != CB_BF16 && dtype != CB_F16) || cu_seqlens == nullptr || window < 0)
+    return (int)cudaErrorInvalidValue;
+  if (head_dim == 128)
+    return launch_flash_fwd<128>(q, k, v, out, lse, batch, 0, 0, hq, hkv, 1, scale, dtype, stream, cu_seqlens,
+                                 total_tokens, nullptr, 0, window, alibi_slopes);
+  if (head_dim == 64)
+    return launch_flash_fwd<64>(q, k, v, out, lse, batch, 0, 0, hq, hkv, 1, scale, dtype, stream, cu_seqlens,
+                                total_tokens, nullptr, 0, window, alibi_slopes);
   return (int)cudaErrorInvalidValue;
 }
 

@@ -92,6 +92,28 @@ def flash_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, cau
     return out, lse
 
 
+def flash_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, scale: Optional[float],
+                  window: int = 0, alibi_slopes: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inference prefill over a packed batch (causal, forward only) with the two mask families the serving models need
+    inside the kernel: a sliding window (`window` > 0: query q sees keys (q - window, q]; key tiles left of every
+    window are never loaded) and ALiBi (`alibi_slopes` [Hq] fp32: score += slope * (key - query)).  Replaces the
+    per-sequence fp32 reference loops of the paged runtime (reference `kernel/triton/context_attn_unpad.py:193`,
+    alibi variant)."""
+    T, Hq, D = q.shape
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    out = torch.empty_like(q)
+    lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
+    cu = _cu32(cu_seqlens, q.device)
+    slopes = alibi_slopes.to(device=q.device, dtype=torch.float32).contiguous() if alibi_slopes is not None else None
+    rc = _get_lib().cb_flash_attn_varlen_fwd_ex(
+        loader.ptr(q), loader.ptr(k), loader.ptr(v), loader.ptr(out), loader.ptr(lse), loader.ptr(cu), cu.numel() - 1,
+        ctypes.c_longlong(T), Hq, k.shape[1], D, ctypes.c_float(scale), int(window or 0),
+        loader.ptr(slopes) if slopes is not None else ctypes.c_void_p(0), code(q.dtype), loader.stream_ptr())
+    loader.check(rc, "flash_attn_varlen_fwd_ex")
+    loader.launch_counter.add("flash_attn_prefill")
+    return out
+
+
 def bwd_supported(q: torch.Tensor, k: torch.Tensor, batch: int) -> bool:
     return (os.environ.get("CB200_FLASH_BWD", "native") == "native" and q.shape[-1] == 128 and q.shape[0] == k.shape[0])
 

@@ -119,6 +119,42 @@ def test_flash_varlen_fwd_bwd(lens, causal, Hq, Hkv):
         assert err <= 2e-2 * ref.abs().max().item() + 1e-3, f"{name}: max err {err:.4g}"
 
 
+@pytest.mark.parametrize("lens", [[300, 1000], [128, 640, 77], [2048]])
+@pytest.mark.parametrize("window,alibi", [(0, True), (100, False), (256, False), (130, True), (4096, False)])
+@pytest.mark.parametrize("Hq,Hkv,D", [(8, 2, 128), (4, 4, 64)])
+def test_flash_prefill_window_and_alibi(lens, window, alibi, Hq, Hkv, D):
+    """Inference prefill variant: sliding window and / or ALiBi inside the kernel vs an fp32 masked softmax."""
+    from colossalai_b200.ops import flash_attn_native as fa
+
+    dtype = torch.bfloat16
+    T = sum(lens)
+    torch.manual_seed(4)
+    q = torch.randn(T, Hq, D, device="cuda", dtype=dtype)
+    k = torch.randn(T, Hkv, D, device="cuda", dtype=dtype)
+    v = torch.randn(T, Hkv, D, device="cuda", dtype=dtype)
+    slopes = (2.0 ** -(torch.arange(1, Hq + 1, device="cuda").float() * 8.0 / Hq)) if alibi else None
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    out = fa.flash_prefill(q, k, v, cu, None, window=window, alibi_slopes=slopes)
+    torch.cuda.synchronize()
+    s0 = 0
+    g = Hq // Hkv
+    for n in lens:
+        qs = q[s0:s0 + n].float().transpose(0, 1)                                  # [Hq, n, D]
+        ks = k[s0:s0 + n].float().transpose(0, 1).repeat_interleave(g, 0)
+        vs = v[s0:s0 + n].float().transpose(0, 1).repeat_interleave(g, 0)
+        sc = qs @ ks.transpose(1, 2) / D ** 0.5
+        pos = torch.arange(n, device="cuda")
+        rel = pos[None, :] - pos[:, None]                                          # key - query
+        if alibi:
+            sc = sc + slopes[:, None, None] * rel[None].float()
+        keep = rel <= 0
+        if window > 0:
+            keep = keep & (rel > -window)
+        ref = (sc.masked_fill(~keep[None], float("-inf")).softmax(-1) @ vs).transpose(0, 1)
+        torch.testing.assert_close(out[s0:s0 + n].float(), ref, atol=2e-2, rtol=2e-2)
+        s0 += n
+
+
 @pytest.mark.parametrize("B,S", [(2, 200), (3, 64), (1, 1000)])
 def test_flash_ragged_uniform_lengths(B, S):
     """Equal-length batches whose length is not a multiple of 128."""
