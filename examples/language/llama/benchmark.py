@@ -46,11 +46,14 @@ def main():
     ap.add_argument("--comm_backend", default="nccl", choices=["nccl", "fused"])
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--offload", action="store_true", help="gemini: keep optimizer states on the host")
+    ap.add_argument("--offload_optim_frac", type=float, default=0.0,
+                    help="3d plugin: fraction of the ZeRO optimizer state tiered to pinned host memory (needs --zero 1/2)")
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (reduced-depth runs)")
     args = ap.parse_args()
 
     colossalai_b200.launch_from_torch()
     rank, world = dist.get_rank(), dist.get_world_size()
-    cfg = get_config(args.config)
+    cfg = get_config(args.config, **({"num_hidden_layers": args.layers} if args.layers else {}))
     if args.plugin == "3d":
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, sp_size=args.sp if args.sp > 1 else None,
                                       zero_stage=args.zero, precision=args.precision,
@@ -59,7 +62,9 @@ def main():
                                       microbatch_size=None if args.pp_style == "zbv" else args.mbs,
                                       num_microbatches=(args.batch_size // args.mbs) if args.pp_style == "zbv" else None,
                                       pp_style=args.pp_style, num_model_chunks=args.n_chunks, max_norm=1.0,
-                                      comm_backend=args.comm_backend)
+                                      comm_backend=args.comm_backend,
+                                      cpu_offload=args.offload_optim_frac > 0,
+                                      offload_optim_frac=args.offload_optim_frac if args.offload_optim_frac > 0 else 1.0)
     elif args.plugin in ("zero1", "zero2"):
         plugin = LowLevelZeroPlugin(stage=int(args.plugin[-1]), precision=args.precision, max_norm=1.0)
     elif args.plugin == "gemini":
@@ -117,6 +122,11 @@ def main():
         tok = args.batch_size * dp_size * args.max_length / t.item()
         if rank == 0:
             print(f"throughput: {tok:,.0f} tokens/s (max over ranks), {t.item() * 1e3:.1f} ms/step")
+        if use_events:
+            peak = torch.tensor(torch.cuda.max_memory_allocated() / 2**30, device=dev)
+            dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"peak device memory: {peak.item():.1f} GiB (max over ranks)")
     dist.barrier()
     colossalai_b200.initialize.shutdown()
 
