@@ -75,7 +75,44 @@ def decode():
         iops.paged_decode_attention(q, kc, vc, bt, sl, 0.088)
 
 
+def moe():
+    from colossalai_b200.moe import dispatch_combine as dc
+    from colossalai_b200.moe.grouped_gemm import grouped_linear
+    dc.set_moe_backend("fused")
+    x = torch.randn(8192, 4096, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(8, 4096, 4096, device="cuda", dtype=torch.bfloat16) * 0.02
+    lg = torch.randn(8192, 8, device="cuda")
+    for _ in range(4):
+        tw, ti = lg.softmax(-1).topk(2, -1)
+        dc.moe_forward(x, tw, ti, lambda r, c: grouped_linear(r, w, c), 8, None)
+
+
+def ce_rope():
+    from colossalai_b200.ops import cross_entropy as ce
+    logits = torch.randn(8192, 128256, device="cuda", dtype=torch.bfloat16)
+    tgt = torch.randint(0, 128256, (8192,), device="cuda")
+    one = torch.ones((), device="cuda")
+    for _ in range(4):
+        gmax = ce.row_max(logits)
+        st = ce.sumexp_and_target(logits, tgt, gmax, 0, -100)
+        ce.softmax_grad(logits, tgt, gmax, st[0], one, 0, -100)
+
+
+def kv_write():
+    from colossalai_b200.ops import inference as iops
+    T, Hkv, D, bs = 16384, 8, 128, 64
+    k = torch.randn(T, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn_like(k)
+    kc = torch.zeros(T // bs, bs, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    bt = torch.arange(T // bs, device="cuda", dtype=torch.int32).view(16, -1)
+    seq = torch.arange(T, device="cuda", dtype=torch.int32) // (T // 16)
+    pos = torch.arange(T, device="cuda", dtype=torch.int32) % (T // 16)
+    for _ in range(4):
+        iops.kv_cache_write(k, v, kc, vc, bt, seq, pos)
+
+
 if __name__ == "__main__":
     {"gemm": gemm, "flash_fwd": flash_fwd, "flash_bwd": flash_bwd, "grouped": grouped, "norm_glu": norm_glu, "adam": adam,
-     "decode": decode}[sys.argv[1]]()
+     "decode": decode, "moe": moe, "ce_rope": ce_rope, "kv_write": kv_write}[sys.argv[1]]()
     torch.cuda.synchronize()
