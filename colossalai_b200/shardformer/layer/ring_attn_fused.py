@@ -7,10 +7,15 @@ pass per hop on a second stream, and fp32 dKV buffers circulating around the rin
 B200-first design (one NVSwitch domain: every peer is one hop away at full bandwidth):
 
   * every rank PUBLISHES its K / V once per layer (GQA heads only) in a symmetric buffer; nobody forwards anything;
-  * the attention kernel of rank r reads the key / value tiles of block `src` STRAIGHT FROM RANK `src`'s HBM: the TMA
-    loads of its main loop are issued on a tensor map over the peer-mapped address, so the NVLink transfer is the
-    kernel's own operand fetch, tile by tile, overlapped with the tensor-core work of the previous tile (no staging
-    copy, no up-front gather);
+  * BACKWARD: the kernel of rank r reads the key / value tiles of block `src` STRAIGHT FROM RANK `src`'s HBM - its TMA
+    loads are issued on a tensor map over the peer-mapped address, so the NVLink transfer is the kernel's own operand
+    fetch (one CTA owns one key tile, so every remote byte crosses NVLink exactly once);
+  * FORWARD: one CTA owns one QUERY tile and walks over the whole key block, so direct peer loads would pull the block
+    once per query tile (peer memory is not cached in the local L2: measured at sp = 8, 16k local tokens, 34 GB per
+    hop over NVLink and 1.47x slower than the library ring).  The forward therefore pulls the next hop's K/V block
+    (GQA heads only, 67 MB at 16k tokens) over NVLink into a double-buffered local copy on a side stream while the
+    tensor cores work on the current hop; the kernels then read it through the L2 like local K/V.  No up-front
+    gather of all blocks, one hop of look-ahead;
   * the online-softmax state (fp32 output + log-sum-exp per query row) is carried from block to block INSIDE the
     kernel (`has_prev`): no separate merge / rescale pass, no fp32 `[T, H, D]` temporaries per hop;
   * backward: dQ accumulates locally in fp32 across blocks; the dK / dV contribution of rank r to block `src` is
@@ -80,10 +85,17 @@ class _RingWorkspace:
         self.rank = comm.group_rank(group)
         self.kv = [_SymmBuffer(kv_bytes, group), _SymmBuffer(kv_bytes, group)]
         self.dkv = _SymmBuffer(2 * kv_bytes, group, zero=True)        # fp32 accumulators: twice the 16-bit bytes
+        # forward: local landing buffers for the next hop's K/V block + the side stream that fills them
+        self.stage = [torch.empty(kv_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
         self.toggle = 0
         self.token = torch.zeros(1, device="cuda", dtype=torch.float32)
         torch.cuda.synchronize()
         dist.barrier(group=group)
+
+    def peer_bytes(self, which: int, src: int, nbytes: int) -> torch.Tensor:
+        """uint8 view of the first `nbytes` of rank `src`'s copy of published buffer `which` (peer-mapped memory)."""
+        return self.kv[which].handle.get_buffer(src, (nbytes,), torch.uint8)
 
     def barrier(self) -> None:
         """Stream-ordered rendezvous of the group (control plane, 4 bytes over NCCL)."""
@@ -128,13 +140,33 @@ class _FusedRing(torch.autograd.Function):
         es = q.element_size()
         kv_elems = T * Hkv * D
         ws = _workspace(sp_group, 2 * kv_elems * es)
-        buf = ws.kv[ws.toggle]
+        which = ws.toggle
+        buf = ws.kv[which]
         ws.toggle ^= 1
         # publish K then V (one contiguous [2, T, Hkv, D] block in the symmetric buffer)
-        pub = buf.tensor[: 2 * kv_elems * es].view(q.dtype).view(2, T, Hkv, D)
+        kv_bytes = 2 * kv_elems * es
+        pub = buf.tensor[:kv_bytes].view(q.dtype).view(2, T, Hkv, D)
         pub[0].copy_(k)
         pub[1].copy_(v)
         ws.barrier()
+        main = torch.cuda.current_stream()
+        published = torch.cuda.Event()
+        published.record(main)
+        order = _visit_order(r, sp)
+        landed = [None] * sp            # event: hop i's block is in stage[i % 2]
+        consumed = [None] * sp          # event: hop i's kernels are done with their K/V source
+
+        def pull(i: int) -> None:
+            with torch.cuda.stream(ws.copy_stream):
+                ws.copy_stream.wait_event(published)
+                if i >= 2 and consumed[i - 2] is not None:
+                    ws.copy_stream.wait_event(consumed[i - 2])      # stage[i % 2] was read by hop i - 2
+                ws.stage[i % 2][:kv_bytes].copy_(ws.peer_bytes(which, order[i], kv_bytes), non_blocking=True)
+                landed[i] = torch.cuda.Event()
+                landed[i].record(ws.copy_stream)
+
+        if sp > 1:
+            pull(1)
         o_state = torch.empty(T, Hq, D, dtype=torch.float32, device=q.device)
         lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
         lib = _get_lib()
@@ -142,8 +174,14 @@ class _FusedRing(torch.autograd.Function):
         stream = loader.stream_ptr()
         row_q, row_kv, row_o, row_l = Hq * D * es, Hkv * D * es, Hq * D * 4, Hq * 4
         started = [[False, False] for _ in range(batch)]
-        for src in _visit_order(r, sp):
-            base = buf.peer_ptrs[src]
+        for i, src in enumerate(order):
+            if i == 0:
+                base = buf.peer_ptrs[r]                      # own block: the published copy itself
+            else:
+                main.wait_event(landed[i])
+                base = ws.stage[i % 2].data_ptr()
+            if i + 1 < sp:
+                pull(i + 1)                                  # overlaps with this hop's kernels
             for b in range(batch):
                 for qh, kh, causal in _blocks(r, src):
                     q_off = b * S + qh * half
@@ -156,6 +194,8 @@ class _FusedRing(torch.autograd.Function):
                     loader.check(rc, "flash_attn_block_fwd")
                     started[b][qh] = True
                     stats["fwd_blocks"] += 1
+            consumed[i] = torch.cuda.Event()
+            consumed[i].record(main)
         loader.launch_counter.add("ring_attn_block_fwd", sp * batch * 2 + batch)
         stats["layers_fwd"] += 1
         out = o_state.to(q.dtype)
