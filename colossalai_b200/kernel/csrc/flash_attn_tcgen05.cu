@@ -41,7 +41,7 @@ template <int D> struct FaCfg {
   static constexpr int V_BYTES = BLOCK_KV * D * 2;
   static constexpr int P_BYTES = BLOCK_Q * BLOCK_KV * 2;
   static constexpr int KV_STAGE_BYTES = K_BYTES + V_BYTES;
-  static constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE_BYTES + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * KV_STAGE_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 512;
   static constexpr int O_COL = 256;
 };
@@ -84,7 +84,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint8_t* smem_q = smem;
   uint8_t* smem_kv = smem + C::Q_BYTES;
   uint8_t* smem_p = smem_kv + KV_STAGES * C::KV_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + C::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * C::P_BYTES);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [2]
   uint64_t* kv_empty = bars + 3;           // [2]
@@ -129,6 +129,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int kv_first = (EXTRA && p.window > 0) ? max(0, q_tile * BLOCK_Q - p.window + 1) / BLOCK_KV : 0;
   const int kv_tiles = kv_last - kv_first;         // tiles walked; loop index j <-> key tile kv_first + j
   const bool ragged_k = (len_k % BLOCK_KV) != 0;   // the last key tile runs past the end of the sequence
+  const bool resume = p.o_state != nullptr && p.has_prev != 0;   // block mode: continue from the stored state
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_q);
@@ -211,17 +212,21 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int j = 0; j < kv_tiles; ++j) {
       if (j + 1 < kv_tiles) issue_qk(j + 1);            // tensor pipe works on the next scores during softmax(j)
       const int stage = j % KV_STAGES;
-      mbar_wait(p_full, (uint32_t)(j & 1));
-      mbar_wait(o_empty, (uint32_t)((j & 1) ^ 1));
+      mbar_wait(p_full, (uint32_t)(j & 1));             // P_j is in shared memory (and O was rescaled if it had to be)
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sv = smem_u32(smem_kv + stage * C::KV_STAGE_BYTES + C::K_BYTES);
         const uint64_t dv = make_smem_desc_sw128(sv, BLOCK_KV * 128, 1024);        // MN-major: [keys, D] row-major
+        const uint64_t dpj = advance_desc(dp, (uint32_t)(j & 1) * C::P_BYTES);
+        // O accumulates in TMEM over all key tiles (the first MMA of the first tile overwrites, unless the
+        // accumulator was pre-loaded with the state of earlier launches)
+        const bool fresh = (j == 0) && !resume;
 #pragma unroll
         for (int k = 0; k < BLOCK_KV / UMMA_K; ++k) {
           const uint32_t ao = (k >> 2) * (128 * 128) + (k & 3) * (UMMA_K * 2);
           const uint32_t bo = k * (UMMA_K * 128);
-          umma_f16_ss(tmem_base + C::O_COL, advance_desc(dp, ao), advance_desc(dv, bo), p.idesc_pv, k > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + C::O_COL, advance_desc(dpj, ao), advance_desc(dv, bo), p.idesc_pv,
+                      (fresh && k == 0) ? 0u : 1u);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[stage]);                  // K_j and V_j are consumed once P_j V_j has retired
@@ -230,31 +235,42 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else {
     // ================================================================ softmax + output (warps 2..5)
+    // Thread = query row.  The output accumulator lives in TMEM for the whole walk (P_j V_j accumulates onto it in the
+    // tensor core); the exponentials are taken against a LAGGING row max: the accumulator is only rescaled when the
+    // true max has grown by more than 2^TAU since the last rescale (exact: numerator and denominator use the same
+    // reference, which is what the log-sum-exp is reported against).  Per key tile a thread therefore reads its 128
+    // scores ONCE (four tcgen05.ld in flight, one wait), releases the score buffer at once, and touches the
+    // accumulator only on the rare rescale.
+    constexpr float TAU = 8.f;
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;                   // query row inside the tile
     const int q_pos = q_tile * BLOCK_Q + r;              // position inside the sequence
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    float o_acc[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY;                             // running max in the exp2 domain
+    const uint32_t o_addr = tmem_base + lane_addr + C::O_COL;
+    float m_run = -INFINITY;                             // reference max of the exponentials (exp2 domain)
     float l_run = 0.f;
-    if (p.o_state != nullptr && p.has_prev && q_pos < len_q) {
-      // resume from the merged result of the key blocks processed by earlier launches (normalised output + LSE)
+    if (resume) {
+      // resume from the merged result of the key blocks processed by earlier launches (normalised output + LSE):
+      // every row stores its previous output (or zeros) into the TMEM accumulator, P_0 V_0 accumulates onto it
       const size_t row_ = (size_t)q_row0 + r;
-      const float lse_prev = p.lse[row_ * p.hq + head];
-      if (lse_prev > -INFINITY) {
-        m_run = lse_prev * 1.4426950408889634f;
-        l_run = 1.f;
-        const float4* src = reinterpret_cast<const float4*>(p.o_state + row_ * ((size_t)p.hq * D) + (size_t)head * D);
+      float lse_prev = -INFINITY;
+      if (q_pos < len_q) lse_prev = p.lse[row_ * p.hq + head];
+      const bool live = lse_prev > -INFINITY;
+      if (live) { m_run = lse_prev * 1.4426950408889634f; l_run = 1.f; }
+      const float4* src = reinterpret_cast<const float4*>(p.o_state + row_ * ((size_t)p.hq * D) + (size_t)head * D);
 #pragma unroll
-        for (int i = 0; i < D / 4; ++i) {
-          const float4 t4 = src[i];
-          o_acc[4 * i] = t4.x; o_acc[4 * i + 1] = t4.y; o_acc[4 * i + 2] = t4.z; o_acc[4 * i + 3] = t4.w;
+      for (int c = 0; c < D; c += 16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = live ? src[(c >> 2) + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          w[4 * i] = __float_as_uint(t4.x); w[4 * i + 1] = __float_as_uint(t4.y);
+          w[4 * i + 2] = __float_as_uint(t4.z); w[4 * i + 3] = __float_as_uint(t4.w);
         }
+        tmem_st_32x32b_x16(o_addr + c, w);
       }
+      tmem_st_wait();
     }
-    uint8_t* p_row = smem_p + r * 128;
     const float slope2 = (EXTRA && p.alibi != nullptr) ? p.alibi[head] * 1.4426950408889634f : 0.f;
     (void)slope2;
     for (int j = 0; j < kv_tiles; ++j) {
@@ -269,48 +285,62 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const int k_lim = diag ? min(q_pos, len_k - 1) : (len_k - 1);      // last visible key position of this row
       const int k_low = (EXTRA && p.window > 0) ? q_pos - p.window + 1 : 0;   // first visible key position
       const int k_base = kt * BLOCK_KV;
-      // ---- pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_addr + c, v);
-        tmem_ld_wait();
+      // ---- the whole score row into registers
+      uint32_t v[BLOCK_KV];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (EXTRA) s = fmaf(slope2, (float)(k_base + c + i - q_pos), s);
-          if (masked && ((k_base + c + i) > k_lim || (EXTRA && (k_base + c + i) < k_low))) s = -INFINITY;
-          m_tile = fmaxf(m_tile, s);
+      for (int c = 0; c < BLOCK_KV; c += 32) tmem_ld_32x32b_x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);          // S buffer may be overwritten by Q K_{j+2}^T
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BLOCK_KV; ++i) {
+        float sc = __uint_as_float(v[i]) * p.scale_log2;
+        if (EXTRA) sc = fmaf(slope2, (float)(k_base + i - q_pos), sc);
+        if (masked && ((k_base + i) > k_lim || (EXTRA && (k_base + i) < k_low))) sc = -INFINITY;
+        v[i] = __float_as_uint(sc);
+        m_tile = fmaxf(m_tile, sc);
+      }
+      // ---- lagging max / rare rescale of the TMEM accumulator
+      const float m_new = fmaxf(m_run, m_tile);
+      if (j == 0 && !resume) {
+        m_run = m_new;                                   // nothing accumulated yet
+      } else {
+        const bool need = (m_new - m_run) > TAU;         // (-inf) - (-inf) = NaN -> false
+        if (__any_sync(0xffffffffu, need)) {
+          if (j > 0) {                                   // P_{j-1} V_{j-1} has retired: the accumulator is stable
+            mbar_wait(o_full, (uint32_t)((j - 1) & 1));
+            tc_fence_after();
+          }
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < D; c += 32) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(o_addr + c, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st_32x32b_x16(o_addr + c, *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
+            tmem_st_32x32b_x16(o_addr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&t[16]));
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (need) m_run = m_new;
         }
       }
-      const float m_new = fmaxf(m_run, m_tile);
-      // a fully masked row cannot happen under the causal layout used here (key 0 is always visible), but keep the
-      // exponent finite anyway
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(m_run - m_safe);
-      // ---- pass 2: p = exp2(s - m), row sum, bf16 P into the swizzled K-major tile
-      // (the P buffer is free: o_full of tile j-1 - i.e. P_{j-1} V_{j-1} retired - was waited on in the accumulate
-      //  step of the previous iteration)
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;     // keeps the exponent finite on a fully masked row
+      // ---- p = exp2(s - m), row sum, 16-bit P into the swizzled K-major tile of buffer j & 1
+      // (that buffer was last read by P_{j-2} V_{j-2}, which retired before Q K_j^T - issued after it - completed)
+      uint8_t* p_row = smem_p + (j & 1) * C::P_BYTES + r * 128;
       float l_tile = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_addr + c, v);
-        tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]) * p.scale_log2;
-          float s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-          if (EXTRA) {
-            s0 = fmaf(slope2, (float)(k_base + c + i - q_pos), s0);
-            s1 = fmaf(slope2, (float)(k_base + c + i + 1 - q_pos), s1);
-          }
-          if (masked && ((k_base + c + i) > k_lim || (EXTRA && (k_base + c + i) < k_low))) s0 = -INFINITY;
-          if (masked && ((k_base + c + i + 1) > k_lim || (EXTRA && (k_base + c + i + 1) < k_low))) s1 = -INFINITY;
-          const float p0 = fast_exp2(s0 - m_safe);
-          const float p1 = fast_exp2(s1 - m_safe);
+          const float p0 = fast_exp2(__uint_as_float(v[c + i]) - m_use);
+          const float p1 = fast_exp2(__uint_as_float(v[c + i + 1]) - m_use);
           l_tile += p0 + p1;
           if (p.out_dtype == CB_BF16) {
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
@@ -330,65 +360,49 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
         }
       }
+      l_run += l_tile;
       tc_fence_before();
       fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);                       // S buffer may be overwritten by Q K_{j+2}^T
-        mbar_arrive(p_full);                             // P_j is in shared memory
-      }
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
-      // ---- O_j = P_j V_j back from TMEM: acc = acc * alpha + O_j
-      mbar_wait(o_full, (uint32_t)(j & 1));
-      tc_fence_after();
-      const uint32_t o_addr = tmem_base + lane_addr + C::O_COL;
-#pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(o_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);               // next P V may overwrite O_j (and P_j is free again)
+      if (lane == 0) mbar_arrive(p_full);                // P_j is in shared memory, the accumulator is consistent
     }
-    // ---- epilogue: normalise and store this thread's row
+    // ---- epilogue: the last P V has retired; normalise and store this thread's row
+    mbar_wait(o_full, (uint32_t)((kv_tiles - 1) & 1));
+    tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
     const size_t row = (size_t)q_row0 + r;
-    if (q_pos >= len_q) {
-      // a row past the end of its (packed) sequence: computed on garbage, never stored
-    } else if (p.o_state != nullptr) {
-      float4* dst = reinterpret_cast<float4*>(p.o_state + row * ((size_t)p.hq * D) + (size_t)head * D);
+    const bool row_ok = q_pos < len_q;                   // rows past the end of a (packed) sequence are never stored
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      uint32_t t[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(o_addr + c, t);                 // executed by every lane (warp-collective), stores predicated
+      tmem_ld_wait();
+      if (!row_ok) {
+        // a row past the end of its (packed) sequence: computed on garbage, never stored
+      } else if (p.o_state != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(p.o_state + row * ((size_t)p.hq * D) + (size_t)head * D + c);
 #pragma unroll
-      for (int i = 0; i < D / 4; ++i)
-        dst[i] = make_float4(o_acc[4 * i] * inv_l, o_acc[4 * i + 1] * inv_l, o_acc[4 * i + 2] * inv_l,
-                             o_acc[4 * i + 3] * inv_l);
-    } else if (p.out_dtype == CB_BF16) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * ((size_t)p.hq * D) + (size_t)head * D;
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(t[4 * i]) * inv_l, __uint_as_float(t[4 * i + 1]) * inv_l,
+                               __uint_as_float(t[4 * i + 2]) * inv_l, __uint_as_float(t[4 * i + 3]) * inv_l);
+      } else {
+        uint32_t w[16];
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(o_acc[c + 2 * i] * inv_l, o_acc[c + 2 * i + 1] * inv_l);
-          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = __uint_as_float(t[2 * i]) * inv_l, a1 = __uint_as_float(t[2 * i + 1]) * inv_l;
+          if (p.out_dtype == CB_BF16) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __half2 h = __floats2half2_rn(a0, a1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
         }
-        *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    } else {
-      __half* dst = reinterpret_cast<__half*>(p.out) + row * ((size_t)p.hq * D) + (size_t)head * D;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                              (row * ((size_t)p.hq * D) + (size_t)head * D + c) * 2);
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half2 h = __floats2half2_rn(o_acc[c + 2 * i] * inv_l, o_acc[c + 2 * i + 1] * inv_l);
-          w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
       }
     }
     if (p.lse && q_pos < len_q)
@@ -776,10 +790,10 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after();
     const size_t row = (size_t)kv_row0 + r;
     const size_t ld = (size_t)p.hkv * D;
-#pragma unroll 1
     // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every lane runs the loads, only the STORES are predicated on
     // the key being inside the sequence (a ragged last tile leaves some lanes of a warp without a row)
     const bool key_ok = key_pos < len;
+#pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t col0 = which == 0 ? C::COL_DV : C::COL_DK;
       const float mul = which == 0 ? 1.f : p.scale;
