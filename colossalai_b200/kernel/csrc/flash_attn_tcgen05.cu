@@ -293,15 +293,19 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);          // S buffer may be overwritten by Q K_{j+2}^T
+      // plain variant: the softmax scale (> 0) is folded into the exponent's FMA, the max is taken on the raw scores;
+      // EXTRA variant: scale and ALiBi bias are applied here and the exponent uses a unit multiplier
       float m_tile = -INFINITY;
 #pragma unroll
       for (int i = 0; i < BLOCK_KV; ++i) {
-        float sc = __uint_as_float(v[i]) * p.scale_log2;
-        if (EXTRA) sc = fmaf(slope2, (float)(k_base + i - q_pos), sc);
+        float sc = __uint_as_float(v[i]);
+        if (EXTRA) sc = fmaf(slope2, (float)(k_base + i - q_pos), sc * p.scale_log2);
         if (masked && ((k_base + i) > k_lim || (EXTRA && (k_base + i) < k_low))) sc = -INFINITY;
         v[i] = __float_as_uint(sc);
         m_tile = fmaxf(m_tile, sc);
       }
+      const float ex_mul = EXTRA ? 1.f : p.scale_log2;
+      m_tile *= ex_mul;
       // ---- lagging max / rare rescale of the TMEM accumulator
       const float m_new = fmaxf(m_run, m_tile);
       if (j == 0 && !resume) {
@@ -339,8 +343,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(__uint_as_float(v[c + i]) - m_use);
-          const float p1 = fast_exp2(__uint_as_float(v[c + i + 1]) - m_use);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c + i]), ex_mul, -m_use));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + i + 1]), ex_mul, -m_use));
           l_tile += p0 + p1;
           if (p.out_dtype == CB_BF16) {
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
