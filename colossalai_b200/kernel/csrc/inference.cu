@@ -172,14 +172,16 @@ __global__ void __launch_bounds__(256) rope_kv_cache_write_vec_kernel(
 // flight per SM and to spend few instructions per byte):
 //   * a K or V row of one (token, kv head) is D contiguous elements; LPT = D/16 adjacent lanes cover one row with two
 //     16-byte loads each, so a warp reads 32/LPT whole rows per pass (fully used 32-byte sectors, 128-byte lines);
-//   * DEC_U passes are issued back to back before anything is consumed: 4 x (K + V) x 32 lanes x 32 B = 8 KB in flight
-//     per warp, all through registers (no shared-memory staging, no block-wide barrier in the main loop);
+//   * two register stages of DEC_U passes each form a software pipeline: the loads of the next stage (2 x (K + V) x 32
+//     lanes x 32 B = 4 KB per warp) are issued before the current stage is consumed, so the FMA work of a warp overlaps
+//     its own memory latency (the first version, ncu: 8 warps / SM, 43 % issue-active, 2.4 TB/s, alternated load and
+//     compute); no shared-memory staging, no block-wide barrier in the main loop;
 //   * the query rows live in registers (GH = 4 query heads per warp, the lane's 16 dims of each); a GQA group wider
 //     than 4 is split over the CTA's warps (the second read of a K/V row by the sibling warp set is an L1/L2 hit);
 //   * every lane group keeps its OWN online-softmax state (m, l, o) for the tokens it sees - no cross-lane traffic in
 //     the loop except the log2(LPT) shuffles that finish a dot product; the 32/LPT states of a warp are merged once at
 //     the end, then the warps through shared memory.
-constexpr int DEC_U = 4;    // passes in flight
+constexpr int DEC_U = 2;    // passes per register stage (two stages: one being consumed, one in flight)
 constexpr int DEC_GH = 4;   // query heads per warp
 
 template <typename T, typename TC, int D>
@@ -229,60 +231,76 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
     for (int e = 0; e < EPL; ++e) o[g][e] = 0.f;
   }
   const int* bt = block_tables + seq * max_blocks_per_seq;
-  if (ng > 0) {
-    for (int base = t0 + wi * (TPW * U); base < t1; base += wps * (TPW * U)) {
-      Vec16<TC> kk[U][2], vv[U][2];
-      bool ok[U];
+  // one stage = U passes of the warp (U * TPW token rows): K and V vectors of this lane + validity of its rows
+  struct Stage { Vec16<TC> kk[U][2], vv[U][2]; bool ok[U]; };
+  auto load_stage = [&](int base, Stage& st) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = base + u * TPW + grp;
-        ok[u] = t < t1;
-        if (ok[u]) {
-          const int blk = bt[t / block_size];
-          const int64_t row = (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D + sub * EPL;
-          kk[u][0].load_nc(k_cache + row); kk[u][1].load_nc(k_cache + row + 8);
-          vv[u][0].load_nc(v_cache + row); vv[u][1].load_nc(v_cache + row + 8);
-        } else {
-          kk[u][0].raw = kk[u][1].raw = vv[u][0].raw = vv[u][1].raw = make_uint4(0u, 0u, 0u, 0u);
-        }
+    for (int u = 0; u < U; ++u) {
+      const int t = base + u * TPW + grp;
+      st.ok[u] = t < t1;
+      if (st.ok[u]) {
+        const int blk = bt[t / block_size];
+        const int64_t row = (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D + sub * EPL;
+        st.kk[u][0].load_nc(k_cache + row); st.kk[u][1].load_nc(k_cache + row + 8);
+        st.vv[u][0].load_nc(v_cache + row); st.vv[u][1].load_nc(v_cache + row + 8);
+      } else {
+        st.kk[u][0].raw = st.kk[u][1].raw = st.vv[u][0].raw = st.vv[u][1].raw = make_uint4(0u, 0u, 0u, 0u);
       }
-      float sc[U][GH];
+    }
+  };
+  auto consume = [&](int base, const Stage& st) {
+    float sc[U][GH];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int g = 0; g < GH; ++g) {
-          float acc = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc += qr[g][e] * kk[u][0].get(e);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * kk[u][1].get(e);
-#pragma unroll
-          for (int off = LPT / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-          const int t = base + u * TPW + grp;
-          acc += slope[g] * (float)(t - (len - 1));
-          sc[u][g] = ok[u] ? acc : -INFINITY;
-        }
-      }
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int g = 0; g < GH; ++g) {
-        float nm = m[g];
+        float acc = 0.f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) nm = fmaxf(nm, sc[u][g]);
-        const float corr = (nm == -INFINITY) ? 1.f : __expf(m[g] - nm);
-        l[g] *= corr;
+        for (int e = 0; e < 8; ++e) acc += qr[g][e] * st.kk[u][0].get(e);
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
+        for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * st.kk[u][1].get(e);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float p = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
-          l[g] += p;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[g][e] += p * vv[u][0].get(e);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[g][8 + e] += p * vv[u][1].get(e);
-        }
-        m[g] = nm;
+        for (int off = LPT / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        const int t = base + u * TPW + grp;
+        acc += slope[g] * (float)(t - (len - 1));
+        sc[u][g] = st.ok[u] ? acc : -INFINITY;
       }
+    }
+#pragma unroll
+    for (int g = 0; g < GH; ++g) {
+      float nm = m[g];
+#pragma unroll
+      for (int u = 0; u < U; ++u) nm = fmaxf(nm, sc[u][g]);
+      const float corr = (nm == -INFINITY) ? 1.f : __expf(m[g] - nm);
+      l[g] *= corr;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float p = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
+        l[g] += p;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[g][e] += p * st.vv[u][0].get(e);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[g][8 + e] += p * st.vv[u][1].get(e);
+      }
+      m[g] = nm;
+    }
+  };
+  if (ng > 0) {
+    // software pipeline over two register stages: the loads of the next stage are in flight while this one is consumed
+    const int step = wps * (TPW * U);
+    int base = t0 + wi * (TPW * U);
+    Stage sa, sb;
+    if (base < t1) load_stage(base, sa);
+    while (base < t1) {
+      if (base + step < t1) load_stage(base + step, sb);
+      consume(base, sa);
+      base += step;
+      if (base >= t1) break;
+      if (base + step < t1) load_stage(base + step, sa);
+      consume(base, sb);
+      base += step;
     }
   }
   // merge the TPW lane-group states of the warp (butterfly over the group index)
