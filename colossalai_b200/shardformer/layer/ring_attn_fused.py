@@ -165,7 +165,8 @@ class _FusedRing(torch.autograd.Function):
                 landed[i] = torch.cuda.Event()
                 landed[i].record(ws.copy_stream)
 
-        if sp > 1:
+        staged = os.environ.get("CB200_RING_STAGE", "1") == "1"      # 0: the kernels read the peer block directly
+        if sp > 1 and staged:
             pull(1)
         o_state = torch.empty(T, Hq, D, dtype=torch.float32, device=q.device)
         lse = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
@@ -175,12 +176,12 @@ class _FusedRing(torch.autograd.Function):
         row_q, row_kv, row_o, row_l = Hq * D * es, Hkv * D * es, Hq * D * 4, Hq * 4
         started = [[False, False] for _ in range(batch)]
         for i, src in enumerate(order):
-            if i == 0:
-                base = buf.peer_ptrs[r]                      # own block: the published copy itself
+            if i == 0 or not staged:
+                base = buf.peer_ptrs[src]                    # own block: the published copy itself
             else:
                 main.wait_event(landed[i])
                 base = ws.stage[i % 2].data_ptr()
-            if i + 1 < sp:
+            if i + 1 < sp and staged:
                 pull(i + 1)                                  # overlaps with this hop's kernels
             for b in range(batch):
                 for qh, kh, causal in _blocks(r, src):

@@ -198,3 +198,48 @@ def test_attention_frontend_packed_uses_native_kernels():
     _, _, rdq, rdk, rdv = _packed_reference(q.detach(), k.detach(), v.detach(), dout, lens, True)
     for got, ref in ((q.grad, rdq), (k.grad, rdk), (v.grad, rdv)):
         assert (got.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("rows,Hq,Hkv", [(256, 8, 2), (512, 4, 4), (1024, 8, 8)])
+@pytest.mark.parametrize("big_second", [False, True])
+def test_flash_block_mode_state_carry(rows, Hq, Hkv, big_second):
+    """Block mode (ring attention building block): the keys are visited as two blocks by two launches; the second
+    launch resumes from the fp32 (output, LSE) state of the first.  `big_second` scales the second block's keys so that
+    its scores dominate (the carried accumulator has to be rescaled inside the kernel)."""
+    import ctypes
+    import math
+
+    from colossalai_b200.kernel import loader
+    from colossalai_b200.ops._dtypes import code
+    from colossalai_b200.ops.attention import attention_with_lse_ref
+
+    D, dtype = 128, torch.bfloat16
+    lib = loader.load("cb200_attn")
+    torch.manual_seed(7)
+    q = torch.randn(rows, Hq, D, device="cuda", dtype=dtype)
+    k = torch.randn(2 * rows, Hkv, D, device="cuda", dtype=dtype)
+    v = torch.randn(2 * rows, Hkv, D, device="cuda", dtype=dtype)
+    if big_second:
+        k[rows:] *= 4.0
+    o_state = torch.empty(rows, Hq, D, device="cuda", dtype=torch.float32)
+    lse = torch.empty(rows, Hq, device="cuda", dtype=torch.float32)
+    scale = 1.0 / math.sqrt(D)
+    for blk, (causal, has_prev) in enumerate([(0, 0), (1, 1)]):
+        rc = lib.cb_flash_attn_block_fwd(loader.ptr(q), loader.ptr(k[blk * rows:]), loader.ptr(v[blk * rows:]),
+                                         loader.ptr(o_state), loader.ptr(lse), rows, Hq, Hkv, D, causal, has_prev,
+                                         ctypes.c_float(scale), code(dtype), loader.stream_ptr())
+        loader.check(rc, "flash_attn_block_fwd")
+    torch.cuda.synchronize()
+    # oracle: queries are the LAST `rows` positions of a 2*rows sequence (first block fully visible, second causal)
+    g = Hq // Hkv
+    qs = q.float().transpose(0, 1)
+    ks = k.float().transpose(0, 1).repeat_interleave(g, 0)
+    vs = v.float().transpose(0, 1).repeat_interleave(g, 0)
+    sc = qs @ ks.transpose(1, 2) * scale
+    qpos = torch.arange(rows, device="cuda") + rows
+    keep = torch.arange(2 * rows, device="cuda")[None, :] <= qpos[:, None]
+    sc = sc.masked_fill(~keep[None], float("-inf"))
+    ref = (sc.softmax(-1) @ vs).transpose(0, 1)
+    ref_lse = torch.logsumexp(sc, -1).transpose(0, 1)
+    torch.testing.assert_close(lse, ref_lse, atol=3e-3, rtol=3e-3)
+    torch.testing.assert_close(o_state, ref, atol=2e-2, rtol=2e-2)
