@@ -365,6 +365,11 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       l_run += l_tile;
+      // keep in step with the accumulator barrier: observe "P_{j-1} V_{j-1} retired" once per tile.  It completed long
+      // ago in the common case (no stall), but a parity wait is only unambiguous while the waiter is at most ONE phase
+      // behind - the epilogue's wait for the last tile would otherwise pass on the phase before the previous one
+      // (seen on hardware with two-tile launches: output read before the last two P V had landed).
+      if (j > 0) mbar_wait(o_full, (uint32_t)((j - 1) & 1));
       tc_fence_before();
       fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
       __syncwarp();

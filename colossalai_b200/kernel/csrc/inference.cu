@@ -26,6 +26,14 @@ constexpr int MAX_GROUP = 8;   // q heads per kv head handled by one CTA
 
 template <typename T> CB_DEVICE float kv_to_f32(T v) { return to_f32<T>(v); }
 
+// 16-byte asynchronous global -> shared copy; src_bytes < 16 zero-fills the rest (0 = pure zero fill)
+CB_DEVICE void cp_async_16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+CB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> CB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T, typename TC>
 __global__ void __launch_bounds__(256) kv_cache_write_kernel(const T* __restrict__ k, const T* __restrict__ v,
                                                              TC* __restrict__ k_cache, TC* __restrict__ v_cache,
@@ -172,16 +180,18 @@ __global__ void __launch_bounds__(256) rope_kv_cache_write_vec_kernel(
 // flight per SM and to spend few instructions per byte):
 //   * a K or V row of one (token, kv head) is D contiguous elements; LPT = D/16 adjacent lanes cover one row with two
 //     16-byte loads each, so a warp reads 32/LPT whole rows per pass (fully used 32-byte sectors, 128-byte lines);
-//   * two register stages of DEC_U passes each form a software pipeline: the loads of the next stage (2 x (K + V) x 32
-//     lanes x 32 B = 4 KB per warp) are issued before the current stage is consumed, so the FMA work of a warp overlaps
-//     its own memory latency (the first version, ncu: 8 warps / SM, 43 % issue-active, 2.4 TB/s, alternated load and
-//     compute); no shared-memory staging, no block-wide barrier in the main loop;
+//   * the rows travel through a per-warp cp.async ring in shared memory (DEC_STAGES stages of DEC_U passes = 4 KB each):
+//     3 stages = 12 KB per warp, ~96 KB per SM stay in flight while one stage is consumed - enough to cover the HBM
+//     latency at full bandwidth, independent of the register budget (the first two versions kept the rows in
+//     registers: 8 warps / SM at 255 registers, 43 % issue-active, 2.4 TB/s under ncu - load and FMA phases of a warp
+//     alternated, then only 32 KB per SM in flight); no block-wide barrier in the main loop;
 //   * the query rows live in registers (GH = 4 query heads per warp, the lane's 16 dims of each); a GQA group wider
 //     than 4 is split over the CTA's warps (the second read of a K/V row by the sibling warp set is an L1/L2 hit);
 //   * every lane group keeps its OWN online-softmax state (m, l, o) for the tokens it sees - no cross-lane traffic in
 //     the loop except the log2(LPT) shuffles that finish a dot product; the 32/LPT states of a warp are merged once at
 //     the end, then the warps through shared memory.
-constexpr int DEC_U = 2;    // passes per register stage (two stages: one being consumed, one in flight)
+constexpr int DEC_U = 2;    // passes of the warp per pipeline stage
+constexpr int DEC_STAGES = 4;   // shared-memory ring depth per warp (DEC_STAGES - 1 stages in flight)
 constexpr int DEC_GH = 4;   // query heads per warp
 
 template <typename T, typename TC, int D>
@@ -231,41 +241,55 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
     for (int e = 0; e < EPL; ++e) o[g][e] = 0.f;
   }
   const int* bt = block_tables + seq * max_blocks_per_seq;
-  // one stage = U passes of the warp (U * TPW token rows): K and V vectors of this lane + validity of its rows
-  struct Stage { Vec16<TC> kk[U][2], vv[U][2]; bool ok[U]; };
-  auto load_stage = [&](int base, Stage& st) {
+  // K/V travel through a per-warp ring of DEC_STAGES shared-memory stages filled with cp.async (16 bytes per lane and
+  // vector; a stage = U passes of the warp = U * TPW token rows, K and V): the bytes in flight are bounded by shared
+  // memory, not by registers, so DEC_STAGES - 1 stages (6 KB) per warp stay outstanding while one is consumed.  Every
+  // lane reads back exactly the vectors it requested itself (slot = [stage][k|v][pass][half][lane]), so no barrier is
+  // needed beyond cp.async.wait_group, and the 16-byte slots of a warp are consecutive (conflict-free LDS.128).
+  extern __shared__ __align__(16) unsigned char dec_smem[];
+  constexpr int NST = DEC_STAGES;
+  constexpr int STAGE_VECS = 2 * U * 2 * 32;                      // uint4 slots per stage: (K|V) x pass x half x lane
+  uint4* ring = reinterpret_cast<uint4*>(dec_smem) + (size_t)warp * NST * STAGE_VECS;
+  auto issue_stage = [&](int base, int stage) {
+    uint4* st = ring + stage * STAGE_VECS;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int t = base + u * TPW + grp;
-      st.ok[u] = t < t1;
-      if (st.ok[u]) {
-        const int blk = bt[t / block_size];
-        const int64_t row = (((int64_t)blk * block_size + t % block_size) * Hkv + kvh) * D + sub * EPL;
-        st.kk[u][0].load_nc(k_cache + row); st.kk[u][1].load_nc(k_cache + row + 8);
-        st.vv[u][0].load_nc(v_cache + row); st.vv[u][1].load_nc(v_cache + row + 8);
-      } else {
-        st.kk[u][0].raw = st.kk[u][1].raw = st.vv[u][0].raw = st.vv[u][1].raw = make_uint4(0u, 0u, 0u, 0u);
+      const bool ok = t < t1;
+      const int tt = ok ? t : t0;                                 // any valid row: src-size 0 zero-fills instead
+      const int blk = bt[tt / block_size];
+      const int64_t row = (((int64_t)blk * block_size + tt % block_size) * Hkv + kvh) * D + sub * EPL;
+      const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        cp_async_16(st + ((0 * U + u) * 2 + h) * 32 + lane, k_cache + row + h * 8, nbytes);
+        cp_async_16(st + ((1 * U + u) * 2 + h) * 32 + lane, v_cache + row + h * 8, nbytes);
       }
     }
   };
-  auto consume = [&](int base, const Stage& st) {
+  auto consume = [&](int base, int stage) {
+    const uint4* st = ring + stage * STAGE_VECS;
     float sc[U][GH];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      Vec16<TC> k0, k1;
+      k0.raw = st[((0 * U + u) * 2 + 0) * 32 + lane];
+      k1.raw = st[((0 * U + u) * 2 + 1) * 32 + lane];
+      const int t = base + u * TPW + grp;
 #pragma unroll
       for (int g = 0; g < GH; ++g) {
         float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc += qr[g][e] * st.kk[u][0].get(e);
+        for (int e = 0; e < 8; ++e) acc += qr[g][e] * k0.get(e);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * st.kk[u][1].get(e);
+        for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * k1.get(e);
 #pragma unroll
         for (int off = LPT / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        const int t = base + u * TPW + grp;
         acc += slope[g] * (float)(t - (len - 1));
-        sc[u][g] = st.ok[u] ? acc : -INFINITY;
+        sc[u][g] = (t < t1) ? acc : -INFINITY;
       }
     }
+    float pr[U][GH];
 #pragma unroll
     for (int g = 0; g < GH; ++g) {
       float nm = m[g];
@@ -277,31 +301,43 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
       for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float p = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
-        l[g] += p;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[g][e] += p * st.vv[u][0].get(e);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[g][8 + e] += p * st.vv[u][1].get(e);
+        pr[u][g] = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
+        l[g] += pr[u][g];
       }
       m[g] = nm;
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      Vec16<TC> v0, v1;
+      v0.raw = st[((1 * U + u) * 2 + 0) * 32 + lane];
+      v1.raw = st[((1 * U + u) * 2 + 1) * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < GH; ++g) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[g][e] += pr[u][g] * v0.get(e);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[g][8 + e] += pr[u][g] * v1.get(e);
+      }
+    }
   };
   if (ng > 0) {
-    // software pipeline over two register stages: the loads of the next stage are in flight while this one is consumed
     const int step = wps * (TPW * U);
-    int base = t0 + wi * (TPW * U);
-    Stage sa, sb;
-    if (base < t1) load_stage(base, sa);
-    while (base < t1) {
-      if (base + step < t1) load_stage(base + step, sb);
-      consume(base, sa);
-      base += step;
-      if (base >= t1) break;
-      if (base + step < t1) load_stage(base + step, sa);
-      consume(base, sb);
-      base += step;
+    const int first = t0 + wi * (TPW * U);
+    // prologue: NST - 1 stages in flight (empty groups keep the group count uniform at the tail)
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+      if (first + s * step < t1) issue_stage(first + s * step, s);
+      cp_async_commit();
     }
+    int it = 0;
+    for (int base = first; base < t1; base += step, ++it) {
+      const int ahead = base + (NST - 1) * step;
+      if (ahead < t1) issue_stage(ahead, (it + NST - 1) % NST);
+      cp_async_commit();
+      cp_async_wait<NST - 1>();                                   // the group of stage `it` has landed
+      consume(base, it % NST);
+    }
+    cp_async_wait<0>();
   }
   // merge the TPW lane-group states of the warp (butterfly over the group index)
 #pragma unroll
@@ -466,8 +502,16 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
   if (num_seqs == 0) return 0;
   if (Hq % Hkv != 0 || Hq / Hkv > MAX_GROUP) return (int)cudaErrorInvalidValue;
   dim3 grid(num_seqs, Hkv, splits);
+  constexpr int dec_smem = (DEC_THREADS / 32) * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;   // per-warp cp.async rings
 #define LAUNCH_DEC(T, DD)                                                                                           \
-  paged_decode_kernel<T, T, DD><<<grid, DEC_THREADS, 0, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache,      \
+  {                                                                                                                  \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      cudaFuncSetAttribute(paged_decode_kernel<T, T, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem);    \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+  }                                                                                                                  \
+  paged_decode_kernel<T, T, DD><<<grid, DEC_THREADS, dec_smem, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache, \
       block_tables, seq_lens, o_part, ml_part, Hq, Hkv, block_size, max_blocks_per_seq, splits, part_len, scale,     \
       alibi_slopes, q_stride, window);                                                                               \
   decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride)
