@@ -6,9 +6,10 @@
 //   cb_kv_cache_write        : scatter this step's K,V rows [tokens, kv_heads, D] into their paged slots (prefill: all
 //                              prompt tokens via cu_seqlens; decode: one token per sequence), optional fp8(e5m2) cast
 //   cb_rope_kv_cache_write   : fused RoPE(q,k) in place + cache write of rotated K and of V (decode path)
-//   cb_paged_decode_attention: split-KV flash-decoding: grid (seq, kv_head, split); one CTA serves the whole GQA group
-//                              of a kv head so K/V are read once per group; fp32 online softmax; second pass merges
-//                              splits
+//   cb_paged_decode_attention: split-KV flash-decoding: grid (seq, group of <= 8 kv heads, split); one WARP serves a
+//                              kv head (its whole GQA group, so K/V are read once per group) and the warps of a CTA
+//                              stream adjacent head slices of the same token rows; fp32 online softmax; second pass
+//                              merges splits
 //   cb_gather_cos_sin        : per-token cos/sin rows from the [max_pos, D/2] caches
 //   cb_convert_fp8           : fp16/bf16/fp32 <-> fp8 e5m2 storage
 //
@@ -21,7 +22,7 @@
 
 namespace {
 
-constexpr int DEC_THREADS = 128;
+constexpr int DEC_THREADS = 256;   // at most 8 (kv head, query-head set) units per CTA
 constexpr int MAX_GROUP = 8;   // q heads per kv head handled by one CTA
 
 template <typename T> CB_DEVICE float kv_to_f32(T v) { return to_f32<T>(v); }
@@ -186,16 +187,16 @@ __global__ void __launch_bounds__(256) rope_kv_cache_write_vec_kernel(
 //     registers: 8 warps / SM at 255 registers, 43 % issue-active, 2.4 TB/s under ncu - load and FMA phases of a warp
 //     alternated, then only 32 KB per SM in flight); no block-wide barrier in the main loop;
 //   * the query rows live in registers (GH = 4 query heads per warp, the lane's 16 dims of each); a GQA group wider
-//     than 4 is split over the CTA's warps (the second read of a K/V row by the sibling warp set is an L1/L2 hit);
+//     than 4 takes two warps of the CTA (the second read of a K/V row by the sibling warp is an L1/L2 hit);
 //   * every lane group keeps its OWN online-softmax state (m, l, o) for the tokens it sees - no cross-lane traffic in
 //     the loop except the log2(LPT) shuffles that finish a dot product; the 32/LPT states of a warp are merged once at
-//     the end, then the warps through shared memory.
+//     the end and written as this (head set, partition)'s partial result - no shared-memory reduction, no barrier.
 constexpr int DEC_U = 2;    // passes of the warp per pipeline stage
 constexpr int DEC_STAGES = 4;   // shared-memory ring depth per warp (DEC_STAGES - 1 stages in flight)
 constexpr int DEC_GH = 4;   // query heads per warp
 
 template <typename T, typename TC, int D>
-__global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
+__global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
     const T* __restrict__ q, const TC* __restrict__ k_cache, const TC* __restrict__ v_cache,
     const int* __restrict__ block_tables, const int* __restrict__ seq_lens, float* __restrict__ o_part,
     float* __restrict__ ml_part, int Hq, int Hkv, int block_size, int max_blocks_per_seq, int splits, int part_len,
@@ -204,24 +205,26 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
   constexpr int EPL = 16;                       // elements of a row owned by a lane
   constexpr int LPT = D / EPL;                  // lanes per token row: 4 / 8 / 16
   constexpr int TPW = 32 / LPT;                 // token rows per warp pass
-  constexpr int NW = DEC_THREADS / 32;
   constexpr int GH = DEC_GH, U = DEC_U;
-  const int seq = blockIdx.x, kvh = blockIdx.y, split = blockIdx.z;
+  // CTA = (sequence, group of kv heads, KV partition); warp = one (kv head, set of <= 4 query heads) unit walking ALL
+  // tokens of the partition.  The warps of a CTA read ADJACENT 256-byte head slices of the same token rows at the same
+  // time, so the CTA streams contiguous [tokens x heads x D] spans of the cache (with one CTA per kv head the 2 KB
+  // stride between a head's rows cost ~60 % of the DRAM bandwidth: 2.4 TB/s whatever the number of bytes in flight).
+  const int seq = blockIdx.x, split = blockIdx.z;
   const int G = Hq / Hkv;
+  const int nsets = (G + GH - 1) / GH;          // sets of <= 4 query heads per kv head
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.y * (blockDim.x >> 5) + warp;
+  const int kvh = unit / nsets, set = unit - kvh * nsets;
+  if (kvh >= Hkv) return;                       // (no block-wide barrier anywhere in this kernel)
   const int len = seq_lens[seq];
   // sliding-window attention (Mistral): only the last `window` cached tokens are visible - partitions that lie before
   // the window start contribute nothing (m = -inf, l = 0) and are skipped by the merge
   const int window_start = window > 0 ? max(0, len - window) : 0;
   const int t0 = max(split * part_len, window_start), t1 = min(len, split * part_len + part_len);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsets = (G + GH - 1) / GH;          // sets of <= 4 query heads; each set is served by NW / nsets warps
-  const int wps = NW / nsets;
-  const int set = warp / wps, wi = warp - set * wps;
   const int g0 = set * GH;
-  const int ng = set < nsets ? min(GH, G - g0) : 0;
+  const int ng = min(GH, G - g0);
   const int grp = lane / LPT, sub = lane - grp * LPT;
-  __shared__ float red_m[NW][GH], red_l[NW][GH];
-  __shared__ float red_o[NW][GH][D];
 
   float qr[GH][EPL];
 #pragma unroll
@@ -320,9 +323,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
       }
     }
   };
-  if (ng > 0) {
-    const int step = wps * (TPW * U);
-    const int first = t0 + wi * (TPW * U);
+  {
+    const int step = TPW * U;
+    const int first = t0;
     // prologue: NST - 1 stages in flight (empty groups keep the group count uniform at the tail)
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
@@ -355,30 +358,18 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) paged_decode_kernel(
       m[g] = nm;
     }
   }
+  // every lane group now holds the merged state; group 0 writes this unit's partial result
   if (grp == 0) {
 #pragma unroll
     for (int g = 0; g < GH; ++g) {
-      if (sub == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
+      if (g < ng) {
+        const int64_t oi = (((int64_t)seq * Hq + kvh * G + g0 + g) * splits + split);
+        float4* dst = reinterpret_cast<float4*>(o_part + oi * D + sub * EPL);
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) red_o[warp][g][sub * EPL + e] = o[g][e];
+        for (int e = 0; e < EPL; e += 4) dst[e >> 2] = make_float4(o[g][e], o[g][e + 1], o[g][e + 2], o[g][e + 3]);
+        if (sub == 0) { ml_part[oi * 2] = m[g]; ml_part[oi * 2 + 1] = l[g]; }
+      }
     }
-  }
-  __syncthreads();
-  // merge the warps of each query-head set
-  for (int i = threadIdx.x; i < G * D; i += DEC_THREADS) {
-    const int g = i / D, d = i - g * D;
-    const int st = g / GH, gl = g - st * GH;
-    float gm = -INFINITY;
-    for (int w = st * wps; w < (st + 1) * wps; ++w) gm = fmaxf(gm, red_m[w][gl]);
-    float acc = 0.f, ls = 0.f;
-    for (int w = st * wps; w < (st + 1) * wps; ++w) {
-      const float c = (red_m[w][gl] == -INFINITY) ? 0.f : __expf(red_m[w][gl] - gm);
-      acc += red_o[w][gl][d] * c;
-      ls += red_l[w][gl] * c;
-    }
-    const int64_t oi = (((int64_t)seq * Hq + kvh * G + g) * splits + split);
-    o_part[oi * D + d] = acc;
-    if (d == 0) { ml_part[oi * 2] = gm; ml_part[oi * 2 + 1] = ls; }
   }
 }
 
@@ -479,10 +470,11 @@ int cb_rope_kv_cache_write(void* q, void* k, const void* v, void* k_cache, void*
 }
 
 int cb_decode_num_splits(int num_seqs, int kv_heads, int max_len, int* part_len_out) {
-  // two CTAs are resident per SM: aim at >= 2 waves of 2 x SMs CTAs, partitions of >= 128 tokens
-  const int target = 4 * cb_num_sms();
-  int splits = (target + num_seqs * kv_heads - 1) / (num_seqs * kv_heads);
-  const int max_splits = (max_len + 127) / 128;
+  // one CTA (up to 8 warps, one per kv head) per SM: aim at >= 2 waves of CTAs, partitions of >= 64 tokens
+  const int ctas_per_split = num_seqs * ((kv_heads + 7) / 8);
+  const int target = 2 * cb_num_sms();
+  int splits = (target + ctas_per_split - 1) / ctas_per_split;
+  const int max_splits = (max_len + 63) / 64;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int part = (max_len + splits - 1) / splits;
@@ -501,17 +493,21 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
                               int window, cudaStream_t s) {
   if (num_seqs == 0) return 0;
   if (Hq % Hkv != 0 || Hq / Hkv > MAX_GROUP) return (int)cudaErrorInvalidValue;
-  dim3 grid(num_seqs, Hkv, splits);
-  constexpr int dec_smem = (DEC_THREADS / 32) * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;   // per-warp cp.async rings
+  const int G = Hq / Hkv;
+  const int units = Hkv * ((G + DEC_GH - 1) / DEC_GH);             // (kv head, query-head set) pairs = warps needed
+  const int warps = units < DEC_THREADS / 32 ? units : DEC_THREADS / 32;
+  dim3 grid(num_seqs, (units + warps - 1) / warps, splits);
+  const int dec_smem = warps * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;                    // per-warp cp.async rings
+  constexpr int dec_smem_max = (DEC_THREADS / 32) * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;
 #define LAUNCH_DEC(T, DD)                                                                                           \
   {                                                                                                                  \
     static bool attr_done = false;                                                                                   \
     if (!attr_done) {                                                                                                \
-      cudaFuncSetAttribute(paged_decode_kernel<T, T, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem);    \
+      cudaFuncSetAttribute(paged_decode_kernel<T, T, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem_max);\
       attr_done = true;                                                                                              \
     }                                                                                                                \
   }                                                                                                                  \
-  paged_decode_kernel<T, T, DD><<<grid, DEC_THREADS, dec_smem, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache, \
+  paged_decode_kernel<T, T, DD><<<grid, warps * 32, dec_smem, s>>>((const T*)q, (const T*)k_cache, (const T*)v_cache, \
       block_tables, seq_lens, o_part, ml_part, Hq, Hkv, block_size, max_blocks_per_seq, splits, part_len, scale,     \
       alibi_slopes, q_stride, window);                                                                               \
   decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride)
