@@ -295,15 +295,17 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane == 0) mbar_arrive(&s_empty[sb]);          // S buffer may be overwritten by Q K_{j+2}^T
       // plain variant: the softmax scale (> 0) is folded into the exponent's FMA, the max is taken on the raw scores;
       // EXTRA variant: scale and ALiBi bias are applied here and the exponent uses a unit multiplier
-      float m_tile = -INFINITY;
+      // (four independent partial maxima / sums: a single running value would be a 128-long dependent chain)
+      float mt[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < BLOCK_KV; ++i) {
         float sc = __uint_as_float(v[i]);
         if (EXTRA) sc = fmaf(slope2, (float)(k_base + i - q_pos), sc * p.scale_log2);
         if (masked && ((k_base + i) > k_lim || (EXTRA && (k_base + i) < k_low))) sc = -INFINITY;
         v[i] = __float_as_uint(sc);
-        m_tile = fmaxf(m_tile, sc);
+        mt[i & 3] = fmaxf(mt[i & 3], sc);
       }
+      float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
       const float ex_mul = EXTRA ? 1.f : p.scale_log2;
       m_tile *= ex_mul;
       // ---- lagging max / rare rescale of the TMEM accumulator
@@ -337,7 +339,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // ---- p = exp2(s - m), row sum, 16-bit P into the swizzled K-major tile of buffer j & 1
       // (that buffer was last read by P_{j-2} V_{j-2}, which retired before Q K_j^T - issued after it - completed)
       uint8_t* p_row = smem_p + (j & 1) * C::P_BYTES + r * 128;
-      float l_tile = 0.f;
+      float lt[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < BLOCK_KV; c += 32) {
         uint32_t packed[16];
@@ -345,7 +347,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int i = 0; i < 32; i += 2) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(v[c + i]), ex_mul, -m_use));
           const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + i + 1]), ex_mul, -m_use));
-          l_tile += p0 + p1;
+          lt[(i >> 1) & 3] += p0 + p1;
           if (p.out_dtype == CB_BF16) {
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
             packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
@@ -364,6 +366,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
         }
       }
+      const float l_tile = (lt[0] + lt[1]) + (lt[2] + lt[3]);
       l_run += l_tile;
       // keep in step with the accumulator barrier: observe "P_{j-1} V_{j-1} retired" once per tile.  It completed long
       // ago in the common case (no stall), but a parity wait is only unambiguous while the waiter is at most ONE phase

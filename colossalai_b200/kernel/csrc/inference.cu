@@ -32,6 +32,11 @@ CB_DEVICE void cp_async_16(void* smem_dst, const void* gmem_src, uint32_t src_by
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+CB_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 CB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> CB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
   constexpr int LPT = D / EPL;                  // lanes per token row: 4 / 8 / 16
   constexpr int TPW = 32 / LPT;                 // token rows per warp pass
   constexpr int GH = DEC_GH, U = DEC_U;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   // CTA = (sequence, group of kv heads, KV partition); warp = one (kv head, set of <= 4 query heads) unit walking ALL
   // tokens of the partition.  The warps of a CTA read ADJACENT 256-byte head slices of the same token rows at the same
   // time, so the CTA streams contiguous [tokens x heads x D] spans of the cache (with one CTA per kv head the 2 KB
@@ -231,11 +237,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
   for (int g = 0; g < GH; ++g) {
     const T* qp = q + (int64_t)seq * q_stride + (int64_t)(kvh * G + g0 + (g < ng ? g : 0)) * D + sub * EPL;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) qr[g][e] = g < ng ? to_f32<T>(qp[e]) * scale : 0.f;
+    for (int e = 0; e < EPL; ++e) qr[g][e] = g < ng ? to_f32<T>(qp[e]) * (scale * LOG2E) : 0.f;   // scores in the exp2 domain
   }
   float slope[GH];
 #pragma unroll
-  for (int g = 0; g < GH; ++g) slope[g] = (alibi_slopes && g < ng) ? alibi_slopes[kvh * G + g0 + g] : 0.f;
+  for (int g = 0; g < GH; ++g) slope[g] = (alibi_slopes && g < ng) ? alibi_slopes[kvh * G + g0 + g] * LOG2E : 0.f;
+  const bool has_alibi = alibi_slopes != nullptr;
   float m[GH], l[GH], o[GH][EPL];
 #pragma unroll
   for (int g = 0; g < GH; ++g) {
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
     for (int e = 0; e < EPL; ++e) o[g][e] = 0.f;
   }
   const int* bt = block_tables + seq * max_blocks_per_seq;
+  const int bs_shift = (block_size & (block_size - 1)) == 0 ? 31 - __clz(block_size) : -1;   // power-of-two blocks: no division
   // K/V travel through a per-warp ring of DEC_STAGES shared-memory stages filled with cp.async (16 bytes per lane and
   // vector; a stage = U passes of the warp = U * TPW token rows, K and V): the bytes in flight are bounded by shared
   // memory, not by registers, so DEC_STAGES - 1 stages (6 KB) per warp stay outstanding while one is consumed.  Every
@@ -260,8 +268,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
       const int t = base + u * TPW + grp;
       const bool ok = t < t1;
       const int tt = ok ? t : t0;                                 // any valid row: src-size 0 zero-fills instead
-      const int blk = bt[tt / block_size];
-      const int64_t row = (((int64_t)blk * block_size + tt % block_size) * Hkv + kvh) * D + sub * EPL;
+      const int blk = bt[bs_shift >= 0 ? (tt >> bs_shift) : (tt / block_size)];
+      const int slot = bs_shift >= 0 ? (tt & (block_size - 1)) : (tt % block_size);
+      const int64_t row = (((int64_t)blk * block_size + slot) * Hkv + kvh) * D + sub * EPL;
       const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
         for (int e = 0; e < 8; ++e) acc += qr[g][8 + e] * k1.get(e);
 #pragma unroll
         for (int off = LPT / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        acc += slope[g] * (float)(t - (len - 1));
+        if (has_alibi) acc += slope[g] * (float)(t - (len - 1));
         sc[u][g] = (t < t1) ? acc : -INFINITY;
       }
     }
@@ -298,13 +307,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
       float nm = m[g];
 #pragma unroll
       for (int u = 0; u < U; ++u) nm = fmaxf(nm, sc[u][g]);
-      const float corr = (nm == -INFINITY) ? 1.f : __expf(m[g] - nm);
-      l[g] *= corr;
+      if (__any_sync(0xffffffffu, nm > m[g])) {                   // the running max moved for some row group: rescale
+        const float corr = (nm == -INFINITY) ? 1.f : ex2_approx(m[g] - nm);
+        l[g] *= corr;
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
+        for (int e = 0; e < EPL; ++e) o[g][e] *= corr;
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        pr[u][g] = (sc[u][g] == -INFINITY) ? 0.f : __expf(sc[u][g] - nm);
+        pr[u][g] = (sc[u][g] == -INFINITY) ? 0.f : ex2_approx(sc[u][g] - nm);
         l[g] += pr[u][g];
       }
       m[g] = nm;
@@ -350,8 +361,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
       const float mo = __shfl_xor_sync(0xffffffffu, m[g], off);
       const float lo = __shfl_xor_sync(0xffffffffu, l[g], off);
       const float nm = fmaxf(m[g], mo);
-      const float c1 = (m[g] == -INFINITY) ? 0.f : __expf(m[g] - nm);
-      const float c2 = (mo == -INFINITY) ? 0.f : __expf(mo - nm);
+      const float c1 = (m[g] == -INFINITY) ? 0.f : ex2_approx(m[g] - nm);
+      const float c2 = (mo == -INFINITY) ? 0.f : ex2_approx(mo - nm);
       l[g] = l[g] * c1 + lo * c2;
 #pragma unroll
       for (int e = 0; e < EPL; ++e) o[g][e] = o[g][e] * c1 + __shfl_xor_sync(0xffffffffu, o[g][e], off) * c2;
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
         float4* dst = reinterpret_cast<float4*>(o_part + oi * D + sub * EPL);
 #pragma unroll
         for (int e = 0; e < EPL; e += 4) dst[e >> 2] = make_float4(o[g][e], o[g][e + 1], o[g][e + 2], o[g][e + 3]);
-        if (sub == 0) { ml_part[oi * 2] = m[g]; ml_part[oi * 2 + 1] = l[g]; }
+        if (sub == 0) { ml_part[oi * 2] = m[g] * LN2; ml_part[oi * 2 + 1] = l[g]; }   // max back in natural-log units
       }
     }
   }
