@@ -114,6 +114,11 @@ def main():
             dt = time.perf_counter() - t0
         if step >= args.ignore_steps:
             times.append(dt)
+        if args.plugin == "3d" and args.pp > 1:
+            # the loss lives on the last pipeline stage: share it for the log line
+            lt = torch.full((1,), float("-inf"), device=dev) if loss is None else loss.detach().float().reshape(1).to(dev)
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            loss = lt[0]
         if rank == 0:
             print(f"step {step}: loss {float(loss) if loss is not None else float('nan'):.4f}  {dt * 1e3:.1f} ms")
     if times:
