@@ -384,6 +384,219 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Tensor-core formulation of the same split-KV decode step (`CB200_DECODE=mma`).
+//
+// The CUDA-core kernel above executes ~89 warp-instructions per (token, kv head) - two FMAs per cached element and q
+// head - which is as much issue time as the HBM transfer takes (ncu: 93 M warp-instructions, 45 % issue-active,
+// 2.2-2.4 TB/s).  Here the GQA group of a kv head (<= 8 q heads, padded to the 16 rows of an MMA) is the M dimension of
+// `mma.sync.m16n8k16`:  S[heads x 16 tokens] = Q K^T  and  O[heads x D] += P V  per 16-token tile, i.e. 32 MMAs instead of
+// ~4000 FMAs per tile and lane.
+//   * warp = (sequence, kv head, partition) unit, as above; Q fragments (A operand) live in registers;
+//   * a tile of 16 token rows of K and of V (16 x D 16-bit values each) is fetched with cp.async into a per-warp ring
+//     (DEC_MMA_STAGES deep); a row's 16-byte chunks are stored XOR-swizzled by (token mod 8), so the ldmatrix reads - K
+//     plain (B operand of Q K^T), V transposed (B operand of P V) - are bank-conflict free;
+//   * softmax state per head row is replicated over the four lanes of a quad; the probabilities go straight from the
+//     accumulator layout of S to the A-operand layout of P V (no shared-memory round trip); the output accumulator is
+//     rescaled only when a row max moved;
+//   * partial results use the same (o_part, ml_part) format, so the reduce kernel is shared.
+constexpr int DEC_MMA_TOKENS = 16;
+constexpr int DEC_MMA_STAGES = 3;
+
+CB_DEVICE void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+CB_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <typename T> CB_DEVICE void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> CB_DEVICE void mma_16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> CB_DEVICE void mma_16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T> CB_DEVICE uint32_t pack2(float lo, float hi);
+template <> CB_DEVICE uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> CB_DEVICE uint32_t pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_mma_kernel(
+    const T* __restrict__ q, const T* __restrict__ k_cache, const T* __restrict__ v_cache,
+    const int* __restrict__ block_tables, const int* __restrict__ seq_lens, float* __restrict__ o_part,
+    float* __restrict__ ml_part, int Hq, int Hkv, int block_size, int max_blocks_per_seq, int splits, int part_len,
+    float scale, const float* __restrict__ alibi_slopes, int64_t q_stride, int window) {
+  constexpr int NT = DEC_MMA_TOKENS, NST = DEC_MMA_STAGES;
+  constexpr int KS = D / 16;                    // k-steps of Q K^T
+  constexpr int NO = D / 8;                     // 8-wide column tiles of the output
+  constexpr int CPR = D / 8;                    // 16-byte chunks per token row
+  constexpr int ROW_BYTES = D * 2;
+  constexpr int TILE_BYTES = NT * ROW_BYTES;    // one operand (K or V) of one stage
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const int seq = blockIdx.x, split = blockIdx.z;
+  const int G = Hq / Hkv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvh = blockIdx.y * (blockDim.x >> 5) + warp;
+  if (kvh >= Hkv) return;                       // (no block-wide barrier in this kernel)
+  const int len = seq_lens[seq];
+  const int window_start = window > 0 ? max(0, len - window) : 0;
+  const int t0 = max(split * part_len, window_start), t1 = min(len, split * part_len + part_len);
+  const int row = lane >> 2, quad = lane & 3;   // accumulator layout: head row, column pair inside an 8-wide tile
+  const bool row_ok = row < G;                  // rows G..15 of the MMA are padding
+  const float scale2 = scale * LOG2E;           // scores in the exp2 domain
+  const float slope2 = (alibi_slopes != nullptr && row_ok) ? alibi_slopes[kvh * G + row] * LOG2E : 0.f;
+  const bool has_alibi = alibi_slopes != nullptr;
+
+  // ---- Q fragments: A operand [16 heads x 16 d] per k-step; a1 / a3 are head rows 8..15 = zero (G <= 8)
+  uint32_t qa[KS][4];
+  {
+    const T* qrow = q + (int64_t)seq * q_stride + (int64_t)(kvh * G + (row_ok ? row : 0)) * D;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t lo = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + quad * 2);
+      const uint32_t hi = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + quad * 2);
+      qa[ks][0] = row_ok ? lo : 0u; qa[ks][1] = 0u; qa[ks][2] = row_ok ? hi : 0u; qa[ks][3] = 0u;
+    }
+  }
+  float o[NO][4];
+#pragma unroll
+  for (int j = 0; j < NO; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m_run = -INFINITY, l_run = 0.f;         // per head row, replicated over the quad (l: this lane's share)
+
+  extern __shared__ __align__(128) unsigned char dec_smem[];
+  unsigned char* ring = dec_smem + (size_t)warp * NST * 2 * TILE_BYTES;
+  const int* bt = block_tables + seq * max_blocks_per_seq;
+  const int bs_shift = (block_size & (block_size - 1)) == 0 ? 31 - __clz(block_size) : -1;
+  auto issue_stage = [&](int base, int stage) {
+    unsigned char* kt = ring + (size_t)stage * 2 * TILE_BYTES;
+    unsigned char* vt = kt + TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < NT * CPR / 32; ++i) {
+      const int cid = lane + 32 * i;
+      const int tr = cid / CPR, c = cid - tr * CPR;          // token row inside the tile, 16-byte chunk inside the row
+      const int t = base + tr;
+      const bool ok = t < t1;
+      const int tt = ok ? t : t0;
+      const int blk = bt[bs_shift >= 0 ? (tt >> bs_shift) : (tt / block_size)];
+      const int slot = bs_shift >= 0 ? (tt & (block_size - 1)) : (tt % block_size);
+      const int64_t src = (((int64_t)blk * block_size + slot) * Hkv + kvh) * D + c * 8;
+      const int dst = tr * ROW_BYTES + ((c ^ (tr & 7)) << 4);
+      const uint32_t nbytes = ok ? 16u : 0u;
+      cp_async_16(kt + dst, k_cache + src, nbytes);
+      cp_async_16(vt + dst, v_cache + src, nbytes);
+    }
+  };
+  auto consume = [&](int base, int stage) {
+    const unsigned char* kt = ring + (size_t)stage * 2 * TILE_BYTES;
+    const unsigned char* vt = kt + TILE_BYTES;
+    // ---- S = Q K^T for 16 tokens (two 8-token column tiles)
+    float sacc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+      const int tr = nt * 8 + (lane & 7);                    // token row whose address this lane supplies
+#pragma unroll
+      for (int ks = 0; ks < KS; ks += 2) {
+        // matrices: (ks, d 0..7), (ks, d 8..15), (ks + 1, d 0..7), (ks + 1, d 8..15)
+        const int c = 2 * ks + (lane >> 3);
+        uint32_t b[4];
+        ldmatrix_x4(b, kt + tr * ROW_BYTES + ((c ^ (tr & 7)) << 4));
+        mma_16816<T>(sacc[nt], qa[ks], b[0], b[1]);
+        mma_16816<T>(sacc[nt], qa[ks + 1], b[2], b[3]);
+      }
+    }
+    // ---- online softmax of head row `row` (this lane: tokens nt * 8 + quad * 2 + {0, 1})
+    float sv[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int t = base + nt * 8 + quad * 2 + e;
+        float x = sacc[nt][e] * scale2;
+        if (has_alibi) x = fmaf(slope2, (float)(t - (len - 1)), x);
+        x = (t < t1) ? x : -INFINITY;
+        sv[nt * 2 + e] = x;
+        mx = fmaxf(mx, x);
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    if (__any_sync(0xffffffffu, m_new > m_run)) {
+      const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+      l_run *= corr;
+#pragma unroll
+      for (int j = 0; j < NO; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
+    }
+    m_run = m_new;
+    float pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pv[i] = (sv[i] == -INFINITY) ? 0.f : ex2_approx(sv[i] - m_new);
+      l_run += pv[i];
+    }
+    // P as A operand [16 heads x 16 tokens]: a0 = tokens 0..7 of this row, a2 = tokens 8..15; rows 8..15 are zero
+    uint32_t pa[4];
+    pa[0] = row_ok ? pack2<T>(pv[0], pv[1]) : 0u; pa[1] = 0u;
+    pa[2] = row_ok ? pack2<T>(pv[2], pv[3]) : 0u; pa[3] = 0u;
+    // ---- O += P V: V^T fragments through ldmatrix.trans
+    {
+      const int tr = (lane & 7) + ((lane >> 3) & 1) * 8;     // matrices: (tok 0..7, j), (tok 8..15, j), (0..7, j+1), (8..15, j+1)
+#pragma unroll
+      for (int j = 0; j < NO; j += 2) {
+        const int c = j + (lane >> 4);
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, vt + tr * ROW_BYTES + ((c ^ (tr & 7)) << 4));
+        mma_16816<T>(o[j], pa, b[0], b[1]);
+        mma_16816<T>(o[j + 1], pa, b[2], b[3]);
+      }
+    }
+  };
+  {
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+      if (t0 + s * NT < t1) issue_stage(t0 + s * NT, s);
+      cp_async_commit();
+    }
+    int it = 0;
+    for (int base = t0; base < t1; base += NT, ++it) {
+      const int ahead = base + (NST - 1) * NT;
+      if (ahead < t1) issue_stage(ahead, (it + NST - 1) % NST);
+      cp_async_commit();
+      cp_async_wait<NST - 1>();
+      __syncwarp();                                          // the tile was written by all lanes of the warp
+      consume(base, it % NST);
+      __syncwarp();                                          // all lanes done reading before the stage is refilled
+    }
+    cp_async_wait<0>();
+  }
+  // ---- this unit's partial result (row sum over the quad first)
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (row_ok) {
+    const int64_t oi = (((int64_t)seq * Hq + kvh * G + row) * splits + split);
+    float* dst = o_part + oi * D + quad * 2;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) *reinterpret_cast<float2*>(dst + j * 8) = make_float2(o[j][0], o[j][1]);
+    if (quad == 0) { ml_part[oi * 2] = m_run * LN2; ml_part[oi * 2 + 1] = l_run; }
+  }
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(128) decode_reduce_kernel(const float* __restrict__ o_part,
                                                             const float* __restrict__ ml_part, T* __restrict__ out,
@@ -510,6 +723,25 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
   dim3 grid(num_seqs, (units + warps - 1) / warps, splits);
   const int dec_smem = warps * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;                    // per-warp cp.async rings
   constexpr int dec_smem_max = (DEC_THREADS / 32) * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;
+  // CB200_DECODE=mma: tensor-core formulation (mma.sync over the GQA group); default: the CUDA-core kernel
+  const char* impl_env = getenv("CB200_DECODE");
+  const bool use_mma = impl_env != nullptr && impl_env[0] == 'm' && G <= 8 && (D == 128 || D == 64);
+  const int mma_warps = Hkv < DEC_THREADS / 32 ? Hkv : DEC_THREADS / 32;
+  dim3 mma_grid(num_seqs, (Hkv + mma_warps - 1) / mma_warps, splits);
+#define LAUNCH_DEC_MMA(T, DD)                                                                                       \
+  {                                                                                                                  \
+    constexpr int per_warp = DEC_MMA_STAGES * 2 * DEC_MMA_TOKENS * DD * 2;                                           \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      cudaFuncSetAttribute(paged_decode_mma_kernel<T, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                           (DEC_THREADS / 32) * per_warp);                                                           \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    paged_decode_mma_kernel<T, DD><<<mma_grid, mma_warps * 32, mma_warps * per_warp, s>>>(                           \
+        (const T*)q, (const T*)k_cache, (const T*)v_cache, block_tables, seq_lens, o_part, ml_part, Hq, Hkv,        \
+        block_size, max_blocks_per_seq, splits, part_len, scale, alibi_slopes, q_stride, window);                   \
+    decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride); \
+  }
 #define LAUNCH_DEC(T, DD)                                                                                           \
   {                                                                                                                  \
     static bool attr_done = false;                                                                                   \
@@ -523,12 +755,15 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
       alibi_slopes, q_stride, window);                                                                               \
   decode_reduce_kernel<T, DD><<<dim3(num_seqs, Hq), 128, 0, s>>>(o_part, ml_part, (T*)out, Hq, splits, out_stride)
   CB_DISPATCH_HALF(dtype, T, {
-    if (D == 128) { LAUNCH_DEC(T, 128); }
+    if (use_mma && D == 128) { LAUNCH_DEC_MMA(T, 128); }
+    else if (use_mma && D == 64) { LAUNCH_DEC_MMA(T, 64); }
+    else if (D == 128) { LAUNCH_DEC(T, 128); }
     else if (D == 64) { LAUNCH_DEC(T, 64); }
     else if (D == 256) { LAUNCH_DEC(T, 256); }
     else return (int)cudaErrorInvalidValue;
   });
 #undef LAUNCH_DEC
+#undef LAUNCH_DEC_MMA
   return CB_LAUNCH_CHECK();
 }
 
