@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) paged_decode_kernel(
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Tensor-core formulation of the same split-KV decode step (`CB200_DECODE=mma`).
+// Tensor-core formulation of the same split-KV decode step (the default; `CB200_DECODE=simt` selects the kernel above).
 //
 // The CUDA-core kernel above executes ~89 warp-instructions per (token, kv head) - two FMAs per cached element and q
 // head - which is as much issue time as the HBM transfer takes (ncu: 93 M warp-instructions, 45 % issue-active,
@@ -723,9 +723,10 @@ int cb_paged_decode_attention(const void* q, const void* k_cache, const void* v_
   dim3 grid(num_seqs, (units + warps - 1) / warps, splits);
   const int dec_smem = warps * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;                    // per-warp cp.async rings
   constexpr int dec_smem_max = (DEC_THREADS / 32) * DEC_STAGES * (2 * DEC_U * 2 * 32) * 16;
-  // CB200_DECODE=mma: tensor-core formulation (mma.sync over the GQA group); default: the CUDA-core kernel
+  // default: the tensor-core formulation (mma.sync over the GQA group) where it applies (head_dim 64 / 128, groups of
+  // <= 8 q heads); CB200_DECODE=simt forces the CUDA-core kernel (also used for head_dim 256)
   const char* impl_env = getenv("CB200_DECODE");
-  const bool use_mma = impl_env != nullptr && impl_env[0] == 'm' && G <= 8 && (D == 128 || D == 64);
+  const bool use_mma = !(impl_env != nullptr && impl_env[0] == 's') && G <= 8 && (D == 128 || D == 64);
   const int mma_warps = Hkv < DEC_THREADS / 32 ? Hkv : DEC_THREADS / 32;
   dim3 mma_grid(num_seqs, (Hkv + mma_warps - 1) / mma_warps, splits);
 #define LAUNCH_DEC_MMA(T, DD)                                                                                       \
