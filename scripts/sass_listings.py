@@ -56,7 +56,7 @@ def main():
             continue
         body = []
         for line in cache[lib][hits[0]]:
-            m = re.match(r"\s*/\*([0-9a-f]{4})\*/\s+(.*?);\s*/\*", line)
+            m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(.*?);\s*/\*", line)
             if m:
                 body.append(f"/*{m.group(1)}*/  {m.group(2)} ;")
         with open(os.path.join(OUT, out_name + ".sass"), "w") as f:
