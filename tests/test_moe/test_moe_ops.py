@@ -91,6 +91,40 @@ def test_expert_parallel_matches_single_rank_gloo():
     spawn(_ep_worker, 2)
 
 
+def test_padded_expert_layout_matches_packed_layout_cpu(monkeypatch):
+    """The 128-row padded expert layout of the sorted path (used on the GPU so that the grouped weight-gradient GEMM
+    needs no re-layout) is an index transformation only: forced on for CPU tensors it must reproduce the packed path
+    bit for bit - output and all gradients - including experts that receive no token."""
+    from colossalai_b200.moe.grouped_gemm import _pad_groups, grouped_linear
+
+    torch.manual_seed(0)
+    T, H, E, K = 50, 16, 6, 2
+    w = torch.randn(E, H, H, requires_grad=True)
+    x = torch.randn(T, H, requires_grad=True)
+    lg = torch.randn(T, E)
+    lg[:, 4] = -1e9                                         # expert 4 never selected
+    lg.requires_grad_()
+
+    def run(aligned):
+        monkeypatch.setattr(dc, "_aligned_rows", lambda t: aligned)
+        for t in (w, x, lg):
+            t.grad = None
+        tw, ti = lg.softmax(-1).topk(K, -1)
+        y = dc.moe_forward(x, tw, ti, lambda r, c: grouped_linear(r, w, c), E, None)
+        y.square().sum().backward()
+        return y.detach().clone(), x.grad.clone(), lg.grad.clone(), w.grad.clone()
+
+    for a, b in zip(run(False), run(True)):
+        torch.testing.assert_close(a, b, rtol=0, atol=0)
+    # layout helper: every group starts on a multiple of 128, rows keep their order inside a group, rows of an
+    # over-allocated buffer behind the last group go to the dump row
+    counts = torch.tensor([3, 0, 130, 1])
+    dest, pends, bound = _pad_groups(counts, 140, "cpu")
+    assert pends.tolist() == [128, 128, 384, 512] and bound % 128 == 0 and bound >= 512
+    assert dest[:3].tolist() == [0, 1, 2] and dest[3:133].tolist() == list(range(128, 258)) and dest[133].item() == 384
+    assert (dest[134:] == bound).all()
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

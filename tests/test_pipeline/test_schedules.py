@@ -11,7 +11,8 @@ from colossalai_b200.booster import Booster
 from colossalai_b200.booster.plugin import HybridParallelPlugin
 from colossalai_b200.models import build_model
 from colossalai_b200.nn.optimizer import FusedAdam
-from colossalai_b200.pipeline.schedule.v_schedule import PipelineGraph, interleaved_1f1b_schedule
+from colossalai_b200.pipeline.schedule.v_schedule import (PipelineGraph, interleaved_1f1b_schedule,
+                                                         one_f_one_b_schedule)
 from colossalai_b200.testing import rerun_if_address_is_in_use, spawn
 
 
@@ -26,6 +27,40 @@ def test_schedule_graphs_are_complete():
         for s in range(n_stage):
             assert sum(1 for n in sched[s] if n.type == "F") == 2 * n_micro
             assert sum(1 for n in sched[s] if n.type == "B") == 2 * n_micro
+
+
+def test_one_f_one_b_node_list_is_classic_1f1b():
+    """The generated 1F1B node list: every micro-batch forward before its backward, warm-up depth n_stage - stage - 1,
+    at most n_stage - stage forwards in flight, strict F/B alternation in the steady state, FIFO channels."""
+    for n_stage, n_micro in [(2, 4), (4, 8), (4, 3), (8, 16), (3, 1)]:
+        sched = one_f_one_b_schedule(n_stage, n_micro)
+        for s, nodes in enumerate(sched):
+            comp = [(n.type, n.minibatch) for n in nodes if n.type in ("F", "B")]
+            assert sorted(m for t, m in comp if t == "F") == list(range(n_micro))
+            assert sorted(m for t, m in comp if t == "B") == list(range(n_micro))
+            assert [m for t, m in comp if t == "F"] == list(range(n_micro))      # micro-batches in order
+            assert [m for t, m in comp if t == "B"] == list(range(n_micro))
+            inflight = peak = 0
+            for t, m in comp:
+                inflight += 1 if t == "F" else -1
+                assert inflight >= 0
+                peak = max(peak, inflight)
+            assert peak == min(n_stage - s, n_micro), (n_stage, n_micro, s, peak)
+            warm = 0
+            while warm < len(comp) and comp[warm][0] == "F":
+                warm += 1
+            assert warm == min(n_stage - s, n_micro)                              # warm-up forwards + the first steady F
+            steady = comp[warm:len(comp) - (warm - 1)] if warm > 1 else comp[warm:]
+            for a, b in zip(steady, steady[1:]):
+                assert a[0] != b[0], (n_stage, n_micro, s, comp)                  # B F B F ... alternation
+            # every send has exactly one matching receive on the neighbour, in the same order
+            if s + 1 < n_stage:
+                sent = [n.minibatch for n in nodes if n.type == "SEND_FORWARD"]
+                recv = [n.minibatch for n in sched[s + 1] if n.type == "RECV_FORWARD"]
+                assert sent == recv == list(range(n_micro))
+                sent_b = [n.minibatch for n in sched[s + 1] if n.type == "SEND_BACKWARD"]
+                recv_b = [n.minibatch for n in nodes if n.type == "RECV_BACKWARD"]
+                assert sent_b == recv_b == list(range(n_micro))
 
 
 def _run(pp_style, num_model_chunks, tied=False, **plugin_kw):
