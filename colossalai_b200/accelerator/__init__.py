@@ -13,6 +13,44 @@ import torch
 __all__ = ["BaseAccelerator", "CudaAccelerator", "CpuAccelerator", "get_accelerator", "set_accelerator", "auto_set_accelerator"]
 
 
+class _NullEvent:
+    """Event of a device without asynchronous streams (the CPU tier): everything has already happened."""
+
+    def record(self, stream=None) -> None:
+        pass
+
+    def wait(self, stream=None) -> None:
+        pass
+
+    def synchronize(self) -> None:
+        pass
+
+    def query(self) -> bool:
+        return True
+
+    def elapsed_time(self, other) -> float:
+        return 0.0
+
+
+class _NullStream:
+    """Stream stand-in of the CPU tier: work is synchronous, so every ordering primitive is a no-op."""
+
+    def wait_event(self, event) -> None:
+        pass
+
+    def wait_stream(self, stream) -> None:
+        pass
+
+    def record_event(self, event=None):
+        return event if event is not None else _NullEvent()
+
+    def synchronize(self) -> None:
+        pass
+
+    def query(self) -> bool:
+        return True
+
+
 class BaseAccelerator:
     name = "base"
     communication_backend = "gloo"
@@ -86,13 +124,13 @@ class BaseAccelerator:
 
     # ---- streams / events
     def Stream(self, *a, **k):
-        return None
+        return _NullStream()
 
     def Event(self, *a, **k):
-        return None
+        return _NullEvent()
 
     def current_stream(self, device=None):
-        return None
+        return _NullStream()
 
     def stream(self, stream_):
         return contextlib.nullcontext()

@@ -43,7 +43,7 @@ class Config(dict):
             raise AttributeError(key)
 
     def __setattr__(self, key, value):
-        super().__setitem__(key, value)
+        self._add_item(key, value)          # assigned dicts become Configs too (attribute access all the way down)
 
     def _add_item(self, key, value):
         self[key] = Config(value) if isinstance(value, dict) and not isinstance(value, Config) else value
