@@ -48,6 +48,30 @@ def rouge_l(pred: str, ref: str) -> float:
 
 
 @torch.no_grad()
+def bleu(pred: str, ref: str, max_n: int = 4) -> float:
+    """Sentence BLEU (uniform n-gram weights up to `max_n`, brevity penalty, +1 smoothing above unigrams)."""
+    import math
+    from collections import Counter
+
+    p, r = _norm(pred).split(), _norm(ref).split()
+    if not p or not r:
+        return 0.0
+    logs = 0.0
+    for n in range(1, max_n + 1):
+        pn = Counter(tuple(p[i:i + n]) for i in range(len(p) - n + 1))
+        rn = Counter(tuple(r[i:i + n]) for i in range(len(r) - n + 1))
+        hit = sum(min(c, rn[g]) for g, c in pn.items())
+        tot = max(1, sum(pn.values()))
+        if n == 1:
+            if hit == 0:
+                return 0.0
+            logs += math.log(hit / tot)
+        else:
+            logs += math.log((hit + 1) / (tot + 1))
+    bp = 1.0 if len(p) > len(r) else math.exp(1 - len(r) / len(p))
+    return bp * math.exp(logs / max_n)
+
+
 def _token_logprobs(model, ids: torch.Tensor) -> torch.Tensor:
     logits = model(input_ids=ids)["logits"].reshape(ids.shape[0], ids.shape[1], -1)[..., : model.cfg.vocab_size]
     return torch.gather(F.log_softmax(logits[:, :-1].float(), -1), -1, ids[:, 1:, None]).squeeze(-1)
@@ -89,7 +113,7 @@ def multiple_choice_accuracy(model, tokenizer: Callable, items: Sequence[Dict]) 
 class Evaluator:
     """`Evaluator(model, tokenizer).evaluate({"mmlu-like": items, "qa": items}, metrics={"qa": ["exact_match", "f1"]})`."""
 
-    METRICS = {"exact_match": exact_match, "f1": f1_score, "rouge_l": rouge_l}
+    METRICS = {"exact_match": exact_match, "f1": f1_score, "rouge_l": rouge_l, "bleu": bleu}
 
     def __init__(self, model, tokenizer: Callable, decode: Optional[Callable] = None, max_new_tokens: int = 32,
                  eos_token_id: int = 2) -> None:
@@ -120,7 +144,34 @@ class Evaluator:
             agg = {m: 0.0 for m in names}
             for it in items:
                 pred = self.generate(it["instruction"])
+                if it.get("postprocess") == "last_number":                 # GSM8K protocol
+                    from .dataset import extract_last_number
+
+                    pred = extract_last_number(pred) or ""
                 for m in names:
                     agg[m] += self.METRICS[m](pred, it["target"])
             res[name] = {m: v / max(1, len(items)) for m, v in agg.items()}
         return res
+
+    def evaluate_by_category(self, items: Sequence[Dict], metrics: Optional[List[str]] = None,
+                             shots: Optional[Sequence[Dict]] = None, header: str = "") -> Dict[str, Dict[str, float]]:
+        """One benchmark with a `category` per item (MMLU subjects, ...): per-category scores, the macro average over
+        categories and the micro average over items; `shots` are prepended to every item (k-shot prompting)."""
+        from .dataset import few_shot_prompt, group_by_category
+
+        if shots:
+            items = [few_shot_prompt(it, shots, header) for it in items]
+        groups = group_by_category(items)
+        per = self.evaluate(groups, {k: (metrics or ["exact_match"]) for k in groups})
+        keys = sorted({m for v in per.values() for m in v})
+        total = sum(len(g) for g in groups.values())
+        per["macro_avg"] = {m: sum(per[c][m] for c in groups) / max(1, len(groups)) for m in keys}
+        per["micro_avg"] = {m: sum(per[c][m] * len(groups[c]) for c in groups) / max(1, total) for m in keys}
+        return per
+
+    def save(self, results: Dict, path) -> None:
+        import json
+        from pathlib import Path
+
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        Path(path).write_text(json.dumps(results, indent=2, sort_keys=True))

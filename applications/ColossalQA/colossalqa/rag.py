@@ -98,13 +98,21 @@ class RetrievalQA:
     PROMPT = ("Answer the question using only the context. If the context is not enough, say you do not know.\n"
               "{memory}\ncontext:\n{context}\nquestion: {question}\nanswer:")
 
-    def __init__(self, index: EmbeddingIndex, generate: Callable[[str], str], k: int = 3, min_score: float = 0.05,
-                 memory: Optional[ConversationMemory] = None) -> None:
+    def __init__(self, index, generate: Callable[[str], str], k: int = 3, min_score: float = 0.05,
+                 memory: Optional[ConversationMemory] = None, rewrite: bool = False) -> None:
+        """`index`: anything with `search(query, k, source=None)` (EmbeddingIndex, BM25Index, HybridRetriever).
+        `rewrite`: make follow-up questions stand alone (with the same generator) before retrieving."""
         self.index, self.generate, self.k, self.min_score = index, generate, k, min_score
         self.memory = memory or ConversationMemory()
+        self.rewrite = rewrite
 
     def build_prompt(self, question: str) -> Tuple[str, List[Dict]]:
-        hits = [(d, s) for d, s in self.index.search(question, self.k) if s >= self.min_score]
+        query = question
+        if self.rewrite:
+            from .retrieval import rewrite_follow_up
+
+            query = rewrite_follow_up(question, self.memory, self.generate)
+        hits = [(d, s) for d, s in self.index.search(query, self.k) if s >= self.min_score]
         ctx = "\n".join(f"[{i + 1}] ({d['source']}) {d['text']}" for i, (d, _) in enumerate(hits))
         return self.PROMPT.format(memory=self.memory.render(), context=ctx or "(none)", question=question), [d for d, _ in hits]
 

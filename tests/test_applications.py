@@ -248,3 +248,79 @@ def test_colossal_llama_eval_and_qa_utilities(tmp_path):
     qa = RetrievalQA(index, generate=lambda prompt: prompt.split("context:\n")[1].split("\n")[0])
     ans, src = qa.run("How many streaming multiprocessors does the B200 have?")
     assert "148" in ans and src and "question:" in qa.build_prompt("x")[0] and len(qa.memory.turns) == 1
+
+
+def test_eval_dataset_adapters_and_category_report(tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "ColossalEval"))
+    from colossal_eval import (Evaluator, bleu, cloze_items, extract_last_number, few_shot_prompt, gsm8k_items,
+                               load_mmlu_csv, mmlu_items)
+
+    rows = [{"question": "2+2?", "choices": ["3", "4", "5", "6"], "answer": "B", "subject": "math"},
+            {"question": "Capital of France?", "A": "Paris", "B": "Rome", "C": "Oslo", "D": "Bern", "answer": 0,
+             "subject": "geo"}]
+    items = mmlu_items(rows)
+    assert items[0]["answer"] == 1 and items[0]["choices"] == [" A", " B", " C", " D"] and "B. 4" in items[0]["instruction"]
+    assert items[1]["answer"] == 0 and items[1]["category"] == "geo" and items[1]["instruction"].endswith("Answer:")
+    csv_path = tmp_path / "astronomy_test.csv"
+    csv_path.write_text('"Which is a planet?",Sun,Mars,Moon,Vega,B\n')
+    (csv_item,) = load_mmlu_csv(csv_path)
+    assert csv_item["category"] == "astronomy" and csv_item["answer"] == 1
+    g = gsm8k_items([{"question": "3 apples + 4 apples?", "answer": "3 + 4 = 7\n#### 7"}])[0]
+    assert g["target"] == "7" and g["postprocess"] == "last_number"
+    assert extract_last_number("so we get 1,234.0 apples.") == "1234" and extract_last_number("none") is None
+    shot = few_shot_prompt(items[0], [items[1], g], header="The following are questions.")
+    assert shot["instruction"].startswith("The following are questions.") and "Answer: A" in shot["instruction"]
+    assert "#### 7" not in shot["instruction"] and shot["instruction"].rstrip().endswith("Answer:")
+    assert cloze_items([{"context": "He opened the", "endings": ["door", "sky"], "label": 0}])[0]["choices"] == [" door", " sky"]
+    assert bleu("the cat sat on the mat", "the cat sat on the mat") > 0.99 and bleu("a b", "c d") == 0.0
+    assert 0 < bleu("the cat slept on the mat today", "the cat sat on the mat today") < 1
+    ev = Evaluator(_tiny(2), _tok, max_new_tokens=2)
+    rep = ev.evaluate_by_category(items, shots=[items[1]])
+    assert set(rep) == {"math", "geo", "macro_avg", "micro_avg"} and 0.0 <= rep["macro_avg"]["accuracy"] <= 1.0
+    ev.save(rep, tmp_path / "out" / "mmlu.json")
+    assert (tmp_path / "out" / "mmlu.json").exists()
+
+
+def test_qa_bm25_hybrid_and_loaders(tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "ColossalQA"))
+    from colossalqa import (BM25Index, ConversationMemory, EmbeddingIndex, HybridRetriever, RetrievalQA, load_documents,
+                            rewrite_follow_up, tokenize)
+
+    assert tokenize("NVLink-5 给每个GPU 900 GB/s!") == ["nvlink", "5", "给", "每", "个", "gpu", "900", "gb", "s"]
+    (tmp_path / "b200.md").write_text("# Compute\nThe B200 has 148 streaming multiprocessors.\n"
+                                      "# Memory\nIts HBM3e capacity is 180 gigabytes.\n")
+    (tmp_path / "misc.jsonl").write_text('{"text": "Bananas are yellow and rich in potassium."}\n'
+                                         '{"text": "NVLink 5 gives every GPU 900 gigabytes per second to each peer."}\n')
+    docs = load_documents([tmp_path / "b200.md", tmp_path / "misc.jsonl"], chunk_size=120, chunk_overlap=0)
+    assert {d["source"] for d in docs} == {"b200.md", "misc.jsonl"} and len(docs) == 4
+    assert not any("148" in d["text"] and "180" in d["text"] for d in docs)      # sections are not merged
+    bm = BM25Index()
+    for src in ("b200.md", "misc.jsonl"):
+        bm.add_documents([d["text"] for d in docs if d["source"] == src], source=src)
+    assert bm.add_documents([docs[0]["text"]], source=docs[0]["source"]) == 0       # deduplicated
+    top = bm.search("how many gigabytes of HBM3e capacity", k=2)
+    assert "180" in top[0][0]["text"] and top[0][1] > 0
+    assert bm.search("potassium", k=3, source="b200.md") == []
+    emb = EmbeddingIndex()
+    for src in ("b200.md", "misc.jsonl"):
+        emb.add_documents([d["text"] for d in docs if d["source"] == src], source=src)
+    hy = HybridRetriever([emb, bm], weights=[1.0, 1.0], k_per_source=1)
+    res = hy.search("NVLink gigabytes per second", k=3)
+    assert "900" in res[0][0]["text"] and len({d["source"] for d, _ in res}) == len(res) <= 2   # one chunk per source
+    # follow-up rewriting + the QA chain on top of the hybrid retriever
+    mem = ConversationMemory()
+    mem.add("How many SMs does the B200 have?", "148.")
+    calls = []
+
+    def gen(prompt):
+        calls.append(prompt)
+        if prompt.startswith("Rewrite"):
+            return "What is the HBM3e capacity of the B200?"
+        return prompt.split("context:\n")[1].split("\n")[0]
+
+    assert rewrite_follow_up("And its memory?", mem, gen) == "What is the HBM3e capacity of the B200?"
+    assert rewrite_follow_up("And its memory?", ConversationMemory(), gen) == "And its memory?"
+    qa = RetrievalQA(HybridRetriever([emb, bm], weights=[0.5, 1.0]), gen, k=2, min_score=0.0, memory=mem, rewrite=True)
+    ans, src = qa.run("And its memory?")
+    assert any("180" in d["text"] for d in src) and ans and any(c.startswith("Rewrite") for c in calls)
+    assert "HBM3e capacity" not in calls[-1].split("question:")[1]      # the user's wording goes into the prompt
