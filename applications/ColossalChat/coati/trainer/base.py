@@ -43,7 +43,10 @@ class CycledDataLoader:
 
 class _TrainerBase(ABC):
     def __init__(self, booster: Optional[Booster], optimizer, lr_scheduler=None, accumulation_steps: int = 1,
-                 device=None) -> None:
+                 device=None, callbacks: Optional[List] = None) -> None:
+        from .callbacks import CallbackList
+
+        self.callbacks = CallbackList(callbacks)
         self.booster, self.optimizer, self.lr_scheduler = booster, optimizer, lr_scheduler
         self.accumulation_steps = max(1, accumulation_steps)
         self.device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
@@ -66,6 +69,11 @@ class _TrainerBase(ABC):
             return True
         return False
 
+    def add_callbacks(self, *callbacks) -> "_TrainerBase":
+        """Attach callbacks after construction (every concrete trainer gets them without a signature change)."""
+        self.callbacks.callbacks.extend(callbacks)
+        return self
+
     def _to_device(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         return {k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in batch.items()}
 
@@ -77,8 +85,8 @@ class SLTrainer(_TrainerBase):
     """Epoch loop over a dataloader calling `_train_step(batch) -> (loss, metrics)`."""
 
     def __init__(self, booster, max_epochs: int, model: nn.Module, optimizer, lr_scheduler=None,
-                 accumulation_steps: int = 1, device=None) -> None:
-        super().__init__(booster, optimizer, lr_scheduler, accumulation_steps, device)
+                 accumulation_steps: int = 1, device=None, callbacks: Optional[List] = None) -> None:
+        super().__init__(booster, optimizer, lr_scheduler, accumulation_steps, device, callbacks)
         self.max_epochs, self.model = max_epochs, model
 
     @abstractmethod
@@ -91,12 +99,17 @@ class SLTrainer(_TrainerBase):
         return {"loss": float(loss), **metrics}
 
     def fit(self, train_dataloader: Iterable, eval_dataloader: Optional[Iterable] = None) -> List[Dict[str, float]]:
+        self.callbacks.on_fit_start(self)
         for epoch in range(self.max_epochs):
             self.model.train()
+            self.callbacks.on_epoch_start(self, epoch)
             for batch in train_dataloader:
-                loss, metrics = self._train_step(self._to_device(batch))
+                batch = self._to_device(batch)
+                self.callbacks.on_batch_start(self, batch)
+                loss, metrics = self._train_step(batch)
                 self._backward_and_maybe_step(loss)
                 self.log(epoch=epoch, loss=all_reduce_mean(loss.detach()), **metrics)
+                self.callbacks.on_batch_end(self, batch, self.history[-1])
             if eval_dataloader is not None:
                 self.model.eval()
                 agg: Dict[str, float] = {}
@@ -106,14 +119,17 @@ class SLTrainer(_TrainerBase):
                         agg[k] = agg.get(k, 0.0) + v
                     n += 1
                 self.log(epoch=epoch, **{f"eval_{k}": v / max(n, 1) for k, v in agg.items()})
+            self.callbacks.on_epoch_end(self, epoch)
+        self.callbacks.on_fit_end(self)
         return self.history
 
 
 class OLTrainer(_TrainerBase):
     """`fit(prompts, num_episodes, num_collect_steps, num_update_steps)`: collect rollouts, then update on them."""
 
-    def __init__(self, booster, optimizer, lr_scheduler=None, accumulation_steps: int = 1, device=None) -> None:
-        super().__init__(booster, optimizer, lr_scheduler, accumulation_steps, device)
+    def __init__(self, booster, optimizer, lr_scheduler=None, accumulation_steps: int = 1, device=None,
+                 callbacks: Optional[List] = None) -> None:
+        super().__init__(booster, optimizer, lr_scheduler, accumulation_steps, device, callbacks)
 
     @abstractmethod
     def _collect(self, prompts: Dict[str, torch.Tensor]) -> None:
@@ -129,10 +145,19 @@ class OLTrainer(_TrainerBase):
     def fit(self, prompt_dataloader: Iterable, num_episodes: int = 1, num_collect_steps: int = 1,
             num_update_steps: int = 1) -> List[Dict[str, float]]:
         prompts = CycledDataLoader(prompt_dataloader)
+        self.callbacks.on_fit_start(self)
         for episode in range(num_episodes):
+            self.callbacks.on_epoch_start(self, episode)
             for _ in range(num_collect_steps):
-                self._collect(self._to_device(prompts.next()))
+                batch = self._to_device(prompts.next())
+                self.callbacks.on_collect_start(self)
+                self._collect(batch)
+                self.callbacks.on_collect_end(self, batch)
             for _ in range(num_update_steps):
+                self.callbacks.on_update_start(self)
                 self.log(episode=episode, **self._update())
+                self.callbacks.on_update_end(self, self.history[-1])
             self._after_episode()
+            self.callbacks.on_epoch_end(self, episode)
+        self.callbacks.on_fit_end(self)
         return self.history

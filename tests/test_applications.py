@@ -324,3 +324,47 @@ def test_qa_bm25_hybrid_and_loaders(tmp_path):
     ans, src = qa.run("And its memory?")
     assert any("180" in d["text"] for d in src) and ans and any(c.startswith("Rewrite") for c in calls)
     assert "HBM3e capacity" not in calls[-1].split("question:")[1]      # the user's wording goes into the prompt
+
+
+def test_trainer_callbacks_performance_checkpoint_and_metrics(tmp_path):
+    from coati.trainer.callbacks import Callback, MetricsLogger, PerformanceEvaluator, SaveCheckpoint
+
+    sft_items = [tokenize_sft([{"role": "user", "content": "ping"}, {"role": "assistant", "content": "pong"}], _tok)] * 8
+    dl = torch.utils.data.DataLoader(ListDataset(sft_items), batch_size=4, collate_fn=DataCollatorForSupervisedDataset())
+    m = _tiny()
+    n_params = sum(p.numel() for p in m.parameters())
+    events = []
+
+    class Recorder(Callback):
+        def on_fit_start(self, trainer):
+            events.append("fit_start")
+
+        def on_epoch_end(self, trainer, epoch):
+            events.append(f"epoch_end_{epoch}")
+
+        def on_batch_end(self, trainer, batch, metrics):
+            events.append("batch_end")
+            assert "loss" in metrics and torch.is_tensor(batch["input_ids"])
+
+    perf = PerformanceEvaluator(n_params, num_layers=m.cfg.num_hidden_layers, hidden_size=m.cfg.hidden_size, ignore_steps=1)
+    tr = SFTTrainer(m, None, torch.optim.AdamW(m.parameters(), lr=1e-3), max_epochs=2)
+    tr.add_callbacks(Recorder(), perf, SaveCheckpoint(str(tmp_path / "ckpt"), interval=2), MetricsLogger(str(tmp_path / "log.jsonl")))
+    tr.fit(dl)
+    assert events == ["fit_start", "batch_end", "batch_end", "epoch_end_0", "batch_end", "batch_end", "epoch_end_1"]
+    s = tr.performance
+    assert s["steps"] == 4 and s["train_tokens_per_s"] > 0 and s["train_samples_per_s"] > 0 and s["train_tflops_per_device"] > 0
+    # the flop model: 3 x (2 N + 4 L H S) per token for a training step
+    ids = next(iter(dl))["input_ids"]
+    per_tok = 3 * (2 * n_params + 4 * m.cfg.num_hidden_layers * m.cfg.hidden_size * ids.shape[1])
+    assert abs(perf.train_flops / perf.train_tokens - per_tok) / per_tok < 0.35     # masks make tokens < B x S
+    assert (tmp_path / "ckpt" / "epoch_1" / "model.pt").exists() and not (tmp_path / "ckpt" / "epoch_0").exists()
+    lines = (tmp_path / "log.jsonl").read_text().strip().splitlines()
+    assert len(lines) == len(tr.history) == 4
+    # online loop: collect / update hooks
+    actor, init = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    g = GRPOTrainer(None, actor, init, torch.optim.AdamW(actor.parameters(), lr=1e-3), _count_reward, num_generations=4,
+                    generate_kwargs=dict(max_new_tokens=4))
+    perf2 = PerformanceEvaluator(sum(p.numel() for p in actor.parameters()))
+    g.add_callbacks(perf2)
+    g.fit(_prompt_loader(), num_episodes=1, num_collect_steps=2, num_update_steps=1)
+    assert g.performance["generate_tokens_per_s"] > 0 and g.performance["steps"] == 1
