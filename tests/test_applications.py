@@ -368,3 +368,31 @@ def test_trainer_callbacks_performance_checkpoint_and_metrics(tmp_path):
     g.add_callbacks(perf2)
     g.fit(_prompt_loader(), num_episodes=1, num_collect_steps=2, num_update_steps=1)
     assert g.performance["generate_tokens_per_s"] > 0 and g.performance["steps"] == 1
+
+
+def test_generation_controls():
+    from coati.models.generation import _apply_repetition_penalty, generate
+
+    m = _tiny(3, vocab_size=32)
+    ids = torch.tensor([[5, 6, 7], [8, 9, 10]])
+    torch.manual_seed(0)
+    greedy = generate(m, ids, max_new_tokens=6, do_sample=False)
+    assert greedy.shape == (2, 9) and torch.equal(greedy[:, :3], ids)
+    # EOS = the first greedy token: without min_new_tokens the rows stop at once, with it they run on
+    eos = int(greedy[0, 3])
+    short, amask = generate(m, ids[:1], max_new_tokens=6, do_sample=False, eos_token_id=eos, pad_token_id=0,
+                            return_action_mask=True)
+    assert int(short[0, 3]) == eos and amask[0].tolist() == [True] + [False] * 5 and (short[0, 4:] == 0).all()
+    longer, amask2 = generate(m, ids[:1], max_new_tokens=6, do_sample=False, eos_token_id=eos, min_new_tokens=3,
+                              return_action_mask=True)
+    assert (longer[0, 3:6] != eos).all() and amask2[0, :3].all()
+    # a two-token stop sequence taken from the greedy continuation ends the row right after it
+    stop = greedy[1, 4:6].tolist()
+    stopped, am = generate(m, ids[1:], max_new_tokens=6, do_sample=False, stop_sequences=[stop], return_action_mask=True)
+    assert stopped[0, 4:6].tolist() == stop and am[0].tolist() == [True, True, True, False, False, False]
+    # repetition penalty: seen tokens are pushed down, unseen ones untouched, padding positions do not count as seen
+    lg = torch.tensor([[2.0, -2.0, 1.0, 0.5]])
+    out = _apply_repetition_penalty(lg, torch.tensor([[0, 1, 3]]), torch.tensor([[1, 1, 0]]), 2.0)
+    assert out.tolist() == [[1.0, -4.0, 1.0, 0.5]]
+    rep = generate(m, ids, max_new_tokens=6, do_sample=False, repetition_penalty=50.0)
+    assert all(len(set(r[3:].tolist())) == 6 for r in rep)        # a huge penalty forbids repeats
