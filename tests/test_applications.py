@@ -396,3 +396,40 @@ def test_generation_controls():
     assert out.tolist() == [[1.0, -4.0, 1.0, 0.5]]
     rep = generate(m, ids, max_new_tokens=6, do_sample=False, repetition_penalty=50.0)
     assert all(len(set(r[3:].tolist())) == 6 for r in rep)        # a huge penalty forbids repeats
+
+
+def test_colossal_llama_tuning_helpers():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "Colossal-LLaMA"))
+    from colossal_llama import (activate_neftune, deactivate_neftune, expand_vocab, format_numel_str,
+                                freeze_non_embeds_parameters, get_model_numel, plan_vocab_expansion, unfreeze_parameters)
+
+    m = _tiny(0, vocab_size=32)
+    ids = torch.randint(0, 32, (2, 8))
+    clean = m.model.embed_tokens(ids)
+    activate_neftune(m, neftune_noise_alpha=5.0, generator=torch.Generator().manual_seed(0))
+    m.train()
+    noisy = m.model.embed_tokens(ids)
+    mag = 5.0 / (8 * clean.shape[-1]) ** 0.5
+    diff = (noisy - clean).abs()
+    assert 0 < diff.max() <= mag + 1e-6 and diff.mean() > 0.3 * mag          # uniform in [-mag, mag]
+    m.eval()
+    assert torch.equal(m.model.embed_tokens(ids), clean)                       # no noise at evaluation time
+    m.train()
+    deactivate_neftune(m)
+    assert torch.equal(m.model.embed_tokens(ids), clean)
+    # stage 1 of vocabulary expansion: only embeddings + head train
+    tokens, sources = plan_vocab_expansion({"hello": 50, "hi": 500, "a": 1000, "worlds": 10},
+                                           encode=lambda t: [ord(c) % 32 for c in t], old_vocab_size=32, max_new_tokens=2)
+    assert tokens == ["hi", "hello"] and sources == {32: [ord("h") % 32, ord("i") % 32],
+                                                     33: [ord(c) % 32 for c in "hello"]}     # gain 500 > 200 > 50
+    m = expand_vocab(m, 34, sources)
+    kept = freeze_non_embeds_parameters(m)
+    assert kept and all(("embed_tokens" in n) or ("lm_head" in n) for n in kept)
+    assert get_model_numel(m, trainable_only=True) < get_model_numel(m)
+    loss = m(input_ids=torch.randint(0, 34, (1, 6)), labels=torch.randint(0, 34, (1, 6)))["loss"]
+    loss.backward()
+    assert m.model.embed_tokens.weight.grad is not None and all(
+        p.grad is None for n, p in m.named_parameters() if "embed_tokens" not in n and "lm_head" not in n)
+    unfreeze_parameters(m)
+    assert get_model_numel(m, trainable_only=True) == get_model_numel(m)
+    assert format_numel_str(8_030_000_000) == "8.03 B" and format_numel_str(1500) == "1.50 K" and format_numel_str(7) == "7"
