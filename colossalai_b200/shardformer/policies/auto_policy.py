@@ -70,6 +70,10 @@ for _fam, _classes in _FAMILIES.items():
 for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3")):
     for _suffix in ("Model", "ForCausalLM"):
         register_policy(f"transformers.models.{_mod}.modeling_{_mod}.{_pre}{_suffix}", "hf_decoder", "HFDecoderPolicy")
+for _c in ("GPT2Model", "GPT2LMHeadModel"):
+    register_policy(f"transformers.models.gpt2.modeling_gpt2.{_c}", "hf_gpt", "HFGPT2Policy")
+for _c in ("OPTModel", "OPTForCausalLM"):
+    register_policy(f"transformers.models.opt.modeling_opt.{_c}", "hf_gpt", "HFOPTPolicy")
 
 
 def import_policy(loc: PolicyLocation) -> type:

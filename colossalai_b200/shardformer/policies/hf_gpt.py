@@ -1,0 +1,123 @@
+"""Policies that shard a user's HuggingFace GPT-2 / OPT model in place (tensor parallelism by sub-module and attribute
+replacement; reference `policies/gpt2.py:26-190`, `policies/opt.py:27-160`).
+
+These two families need more than the llama-like decoders of `hf_decoder.py`:
+  * GPT-2 keeps q|k|v in ONE `Conv1D` ([in, 3 * hidden] weight): the column shard has to take each rank's slice of q, of
+    k and of v (`GPT2FusedLinearConv1D_Col` with split sizes), and `GPT2Attention.split_size` - the width the module
+    uses to cut the fused output apart again - becomes the local width;
+  * OPT's attention views its projections with `self.num_heads`, so that attribute (and `embed_dim`) is replaced by the
+    local value;
+  * both tie the LM head to the token embedding: both sides are sharded along the vocabulary identically and re-tied;
+    the learned position embeddings stay replicated.
+LayerNorms are left to PyTorch (replicated parameters, tiny).  Pipeline / sequence parallelism of HF modules: use the
+native zoo (`models.hf_io`), as for `hf_decoder.py`."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch.nn as nn
+
+from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
+from ..layer.qkv_fused_linear import GPT2FusedLinearConv1D_Col, GPT2FusedLinearConv1D_Row
+from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
+
+__all__ = ["HFGPT2Policy", "HFOPTPolicy"]
+
+
+class _HFTiedDecoderPolicy(Policy):
+    def config_sanity_check(self) -> None:
+        cfg = self.model.config
+        tp = self.shard_config.tensor_parallel_size
+        if self.shard_config.enable_tensor_parallelism:
+            heads = getattr(cfg, "num_attention_heads", None) or cfg.n_head
+            assert heads % tp == 0, "the number of attention heads must be divisible by the TP size"
+        assert not self.shard_config.enable_sequence_parallelism, \
+            "sequence parallelism of HF modules is not supported; build the model from the native zoo (models.hf_io)"
+
+    def preprocess(self) -> nn.Module:
+        self.tie_weight = self.tie_weight_check()
+        return self.model
+
+    def postprocess(self) -> nn.Module:
+        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism:
+            emb, head = self.model.get_input_embeddings(), self.model.get_output_embeddings()
+            if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
+                head.weight = emb.weight
+        return self.model
+
+    def get_held_layers(self) -> List[nn.Module]:
+        if self.pipeline_stage_manager is not None:
+            raise NotImplementedError("pipeline parallelism of HuggingFace modules: import the weights into the native "
+                                      "zoo (`models.hf_io.load_hf_checkpoint`) and use its policy")
+        return []
+
+    def get_shared_params(self):
+        return []
+
+    def _vocab_kwargs(self) -> dict:
+        sc = self.shard_config
+        return dict(make_vocab_size_divisible_by=sc.make_vocab_size_divisible_by, fp8_communication=sc.fp8_communication)
+
+
+class HFGPT2Policy(_HFTiedDecoderPolicy):
+    """`GPT2Model`, `GPT2LMHeadModel`."""
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        hidden = cfg.hidden_size
+        inner = cfg.n_inner if getattr(cfg, "n_inner", None) is not None else 4 * hidden
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        policy["GPT2Attention"] = ModulePolicyDescription(attribute_replacement={
+            "embed_dim": hidden // tp, "split_size": hidden // tp, "num_heads": cfg.num_attention_heads // tp})
+        policy["GPT2Block"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("attn.c_attn", GPT2FusedLinearConv1D_Col,
+                                            kwargs=dict(split_sizes=[hidden] * 3, **fp8)),
+            SubModuleReplacementDescription("attn.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.c_fc", GPT2FusedLinearConv1D_Col,
+                                            kwargs=dict(split_sizes=[inner], **fp8)),
+            SubModuleReplacementDescription("mlp.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(fp8)),
+        ])
+        policy["GPT2Model"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+        policy["GPT2LMHeadModel"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
+                                            kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
+        return policy
+
+
+class HFOPTPolicy(_HFTiedDecoderPolicy):
+    """`OPTModel`, `OPTForCausalLM` (models without `project_in / project_out`, i.e. word_embed_proj_dim == hidden)."""
+
+    def config_sanity_check(self) -> None:
+        super().config_sanity_check()
+        cfg = self.model.config
+        assert getattr(cfg, "word_embed_proj_dim", cfg.hidden_size) == cfg.hidden_size, \
+            "OPT variants with project_in / project_out (word_embed_proj_dim != hidden_size) are not supported"
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        policy["OPTAttention"] = ModulePolicyDescription(attribute_replacement={
+            "embed_dim": cfg.hidden_size // tp, "num_heads": cfg.num_attention_heads // tp})
+        policy["OPTDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attn.out_proj", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("fc1", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("fc2", Linear1D_Row, kwargs=dict(fp8)),
+        ])
+        policy["OPTDecoder"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+        policy["OPTForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
+                                            kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
+        return policy

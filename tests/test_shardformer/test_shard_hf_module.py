@@ -71,10 +71,66 @@ def _check(family):
     assert n > 10
 
 
+def _check_tied(family):
+    """GPT-2 (fused Conv1D q|k|v, `split_size` attribute) and OPT (`num_heads` attribute), both with tied LM heads."""
+    import transformers
+
+    torch.manual_seed(0)
+    if family == "gpt2":
+        cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
+                                      embd_pdrop=0.0, attn_pdrop=0.0)
+        cfg._attn_implementation = "eager"
+        org = transformers.GPT2LMHeadModel(cfg).float()
+    else:
+        cfg = transformers.OPTConfig(vocab_size=320, hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4,
+                                     max_position_embeddings=64, word_embed_proj_dim=64, dropout=0.0)
+        cfg._attn_implementation = "eager"
+        org = transformers.OPTForCausalLM(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    if family == "gpt2":
+        blk = sharded.transformer.h[0]
+        assert type(blk.attn.c_attn).__name__ == "GPT2FusedLinearConv1D_Col" and blk.attn.split_size == 32
+        assert type(blk.mlp.c_proj).__name__ == "GPT2FusedLinearConv1D_Row"
+        assert sharded.lm_head.weight is sharded.transformer.wte.weight and sharded.lm_head.weight.shape[0] == 192   # 320 -> 384 / 2
+    else:
+        layer = sharded.model.decoder.layers[0]
+        assert type(layer.self_attn.q_proj).__name__ == "Linear1D_Col" and layer.self_attn.num_heads == 2
+        assert type(layer.fc2).__name__ == "Linear1D_Row"
+        assert sharded.lm_head.weight is sharded.model.decoder.embed_tokens.weight
+    torch.manual_seed(6)
+    ids = torch.randint(0, 320, (2, 16))
+    ref = org(input_ids=ids, labels=ids)
+    out = sharded(input_ids=ids, labels=ids)
+    torch.testing.assert_close(out.logits, ref.logits, atol=2e-4, rtol=2e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    # replicated parameters (LayerNorms, position embeddings) must carry the full gradient on every rank
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    checked = 0
+    for name, p in sharded.named_parameters():
+        if hasattr(p, "dist_shard") or hasattr(p, "gather_fn") or p.shape != ref_grads.get(name, p).shape:
+            continue
+        torch.testing.assert_close(p.grad, ref_grads[name], atol=2e-4, rtol=2e-3, msg=lambda m: f"{family} {name}: {m}")
+        checked += 1
+    assert checked >= 6
+    # the tied vocabulary shard: this rank's rows of the reference gradient
+    emb = sharded.get_input_embeddings().weight
+    r = dist.get_rank()
+    full = ref_grads["transformer.wte.weight" if family == "gpt2" else "model.decoder.embed_tokens.weight"]
+    rows = full[r * 192:(r + 1) * 192]                       # the vocabulary is padded to 384 rows: the tail shard is short
+    torch.testing.assert_close(emb.grad[: rows.shape[0]], rows, atol=2e-4, rtol=2e-3)
+    assert emb.grad[rows.shape[0]:].abs().max() < 1e-6 if rows.shape[0] < 192 else True
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
         _check(family)
+    for family in ("gpt2", "opt"):
+        _check_tied(family)
     dist.destroy_process_group()
 
 
