@@ -74,6 +74,11 @@ for _c in ("GPT2Model", "GPT2LMHeadModel"):
     register_policy(f"transformers.models.gpt2.modeling_gpt2.{_c}", "hf_gpt", "HFGPT2Policy")
 for _c in ("OPTModel", "OPTForCausalLM"):
     register_policy(f"transformers.models.opt.modeling_opt.{_c}", "hf_gpt", "HFOPTPolicy")
+for _c in ("GPTJModel", "GPTJForCausalLM"):
+    register_policy(f"transformers.models.gptj.modeling_gptj.{_c}", "hf_gpt", "HFGPTJPolicy")
+for _c in ("BertModel", "BertForSequenceClassification", "BertForTokenClassification", "BertForQuestionAnswering",
+           "BertForMultipleChoice", "BertForNextSentencePrediction"):
+    register_policy(f"transformers.models.bert.modeling_bert.{_c}", "hf_encoder", "HFBertPolicy")
 
 
 def import_policy(loc: PolicyLocation) -> type:

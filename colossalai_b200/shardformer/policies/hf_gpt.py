@@ -21,7 +21,7 @@ from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabP
 from ..layer.qkv_fused_linear import GPT2FusedLinearConv1D_Col, GPT2FusedLinearConv1D_Row
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFGPT2Policy", "HFOPTPolicy"]
+__all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy"]
 
 
 class _HFTiedDecoderPolicy(Policy):
@@ -118,6 +118,36 @@ class HFOPTPolicy(_HFTiedDecoderPolicy):
         policy["OPTDecoder"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
         policy["OPTForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
+                                            kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
+        return policy
+
+
+class HFGPTJPolicy(_HFTiedDecoderPolicy):
+    """`GPTJModel`, `GPTJForCausalLM` (parallel attention + MLP block, partial rotary inside the attention module: the
+    rotary slice is per head, so splitting heads over ranks leaves it untouched).  The LM head is not tied and has a
+    bias; it becomes a gathered vocab-parallel head."""
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        policy["GPTJAttention"] = ModulePolicyDescription(attribute_replacement={
+            "embed_dim": cfg.hidden_size // tp, "num_attention_heads": cfg.num_attention_heads // tp})
+        policy["GPTJBlock"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attn.out_proj", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.fc_in", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.fc_out", Linear1D_Row, kwargs=dict(fp8)),
+        ])
+        policy["GPTJModel"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+        policy["GPTJForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
         return policy

@@ -76,7 +76,12 @@ def _check_tied(family):
     import transformers
 
     torch.manual_seed(0)
-    if family == "gpt2":
+    if family == "gptj":
+        cfg = transformers.GPTJConfig(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, rotary_dim=8,
+                                      resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+        cfg._attn_implementation = "eager"
+        org = transformers.GPTJForCausalLM(cfg).float()
+    elif family == "gpt2":
         cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
                                       embd_pdrop=0.0, attn_pdrop=0.0)
         cfg._attn_implementation = "eager"
@@ -89,7 +94,11 @@ def _check_tied(family):
     sharded = copy.deepcopy(org)
     sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
     sharded, _ = ShardFormer(sc).optimize(sharded)
-    if family == "gpt2":
+    if family == "gptj":
+        blk = sharded.transformer.h[0]
+        assert type(blk.attn.q_proj).__name__ == "Linear1D_Col" and blk.attn.num_attention_heads == 2
+        assert type(blk.mlp.fc_out).__name__ == "Linear1D_Row" and type(sharded.lm_head).__name__ == "VocabParallelLMHead1D"
+    elif family == "gpt2":
         blk = sharded.transformer.h[0]
         assert type(blk.attn.c_attn).__name__ == "GPT2FusedLinearConv1D_Col" and blk.attn.split_size == 32
         assert type(blk.mlp.c_proj).__name__ == "GPT2FusedLinearConv1D_Row"
@@ -119,18 +128,58 @@ def _check_tied(family):
     # the tied vocabulary shard: this rank's rows of the reference gradient
     emb = sharded.get_input_embeddings().weight
     r = dist.get_rank()
-    full = ref_grads["transformer.wte.weight" if family == "gpt2" else "model.decoder.embed_tokens.weight"]
+    full = ref_grads["model.decoder.embed_tokens.weight" if family == "opt" else "transformer.wte.weight"]
     rows = full[r * 192:(r + 1) * 192]                       # the vocabulary is padded to 384 rows: the tail shard is short
     torch.testing.assert_close(emb.grad[: rows.shape[0]], rows, atol=2e-4, rtol=2e-3)
     assert emb.grad[rows.shape[0]:].abs().max() < 1e-6 if rows.shape[0] < 192 else True
+
+
+def _check_bert():
+    import transformers
+
+    torch.manual_seed(0)
+    cfg = transformers.BertConfig(vocab_size=320, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                  intermediate_size=128, max_position_embeddings=64, hidden_dropout_prob=0.0,
+                                  attention_probs_dropout_prob=0.0, num_labels=3)
+    cfg._attn_implementation = "eager"
+    org = transformers.BertForSequenceClassification(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    layer = sharded.bert.encoder.layer[0]
+    assert type(layer.attention.self.query).__name__ == "Linear1D_Col" and layer.attention.self.num_attention_heads == 2
+    assert type(layer.output.dense).__name__ == "Linear1D_Row"
+    assert type(sharded.bert.embeddings.word_embeddings).__name__ == "VocabParallelEmbedding1D"
+    torch.manual_seed(8)
+    ids = torch.randint(0, 320, (3, 16))
+    mask = torch.ones(3, 16, dtype=torch.long)
+    mask[0, 10:] = 0
+    labels = torch.tensor([0, 2, 1])
+    ref = org(input_ids=ids, attention_mask=mask, labels=labels)
+    out = sharded(input_ids=ids, attention_mask=mask, labels=labels)
+    torch.testing.assert_close(out.logits, ref.logits, atol=2e-4, rtol=2e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        full = _gather_grad(p)
+        r = ref_grads[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        torch.testing.assert_close(full, r, atol=2e-4, rtol=2e-3, msg=lambda m: f"bert {name}: {m}")
+        n += 1
+    assert n > 20
 
 
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
         _check(family)
-    for family in ("gpt2", "opt"):
+    for family in ("gpt2", "opt", "gptj"):
         _check_tied(family)
+    _check_bert()
     dist.destroy_process_group()
 
 
