@@ -1,4 +1,4 @@
-"""Policy that shards a user's HuggingFace BERT encoder in place (reference `policies/bert.py:30-260`): query / key /
+"""Policies that shard a user's HuggingFace BERT / ViT encoder in place (reference `policies/bert.py:30-260`): query / key /
 value and `intermediate.dense` become column-parallel, `attention.output.dense` and `output.dense` row-parallel, the
 word embedding vocab-parallel; the attention module sizes its head views with `-1`, so only the bookkeeping attributes
 (`num_attention_heads`, `all_head_size`) are replaced.  Covers `BertModel` and the heads that sit on the pooled /
@@ -13,7 +13,7 @@ import torch.nn as nn
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFBertPolicy"]
+__all__ = ["HFBertPolicy", "HFViTPolicy"]
 
 
 class HFBertPolicy(Policy):
@@ -63,3 +63,29 @@ class HFBertPolicy(Policy):
 
     def get_shared_params(self):
         return []
+
+
+class HFViTPolicy(HFBertPolicy):
+    """`ViTModel`, `ViTForImageClassification` (reference `policies/vit.py`): the same column / row pattern on
+    `attention.attention.{query,key,value}`, `attention.output.dense`, `intermediate.dense`, `output.dense`;
+    `ViTSelfAttention` reshapes with `num_attention_heads` and `all_head_size`, so both become local values.  Patch and
+    position embeddings stay replicated."""
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        policy["ViTSelfAttention"] = ModulePolicyDescription(attribute_replacement={
+            "num_attention_heads": cfg.num_attention_heads // tp, "all_head_size": cfg.hidden_size // tp})
+        policy["ViTLayer"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("attention.attention.query", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attention.attention.key", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attention.attention.value", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attention.output.dense", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("intermediate.dense", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("output.dense", Linear1D_Row, kwargs=dict(fp8)),
+        ])
+        return policy

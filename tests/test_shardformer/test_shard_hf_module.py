@@ -173,6 +173,36 @@ def _check_bert():
     assert n > 20
 
 
+def _check_vit():
+    import transformers
+
+    torch.manual_seed(0)
+    cfg = transformers.ViTConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                                 image_size=32, patch_size=8, num_channels=3, hidden_dropout_prob=0.0,
+                                 attention_probs_dropout_prob=0.0, num_labels=5)
+    cfg._attn_implementation = "eager"
+    org = transformers.ViTForImageClassification(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    layer = sharded.vit.encoder.layer[0]
+    assert type(layer.attention.attention.key).__name__ == "Linear1D_Col" and layer.attention.attention.all_head_size == 32
+    torch.manual_seed(9)
+    px = torch.randn(2, 3, 32, 32)
+    labels = torch.tensor([1, 4])
+    ref = org(pixel_values=px, labels=labels)
+    out = sharded(pixel_values=px, labels=labels)
+    torch.testing.assert_close(out.logits, ref.logits, atol=2e-4, rtol=2e-4)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        torch.testing.assert_close(_gather_grad(p), ref_grads[name], atol=2e-4, rtol=2e-3, msg=lambda m: f"vit {name}: {m}")
+        n += 1
+    assert n > 20
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
@@ -180,6 +210,7 @@ def _worker(rank, world_size, port):
     for family in ("gpt2", "opt", "gptj"):
         _check_tied(family)
     _check_bert()
+    _check_vit()
     dist.destroy_process_group()
 
 
