@@ -79,6 +79,8 @@ for _c in ("GPTJModel", "GPTJForCausalLM"):
 for _c in ("BertModel", "BertForSequenceClassification", "BertForTokenClassification", "BertForQuestionAnswering",
            "BertForMultipleChoice", "BertForNextSentencePrediction"):
     register_policy(f"transformers.models.bert.modeling_bert.{_c}", "hf_encoder", "HFBertPolicy")
+for _c in ("WhisperModel", "WhisperForConditionalGeneration"):
+    register_policy(f"transformers.models.whisper.modeling_whisper.{_c}", "hf_encdec", "HFWhisperPolicy")
 for _c in ("ViTModel", "ViTForImageClassification"):
     register_policy(f"transformers.models.vit.modeling_vit.{_c}", "hf_encoder", "HFViTPolicy")
 

@@ -203,6 +203,48 @@ def _check_vit():
     assert n > 20
 
 
+def _check_whisper():
+    import transformers
+
+    torch.manual_seed(0)
+    cfg = transformers.WhisperConfig(d_model=64, encoder_layers=2, decoder_layers=2, encoder_attention_heads=4,
+                                     decoder_attention_heads=4, encoder_ffn_dim=128, decoder_ffn_dim=128, vocab_size=320,
+                                     num_mel_bins=8, max_source_positions=16, max_target_positions=16, pad_token_id=0,
+                                     bos_token_id=1, eos_token_id=2, decoder_start_token_id=1, suppress_tokens=None,
+                                     begin_suppress_tokens=None, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)
+    cfg._attn_implementation = "eager"
+    org = transformers.WhisperForConditionalGeneration(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    dec = sharded.model.decoder.layers[0]
+    assert type(dec.encoder_attn.k_proj).__name__ == "Linear1D_Col" and dec.encoder_attn.num_heads == 2
+    assert type(sharded.model.encoder.layers[1].fc2).__name__ == "Linear1D_Row"
+    assert sharded.proj_out.weight is sharded.model.decoder.embed_tokens.weight
+    torch.manual_seed(10)
+    feats = torch.randn(2, 8, 32)
+    ids = torch.randint(3, 320, (2, 6))
+    ref = org(input_features=feats, decoder_input_ids=ids, labels=ids)
+    out = sharded(input_features=feats, decoder_input_ids=ids, labels=ids)
+    torch.testing.assert_close(out.logits, ref.logits, atol=2e-4, rtol=2e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        if p.grad is None:                                   # the encoder's sinusoidal positions are frozen
+            assert ref_grads[name] is None, name
+            continue
+        full = _gather_grad(p)
+        r = ref_grads[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        torch.testing.assert_close(full, r, atol=2e-4, rtol=2e-3, msg=lambda m: f"whisper {name}: {m}")
+        n += 1
+    assert n > 40
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
@@ -211,6 +253,7 @@ def _worker(rank, world_size, port):
         _check_tied(family)
     _check_bert()
     _check_vit()
+    _check_whisper()
     dist.destroy_process_group()
 
 
