@@ -81,6 +81,8 @@ for _c in ("BertModel", "BertForSequenceClassification", "BertForTokenClassifica
     register_policy(f"transformers.models.bert.modeling_bert.{_c}", "hf_encoder", "HFBertPolicy")
 for _c in ("WhisperModel", "WhisperForConditionalGeneration"):
     register_policy(f"transformers.models.whisper.modeling_whisper.{_c}", "hf_encdec", "HFWhisperPolicy")
+for _c in ("T5Model", "T5ForConditionalGeneration", "T5EncoderModel"):
+    register_policy(f"transformers.models.t5.modeling_t5.{_c}", "hf_encdec", "HFT5Policy")
 for _c in ("ViTModel", "ViTForImageClassification"):
     register_policy(f"transformers.models.vit.modeling_vit.{_c}", "hf_encoder", "HFViTPolicy")
 

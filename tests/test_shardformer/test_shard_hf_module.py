@@ -245,6 +245,45 @@ def _check_whisper():
     assert n > 40
 
 
+def _check_t5(gated, tied):
+    import transformers
+
+    torch.manual_seed(0)
+    cfg = transformers.T5Config(vocab_size=320, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_decoder_layers=2,
+                                num_heads=4, relative_attention_num_buckets=8, relative_attention_max_distance=16,
+                                dropout_rate=0.0, feed_forward_proj="gated-gelu" if gated else "relu",
+                                tie_word_embeddings=tied, decoder_start_token_id=0, pad_token_id=0, eos_token_id=1)
+    cfg._attn_implementation = "eager"
+    org = transformers.T5ForConditionalGeneration(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    sa = sharded.encoder.block[0].layer[0].SelfAttention
+    assert type(sa.q).__name__ == "Linear1D_Col" and sa.n_heads == 2 and sa.relative_attention_bias.weight.shape == (8, 2)
+    assert type(sharded.decoder.block[1].layer[1].EncDecAttention.o).__name__ == "Linear1D_Row"
+    assert sharded.encoder.embed_tokens is sharded.shared and sharded.decoder.embed_tokens is sharded.shared
+    assert (sharded.lm_head.weight is sharded.shared.weight) == (org.lm_head.weight is org.shared.weight)
+    torch.manual_seed(11)
+    ids = torch.randint(2, 320, (2, 12))
+    dec = torch.randint(2, 320, (2, 7))
+    ref = org(input_ids=ids, decoder_input_ids=dec, labels=dec)
+    out = sharded(input_ids=ids, decoder_input_ids=dec, labels=dec)
+    torch.testing.assert_close(out.logits, ref.logits, atol=3e-4, rtol=3e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        full = _gather_grad(p)
+        r = ref_grads[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        torch.testing.assert_close(full, r, atol=3e-4, rtol=3e-3, msg=lambda m: f"t5 {name}: {m}")
+        n += 1
+    assert n > 30
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
@@ -254,6 +293,8 @@ def _worker(rank, world_size, port):
     _check_bert()
     _check_vit()
     _check_whisper()
+    for gated, tied in ((False, True), (True, False)):
+        _check_t5(gated, tied)
     dist.destroy_process_group()
 
 
