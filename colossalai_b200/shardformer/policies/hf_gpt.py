@@ -21,7 +21,7 @@ from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabP
 from ..layer.qkv_fused_linear import GPT2FusedLinearConv1D_Col, GPT2FusedLinearConv1D_Row
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy"]
+__all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy", "HFBloomPolicy"]
 
 
 class _HFTiedDecoderPolicy(Policy):
@@ -148,6 +148,57 @@ class HFGPTJPolicy(_HFTiedDecoderPolicy):
         policy["GPTJModel"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
         policy["GPTJForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
+                                            kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
+        return policy
+
+
+def _bloom_attention_forward(self, hidden_states, residual, alibi, attention_mask, *args, **kwargs):
+    """`BloomModel` builds the ALiBi tensor for ALL heads ([batch * heads, 1, kv]); a tensor-parallel attention block
+    owns a contiguous range of heads, so it takes its slice and runs the module's own forward."""
+    tp, rank = self._cb200_tp_size, self._cb200_tp_rank
+    batch = hidden_states.shape[0]
+    local = self.num_heads
+    alibi = alibi.view(batch, local * tp, *alibi.shape[1:])[:, rank * local:(rank + 1) * local]
+    alibi = alibi.reshape(batch * local, *alibi.shape[2:])
+    return type(self).forward(self, hidden_states, residual, alibi, attention_mask, *args, **kwargs)
+
+
+class HFBloomPolicy(_HFTiedDecoderPolicy):
+    """`BloomModel`, `BloomForCausalLM` (reference `policies/bloom.py:25-240`).  The fused `query_key_value` weight is
+    laid out [heads, 3, head_dim], i.e. head-major: a contiguous row split is a split by heads, so the plain column
+    linear applies; `num_heads` / `hidden_size` become local values and the attention forward is wrapped to slice the
+    ALiBi bias of its heads.  Assumes `pretraining_tp == 1` (the HF default for fine-tuning)."""
+
+    def config_sanity_check(self) -> None:
+        super().config_sanity_check()
+        cfg = self.model.config
+        assert getattr(cfg, "pretraining_tp", 1) == 1 or not getattr(cfg, "slow_but_exact", False), \
+            "slow_but_exact with pretraining_tp > 1 slices the full hidden size inside the module"
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        from ...parallel import comm
+
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        rank = comm.group_rank(sc.tensor_parallel_process_group)
+        policy["BloomAttention"] = ModulePolicyDescription(
+            attribute_replacement={"num_heads": cfg.n_head // tp, "hidden_size": cfg.hidden_size // tp,
+                                   "_cb200_tp_size": tp, "_cb200_tp_rank": rank},
+            method_replacement={"forward": _bloom_attention_forward})
+        policy["BloomBlock"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(fp8)),
+        ])
+        policy["BloomModel"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+        policy["BloomForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
         return policy

@@ -76,7 +76,12 @@ def _check_tied(family):
     import transformers
 
     torch.manual_seed(0)
-    if family == "gptj":
+    if family == "bloom":
+        cfg = transformers.BloomConfig(vocab_size=320, hidden_size=64, n_layer=2, n_head=4, hidden_dropout=0.0,
+                                       attention_dropout=0.0)
+        cfg._attn_implementation = "eager"
+        org = transformers.BloomForCausalLM(cfg).float()
+    elif family == "gptj":
         cfg = transformers.GPTJConfig(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, rotary_dim=8,
                                       resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
         cfg._attn_implementation = "eager"
@@ -94,7 +99,12 @@ def _check_tied(family):
     sharded = copy.deepcopy(org)
     sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
     sharded, _ = ShardFormer(sc).optimize(sharded)
-    if family == "gptj":
+    if family == "bloom":
+        blk = sharded.transformer.h[0]
+        assert type(blk.self_attention.query_key_value).__name__ == "Linear1D_Col" and blk.self_attention.num_heads == 2
+        assert blk.self_attention.forward.__func__.__name__ == "_bloom_attention_forward"
+        assert sharded.lm_head.weight is sharded.transformer.word_embeddings.weight
+    elif family == "gptj":
         blk = sharded.transformer.h[0]
         assert type(blk.attn.q_proj).__name__ == "Linear1D_Col" and blk.attn.num_attention_heads == 2
         assert type(blk.mlp.fc_out).__name__ == "Linear1D_Row" and type(sharded.lm_head).__name__ == "VocabParallelLMHead1D"
@@ -128,7 +138,8 @@ def _check_tied(family):
     # the tied vocabulary shard: this rank's rows of the reference gradient
     emb = sharded.get_input_embeddings().weight
     r = dist.get_rank()
-    full = ref_grads["model.decoder.embed_tokens.weight" if family == "opt" else "transformer.wte.weight"]
+    full = ref_grads[{"opt": "model.decoder.embed_tokens.weight", "bloom": "transformer.word_embeddings.weight"}.get(
+        family, "transformer.wte.weight")]
     rows = full[r * 192:(r + 1) * 192]                       # the vocabulary is padded to 384 rows: the tail shard is short
     torch.testing.assert_close(emb.grad[: rows.shape[0]], rows, atol=2e-4, rtol=2e-3)
     assert emb.grad[rows.shape[0]:].abs().max() < 1e-6 if rows.shape[0] < 192 else True
@@ -288,7 +299,7 @@ def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2"):
         _check(family)
-    for family in ("gpt2", "opt", "gptj"):
+    for family in ("gpt2", "opt", "gptj", "bloom"):
         _check_tied(family)
     _check_bert()
     _check_vit()
