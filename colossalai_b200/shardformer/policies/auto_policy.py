@@ -67,7 +67,7 @@ for _fam, _classes in _FAMILIES.items():
 
 
 # user-supplied HuggingFace modules (sharded in place by sub-module / method replacement)
-for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3")):
+for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3"), ("cohere", "Cohere")):
     for _suffix in ("Model", "ForCausalLM"):
         register_policy(f"transformers.models.{_mod}.modeling_{_mod}.{_pre}{_suffix}", "hf_decoder", "HFDecoderPolicy")
 for _c in ("GPT2Model", "GPT2LMHeadModel"):

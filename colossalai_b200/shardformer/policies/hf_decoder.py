@@ -27,7 +27,7 @@ from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDe
 __all__ = ["HFDecoderPolicy", "HF_FAMILIES"]
 
 # transformers module path -> class-name prefix
-HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3"}
+HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere"}
 
 
 def _fused_rmsnorm_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:

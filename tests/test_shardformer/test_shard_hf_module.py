@@ -19,9 +19,10 @@ def _build(family):
 
     kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
               num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=False)
-    cfg_cls = {"llama": transformers.LlamaConfig, "mistral": transformers.MistralConfig, "qwen2": transformers.Qwen2Config}[family]
+    cfg_cls = {"llama": transformers.LlamaConfig, "mistral": transformers.MistralConfig, "qwen2": transformers.Qwen2Config,
+               "cohere": transformers.CohereConfig}[family]
     model_cls = {"llama": transformers.LlamaForCausalLM, "mistral": transformers.MistralForCausalLM,
-                 "qwen2": transformers.Qwen2ForCausalLM}[family]
+                 "qwen2": transformers.Qwen2ForCausalLM, "cohere": transformers.CohereForCausalLM}[family]
     cfg = cfg_cls(**kw)
     cfg._attn_implementation = "eager"
     torch.manual_seed(0)
@@ -50,7 +51,8 @@ def _check(family):
     assert type(layer.self_attn.q_proj).__name__ == "Linear1D_Col" and type(layer.mlp.down_proj).__name__ == "Linear1D_Row"
     assert layer.self_attn.q_proj.weight.shape[0] == org.model.layers[0].self_attn.q_proj.weight.shape[0] // 2
     assert type(sharded.model.embed_tokens).__name__ == "VocabParallelEmbedding1D"
-    assert layer.input_layernorm.forward.__func__.__name__ == "_fused_rmsnorm_forward"      # method replacement
+    if family != "cohere":                                   # Cohere uses a (bias-free) LayerNorm, left to PyTorch
+        assert layer.input_layernorm.forward.__func__.__name__ == "_fused_rmsnorm_forward"      # method replacement
     torch.manual_seed(5)
     ids = torch.randint(0, 320, (2, 16))
     ref = org(input_ids=ids, labels=ids)
@@ -297,7 +299,7 @@ def _check_t5(gated, tied):
 
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
-    for family in ("llama", "mistral", "qwen2"):
+    for family in ("llama", "mistral", "qwen2", "cohere"):
         _check(family)
     for family in ("gpt2", "opt", "gptj", "bloom"):
         _check_tied(family)
