@@ -21,7 +21,7 @@ from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabP
 from ..layer.qkv_fused_linear import GPT2FusedLinearConv1D_Col, GPT2FusedLinearConv1D_Row
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy", "HFBloomPolicy"]
+__all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy", "HFBloomPolicy", "HFFalconPolicy"]
 
 
 class _HFTiedDecoderPolicy(Policy):
@@ -199,6 +199,54 @@ class HFBloomPolicy(_HFTiedDecoderPolicy):
         policy["BloomModel"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
         policy["BloomForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
+                                            kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
+        return policy
+
+
+class HFFalconPolicy(_HFTiedDecoderPolicy):
+    """`FalconModel`, `FalconForCausalLM` (reference `policies/falcon.py:24-200`) for the two fused-QKV layouts that
+    are group-major and therefore split cleanly by rows: the new decoder architecture ([kv groups, q heads per group
+    + 2, head_dim]: a row split is a split by kv groups) and the original multi-head layout ([heads, 3, head_dim]).
+    The multi-query layout of Falcon-7B keeps ONE key / value head behind all query heads: splitting the query heads
+    would leave K / V replicated inside a column-parallel weight, which this in-place policy does not do (use the native
+    zoo: `models.hf_io` imports Falcon checkpoints with the KV head replicated per rank).  ALiBi variants (falcon-rw) are
+    likewise left to the native zoo."""
+
+    def config_sanity_check(self) -> None:
+        super().config_sanity_check()
+        cfg, tp = self.model.config, self.shard_config.tensor_parallel_size
+        if not self.shard_config.enable_tensor_parallelism:
+            return
+        assert not getattr(cfg, "alibi", False), "Falcon with ALiBi: use the native zoo (models.hf_io)"
+        if cfg.new_decoder_architecture:
+            assert cfg.num_kv_heads % tp == 0, "num_kv_heads must be divisible by the TP size"
+        else:
+            assert not cfg.multi_query, "multi-query Falcon (one shared KV head): use the native zoo (models.hf_io)"
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if not sc.enable_tensor_parallelism:
+            return policy
+        cfg, tp = self.model.config, sc.tensor_parallel_size
+        fp8 = dict(fp8_communication=sc.fp8_communication)
+        attrs = {"num_heads": cfg.num_attention_heads // tp, "hidden_size": cfg.hidden_size // tp,
+                 "split_size": cfg.hidden_size // tp}
+        if cfg.new_decoder_architecture:
+            attrs["num_kv_heads"] = cfg.num_kv_heads // tp
+        elif not cfg.multi_query:
+            attrs["num_kv_heads"] = cfg.num_attention_heads // tp
+        policy["FalconAttention"] = ModulePolicyDescription(attribute_replacement=attrs)
+        policy["FalconDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(fp8)),
+        ])
+        policy["FalconModel"] = ModulePolicyDescription(sub_module_replacement=[
+            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+        policy["FalconForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
         return policy

@@ -78,7 +78,15 @@ def _check_tied(family):
     import transformers
 
     torch.manual_seed(0)
-    if family == "bloom":
+    if family.startswith("falcon"):
+        new_arch = family == "falcon-new"
+        cfg = transformers.FalconConfig(vocab_size=320, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                        num_kv_heads=2 if new_arch else None, new_decoder_architecture=new_arch,
+                                        multi_query=False, parallel_attn=True, bias=False, alibi=False,
+                                        hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=64)
+        cfg._attn_implementation = "eager"
+        org = transformers.FalconForCausalLM(cfg).float()
+    elif family == "bloom":
         cfg = transformers.BloomConfig(vocab_size=320, hidden_size=64, n_layer=2, n_head=4, hidden_dropout=0.0,
                                        attention_dropout=0.0)
         cfg._attn_implementation = "eager"
@@ -101,7 +109,12 @@ def _check_tied(family):
     sharded = copy.deepcopy(org)
     sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
     sharded, _ = ShardFormer(sc).optimize(sharded)
-    if family == "bloom":
+    if family.startswith("falcon"):
+        blk = sharded.transformer.h[0]
+        assert type(blk.self_attention.query_key_value).__name__ == "Linear1D_Col" and blk.self_attention.num_heads == 2
+        assert blk.self_attention.num_kv_heads == (1 if family == "falcon-new" else 2)
+        assert type(blk.mlp.dense_4h_to_h).__name__ == "Linear1D_Row"
+    elif family == "bloom":
         blk = sharded.transformer.h[0]
         assert type(blk.self_attention.query_key_value).__name__ == "Linear1D_Col" and blk.self_attention.num_heads == 2
         assert blk.self_attention.forward.__func__.__name__ == "_bloom_attention_forward"
@@ -140,8 +153,9 @@ def _check_tied(family):
     # the tied vocabulary shard: this rank's rows of the reference gradient
     emb = sharded.get_input_embeddings().weight
     r = dist.get_rank()
-    full = ref_grads[{"opt": "model.decoder.embed_tokens.weight", "bloom": "transformer.word_embeddings.weight"}.get(
-        family, "transformer.wte.weight")]
+    full = ref_grads[{"opt": "model.decoder.embed_tokens.weight", "bloom": "transformer.word_embeddings.weight",
+                      "falcon-new": "transformer.word_embeddings.weight",
+                      "falcon-mha": "transformer.word_embeddings.weight"}.get(family, "transformer.wte.weight")]
     rows = full[r * 192:(r + 1) * 192]                       # the vocabulary is padded to 384 rows: the tail shard is short
     torch.testing.assert_close(emb.grad[: rows.shape[0]], rows, atol=2e-4, rtol=2e-3)
     assert emb.grad[rows.shape[0]:].abs().max() < 1e-6 if rows.shape[0] < 192 else True
@@ -301,7 +315,7 @@ def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2", "cohere"):
         _check(family)
-    for family in ("gpt2", "opt", "gptj", "bloom"):
+    for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new", "falcon-mha"):
         _check_tied(family)
     _check_bert()
     _check_vit()
