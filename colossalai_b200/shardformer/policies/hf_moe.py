@@ -1,0 +1,118 @@
+"""Policy that shards a user's HuggingFace Mixtral in place: tensor-parallel attention + EXPERT-PARALLEL experts
+(reference `policies/mixtral.py:30-250` + `modeling/mixtral.py:50-210` `EPMixtralSparseMoeBlock`).
+
+transformers >= 5 keeps all experts of a layer in one module (`MixtralExperts`: `gate_up_proj [E, 2 I, H]`,
+`down_proj [E, H, I]`) with the interface `forward(hidden_states [T, H], top_k_index [T, k], top_k_weights [T, k])`.
+That is exactly the contract of this framework's MoE data path, so the policy
+  * keeps only the LOCAL experts' slices of the two parameters on every rank of `shard_config.ep_group`
+    (parameter replacement; the slices are tagged so that checkpoints gather them), and
+  * rebinds `MixtralExperts.forward` to `moe.dispatch_combine.moe_forward`: dropless dispatch to the owners (fused
+    NVLink dispatch on sm_100a, uneven all-to-all elsewhere), grouped per-expert GEMMs on the local slices, SwiGLU,
+    combine with the routing weights;
+the router (`gate`) stays replicated.  Attention is tensor-parallel like the llama-likes when TP is enabled.  Expert
+gradients are already sums over every token of the expert-parallel group that chose the expert; the usual 1 / ep scaling
+for data-parallel averaging is the plugin's job (`MoeHybridParallelPlugin`)."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
+from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
+from .hf_decoder import _fused_rmsnorm_forward
+
+__all__ = ["HFMixtralPolicy"]
+
+
+def _ep_experts_forward(self, hidden_states: torch.Tensor, top_k_index: torch.Tensor, top_k_weights: torch.Tensor):
+    from ... import ops
+    from ...moe.dispatch_combine import moe_forward
+    from ...moe.grouped_gemm import grouped_linear
+
+    act = getattr(self, "_cb200_act", "silu")
+
+    def experts(rows: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+        h = grouped_linear(rows, self.gate_up_proj, counts)
+        h = ops.glu(h, act, valid_rows=counts.sum())
+        return grouped_linear(h, self.down_proj, counts)
+
+    shape = hidden_states.shape
+    x = hidden_states.reshape(-1, shape[-1])
+    out = moe_forward(x, top_k_weights.reshape(x.shape[0], -1).float(), top_k_index.reshape(x.shape[0], -1), experts,
+                      self._cb200_num_experts, self._cb200_ep_group)
+    return out.to(hidden_states.dtype).reshape(shape)
+
+
+class HFMixtralPolicy(Policy):
+    """`MixtralModel`, `MixtralForCausalLM`."""
+
+    def config_sanity_check(self) -> None:
+        cfg, sc = self.model.config, self.shard_config
+        if sc.enable_tensor_parallelism:
+            assert cfg.num_attention_heads % sc.tensor_parallel_size == 0 and \
+                cfg.num_key_value_heads % sc.tensor_parallel_size == 0, "attention heads must be divisible by the TP size"
+        if sc.ep_group is not None:
+            assert cfg.num_local_experts % sc.expert_parallel_size == 0, "experts must be divisible by the EP size"
+        assert not sc.enable_sequence_parallelism, \
+            "sequence parallelism of HF modules is not supported; build the model from the native zoo (models.hf_io)"
+
+    def preprocess(self) -> nn.Module:
+        self.tie_weight = self.tie_weight_check()
+        return self.model
+
+    def postprocess(self) -> nn.Module:
+        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism:
+            emb, head = self.model.get_input_embeddings(), self.model.get_output_embeddings()
+            if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
+                head.weight = emb.weight
+        return self.model
+
+    def _slice_experts(self, module: nn.Module) -> None:
+        from ...parallel import comm
+        from ...tensor.d_tensor.api import mark_sharded, sharded_tensor_to_param
+
+        group = self.shard_config.ep_group
+        ep, rank = comm.group_size(group), comm.group_rank(group)
+        n_local = module.num_experts // ep
+        for name in ("gate_up_proj", "down_proj"):
+            full = getattr(module, name).data
+            local = full[rank * n_local:(rank + 1) * n_local].clone()
+            setattr(module, name, sharded_tensor_to_param(mark_sharded(local, 0, group)))
+        module._cb200_num_experts = module.num_experts
+        module._cb200_ep_group = group
+        module._cb200_act = getattr(self.model.config, "hidden_act", "silu")
+        module.num_experts_local = n_local
+
+    def module_policy(self) -> Dict[str, ModulePolicyDescription]:
+        sc = self.shard_config
+        policy: Dict[str, ModulePolicyDescription] = {}
+        if sc.enable_tensor_parallelism:
+            fp8 = dict(fp8_communication=sc.fp8_communication)
+            vocab = dict(make_vocab_size_divisible_by=sc.make_vocab_size_divisible_by, fp8_communication=sc.fp8_communication)
+            policy["MixtralDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
+                SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
+                SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
+                SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
+                SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(fp8)),
+            ])
+            policy["MixtralModel"] = ModulePolicyDescription(sub_module_replacement=[
+                SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=vocab)])
+            policy["MixtralForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+                SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D, kwargs=dict(gather_output=True, **vocab))])
+        if sc.ep_group is not None and sc.expert_parallel_size > 1:
+            policy["MixtralExperts"] = ModulePolicyDescription(param_replacement=[self._slice_experts],
+                                                               method_replacement={"forward": _ep_experts_forward})
+        if sc.enable_fused_normalization:
+            policy["MixtralRMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
+        return policy
+
+    def get_held_layers(self) -> List[nn.Module]:
+        if self.pipeline_stage_manager is not None:
+            raise NotImplementedError("pipeline parallelism of HuggingFace modules: import the weights into the native "
+                                      "zoo (`models.hf_io.load_hf_checkpoint`) and use its policy")
+        return []
+
+    def get_shared_params(self):
+        return []

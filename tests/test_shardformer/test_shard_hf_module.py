@@ -311,6 +311,43 @@ def _check_t5(gated, tied):
     assert n > 30
 
 
+def _check_mixtral_ep():
+    """Expert parallelism of a user's HF Mixtral: every rank keeps half of the experts and runs ITS OWN batch; outputs
+    must equal the unsharded model on that batch, and the local experts' gradients the sum over both ranks' batches."""
+    import transformers
+
+    torch.manual_seed(0)
+    cfg = transformers.MixtralConfig(vocab_size=320, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                     num_attention_heads=4, num_key_value_heads=2, num_local_experts=4,
+                                     num_experts_per_tok=2, max_position_embeddings=64, router_aux_loss_coef=0.0,
+                                     output_router_logits=False)
+    cfg._attn_implementation = "eager"
+    org = transformers.MixtralForCausalLM(cfg).float()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(enable_tensor_parallelism=False, ep_group=dist.group.WORLD)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    ex = sharded.model.layers[0].mlp.experts
+    assert ex.gate_up_proj.shape[0] == 2 and ex.forward.__func__.__name__ == "_ep_experts_forward"
+    r = dist.get_rank()
+    torch.manual_seed(20 + r)                                 # different data on every rank
+    ids = torch.randint(0, 320, (2, 12))
+    ref = org(input_ids=ids, labels=ids)
+    out = sharded(input_ids=ids, labels=ids)
+    torch.testing.assert_close(out.logits, ref.logits, atol=3e-4, rtol=3e-4)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    ref.loss.backward()
+    out.loss.backward()
+    ref_grads = {n: p.grad.clone() for n, p in org.named_parameters()}
+    for name, p in sharded.named_parameters():
+        if "experts" in name:
+            total = ref_grads[name].clone()
+            dist.all_reduce(total)                            # tokens of both ranks reach the owner
+            torch.testing.assert_close(p.grad, total[r * 2:(r + 1) * 2], atol=3e-4, rtol=3e-3,
+                                       msg=lambda m: f"mixtral {name}: {m}")
+        else:
+            torch.testing.assert_close(p.grad, ref_grads[name], atol=3e-4, rtol=3e-3, msg=lambda m: f"mixtral {name}: {m}")
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2", "cohere"):
@@ -322,6 +359,7 @@ def _worker(rank, world_size, port):
     _check_whisper()
     for gated, tied in ((False, True), (True, False)):
         _check_t5(gated, tied)
+    _check_mixtral_ep()
     dist.destroy_process_group()
 
 
