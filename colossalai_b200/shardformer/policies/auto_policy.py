@@ -74,8 +74,10 @@ for _c in ("GPT2Model", "GPT2LMHeadModel"):
     register_policy(f"transformers.models.gpt2.modeling_gpt2.{_c}", "hf_gpt", "HFGPT2Policy")
 for _c in ("OPTModel", "OPTForCausalLM"):
     register_policy(f"transformers.models.opt.modeling_opt.{_c}", "hf_gpt", "HFOPTPolicy")
-for _c in ("MixtralModel", "MixtralForCausalLM"):
-    register_policy(f"transformers.models.mixtral.modeling_mixtral.{_c}", "hf_moe", "HFMixtralPolicy")
+for _mod, _pre in (("mixtral", "Mixtral"), ("qwen3_moe", "Qwen3Moe"), ("qwen2_moe", "Qwen2Moe"),
+                   ("deepseek_v3", "DeepseekV3"), ("deepseek_v2", "DeepseekV2")):
+    for _suffix in ("Model", "ForCausalLM"):
+        register_policy(f"transformers.models.{_mod}.modeling_{_mod}.{_pre}{_suffix}", "hf_moe", f"HF{_pre}Policy")
 for _c in ("FalconModel", "FalconForCausalLM"):
     register_policy(f"transformers.models.falcon.modeling_falcon.{_c}", "hf_gpt", "HFFalconPolicy")
 for _c in ("BloomModel", "BloomForCausalLM"):

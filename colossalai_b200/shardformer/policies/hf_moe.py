@@ -23,7 +23,8 @@ from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabP
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 from .hf_decoder import _fused_rmsnorm_forward
 
-__all__ = ["HFMixtralPolicy"]
+__all__ = ["HFMoEPolicy", "HFMixtralPolicy", "HFQwen3MoePolicy", "HFQwen2MoePolicy", "HFDeepseekV3Policy",
+           "HFDeepseekV2Policy"]
 
 
 def _ep_experts_forward(self, hidden_states: torch.Tensor, top_k_index: torch.Tensor, top_k_weights: torch.Tensor):
@@ -45,16 +46,27 @@ def _ep_experts_forward(self, hidden_states: torch.Tensor, top_k_index: torch.Te
     return out.to(hidden_states.dtype).reshape(shape)
 
 
-class HFMixtralPolicy(Policy):
-    """`MixtralModel`, `MixtralForCausalLM`."""
+class HFMoEPolicy(Policy):
+    """Shared implementation: the HF MoE families of transformers >= 5 all use the same experts module contract
+    (`gate_up_proj [E, 2 I, H]`, `down_proj [E, H, I]`, `forward(hidden_states, top_k_index, top_k_weights)`); a family
+    is described by its class-name prefix, the name of its experts class and whether its attention is the plain
+    q / k / v / o layout that the tensor-parallel replacement understands."""
+
+    FAMILY = "Mixtral"
+    EXPERTS_CLASS = "MixtralExperts"
+    TP_ATTENTION = True
+    NUM_EXPERTS_ATTR = "num_local_experts"
 
     def config_sanity_check(self) -> None:
         cfg, sc = self.model.config, self.shard_config
         if sc.enable_tensor_parallelism:
+            assert self.TP_ATTENTION, (f"tensor parallelism of HF {self.FAMILY} attention (multi-head latent attention) is "
+                                       "not provided in place: use expert parallelism only, or the native zoo")
             assert cfg.num_attention_heads % sc.tensor_parallel_size == 0 and \
                 cfg.num_key_value_heads % sc.tensor_parallel_size == 0, "attention heads must be divisible by the TP size"
         if sc.ep_group is not None:
-            assert cfg.num_local_experts % sc.expert_parallel_size == 0, "experts must be divisible by the EP size"
+            assert getattr(cfg, self.NUM_EXPERTS_ATTR) % sc.expert_parallel_size == 0, \
+                "experts must be divisible by the EP size"
         assert not sc.enable_sequence_parallelism, \
             "sequence parallelism of HF modules is not supported; build the model from the native zoo (models.hf_io)"
 
@@ -91,21 +103,21 @@ class HFMixtralPolicy(Policy):
         if sc.enable_tensor_parallelism:
             fp8 = dict(fp8_communication=sc.fp8_communication)
             vocab = dict(make_vocab_size_divisible_by=sc.make_vocab_size_divisible_by, fp8_communication=sc.fp8_communication)
-            policy["MixtralDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
+            policy[f"{self.FAMILY}DecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
                 SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
                 SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
                 SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(fp8)),
             ])
-            policy["MixtralModel"] = ModulePolicyDescription(sub_module_replacement=[
+            policy[f"{self.FAMILY}Model"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=vocab)])
-            policy["MixtralForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
+            policy[f"{self.FAMILY}ForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D, kwargs=dict(gather_output=True, **vocab))])
         if sc.ep_group is not None and sc.expert_parallel_size > 1:
-            policy["MixtralExperts"] = ModulePolicyDescription(param_replacement=[self._slice_experts],
+            policy[self.EXPERTS_CLASS] = ModulePolicyDescription(param_replacement=[self._slice_experts],
                                                                method_replacement={"forward": _ep_experts_forward})
         if sc.enable_fused_normalization:
-            policy["MixtralRMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
+            policy[f"{self.FAMILY}RMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
         return policy
 
     def get_held_layers(self) -> List[nn.Module]:
@@ -116,3 +128,29 @@ class HFMixtralPolicy(Policy):
 
     def get_shared_params(self):
         return []
+
+
+class HFMixtralPolicy(HFMoEPolicy):
+    """`MixtralModel`, `MixtralForCausalLM`."""
+
+
+class HFQwen3MoePolicy(HFMoEPolicy):
+    """`Qwen3MoeModel`, `Qwen3MoeForCausalLM` (per-head q / k norms stay replicated: they act on head_dim)."""
+    FAMILY, EXPERTS_CLASS, NUM_EXPERTS_ATTR = "Qwen3Moe", "Qwen3MoeExperts", "num_experts"
+
+
+class HFQwen2MoePolicy(HFMoEPolicy):
+    """`Qwen2MoeModel`, `Qwen2MoeForCausalLM` (the shared expert is a dense MLP and stays replicated)."""
+    FAMILY, EXPERTS_CLASS, NUM_EXPERTS_ATTR = "Qwen2Moe", "Qwen2MoeExperts", "num_experts"
+
+
+class HFDeepseekV3Policy(HFMoEPolicy):
+    """`DeepseekV3Model`, `DeepseekV3ForCausalLM`: expert parallelism of the routed experts (`DeepseekV3NaiveMoe`); the
+    router (group-limited top-k with correction bias), the shared experts and the multi-head latent attention are the
+    model's own and stay replicated."""
+    FAMILY, EXPERTS_CLASS, TP_ATTENTION, NUM_EXPERTS_ATTR = "DeepseekV3", "DeepseekV3NaiveMoe", False, "n_routed_experts"
+
+
+class HFDeepseekV2Policy(HFMoEPolicy):
+    """`DeepseekV2Model`, `DeepseekV2ForCausalLM` (expert parallelism only, like V3)."""
+    FAMILY, EXPERTS_CLASS, TP_ATTENTION, NUM_EXPERTS_ATTR = "DeepseekV2", "DeepseekV2Experts", False, "n_routed_experts"

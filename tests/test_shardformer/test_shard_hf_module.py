@@ -311,22 +311,42 @@ def _check_t5(gated, tied):
     assert n > 30
 
 
-def _check_mixtral_ep():
-    """Expert parallelism of a user's HF Mixtral: every rank keeps half of the experts and runs ITS OWN batch; outputs
-    must equal the unsharded model on that batch, and the local experts' gradients the sum over both ranks' batches."""
+def _moe_model(family):
     import transformers
 
     torch.manual_seed(0)
-    cfg = transformers.MixtralConfig(vocab_size=320, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
-                                     num_attention_heads=4, num_key_value_heads=2, num_local_experts=4,
-                                     num_experts_per_tok=2, max_position_embeddings=64, router_aux_loss_coef=0.0,
-                                     output_router_logits=False)
+    if family == "mixtral":
+        cfg = transformers.MixtralConfig(vocab_size=320, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                         num_attention_heads=4, num_key_value_heads=2, num_local_experts=4,
+                                         num_experts_per_tok=2, max_position_embeddings=64, router_aux_loss_coef=0.0,
+                                         output_router_logits=False)
+        cls = transformers.MixtralForCausalLM
+    elif family == "qwen3_moe":
+        cfg = transformers.Qwen3MoeConfig(vocab_size=320, hidden_size=64, intermediate_size=96, moe_intermediate_size=48,
+                                          num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, num_experts=4,
+                                          num_experts_per_tok=2, max_position_embeddings=64, head_dim=16,
+                                          router_aux_loss_coef=0.0)
+        cls = transformers.Qwen3MoeForCausalLM
+    else:
+        cfg = transformers.DeepseekV3Config(vocab_size=320, hidden_size=64, intermediate_size=96, moe_intermediate_size=48,
+                                            num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4,
+                                            n_routed_experts=4, n_shared_experts=1, num_experts_per_tok=2,
+                                            first_k_dense_replace=1, kv_lora_rank=16, q_lora_rank=24, qk_rope_head_dim=8,
+                                            qk_nope_head_dim=16, v_head_dim=16, n_group=2, topk_group=1,
+                                            max_position_embeddings=64)
+        cls = transformers.DeepseekV3ForCausalLM
     cfg._attn_implementation = "eager"
-    org = transformers.MixtralForCausalLM(cfg).float()
+    return cls(cfg).float()
+
+
+def _check_moe_ep(family):
+    """Expert parallelism of a user's HF MoE model: every rank keeps half of the experts and runs ITS OWN batch; outputs
+    must equal the unsharded model on that batch, and the local experts' gradients the sum over both ranks' batches."""
+    org = _moe_model(family)
     sharded = copy.deepcopy(org)
     sc = ShardConfig(enable_tensor_parallelism=False, ep_group=dist.group.WORLD)
     sharded, _ = ShardFormer(sc).optimize(sharded)
-    ex = sharded.model.layers[0].mlp.experts
+    ex = sharded.model.layers[-1].mlp.experts
     assert ex.gate_up_proj.shape[0] == 2 and ex.forward.__func__.__name__ == "_ep_experts_forward"
     r = dist.get_rank()
     torch.manual_seed(20 + r)                                 # different data on every rank
@@ -337,15 +357,21 @@ def _check_mixtral_ep():
     torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
     ref.loss.backward()
     out.loss.backward()
-    ref_grads = {n: p.grad.clone() for n, p in org.named_parameters()}
+    ref_grads = {n: (p.grad.clone() if p.grad is not None else None) for n, p in org.named_parameters()}
+    n_expert = 0
     for name, p in sharded.named_parameters():
-        if "experts" in name:
+        if p.grad is None:
+            assert ref_grads[name] is None, name
+            continue
+        if ".experts." in name:
             total = ref_grads[name].clone()
             dist.all_reduce(total)                            # tokens of both ranks reach the owner
             torch.testing.assert_close(p.grad, total[r * 2:(r + 1) * 2], atol=3e-4, rtol=3e-3,
-                                       msg=lambda m: f"mixtral {name}: {m}")
+                                       msg=lambda m: f"{family} {name}: {m}")
+            n_expert += 1
         else:
-            torch.testing.assert_close(p.grad, ref_grads[name], atol=3e-4, rtol=3e-3, msg=lambda m: f"mixtral {name}: {m}")
+            torch.testing.assert_close(p.grad, ref_grads[name], atol=3e-4, rtol=3e-3, msg=lambda m: f"{family} {name}: {m}")
+    assert n_expert >= 2
 
 
 def _worker(rank, world_size, port):
@@ -359,7 +385,8 @@ def _worker(rank, world_size, port):
     _check_whisper()
     for gated, tied in ((False, True), (True, False)):
         _check_t5(gated, tied)
-    _check_mixtral_ep()
+    for family in ("mixtral", "qwen3_moe", "deepseek_v3"):
+        _check_moe_ep(family)
     dist.destroy_process_group()
 
 
