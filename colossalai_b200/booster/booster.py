@@ -34,7 +34,12 @@ class Booster:
     """
 
     def __init__(self, device: Optional[str] = None, mixed_precision: Optional[Union[MixedPrecision, str]] = None,
-                 plugin: Optional[Plugin] = None) -> None:
+                 plugin: Optional[Plugin] = None, convert_hf_models: bool = True) -> None:
+        """`convert_hf_models`: a `transformers` model handed to `boost` is converted weight-for-weight into the native
+        model of its family (every parallelism, fused kernels).  With False the user's module is kept and sharded IN
+        PLACE by the HuggingFace policies of `shardformer/policies/hf_*.py` (tensor / expert parallelism, ZeRO, DDP;
+        no pipeline or sequence parallelism), like the reference does."""
+        self.convert_hf_models = convert_hf_models
         if plugin is not None:
             assert isinstance(plugin, Plugin), f"plugin must be a Plugin, got {type(plugin)}"
         self.plugin = plugin
@@ -75,7 +80,7 @@ class Booster:
         # reference-style user code hands over a Hugging Face model instance: convert it to our implementation
         from ..models.hf_io import from_hf_model, is_hf_model
 
-        if is_hf_model(model):
+        if is_hf_model(model) and self.convert_hf_models:
             self.logger.info(f"converting {type(model).__name__} (transformers) to the colossalai_b200 model of the "
                              "same family; rebuild the optimizer over the returned model's parameters", ranks=[0])
             if optimizer is not None:

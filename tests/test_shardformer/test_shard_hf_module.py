@@ -374,6 +374,38 @@ def _check_moe_ep(family):
     assert n_expert >= 2
 
 
+def _check_booster_in_place():
+    """`Booster(convert_hf_models=False)`: the plugin shards the user's HF module itself (no conversion to the native
+    zoo) and two optimizer steps under TP2 track the single-process model exactly."""
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    org = _build("llama")
+    model = copy.deepcopy(org)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    ref_opt = torch.optim.AdamW(org.parameters(), lr=1e-2)
+    booster = Booster(plugin=HybridParallelPlugin(tp_size=2, pp_size=1, precision="fp32"), convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    assert type(inner).__name__ == "LlamaForCausalLM" and type(inner.model.layers[0].mlp.up_proj).__name__ == "Linear1D_Col"
+    torch.manual_seed(3)
+    ids = torch.randint(0, 320, (2, 16))
+    for _ in range(2):
+        loss = model(input_ids=ids, labels=ids).loss
+        booster.backward(loss, opt)
+        opt.step()
+        opt.zero_grad()
+        ref = org(input_ids=ids, labels=ids).loss
+        ref.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        torch.testing.assert_close(loss.detach(), ref.detach(), atol=1e-5, rtol=1e-5)
+    w = inner.model.layers[1].self_attn.o_proj.weight                      # row-parallel: columns of the full weight
+    full = org.model.layers[1].self_attn.o_proj.weight
+    r = dist.get_rank()
+    torch.testing.assert_close(w.detach(), full[:, r * 32:(r + 1) * 32].detach(), atol=1e-5, rtol=1e-4)
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2", "cohere"):
@@ -387,6 +419,7 @@ def _worker(rank, world_size, port):
         _check_t5(gated, tied)
     for family in ("mixtral", "qwen3_moe", "deepseek_v3"):
         _check_moe_ep(family)
+    _check_booster_in_place()
     dist.destroy_process_group()
 
 
