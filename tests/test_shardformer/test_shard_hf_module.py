@@ -404,6 +404,27 @@ def _check_booster_in_place():
     full = org.model.layers[1].self_attn.o_proj.weight
     r = dist.get_rank()
     torch.testing.assert_close(w.detach(), full[:, r * 32:(r + 1) * 32].detach(), atol=1e-5, rtol=1e-4)
+    # a sharded save of the in-place sharded module is the plain HuggingFace state dict again (TP shards gathered,
+    # vocabulary padding stripped): it loads straight back into `transformers`
+    import glob
+    import os
+    import tempfile
+
+    path = [tempfile.mkdtemp() if r == 0 else None]
+    dist.broadcast_object_list(path, src=0)
+    booster.save_model(model, path[0], shard=True)
+    dist.barrier()
+    if r == 0:
+        sd = {}
+        for f in glob.glob(os.path.join(path[0], "*.bin")):
+            sd.update(torch.load(f, weights_only=True))
+        ref_sd = org.state_dict()
+        assert set(sd) == set(ref_sd)
+        for k, v in ref_sd.items():
+            torch.testing.assert_close(sd[k].float(), v.float(), atol=5e-4, rtol=1e-3, msg=lambda m: f"checkpoint {k}: {m}")
+        fresh = _build("llama")
+        fresh.load_state_dict(sd)
+    dist.barrier()
 
 
 def _worker(rank, world_size, port):
