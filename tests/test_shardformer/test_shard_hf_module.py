@@ -327,6 +327,20 @@ def _moe_model(family):
                                           num_experts_per_tok=2, max_position_embeddings=64, head_dim=16,
                                           router_aux_loss_coef=0.0)
         cls = transformers.Qwen3MoeForCausalLM
+    elif family == "qwen2_moe":
+        cfg = transformers.Qwen2MoeConfig(vocab_size=320, hidden_size=64, intermediate_size=96, moe_intermediate_size=48,
+                                          shared_expert_intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                          num_key_value_heads=2, num_experts=4, num_experts_per_tok=2,
+                                          max_position_embeddings=64, router_aux_loss_coef=0.0, decoder_sparse_step=1)
+        cls = transformers.Qwen2MoeForCausalLM
+    elif family == "deepseek_v2":
+        cfg = transformers.DeepseekV2Config(vocab_size=320, hidden_size=64, intermediate_size=96, moe_intermediate_size=48,
+                                            num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4,
+                                            n_routed_experts=4, n_shared_experts=1, num_experts_per_tok=2,
+                                            first_k_dense_replace=1, kv_lora_rank=16, q_lora_rank=24, qk_rope_head_dim=8,
+                                            qk_nope_head_dim=16, v_head_dim=16, n_group=2, topk_group=1,
+                                            max_position_embeddings=64)
+        cls = transformers.DeepseekV2ForCausalLM
     else:
         cfg = transformers.DeepseekV3Config(vocab_size=320, hidden_size=64, intermediate_size=96, moe_intermediate_size=48,
                                             num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4,
@@ -438,7 +452,7 @@ def _worker(rank, world_size, port):
     _check_whisper()
     for gated, tied in ((False, True), (True, False)):
         _check_t5(gated, tied)
-    for family in ("mixtral", "qwen3_moe", "deepseek_v3"):
+    for family in ("mixtral", "qwen3_moe", "qwen2_moe", "deepseek_v2", "deepseek_v3"):
         _check_moe_ep(family)
     _check_booster_in_place()
     dist.destroy_process_group()
