@@ -441,6 +441,40 @@ def _check_booster_in_place():
     dist.barrier()
 
 
+def _check_zero_and_ddp_keep_hf_module():
+    """Data-parallel plugins need no policy: with `convert_hf_models=False` the user's module is wrapped as it is
+    (ZeRO-1 in bf16, torch DDP in fp32) and trains."""
+    import transformers
+
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import LowLevelZeroPlugin, TorchDDPPlugin
+
+    for plugin, steps in ((LowLevelZeroPlugin(stage=1, precision="bf16"), 4), (TorchDDPPlugin(), 4)):
+        torch.manual_seed(0)
+        cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
+                                      embd_pdrop=0.0, attn_pdrop=0.0)
+        model = transformers.GPT2LMHeadModel(cfg)
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-3)
+        booster = Booster(plugin=plugin, convert_hf_models=False)
+        model, opt, *_ = booster.boost(model, opt)
+        assert type(model.unwrap()).__name__ == "GPT2LMHeadModel"
+        torch.manual_seed(4 + dist.get_rank())
+        ids = torch.randint(0, 320, (4, 16))
+        losses = []
+        for _ in range(steps):
+            loss = model(input_ids=ids, labels=ids).loss
+            booster.backward(loss, opt)
+            opt.step()
+            opt.zero_grad()
+            losses.append(float(loss))
+        assert all(l == l for l in losses) and losses[-1] < losses[0], (type(plugin).__name__, losses)
+        # replicas stay identical across the data-parallel ranks
+        w = model.unwrap().transformer.h[0].mlp.c_fc.weight.detach().float().clone()
+        other = w.clone()
+        dist.broadcast(other, src=0)
+        torch.testing.assert_close(w, other, atol=1e-6, rtol=1e-6)
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2", "cohere"):
@@ -455,6 +489,7 @@ def _worker(rank, world_size, port):
     for family in ("mixtral", "qwen3_moe", "qwen2_moe", "deepseek_v2", "deepseek_v3"):
         _check_moe_ep(family)
     _check_booster_in_place()
+    _check_zero_and_ddp_keep_hf_module()
     dist.destroy_process_group()
 
 
