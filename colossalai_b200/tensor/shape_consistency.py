@@ -1,7 +1,9 @@
 """`ShapeConsistencyManager`: find (and price) the collective sequence that converts one sharding spec into another.
 Parity: reference `colossalai/tensor/shape_consistency.py` (`shape_consistency(source, target) -> (transform_path,
-comm_action_sequence, total_cost)`, `apply`, `ShapeConsistencyOptions`).  The search itself is the greedy
-all-to-all -> gather -> split planner of `d_tensor.LayoutConverter`; costs come from the mesh's alpha-beta model."""
+comm_action_sequence, total_cost)`, `apply`, `mem_cost`, `ShapeConsistencyOptions`).  The plan comes from
+`d_tensor.LayoutConverter`: a uniform-cost search over one-step transforms (gather / shard / all-to-all) priced with the
+mesh's alpha-beta model - forward + backward, or forward only when `forward_only` is set - with the greedy
+all-to-all -> gather -> split heuristic as the fallback."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -20,7 +22,8 @@ __all__ = ["ShapeConsistencyManager", "ShapeConsistencyOptions", "CommSpec"]
 
 @dataclass
 class ShapeConsistencyOptions:
-    """Placeholder for search options (the reference keeps it empty as well)."""
+    """`method`: "search" (cost-optimal plan) or "greedy" (deterministic heuristic)."""
+    method: str = "search"
 
 
 class ShapeConsistencyManager(metaclass=SingletonMeta):
@@ -48,16 +51,26 @@ class ShapeConsistencyManager(metaclass=SingletonMeta):
     @forward_only.setter
     def forward_only(self, v: bool) -> None:
         self._forward_only = bool(v)
+        self._converter.forward_only = self._forward_only        # plans are searched under the same objective
+
+    def mem_cost(self, transform_path: List[ShardingSpec], dtype_bytes: float = 2.0) -> float:
+        """Peak bytes alive on one device while the plan runs (input + output of its widest step)."""
+        if not transform_path:
+            return 0.0
+        mesh, shape = transform_path[0].device_mesh, transform_path[0].entire_shape
+        layouts = [Layout(mesh, sp, shape) for sp in transform_path]
+        return self._converter.mem_cost(layouts) * dtype_bytes
 
     def shape_consistency(self, source_spec: ShardingSpec, target_spec: ShardingSpec
                           ) -> Tuple[List[ShardingSpec], List[CommSpec], Dict[str, float]]:
-        key = (repr(source_spec), repr(target_spec), tuple(source_spec.entire_shape))
+        method = self._options.method if self._options is not None else "search"
+        key = (repr(source_spec), repr(target_spec), tuple(source_spec.entire_shape), method, self._forward_only)
         if key in self.cached_spec_pairs_transform_path:
             return self.cached_spec_pairs_transform_path[key]
         mesh, shape = source_spec.device_mesh, source_spec.entire_shape
         src = Layout(mesh, source_spec, shape)
         tgt = Layout(mesh, target_spec, shape)
-        layouts, comms = self._converter.layout_converting(src, tgt)
+        layouts, comms = self._converter.layout_converting(src, tgt, method=method)
         path = [ShardingSpec(mesh, shape, dim_partition_dict=l.sharding_spec.dim_partition_dict) for l in layouts]
         cost = {"forward": 0.0, "backward": 0.0, "total": 0.0}
         nbytes_full = float(torch.Size(shape).numel()) * 2.0

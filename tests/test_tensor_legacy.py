@@ -26,6 +26,14 @@ def test_sharding_spec_and_conversion_path():
     assert cost["total"] > 0 and cost["total"] == pytest.approx(cost["forward"] + cost["backward"])
     same = mgr.shape_consistency(a, a)
     assert len(same[1]) == 0 and same[2]["total"] == 0
+    # the searched plan is never dearer than the heuristic one, and the peak memory of a plan is reported
+    from colossalai_b200.tensor.shape_consistency import ShapeConsistencyOptions
+
+    assert mgr.mem_cost(path) >= 2.0 * max(torch.Size(p.get_sharded_shape_per_device()).numel() for p in path)
+    mgr.options = ShapeConsistencyOptions(method="greedy")
+    _, _, greedy_cost = mgr.shape_consistency(a, b)
+    assert cost["total"] <= greedy_cost["total"] * (1 + 1e-9)
+    mgr.options = ShapeConsistencyOptions()
 
 
 def _colo_spec_worker(rank, world_size, port):
