@@ -11,8 +11,13 @@ existing `nn.Module` the framework knows nothing about and rewrite it through th
     HF attention modules size their head views with `-1`, so the sharded projections are all they need;
   * method replacement: every `*RMSNorm.forward` is rebound to our fused RMSNorm kernel (`ops.rms_norm`);
   * data parallel / ZeRO plugins need no policy at all.
-Pipeline parallelism and sequence parallelism of HF modules are NOT provided here (use the native zoo + `hf_io` weight
-import for those): `get_held_layers` raises if a stage manager is present.
+  * pipeline parallelism (1F1B, one chunk per stage) needs NO rewrite of the decoder's forward: the HF backbone accepts
+    `inputs_embeds`, loops over `self.layers` and ends with `self.norm`, so a stage keeps its slice of `layers`
+    (`embed_tokens` on the first stage, `norm` + `lm_head` on the last, the rotary table everywhere), `norm` becomes
+    an identity on the other stages, and a small stage forward on the top-level module feeds `input_ids` (first stage)
+    or the previous stage's `hidden_states` (as `inputs_embeds`) into the backbone and returns hidden states or
+    logits + loss.  Tied embeddings across the first and last stage are reported through `get_shared_params`.
+Sequence parallelism of HF modules is NOT provided here (use the native zoo + `hf_io` weight import).
 """
 from __future__ import annotations
 
@@ -28,6 +33,32 @@ __all__ = ["HFDecoderPolicy", "HF_FAMILIES"]
 
 # transformers module path -> class-name prefix
 HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere"}
+
+
+def _pp_stage_forward(self, input_ids=None, hidden_states=None, labels=None, attention_mask=None, position_ids=None,
+                      **kwargs):
+    """Stage-aware forward bound to the user's `<Family>ForCausalLM` / `<Family>Model` under pipeline parallelism."""
+    sm = self._cb200_stage_manager
+    backbone = self.model if hasattr(self, "lm_head") else self
+    inner = type(backbone).forward                       # the HF backbone's own forward
+    if sm.is_first_stage():
+        out = inner(backbone, input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, use_cache=False)
+    else:
+        out = inner(backbone, inputs_embeds=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                    use_cache=False)
+    h = out.last_hidden_state
+    if not sm.is_last_stage():
+        return {"hidden_states": h}
+    if not hasattr(self, "lm_head"):
+        return {"last_hidden_state": h}
+    logits = self.lm_head(h)
+    scale = getattr(self, "logit_scale", None)           # Cohere
+    if scale is not None:
+        logits = logits * scale
+    loss = None
+    if labels is not None:
+        loss = self.loss_function(logits=logits, labels=labels, vocab_size=self.config.vocab_size)
+    return {"loss": loss, "logits": logits}
 
 
 def _fused_rmsnorm_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
@@ -91,20 +122,56 @@ class HFDecoderPolicy(Policy):
             policy[f"{fam}RMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
         return policy
 
+    def _backbone(self) -> nn.Module:
+        return self.model.model if hasattr(self.model, "lm_head") else self.model
+
+    def _stage_layers(self):
+        sm = self.pipeline_stage_manager
+        layers = self._backbone().layers
+        assert not sm.is_interleave, "HF modules support the 1F1B schedule (one model chunk per stage)"
+        start, end = sm.get_stage_index(sm.distribute_layers(len(layers)))
+        return list(layers[start:end])
+
     def postprocess(self) -> nn.Module:
-        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism:
+        sm = self.pipeline_stage_manager
+        single_stage = sm is None or sm.num_stages == 1 or (sm.is_first_stage() and sm.is_last_stage())
+        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism and single_stage:
             # both sides are sharded along the vocab dimension identically: re-tie the local shards
             emb = self.model.get_input_embeddings()
             head = self.model.get_output_embeddings()
             if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
                 head.weight = emb.weight
+        if sm is not None and sm.num_stages > 1:
+            from types import MethodType
+
+            backbone = self._backbone()
+            backbone.layers = nn.ModuleList(self._held_decoder_layers)     # the HF loop now walks this stage's layers
+            if not sm.is_last_stage():
+                backbone.norm = nn.Identity()
+            self.model._cb200_stage_manager = sm
+            self.model.forward = MethodType(_pp_stage_forward, self.model)
         return self.model
 
     def get_held_layers(self) -> List[nn.Module]:
-        if self.pipeline_stage_manager is not None:
-            raise NotImplementedError("pipeline parallelism of HuggingFace modules: import the weights into the native "
-                                      "zoo (`models.hf_io.load_hf_checkpoint`) and use its policy")
-        return []
+        sm = self.pipeline_stage_manager
+        if sm is None:
+            return []
+        backbone = self._backbone()
+        self._held_decoder_layers = self._stage_layers()
+        held: List[nn.Module] = list(self._held_decoder_layers)
+        if hasattr(backbone, "rotary_emb"):
+            held.append(backbone.rotary_emb)
+        if sm.is_first_stage():
+            held.append(backbone.embed_tokens)
+        if sm.is_last_stage():
+            held.append(backbone.norm)
+            if hasattr(self.model, "lm_head"):
+                held.append(self.model.lm_head)
+        return held
 
     def get_shared_params(self):
-        return []
+        sm = self.pipeline_stage_manager
+        if sm is None or sm.num_stages == 1 or not getattr(self, "tie_weight", False) or not hasattr(self.model, "lm_head"):
+            return []
+        emb_w, head_w = self._backbone().embed_tokens.weight, self.model.lm_head.weight
+        return [{0: emb_w, sm.num_stages - 1: head_w}]

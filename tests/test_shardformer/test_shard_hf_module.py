@@ -475,6 +475,66 @@ def _check_zero_and_ddp_keep_hf_module():
         torch.testing.assert_close(w, other, atol=1e-6, rtol=1e-6)
 
 
+def _check_pipeline_in_place(family, tied):
+    """Pipeline parallelism of a user's HF decoder without converting it: stage 0 keeps the embedding + first layers,
+    stage 1 the rest + norm + head (tied head: gradients of the two copies are synchronised); two 1F1B steps with two
+    micro-batches track the single-process model."""
+    import transformers
+
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+              num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=tied)
+    cfg = {"llama": transformers.LlamaConfig, "qwen2": transformers.Qwen2Config}[family](**kw)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    org = {"llama": transformers.LlamaForCausalLM, "qwen2": transformers.Qwen2ForCausalLM}[family](cfg).float()
+    model = copy.deepcopy(org)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.0)
+    ref_opt = torch.optim.AdamW(org.parameters(), lr=1e-2, weight_decay=0.0)
+    plugin = HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2)
+    booster = Booster(plugin=plugin, convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    r = dist.get_rank()
+    assert len(inner.model.layers) == 2
+    assert (inner.model.embed_tokens.weight is not None) == (r == 0) or tied
+    torch.manual_seed(12)
+    ids = torch.randint(0, 320, (2, 16))
+    for _ in range(2):
+        out = booster.execute_pipeline(iter([{"input_ids": ids, "labels": ids}]), model, lambda o, b: o["loss"], opt,
+                                       return_loss=True)
+        opt.step()
+        opt.zero_grad()
+        total = 0.0
+        for i in range(2):
+            l = org(input_ids=ids[i:i + 1], labels=ids[i:i + 1]).loss / 2
+            l.backward()
+            total += l.item()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        if out["loss"] is not None:
+            assert abs(out["loss"].item() - total) < 2e-4, (family, out["loss"].item(), total)
+    ref_params = dict(org.named_parameters())
+    n = 0
+    for name, p in inner.named_parameters():
+        if p is None:
+            continue
+        # the stage's layers are renumbered from 0: map back to the global layer index
+        ref_name = name
+        if ".layers." in name and r == 1:
+            head, rest = name.split(".layers.")
+            idx, tail = rest.split(".", 1)
+            ref_name = f"{head}.layers.{int(idx) + 2}.{tail}"
+        if ref_name not in ref_params and "lm_head" in ref_name:
+            ref_name = "model.embed_tokens.weight"                      # tied head
+        torch.testing.assert_close(p.detach(), ref_params[ref_name].detach(), atol=3e-4, rtol=3e-3,
+                                   msg=lambda m: f"pp {family} {name}: {m}")
+        n += 1
+    assert n >= 10
+
+
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
     for family in ("llama", "mistral", "qwen2", "cohere"):
@@ -490,6 +550,8 @@ def _worker(rank, world_size, port):
         _check_moe_ep(family)
     _check_booster_in_place()
     _check_zero_and_ddp_keep_hf_module()
+    for family, tied in (("llama", False), ("qwen2", True)):
+        _check_pipeline_in_place(family, tied)
     dist.destroy_process_group()
 
 
