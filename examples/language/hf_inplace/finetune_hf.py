@@ -4,6 +4,7 @@ expert parallelism for the MoE families - and the sharded checkpoint is the plai
 
     torchrun --nproc-per-node 2 --master-addr 127.0.0.1 examples/language/hf_inplace/finetune_hf.py --family llama --tp 2
     torchrun --nproc-per-node 2 --master-addr 127.0.0.1 examples/language/hf_inplace/finetune_hf.py --family mixtral --ep 2
+    torchrun --nproc-per-node 4 --master-addr 127.0.0.1 examples/language/hf_inplace/finetune_hf.py --family llama --tp 2 --pp 2
 
 Runs on CPU (gloo) with the tiny configs below; pass `--pretrained <dir>` for real weights on GPUs.
 Reference counterpart: `examples/language/llama/benchmark.py` with a HF model handed to `booster.boost`."""
@@ -44,6 +45,7 @@ def main():
     ap.add_argument("--pretrained", default=None, help="HuggingFace checkpoint directory (AutoModelForCausalLM)")
     ap.add_argument("--tp", type=int, default=1)
     ap.add_argument("--ep", type=int, default=1)
+    ap.add_argument("--pp", type=int, default=1, help="pipeline stages (llama-like families)")
     ap.add_argument("--zero", type=int, default=0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--save", default=None)
@@ -61,21 +63,30 @@ def main():
     if args.ep > 1:
         plugin = MoeHybridParallelPlugin(tp_size=args.tp, pp_size=1, ep_size=args.ep, zero_stage=args.zero, precision=precision)
     else:
-        plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=1, zero_stage=args.zero, precision=precision)
+        plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, zero_stage=args.zero, precision=precision,
+                                      num_microbatches=2 if args.pp > 1 else None)
     booster = Booster(plugin=plugin, convert_hf_models=False)          # keep the user's module, shard it in place
     optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3)
     model, optimizer, *_ = booster.boost(model, optimizer)
     dev = colossalai_b200.accelerator.get_accelerator().get_current_device()
     vocab = model.unwrap().config.vocab_size
-    g = torch.Generator().manual_seed(dist.get_rank() // max(args.tp, 1))    # same data inside a TP group
+    g = torch.Generator().manual_seed(dist.get_rank() // max(args.tp * args.pp, 1))   # same data inside a model replica
     for step in range(args.steps):
         ids = torch.randint(0, vocab, (2, 32), generator=g).to(dev)
-        loss = model(input_ids=ids, labels=ids).loss
-        booster.backward(loss, optimizer)
+        if args.pp > 1:
+            out = booster.execute_pipeline(iter([{"input_ids": ids, "labels": ids}]), model, lambda o, b: o["loss"],
+                                           optimizer, return_loss=True)
+            loss = out["loss"]
+            lt = torch.full((1,), float("-inf"), device=dev) if loss is None else loss.detach().float().reshape(1)
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)            # the loss lives on the last stage
+            loss = lt[0]
+        else:
+            loss = model(input_ids=ids, labels=ids).loss
+            booster.backward(loss, optimizer)
         optimizer.step()
         optimizer.zero_grad()
         if dist.get_rank() == 0:
-            print(f"step {step}: loss {loss.item():.4f} ({type(model.unwrap()).__name__}, tp={args.tp}, ep={args.ep})")
+            print(f"step {step}: loss {loss.item():.4f} ({type(model.unwrap()).__name__}, tp={args.tp}, pp={args.pp}, ep={args.ep})")
     if args.save:
         booster.save_model(model, args.save, shard=True)               # plain HF names / shapes on disk
     dist.barrier()

@@ -19,11 +19,12 @@ def _torchrun(script, *args, nproc=2, port=29750, timeout=240):
 
 
 @pytest.mark.dist
-@pytest.mark.parametrize("args,port", [(("--family", "gpt2", "--tp", "2", "--steps", "2"), 29751),
-                                       (("--family", "mixtral", "--ep", "2", "--steps", "2"), 29752)])
-def test_hf_inplace_example(args, port):
+@pytest.mark.parametrize("args,port,nproc", [(("--family", "gpt2", "--tp", "2", "--steps", "2"), 29751, 2),
+                                             (("--family", "mixtral", "--ep", "2", "--steps", "2"), 29752, 2),
+                                             (("--family", "llama", "--tp", "2", "--pp", "2", "--steps", "2"), 29754, 4)])
+def test_hf_inplace_example(args, port, nproc):
     pytest.importorskip("transformers")
-    out = _torchrun("examples/language/hf_inplace/finetune_hf.py", *args, port=port)
+    out = _torchrun("examples/language/hf_inplace/finetune_hf.py", *args, port=port, nproc=nproc)
     lines = [l for l in out.splitlines() if l.startswith("step ")]
     assert len(lines) == 2 and all("loss" in l and "nan" not in l for l in lines)
 
