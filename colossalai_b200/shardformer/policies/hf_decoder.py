@@ -29,7 +29,7 @@ import torch.nn as nn
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFDecoderPolicy", "HF_FAMILIES"]
+__all__ = ["HFDecoderPolicy", "HFDecoderPipelineMixin", "HF_FAMILIES"]
 
 # transformers module path -> class-name prefix
 HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere"}
@@ -68,7 +68,59 @@ def _fused_rmsnorm_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
     return ops.rms_norm(hidden_states, self.weight, eps)
 
 
-class HFDecoderPolicy(Policy):
+class HFDecoderPipelineMixin:
+    """1F1B pipeline stages for HF decoders whose backbone (`<Family>Model`) has `embed_tokens`, `layers`, `norm`,
+    `rotary_emb` and accepts `inputs_embeds` (llama-likes and the MoE families built on them)."""
+
+    def _backbone(self) -> nn.Module:
+        return self.model.model if hasattr(self.model, "lm_head") else self.model
+
+    def _stage_layers(self):
+        sm = self.pipeline_stage_manager
+        layers = self._backbone().layers
+        assert not sm.is_interleave, "HF modules support the 1F1B schedule (one model chunk per stage)"
+        start, end = sm.get_stage_index(sm.distribute_layers(len(layers)))
+        return list(layers[start:end])
+
+    def _install_pipeline_stage(self) -> None:
+        sm = self.pipeline_stage_manager
+        if sm is None or sm.num_stages == 1:
+            return
+        from types import MethodType
+
+        backbone = self._backbone()
+        backbone.layers = nn.ModuleList(self._held_decoder_layers)     # the HF loop now walks this stage's layers
+        if not sm.is_last_stage():
+            backbone.norm = nn.Identity()
+        self.model._cb200_stage_manager = sm
+        self.model.forward = MethodType(_pp_stage_forward, self.model)
+
+    def get_held_layers(self) -> List[nn.Module]:
+        sm = self.pipeline_stage_manager
+        if sm is None:
+            return []
+        backbone = self._backbone()
+        self._held_decoder_layers = self._stage_layers()
+        held: List[nn.Module] = list(self._held_decoder_layers)
+        if hasattr(backbone, "rotary_emb"):
+            held.append(backbone.rotary_emb)
+        if sm.is_first_stage():
+            held.append(backbone.embed_tokens)
+        if sm.is_last_stage():
+            held.append(backbone.norm)
+            if hasattr(self.model, "lm_head"):
+                held.append(self.model.lm_head)
+        return held
+
+    def get_shared_params(self):
+        sm = self.pipeline_stage_manager
+        if sm is None or sm.num_stages == 1 or not getattr(self, "tie_weight", False) or not hasattr(self.model, "lm_head"):
+            return []
+        emb_w, head_w = self._backbone().embed_tokens.weight, self.model.lm_head.weight
+        return [{0: emb_w, sm.num_stages - 1: head_w}]
+
+
+class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
     """Works for `<Family>Model`, `<Family>ForCausalLM` of the families in HF_FAMILIES (matched by class NAME, so the
     policy never imports transformers itself)."""
 
@@ -122,16 +174,6 @@ class HFDecoderPolicy(Policy):
             policy[f"{fam}RMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
         return policy
 
-    def _backbone(self) -> nn.Module:
-        return self.model.model if hasattr(self.model, "lm_head") else self.model
-
-    def _stage_layers(self):
-        sm = self.pipeline_stage_manager
-        layers = self._backbone().layers
-        assert not sm.is_interleave, "HF modules support the 1F1B schedule (one model chunk per stage)"
-        start, end = sm.get_stage_index(sm.distribute_layers(len(layers)))
-        return list(layers[start:end])
-
     def postprocess(self) -> nn.Module:
         sm = self.pipeline_stage_manager
         single_stage = sm is None or sm.num_stages == 1 or (sm.is_first_stage() and sm.is_last_stage())
@@ -141,37 +183,5 @@ class HFDecoderPolicy(Policy):
             head = self.model.get_output_embeddings()
             if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
                 head.weight = emb.weight
-        if sm is not None and sm.num_stages > 1:
-            from types import MethodType
-
-            backbone = self._backbone()
-            backbone.layers = nn.ModuleList(self._held_decoder_layers)     # the HF loop now walks this stage's layers
-            if not sm.is_last_stage():
-                backbone.norm = nn.Identity()
-            self.model._cb200_stage_manager = sm
-            self.model.forward = MethodType(_pp_stage_forward, self.model)
+        self._install_pipeline_stage()
         return self.model
-
-    def get_held_layers(self) -> List[nn.Module]:
-        sm = self.pipeline_stage_manager
-        if sm is None:
-            return []
-        backbone = self._backbone()
-        self._held_decoder_layers = self._stage_layers()
-        held: List[nn.Module] = list(self._held_decoder_layers)
-        if hasattr(backbone, "rotary_emb"):
-            held.append(backbone.rotary_emb)
-        if sm.is_first_stage():
-            held.append(backbone.embed_tokens)
-        if sm.is_last_stage():
-            held.append(backbone.norm)
-            if hasattr(self.model, "lm_head"):
-                held.append(self.model.lm_head)
-        return held
-
-    def get_shared_params(self):
-        sm = self.pipeline_stage_manager
-        if sm is None or sm.num_stages == 1 or not getattr(self, "tie_weight", False) or not hasattr(self.model, "lm_head"):
-            return []
-        emb_w, head_w = self._backbone().embed_tokens.weight, self.model.lm_head.weight
-        return [{0: emb_w, sm.num_stages - 1: head_w}]

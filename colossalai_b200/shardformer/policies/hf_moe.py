@@ -11,7 +11,8 @@ That is exactly the contract of this framework's MoE data path, so the policy
     combine with the routing weights;
 the router (`gate`) stays replicated.  Attention is tensor-parallel like the llama-likes when TP is enabled.  Expert
 gradients are already sums over every token of the expert-parallel group that chose the expert; the usual 1 / ep scaling
-for data-parallel averaging is the plugin's job (`MoeHybridParallelPlugin`)."""
+for data-parallel averaging is the plugin's job (`MoeHybridParallelPlugin`).  Pipeline stages work as for the llama-likes
+(`HFDecoderPipelineMixin`): the backbone has the same `embed_tokens / layers / norm` layout."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -21,7 +22,7 @@ import torch.nn as nn
 
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
-from .hf_decoder import _fused_rmsnorm_forward
+from .hf_decoder import HFDecoderPipelineMixin, _fused_rmsnorm_forward
 
 __all__ = ["HFMoEPolicy", "HFMixtralPolicy", "HFQwen3MoePolicy", "HFQwen2MoePolicy", "HFDeepseekV3Policy",
            "HFDeepseekV2Policy"]
@@ -46,7 +47,7 @@ def _ep_experts_forward(self, hidden_states: torch.Tensor, top_k_index: torch.Te
     return out.to(hidden_states.dtype).reshape(shape)
 
 
-class HFMoEPolicy(Policy):
+class HFMoEPolicy(HFDecoderPipelineMixin, Policy):
     """Shared implementation: the HF MoE families of transformers >= 5 all use the same experts module contract
     (`gate_up_proj [E, 2 I, H]`, `down_proj [E, H, I]`, `forward(hidden_states, top_k_index, top_k_weights)`); a family
     is described by its class-name prefix, the name of its experts class and whether its attention is the plain
@@ -75,10 +76,13 @@ class HFMoEPolicy(Policy):
         return self.model
 
     def postprocess(self) -> nn.Module:
-        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism:
+        sm = self.pipeline_stage_manager
+        single_stage = sm is None or sm.num_stages == 1
+        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism and single_stage:
             emb, head = self.model.get_input_embeddings(), self.model.get_output_embeddings()
             if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
                 head.weight = emb.weight
+        self._install_pipeline_stage()                      # 1F1B stages: same backbone layout as the llama-likes
         return self.model
 
     def _slice_experts(self, module: nn.Module) -> None:
@@ -119,15 +123,6 @@ class HFMoEPolicy(Policy):
         if sc.enable_fused_normalization:
             policy[f"{self.FAMILY}RMSNorm"] = ModulePolicyDescription(method_replacement={"forward": _fused_rmsnorm_forward})
         return policy
-
-    def get_held_layers(self) -> List[nn.Module]:
-        if self.pipeline_stage_manager is not None:
-            raise NotImplementedError("pipeline parallelism of HuggingFace modules: import the weights into the native "
-                                      "zoo (`models.hf_io.load_hf_checkpoint`) and use its policy")
-        return []
-
-    def get_shared_params(self):
-        return []
 
 
 class HFMixtralPolicy(HFMoEPolicy):

@@ -61,7 +61,8 @@ def main():
         torch.manual_seed(0)
         model = tiny(args.family)
     if args.ep > 1:
-        plugin = MoeHybridParallelPlugin(tp_size=args.tp, pp_size=1, ep_size=args.ep, zero_stage=args.zero, precision=precision)
+        plugin = MoeHybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, ep_size=args.ep, zero_stage=args.zero,
+                                         precision=precision, num_microbatches=2 if args.pp > 1 else None)
     else:
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, zero_stage=args.zero, precision=precision,
                                       num_microbatches=2 if args.pp > 1 else None)
