@@ -65,7 +65,29 @@ def _fused_rmsnorm_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
     from ... import ops
 
     eps = getattr(self, "variance_epsilon", getattr(self, "eps", 1e-6))
-    return ops.rms_norm(hidden_states, self.weight, eps)
+    weight = self.weight
+    group = getattr(self, "_cb200_tp_group", None)
+    if group is not None:
+        # per-head q / k norm under tensor parallelism: the [head_dim] weight is replicated while every rank only sees
+        # its own heads, so its gradient is a partial sum - identity forward, all-reduce backward over the TP group
+        from ..layer._operation import reduce_backward
+
+        weight = reduce_backward(weight, group)
+    return ops.rms_norm(hidden_states, weight, eps)
+
+
+def mark_head_norms(tp_group):
+    """Parameter-replacement hook for `<Family>Attention`: q_norm / k_norm (Qwen3-style per-head RMSNorm) get the
+    TP-aware forward above."""
+    from types import MethodType
+
+    def hook(attn: nn.Module) -> None:
+        for name in ("q_norm", "k_norm"):
+            norm = getattr(attn, name, None)
+            if norm is not None and getattr(norm, "weight", None) is not None and norm.weight.dim() == 1:
+                norm._cb200_tp_group = tp_group
+                norm.forward = MethodType(_fused_rmsnorm_forward, norm)
+    return hook
 
 
 class HFDecoderPipelineMixin:
@@ -160,6 +182,8 @@ class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
                 SubModuleReplacementDescription("mlp.up_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("mlp.down_proj", Linear1D_Row, kwargs=dict(col)),
             ])
+            policy[f"{fam}Attention"] = ModulePolicyDescription(
+                param_replacement=[mark_head_norms(sc.tensor_parallel_process_group)])
             policy[f"{fam}Model"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription(
                     "embed_tokens", VocabParallelEmbedding1D,

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
-from .hf_decoder import HFDecoderPipelineMixin, _fused_rmsnorm_forward
+from .hf_decoder import HFDecoderPipelineMixin, _fused_rmsnorm_forward, mark_head_norms
 
 __all__ = ["HFMoEPolicy", "HFMixtralPolicy", "HFQwen3MoePolicy", "HFQwen2MoePolicy", "HFDeepseekV3Policy",
            "HFDeepseekV2Policy"]
@@ -113,6 +113,8 @@ class HFMoEPolicy(HFDecoderPipelineMixin, Policy):
                 SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
                 SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(fp8)),
             ])
+            policy[f"{self.FAMILY}Attention"] = ModulePolicyDescription(
+                param_replacement=[mark_head_norms(sc.tensor_parallel_process_group)])
             policy[f"{self.FAMILY}Model"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=vocab)])
             policy[f"{self.FAMILY}ForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[

@@ -20,9 +20,10 @@ def _build(family):
     kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
               num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=False)
     cfg_cls = {"llama": transformers.LlamaConfig, "mistral": transformers.MistralConfig, "qwen2": transformers.Qwen2Config,
-               "cohere": transformers.CohereConfig}[family]
+               "cohere": transformers.CohereConfig, "qwen3": transformers.Qwen3Config}[family]
     model_cls = {"llama": transformers.LlamaForCausalLM, "mistral": transformers.MistralForCausalLM,
-                 "qwen2": transformers.Qwen2ForCausalLM, "cohere": transformers.CohereForCausalLM}[family]
+                 "qwen2": transformers.Qwen2ForCausalLM, "cohere": transformers.CohereForCausalLM,
+                 "qwen3": transformers.Qwen3ForCausalLM}[family]
     cfg = cfg_cls(**kw)
     cfg._attn_implementation = "eager"
     torch.manual_seed(0)
@@ -537,7 +538,7 @@ def _check_pipeline_in_place(family, tied):
 
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
-    for family in ("llama", "mistral", "qwen2", "cohere"):
+    for family in ("llama", "mistral", "qwen2", "cohere", "qwen3"):
         _check(family)
     for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new", "falcon-mha"):
         _check_tied(family)
