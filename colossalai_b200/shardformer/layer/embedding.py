@@ -150,7 +150,11 @@ class VocabParallelEmbedding1D(ParallelModule):
             return F.embedding(ids, self.weight, self.padding_idx)
         mask = (ids < self.vocab_start_index) | (ids >= self.vocab_end_index)
         local = (ids - self.vocab_start_index).masked_fill(mask, 0)
-        out = F.embedding(local, self.weight)
+        # the padding row gets no gradient (as in nn.Embedding) on the rank that owns it
+        pad = self.padding_idx
+        pad = pad - self.vocab_start_index if pad is not None and self.vocab_start_index <= pad < self.vocab_end_index \
+            else None
+        out = F.embedding(local, self.weight, pad)
         out = out.masked_fill(mask.unsqueeze(-1), 0.0)
         if self.sp_scatter_dim is not None:
             return reducescatter_forward_gather_backward(out, self.process_group, self.sp_scatter_dim)

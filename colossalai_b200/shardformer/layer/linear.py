@@ -150,6 +150,10 @@ class Linear1D_Col(ParallelModule):
                 out = linear_gather_forward_reducescatter_backward(x, self.weight, bias, self.process_group,
                                                                    self.seq_parallel_dim, ring=(mode == "ring"),
                                                                    use_zbv=self.use_zbv)
+            elif mode == "pre_gathered":
+                # the caller gathered the sequence once for several column linears (gather-forward /
+                # reduce-scatter-backward in front of q/k/v or gate/up): dX stays a partial sum here
+                out = linear_with_grad_accum(x, self.weight, bias, self.use_zbv)
             else:
                 out = linear_with_async_comm(x, self.weight, bias, self.process_group, True, self.use_zbv)
         if self.gather_output:

@@ -17,7 +17,16 @@ existing `nn.Module` the framework knows nothing about and rewrite it through th
     an identity on the other stages, and a small stage forward on the top-level module feeds `input_ids` (first stage)
     or the previous stage's `hidden_states` (as `inputs_embeds`) into the backbone and returns hidden states or
     logits + loss.  Tied embeddings across the first and last stage are reported through `get_shared_params`.
-Sequence parallelism of HF modules is NOT provided here (use the native zoo + `hf_io` weight import).
+  * sequence parallelism, `split_gather` mode (Megatron SP inside the TP group): HF attention reshapes q/k/v with the
+    sequence length of its INPUT, so the sequence is gathered once in front of each attention / MLP block (forward
+    pre-hook: all-gather forward, reduce-scatter backward - one gather feeds q, k and v instead of one per linear),
+    the column linears then run without communication (`pre_gathered`: their dX stays a partial sum for that
+    reduce-scatter) and the row linears reduce-scatter their output along the sequence (`seq_parallel_dim=1`: HF
+    activations are [batch, seq, hidden]).  The HF backbone computes rotary tables and the causal mask for the FULL
+    sequence before its layer loop, so the only other plumbing is a split of the hidden states in front of the first
+    decoder layer and a gather behind the last one.  The norms inside the layers see sequence shards, so their
+    weights are marked SP-partial (the plugin all-reduces those gradients over the TP group).  The other SP modes
+    (Ulysses, ring attention) need the attention rewritten: native zoo.
 """
 from __future__ import annotations
 
@@ -153,12 +162,61 @@ class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
             assert cfg.num_attention_heads % tp == 0, "num_attention_heads must be divisible by the TP size"
             kv = getattr(cfg, "num_key_value_heads", cfg.num_attention_heads)
             assert kv % tp == 0, "num_key_value_heads must be divisible by the TP size"
-        assert not self.shard_config.enable_sequence_parallelism, \
-            "sequence parallelism of HF modules is not supported; build the model from the native zoo (models.hf_io)"
+        if self.shard_config.enable_sequence_parallelism:
+            assert self.shard_config.sequence_parallelism_mode == "split_gather" and \
+                self.shard_config.enable_tensor_parallelism, (
+                    "HF modules support sequence parallelism in `split_gather` mode (with tensor parallelism); the "
+                    "all_to_all / ring_attn modes need the native zoo (models.hf_io)")
 
     def preprocess(self) -> nn.Module:
         self.tie_weight = self.tie_weight_check()
         return self.model
+
+    def _sp_hooks(self):
+        """Parameter-replacement hook for `<Family>Model`: split the sequence in front of the first decoder layer,
+        gather it behind the last one (autograd-aware), mark the in-layer norm weights SP-partial."""
+        from ..layer._operation import (gather_forward_reducescatter_backward, gather_forward_split_backward,
+                                        split_forward_gather_backward)
+        from ..layer.utils import SeqParallelUtils
+
+        group = self.shard_config.tensor_parallel_process_group
+
+        def install(backbone: nn.Module) -> None:
+            layers = list(backbone.layers)
+            if not layers:
+                return
+
+            def split_in(module, args, kwargs):
+                if args:
+                    return (split_forward_gather_backward(args[0], 1, group),) + tuple(args[1:]), kwargs
+                kwargs = dict(kwargs)
+                kwargs["hidden_states"] = split_forward_gather_backward(kwargs["hidden_states"], 1, group)
+                return args, kwargs
+
+            def gather_out(module, args, output):
+                if isinstance(output, tuple):
+                    return (gather_forward_split_backward(output[0], 1, group),) + tuple(output[1:])
+                return gather_forward_split_backward(output, 1, group)
+
+            def gather_block_input(module, args, kwargs):
+                if args:
+                    return (gather_forward_reducescatter_backward(args[0], group, 1),) + tuple(args[1:]), kwargs
+                kwargs = dict(kwargs)
+                kwargs["hidden_states"] = gather_forward_reducescatter_backward(kwargs["hidden_states"], group, 1)
+                return args, kwargs
+
+            layers[0].register_forward_pre_hook(split_in, with_kwargs=True)
+            layers[-1].register_forward_hook(gather_out)
+            for layer in layers:
+                layer.self_attn.register_forward_pre_hook(gather_block_input, with_kwargs=True)
+                layer.mlp.register_forward_pre_hook(gather_block_input, with_kwargs=True)
+                for name in ("input_layernorm", "post_attention_layernorm", "pre_feedforward_layernorm",
+                             "post_feedforward_layernorm"):
+                    norm = getattr(layer, name, None)
+                    if norm is not None:
+                        for prm in norm.parameters(recurse=False):
+                            SeqParallelUtils.marked_as_sp_partial_derived_param(prm)
+        return install
 
     def _prefix(self) -> str:
         name = self.model.__class__.__name__
@@ -173,22 +231,27 @@ class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
         policy: Dict[str, ModulePolicyDescription] = {}
         if sc.enable_tensor_parallelism:
             col = dict(fp8_communication=sc.fp8_communication)
+            row = dict(col)
+            if sc.enable_sequence_parallelism:
+                col.update(seq_parallel_mode="pre_gathered")
+                row.update(seq_parallel_mode="split_gather", seq_parallel_dim=1)
             policy[f"{fam}DecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(col)),
-                SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(col)),
+                SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(row)),
                 SubModuleReplacementDescription("mlp.gate_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("mlp.up_proj", Linear1D_Col, kwargs=dict(col)),
-                SubModuleReplacementDescription("mlp.down_proj", Linear1D_Row, kwargs=dict(col)),
+                SubModuleReplacementDescription("mlp.down_proj", Linear1D_Row, kwargs=dict(row)),
             ])
             policy[f"{fam}Attention"] = ModulePolicyDescription(
                 param_replacement=[mark_head_norms(sc.tensor_parallel_process_group)])
-            policy[f"{fam}Model"] = ModulePolicyDescription(sub_module_replacement=[
-                SubModuleReplacementDescription(
+            policy[f"{fam}Model"] = ModulePolicyDescription(
+                sub_module_replacement=[SubModuleReplacementDescription(
                     "embed_tokens", VocabParallelEmbedding1D,
                     kwargs=dict(make_vocab_size_divisible_by=sc.make_vocab_size_divisible_by,
-                                fp8_communication=sc.fp8_communication))])
+                                fp8_communication=sc.fp8_communication))],
+                param_replacement=[self._sp_hooks()] if sc.enable_sequence_parallelism else None)
             policy[f"{fam}ForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription(
                     "lm_head", VocabParallelLMHead1D,

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--tp", type=int, default=1)
     ap.add_argument("--ep", type=int, default=1)
     ap.add_argument("--pp", type=int, default=1, help="pipeline stages (llama-like families)")
+    ap.add_argument("--sp", action="store_true", help="split_gather sequence parallelism inside the TP group (llama-like)")
     ap.add_argument("--zero", type=int, default=0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--save", default=None)
@@ -64,8 +65,9 @@ def main():
         plugin = MoeHybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, ep_size=args.ep, zero_stage=args.zero,
                                          precision=precision, num_microbatches=2 if args.pp > 1 else None)
     else:
+        sp = dict(enable_sequence_parallelism=True, sequence_parallelism_mode="split_gather") if args.sp else {}
         plugin = HybridParallelPlugin(tp_size=args.tp, pp_size=args.pp, zero_stage=args.zero, precision=precision,
-                                      num_microbatches=2 if args.pp > 1 else None)
+                                      num_microbatches=2 if args.pp > 1 else None, **sp)
     booster = Booster(plugin=plugin, convert_hf_models=False)          # keep the user's module, shard it in place
     optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3)
     model, optimizer, *_ = booster.boost(model, optimizer)

@@ -442,6 +442,51 @@ def _check_booster_in_place():
     dist.barrier()
 
 
+def _check_sequence_parallel_in_place(family):
+    """`split_gather` sequence parallelism of a user's HF decoder (TP2 + SP inside the TP group): the layers run on
+    sequence shards (checked with a hook), the norm-weight gradients are summed over the group by the plugin, and two
+    SGD steps track the single-process model."""
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    org = _build(family)
+    model = copy.deepcopy(org)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)      # (SGD: Adam turns rounding noise on ~0 gradients into +-lr)
+    ref_opt = torch.optim.SGD(org.parameters(), lr=0.05)
+    plugin = HybridParallelPlugin(tp_size=2, pp_size=1, precision="fp32", enable_sequence_parallelism=True,
+                                  sequence_parallelism_mode="split_gather")
+    booster = Booster(plugin=plugin, convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    seen = {}
+    inner.model.layers[1].mlp.register_forward_hook(lambda m, a, o: seen.update(mlp_out=tuple(o.shape)))
+    inner.model.norm.register_forward_hook(lambda m, a, o: seen.update(final_norm=tuple(o.shape)))
+    torch.manual_seed(3)
+    ids = torch.randint(0, 320, (2, 16))
+    for step in range(2):
+        loss = model(input_ids=ids, labels=ids).loss
+        booster.backward(loss, opt)
+        opt.step()
+        opt.zero_grad()
+        ref = org(input_ids=ids, labels=ids).loss
+        ref.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        torch.testing.assert_close(loss.detach(), ref.detach(), atol=1e-5, rtol=1e-5,
+                                   msg=lambda m: f"sp {family} step {step}: {m}")
+    assert seen["mlp_out"][1] == 8 and seen["final_norm"][1] == 16, seen      # shards inside, full sequence outside
+    ref_params = dict(org.named_parameters())
+    mine = dict(inner.named_parameters())
+    for name in ("model.layers.0.input_layernorm.weight", "model.layers.1.post_attention_layernorm.weight",
+                 "model.norm.weight"):
+        if name not in mine:                                     # (Cohere: one norm per parallel block)
+            continue
+        p = mine[name]
+        torch.testing.assert_close(p.detach(), ref_params[name].detach(), atol=1e-6, rtol=1e-5,
+                                   msg=lambda m: f"sp {family} {name}: {m}")
+    del plugin
+
+
 def _check_zero_and_ddp_keep_hf_module():
     """Data-parallel plugins need no policy: with `convert_hf_models=False` the user's module is wrapped as it is
     (ZeRO-1 in bf16, torch DDP in fp32) and trains."""
@@ -550,6 +595,8 @@ def _worker(rank, world_size, port):
     for family in ("mixtral", "qwen3_moe", "qwen2_moe", "deepseek_v2", "deepseek_v3"):
         _check_moe_ep(family)
     _check_booster_in_place()
+    for family in ("llama", "qwen3", "cohere", "mistral"):
+        _check_sequence_parallel_in_place(family)
     _check_zero_and_ddp_keep_hf_module()
     for family, tied in (("llama", False), ("qwen2", True)):
         _check_pipeline_in_place(family, tied)
