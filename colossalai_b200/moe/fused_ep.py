@@ -26,7 +26,7 @@ __all__ = ["EPWorkspace", "ep_workspace", "available", "dispatch", "combine", "m
 
 _lib = None
 ALIGN = 128     # row alignment of every local expert's segment in the receive layout (k-block of the grouped wgrad GEMM)
-_workspaces: Dict[Tuple[int, int, int], "EPWorkspace"] = {}
+_workspaces: Dict[tuple, "EPWorkspace"] = {}
 
 
 def _get_lib():
@@ -81,6 +81,7 @@ class EPWorkspace:
         self.cursor = torch.zeros(num_experts, dtype=torch.int32, device=dev)
         self.done_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.epoch = 0
+        self.can_overflow = False          # set by `ep_workspace` when the capacity is below the worst case
         self._pending_meta = None
         if self.world > 1:
             torch.cuda.synchronize()
@@ -96,7 +97,10 @@ class EPWorkspace:
         return buf.tensor[: n * self.hidden * esz].view(self.dtype).view(n, self.hidden)
 
     def check_overflow(self) -> None:
-        """Raise if the PREVIOUS dispatch overflowed a receive buffer (checked one op late to stay asynchronous)."""
+        """Raise if the last dispatch overflowed a receive buffer.  Only a workspace sized below the worst case
+        (`CB200_EP_CAPACITY_FACTOR`) can overflow; for those the dispatch leaves an asynchronous copy of its flag in
+        pinned memory and the COMBINE OF THE SAME LAYER reads it (the expert GEMMs sit between the two, so the wait is
+        normally over) - the error surfaces before the layer's output is used, not one MoE layer later."""
         if self._pending_meta is not None:
             host, ev = self._pending_meta
             ev.synchronize()
@@ -126,17 +130,20 @@ def ep_workspace(group, hidden: int, dtype: torch.dtype, num_experts: int, rows_
     factor = float(os.environ.get("CB200_EP_CAPACITY_FACTOR", "0"))
     worst = rows_per_rank * world
     cap = worst if factor <= 0 else min(worst, int(rows_per_rank * factor))
-    cap = (cap + 127) // 128 * 128 + (num_experts // world) * ALIGN      # every local expert's segment is ALIGN-padded
+    pad = (num_experts // world) * ALIGN                                  # every local expert's segment is ALIGN-padded
+    worst_padded = (worst + 127) // 128 * 128 + pad
+    cap = (cap + 127) // 128 * 128 + pad
     if world > 1:
         # symmetric allocations must have the same size on every rank: agree on the largest request
         t = torch.tensor([cap], device="cuda", dtype=torch.int64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         cap = int(t.item())
-    key = (id(group), hidden, dtype, num_experts)
+    key = (comm.group_key(group), hidden, dtype, num_experts)
     ws = _workspaces.get(key)
     if ws is None or ws.capacity < cap:
         ws = EPWorkspace(group, hidden, dtype, num_experts, cap)
         _workspaces[key] = ws
+    ws.can_overflow = ws.capacity < worst_padded
     return ws
 
 
@@ -176,11 +183,12 @@ def _push_assign(ws: EPWorkspace, x: torch.Tensor, idx32: torch.Tensor) -> EPCon
         ctypes.c_uint32(epoch),
         code(x.dtype), loader.stream_ptr()), "moe_ep_dispatch")
     loader.launch_counter.add("moe_ep_dispatch", 5)
-    host = torch.empty(2, dtype=torch.int32, pin_memory=True)
-    host.copy_(meta, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    ws._pending_meta = (host, ev)
+    if ws.can_overflow:
+        host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        host.copy_(meta, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ws._pending_meta = (host, ev)
     return EPContext(ws, idx32, pos, meta, local_counts, local_offs, real_counts, T, K)
 
 
@@ -215,6 +223,7 @@ def _pull(ctx: EPContext, y_rows: torch.Tensor, w: Optional[torch.Tensor], keep:
           ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Publish `y_rows` (local rows in receive-buffer layout) and pull-combine this rank's tokens."""
     ws = ctx.ws
+    ws.check_overflow()
     H = ws.hidden
     out_view = ws.view(ws.rows_out)
     if y_rows.data_ptr() != out_view.data_ptr():

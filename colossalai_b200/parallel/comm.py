@@ -17,7 +17,7 @@ import torch.distributed as dist
 from torch.distributed import ProcessGroup
 
 __all__ = [
-    "group_size", "group_rank", "all_reduce", "all_gather", "reduce_scatter", "all_to_all_single",
+    "group_size", "group_rank", "group_key", "all_reduce", "all_gather", "reduce_scatter", "all_to_all_single",
     "all_to_all_uneven", "broadcast", "split_along", "send_recv_ring",
 ]
 
@@ -32,6 +32,17 @@ def group_rank(group: Optional[ProcessGroup]) -> int:
     if not dist.is_initialized():
         return 0
     return dist.get_rank(group)
+
+
+def group_key(group: Optional[ProcessGroup]):
+    """Identity of a process group for caches that outlive a call (workspaces, symmetric buffers).  `id(group)` can be
+    reused by a NEW group once the old one is destroyed and collected - a cache keyed by it would then hand the new
+    group a workspace mapped for other ranks; torch's `group_name` is a process-wide unique string that is never reused.
+    `None` is the default (world) group."""
+    if group is None and dist.is_initialized():
+        group = dist.group.WORLD
+    name = getattr(group, "group_name", None)
+    return ("pg", name) if name else ("id", id(group))
 
 
 # ---- fp8 communication switch (reference: the `fp8_communication` flag threaded through every parallel layer).

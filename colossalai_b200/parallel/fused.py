@@ -32,7 +32,7 @@ __all__ = ["available", "build_available", "all_gather_gemm", "gemm_reduce_scatt
            "FusedWorkspace", "stats"]
 
 _lib = None
-_workspaces: Dict[int, "FusedWorkspace"] = {}
+_workspaces: Dict[tuple, "FusedWorkspace"] = {}
 _disabled = os.environ.get("CB200_DISABLE_FUSED_COMM", "0") == "1"
 stats = {"ag_gemm": 0, "gemm_rs": 0, "all_gather": 0, "fallback": 0}
 
@@ -72,7 +72,7 @@ def available(group: Optional[ProcessGroup]) -> bool:
         from ..logging import get_dist_logger
 
         get_dist_logger().warning(f"fused comm backend unavailable ({e}); using NCCL", ranks=[0])
-        _workspaces[id(group)] = None  # type: ignore[assignment]
+        _workspaces[comm.group_key(group)] = None  # type: ignore[assignment]
         return False
 
 
@@ -165,7 +165,7 @@ class FusedWorkspace:
 
 
 def workspace(group: Optional[ProcessGroup]) -> Optional[FusedWorkspace]:
-    key = id(group)
+    key = comm.group_key(group)
     if key not in _workspaces:
         _workspaces[key] = FusedWorkspace(group)
     return _workspaces[key]

@@ -45,7 +45,7 @@ from ...parallel import comm
 __all__ = ["available", "ring_attention_fused", "stats"]
 
 stats = {"fwd_blocks": 0, "bwd_blocks": 0, "layers_fwd": 0, "layers_bwd": 0}
-_workspaces: Dict[Tuple[int, int, int], "_RingWorkspace"] = {}
+_workspaces: Dict[tuple, "_RingWorkspace"] = {}
 _lib = None
 
 
@@ -104,7 +104,7 @@ class _RingWorkspace:
 
 def _workspace(group, kv_bytes: int) -> _RingWorkspace:
     size = 1 << max(20, (kv_bytes - 1).bit_length())
-    key = (id(group), size, torch.cuda.current_device())
+    key = (comm.group_key(group), size, torch.cuda.current_device())
     if key not in _workspaces:
         _workspaces[key] = _RingWorkspace(group, size)
     return _workspaces[key]

@@ -100,3 +100,26 @@ def test_model_and_optimizer_wrappers():
     y = wrapped(x)
     opt.backward_by_grad(y, torch.ones_like(y))
     assert net.weight.grad is not None
+
+
+def test_group_key_is_stable_and_not_an_address():
+    """Workspace caches are keyed by torch's unique group name, not by `id(group)` (which a new group can reuse)."""
+    import torch.distributed as dist
+
+    from colossalai_b200.parallel import comm
+    from colossalai_b200.testing import free_port
+
+    assert comm.group_key(None)[0] == "id"                  # no process group yet: falls back, nothing to alias
+    dist.init_process_group("gloo", rank=0, world_size=1, init_method=f"tcp://127.0.0.1:{free_port()}")
+    try:
+        world = comm.group_key(None)
+        assert world == comm.group_key(dist.group.WORLD) and world[0] == "pg"
+        g1 = dist.new_group([0])
+        k1 = comm.group_key(g1)
+        assert k1[0] == "pg" and k1 != world
+        dist.destroy_process_group(g1)
+        del g1
+        g2 = dist.new_group([0])
+        assert comm.group_key(g2) != k1                       # a new group never inherits the old one's key
+    finally:
+        dist.destroy_process_group()
