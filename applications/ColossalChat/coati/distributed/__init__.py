@@ -1,4 +1,4 @@
-from .comm import RolloutBuffer, WeightMailbox, deserialize_rollout, serialize_rollout
+from .comm import RolloutBuffer, WeightMailbox, deserialize_rollout, merge_rollouts, serialize_rollout
 from .consumer import GRPOConsumer
 from .launch import launch_distributed
 from .launch_zero_bubble import launch_zero_bubble
@@ -8,6 +8,6 @@ from .reward import (boxed_math_reward, code_reward, combine_rewards, extract_bo
                      make_reward_fn)
 
 __all__ = ["Producer", "ModelRolloutBackend", "EngineRolloutBackend", "GRPOConsumer", "launch_distributed",
-           "launch_zero_bubble", "RolloutBuffer", "WeightMailbox", "serialize_rollout", "deserialize_rollout",
+           "launch_zero_bubble", "RolloutBuffer", "WeightMailbox", "serialize_rollout", "deserialize_rollout", "merge_rollouts",
            "StepProfiler", "boxed_math_reward", "format_reward", "extract_boxed", "make_reward_fn", "length_penalty",
            "code_reward", "combine_rewards"]

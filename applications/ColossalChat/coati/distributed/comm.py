@@ -19,7 +19,30 @@ from typing import Deque, Dict, Optional, Tuple
 
 import torch
 
-__all__ = ["RolloutBuffer", "WeightMailbox", "serialize_rollout", "deserialize_rollout"]
+__all__ = ["RolloutBuffer", "WeightMailbox", "serialize_rollout", "deserialize_rollout", "merge_rollouts"]
+
+
+def merge_rollouts(rollouts, pad_token_id: int = 0) -> Dict:
+    """One rollout out of several producers' rollouts (same prompt length and `num_generations`; responses are right-
+    padded to the longest).  List fields are concatenated, `model_version` becomes the OLDEST version (staleness is
+    judged by the worst contributor) and `producer` records which rows came from whom."""
+    rollouts = [r for r in rollouts if r is not None]
+    assert rollouts, "no rollout to merge"
+    if len(rollouts) == 1:
+        return rollouts[0]
+    P = rollouts[0]["prompt_len"]
+    assert all(r["prompt_len"] == P for r in rollouts), "producers must pad prompts to the same length"
+    width = max(r["sequences"].shape[1] for r in rollouts)
+    seqs = [torch.nn.functional.pad(r["sequences"], (0, width - r["sequences"].shape[1]), value=pad_token_id)
+            for r in rollouts]
+    out = {"sequences": torch.cat(seqs, 0), "prompt_len": P,
+           "attention_mask": torch.cat([r["attention_mask"] for r in rollouts], 0),
+           "model_version": min(int(r.get("model_version", 0)) for r in rollouts),
+           "producer": [i for i, r in enumerate(rollouts) for _ in range(r["sequences"].shape[0])]}
+    for k in rollouts[0]:
+        if k not in out and isinstance(rollouts[0][k], list):
+            out[k] = [x for r in rollouts for x in r[k]]
+    return out
 
 
 class RolloutBuffer:

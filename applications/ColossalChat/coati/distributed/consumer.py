@@ -81,6 +81,31 @@ class GRPOConsumer:
         self.history.append(metrics)
         return metrics
 
+    def save_checkpoint(self, directory: str, shard: bool = False) -> str:
+        """`<directory>/step_<version>/{model, optimizer, state.json}` through the booster when there is one (sharded,
+        parallel-aware) or `torch.save` otherwise; returns the path (reference `BaseConsumer` saves every
+        `save_interval` updates, `consumer.py:330-360`)."""
+        import json
+        import os
+
+        path = os.path.join(directory, f"step_{self.version}")
+        os.makedirs(path, exist_ok=True)
+        if self.booster is not None:
+            self.booster.save_model(self.policy, os.path.join(path, "model"), shard=shard)
+            self.booster.save_optimizer(self.optimizer, os.path.join(path, "optimizer"), shard=shard)
+        else:
+            torch.save(self.policy.state_dict(), os.path.join(path, "model.pt"))
+            torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pt"))
+        import torch.distributed as dist
+
+        writer = getattr(self, "checkpoint_writer", None)      # set by `launch_distributed` (first consumer rank)
+        if writer is None:
+            writer = not dist.is_initialized() or self.booster is None or dist.get_rank() == 0
+        if writer:
+            with open(os.path.join(path, "state.json"), "w") as f:
+                json.dump({"version": self.version, "last": self.history[-1] if self.history else {}}, f)
+        return path
+
     def state_dict_for_producers(self) -> Dict[str, torch.Tensor]:
         from colossalai_b200.interface import ModelWrapper
 

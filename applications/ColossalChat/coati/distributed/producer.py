@@ -63,12 +63,22 @@ class EngineRolloutBackend:
 
 
 class Producer:
-    def __init__(self, backend, prompt_dataloader, num_generations: int = 4) -> None:
+    """`producer_idx` / `num_producers`: several producers draw from the same prompt dataloader and each keeps every
+    `num_producers`-th batch (the reference gives every producer a `DistributedSampler` shard, `producer.py:120-150`).
+    `rollout_log`: a jsonl file that receives one line per rollout batch (token ids, or text when a `tokenizer` with
+    `batch_decode` is given) - the reference's `rollout_log_file`.  `evaluate` scores greedy / sampled completions of
+    held-out prompts with a verifiable reward (the reference's periodic eval over `eval_dataset_config`)."""
+
+    def __init__(self, backend, prompt_dataloader, num_generations: int = 4, producer_idx: int = 0,
+                 num_producers: int = 1, rollout_log: Optional[str] = None, tokenizer=None) -> None:
+        assert 0 <= producer_idx < num_producers
         self.backend, self.num_generations = backend, num_generations
-        self._loader, self._it = prompt_dataloader, None
+        self.producer_idx, self.num_producers = producer_idx, num_producers
+        self._loader, self._it, self._drawn = prompt_dataloader, None, 0
+        self.rollout_log, self.tokenizer = rollout_log, tokenizer
         self.model_version = 0
 
-    def _next_prompts(self) -> Dict:
+    def _draw(self) -> Dict:
         if self._it is None:
             self._it = iter(self._loader)
         try:
@@ -76,6 +86,27 @@ class Producer:
         except StopIteration:
             self._it = iter(self._loader)
             return next(self._it)
+
+    def _next_prompts(self) -> Dict:
+        while True:
+            batch = self._draw()
+            mine = self._drawn % self.num_producers == self.producer_idx
+            self._drawn += 1
+            if mine:
+                return batch
+
+    def _log(self, rollout: Dict) -> None:
+        import json
+
+        seq, P = rollout["sequences"], rollout["prompt_len"]
+        if self.tokenizer is not None:
+            rec = {"prompt": self.tokenizer.batch_decode(seq[:, :P].tolist()),
+                   "response": self.tokenizer.batch_decode(seq[:, P:].tolist())}
+        else:
+            rec = {"prompt_ids": seq[:, :P].tolist(), "response_ids": seq[:, P:].tolist()}
+        rec.update(model_version=self.model_version, producer=self.producer_idx)
+        with open(self.rollout_log, "a") as f:
+            f.write(json.dumps(rec) + "\n")
 
     def rollout(self) -> Dict:
         batch = self._next_prompts()
@@ -87,7 +118,29 @@ class Producer:
         for k, v in batch.items():
             if isinstance(v, list):
                 out[k] = [x for x in v for _ in range(self.num_generations)]
+        if self.rollout_log is not None:
+            self._log(out)
         return out
+
+    @torch.no_grad()
+    def evaluate(self, eval_dataloaders: Dict[str, object], reward_fn, num_generations: int = 1,
+                 max_batches: Optional[int] = None) -> Dict[str, float]:
+        """Mean reward of `num_generations` completions per held-out prompt, per dataset: {"eval/<name>": score}."""
+        scores: Dict[str, float] = {}
+        for name, loader in eval_dataloaders.items():
+            total, n = 0.0, 0
+            for i, batch in enumerate(loader):
+                if max_batches is not None and i >= max_batches:
+                    break
+                ids, am = batch["input_ids"], batch.get("attention_mask")
+                am = am if am is not None else torch.ones_like(ids)
+                seq = self.backend.generate(ids, am, num_generations)
+                extra = {k: [x for x in v for _ in range(num_generations)] for k, v in batch.items()
+                         if isinstance(v, list)}
+                r = reward_fn(seq, ids.shape[1], **extra).float()
+                total, n = total + float(r.sum()), n + r.numel()
+            scores[f"eval/{name}"] = total / max(n, 1)
+        return scores
 
     def sync_weights(self, state_dict: Dict[str, torch.Tensor], version: int) -> None:
         self.backend.load_state_dict(state_dict)

@@ -1,4 +1,5 @@
-"""Model zoo.  Every family is a thin specialisation of one parallel-aware backbone (`transformer.py`)."""
+"""Model zoo.  One parallel-aware backbone (`transformer.py`, heads in `heads.py`); the text families are rows of
+`_family_table.py` turned into classes by `families.py`, the vision / encoder-decoder / multimodal ones are modules."""
 from .config import MODEL_ZOO, ModelConfig, MoEConfig, get_config
 from .heads import (
     TransformerBackboneModel,
@@ -9,6 +10,8 @@ from .heads import (
     TransformerForTokenClassification,
 )
 from .transformer import Attention, DecoderLayer, MLP, SeqMeta, TransformerLMHeadModel, TransformerModel
+from . import families  # noqa: F401  (generates `models.<family>` for the table-driven families)
+from .families import FAMILIES
 from .llama import LlamaForCausalLM, LlamaForSequenceClassification, LlamaModel
 from .gpt2 import GPT2LMHeadModel, GPT2Model
 from .mixtral import MixtralForCausalLM

@@ -33,41 +33,33 @@ def register_policy(qualname: str, file_name: str, class_name: str) -> None:
 for _cls in ("TransformerLMHeadModel", "TransformerModel"):
     register_policy(f"colossalai_b200.models.transformer.{_cls}", "transformer", "TransformerForCausalLMPolicy")
 
-_FAMILIES = {
-    "llama": ["LlamaModel", "LlamaForCausalLM", "LlamaForSequenceClassification"],
-    "mistral": ["MistralModel", "MistralForCausalLM", "MistralForSequenceClassification"],
-    "qwen2": ["Qwen2Model", "Qwen2ForCausalLM", "Qwen2ForSequenceClassification"],
-    "qwen3": ["Qwen3Model", "Qwen3ForCausalLM", "Qwen3ForSequenceClassification"],
-    "gpt2": ["GPT2Model", "GPT2LMHeadModel", "GPT2DoubleHeadsModel", "GPT2ForQuestionAnswering",
-             "GPT2ForTokenClassification", "GPT2ForSequenceClassification"],
-    "gptj": ["GPTJModel", "GPTJForCausalLM", "GPTJForSequenceClassification", "GPTJForQuestionAnswering"],
-    "opt": ["OPTModel", "OPTForCausalLM", "OPTForSequenceClassification", "OPTForQuestionAnswering"],
-    "bloom": ["BloomModel", "BloomForCausalLM", "BloomForSequenceClassification", "BloomForTokenClassification",
-              "BloomForQuestionAnswering"],
-    "falcon": ["FalconModel", "FalconForCausalLM", "FalconForSequenceClassification",
-               "FalconForTokenClassification", "FalconForQuestionAnswering"],
-    "chatglm": ["ChatGLMModel", "ChatGLMForConditionalGeneration"],
-    "command": ["CohereModel", "CohereForCausalLM"],
-    "mixtral": ["MixtralModel", "MixtralForCausalLM"],
-    "deepseek": ["DeepseekModel", "DeepseekForCausalLM"],
-    "deepseek_v3": ["DeepseekV3Model", "DeepseekV3ForCausalLM"],
-    "bert": ["BertModel", "BertForPreTraining", "BertLMHeadModel", "BertForMaskedLM",
-             "BertForSequenceClassification", "BertForTokenClassification", "BertForNextSentencePrediction",
-             "BertForMultipleChoice", "BertForQuestionAnswering"],
-    "baichuan": ["BaichuanModel", "BaichuanForCausalLM", "BaichuanForSequenceClassification"],
+# text families of the zoo: classes and policies are both generated from `_family_table.py` (`models/families.py`,
+# `policies/zoo.py`); the policy of model class `X` of family `f` is `policies.<f>.XPolicy`
+from ..._family_table import EXTRA_POLICY_FAMILIES, FAMILIES, family_classes  # noqa: E402
+
+for _fam in FAMILIES:
+    for _c in family_classes(_fam):
+        register_policy(f"colossalai_b200.models.{_fam}.{_c}", _fam, f"{_c}Policy")
+for _fam, _classes in EXTRA_POLICY_FAMILIES.items():
+    for _c in _classes:
+        register_policy(f"colossalai_b200.models.{_fam}.{_c}", _fam, f"{_c}Policy")
+
+# families with policies of their own (vision / encoder-decoder / multimodal)
+_OWN_POLICY_FAMILIES = {
     "vit": ["ViTModel", "ViTForImageClassification", "ViTForMaskedImageModeling"],
     "t5": ["T5Model", "T5ForConditionalGeneration", "T5EncoderModel", "T5ForTokenClassification"],
     "whisper": ["WhisperModel", "WhisperForConditionalGeneration", "WhisperForAudioClassification"],
     "blip2": ["Blip2Model", "Blip2ForConditionalGeneration"],
     "sam": ["SamModel"],
 }
-for _fam, _classes in _FAMILIES.items():
+for _fam, _classes in _OWN_POLICY_FAMILIES.items():
     for _c in _classes:
         register_policy(f"colossalai_b200.models.{_fam}.{_c}", _fam, f"{_c}Policy")
 
 
 # user-supplied HuggingFace modules (sharded in place by sub-module / method replacement)
-for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3"), ("cohere", "Cohere")):
+for _mod, _pre in (("llama", "Llama"), ("mistral", "Mistral"), ("qwen2", "Qwen2"), ("qwen3", "Qwen3"), ("cohere", "Cohere"),
+                   ("glm", "Glm")):
     for _suffix in ("Model", "ForCausalLM"):
         register_policy(f"transformers.models.{_mod}.modeling_{_mod}.{_pre}{_suffix}", "hf_decoder", "HFDecoderPolicy")
 for _c in ("GPT2Model", "GPT2LMHeadModel"):
@@ -95,7 +87,15 @@ for _c in ("ViTModel", "ViTForImageClassification"):
     register_policy(f"transformers.models.vit.modeling_vit.{_c}", "hf_encoder", "HFViTPolicy")
 
 
+for _c in ("SamModel", "SamVisionModel"):
+    register_policy(f"transformers.models.sam.modeling_sam.{_c}", "hf_vision", "HFSamPolicy")
+for _c in ("Blip2Model", "Blip2ForConditionalGeneration"):
+    register_policy(f"transformers.models.blip_2.modeling_blip_2.{_c}", "hf_vision", "HFBlip2Policy")
+
+
 def import_policy(loc: PolicyLocation) -> type:
+    from . import zoo  # noqa: F401  (installs the generated per-family policy modules)
+
     module = importlib.import_module(f"{_P}.{loc.file_name}")
     return getattr(module, loc.class_name)
 

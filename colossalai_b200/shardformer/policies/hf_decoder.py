@@ -36,12 +36,17 @@ import torch
 import torch.nn as nn
 
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
+from ..layer.qkv_fused_linear import FusedLinear1D_Col
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
 __all__ = ["HFDecoderPolicy", "HFDecoderPipelineMixin", "HF_FAMILIES"]
 
 # transformers module path -> class-name prefix
-HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere"}
+HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere",
+               "glm": "Glm"}
+# families whose MLP keeps gate and up in ONE linear (`gate_up_proj`, output = [gate | up]): each half is split over the
+# ranks separately so that the module's own `chunk(2, -1)` still yields matching gate / up slices
+FUSED_GATE_UP = ("Glm",)
 
 
 def _pp_stage_forward(self, input_ids=None, hidden_states=None, labels=None, attention_mask=None, position_ids=None,
@@ -235,13 +240,18 @@ class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
             if sc.enable_sequence_parallelism:
                 col.update(seq_parallel_mode="pre_gathered")
                 row.update(seq_parallel_mode="split_gather", seq_parallel_dim=1)
+            if fam in FUSED_GATE_UP:
+                mlp_in = [SubModuleReplacementDescription("mlp.gate_up_proj", FusedLinear1D_Col,
+                                                          kwargs=dict(col, num_splits=2))]
+            else:
+                mlp_in = [SubModuleReplacementDescription("mlp.gate_proj", Linear1D_Col, kwargs=dict(col)),
+                          SubModuleReplacementDescription("mlp.up_proj", Linear1D_Col, kwargs=dict(col))]
             policy[f"{fam}DecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
                 SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(col)),
                 SubModuleReplacementDescription("self_attn.o_proj", Linear1D_Row, kwargs=dict(row)),
-                SubModuleReplacementDescription("mlp.gate_proj", Linear1D_Col, kwargs=dict(col)),
-                SubModuleReplacementDescription("mlp.up_proj", Linear1D_Col, kwargs=dict(col)),
+                *mlp_in,
                 SubModuleReplacementDescription("mlp.down_proj", Linear1D_Row, kwargs=dict(row)),
             ])
             policy[f"{fam}Attention"] = ModulePolicyDescription(

@@ -3,7 +3,7 @@ value and `intermediate.dense` become column-parallel, `attention.output.dense` 
 word embedding vocab-parallel; the attention module sizes its head views with `-1`, so only the bookkeeping attributes
 (`num_attention_heads`, `all_head_size`) are replaced.  Covers `BertModel` and the heads that sit on the pooled /
 sequence output (sequence / token classification, question answering, multiple choice, next-sentence prediction).  The
-masked-LM heads tie a biased decoder to the word embedding and are not handled here (native zoo: `models/bert.py`)."""
+masked-LM heads tie a biased decoder to the word embedding and are not handled here (native zoo: the `bert` row of `_family_table.py`)."""
 from __future__ import annotations
 
 from typing import Dict, List

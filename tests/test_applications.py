@@ -433,3 +433,76 @@ def test_colossal_llama_tuning_helpers():
     unfreeze_parameters(m)
     assert get_model_numel(m, trainable_only=True) == get_model_numel(m)
     assert format_numel_str(8_030_000_000) == "8.03 B" and format_numel_str(1500) == "1.50 K" and format_numel_str(7) == "7"
+
+
+def test_producer_eval_rollout_log_and_consumer_checkpoint(tmp_path):
+    """Sharded prompt draws, periodic evaluation on held-out prompts, the rollout jsonl and consumer checkpoints."""
+    import json
+
+    from coati.distributed import merge_rollouts
+
+    policy, sampler = _tiny(0, vocab_size=32), _tiny(0, vocab_size=32)
+    log = tmp_path / "rollouts.jsonl"
+    prod = Producer(ModelRolloutBackend(sampler, dict(max_new_tokens=4)), _prompt_loader(), num_generations=4,
+                    rollout_log=str(log))
+    cons = GRPOConsumer(policy, torch.optim.AdamW(policy.parameters(), lr=3e-3), _count_reward, num_generations=4)
+    torch.manual_seed(0)
+    h = launch_distributed(prod, cons, num_steps=4, sync_every=1, eval_dataloaders={"held_out": _prompt_loader()},
+                           eval_interval=2, save_dir=str(tmp_path / "ckpt"), save_interval=4)
+    assert "eval/held_out" in h[1] and "eval/held_out" in h[3] and "eval/held_out" not in h[0]
+    assert 0.0 <= h[3]["eval/held_out"] <= 1.0
+    lines = [json.loads(l) for l in log.read_text().splitlines()]
+    assert len(lines) == 4 and len(lines[0]["response_ids"]) == 16 and lines[-1]["model_version"] == 3
+    state = json.loads((tmp_path / "ckpt" / "step_4" / "state.json").read_text())
+    assert state["version"] == 4 and (tmp_path / "ckpt" / "step_4" / "model.pt").exists()
+    fresh = _tiny(1, vocab_size=32)
+    fresh.load_state_dict(torch.load(tmp_path / "ckpt" / "step_4" / "model.pt"))
+    for a, b in zip(fresh.parameters(), policy.parameters()):
+        assert torch.equal(a, b)
+    # two producers over one dataloader: disjoint, alternating batches
+    items = [{"input_ids": [1, 10 + i, 11 + i]} for i in range(8)]
+    mk = lambda: torch.utils.data.DataLoader(ListDataset(items), batch_size=2, collate_fn=DataCollatorForPromptDataset())
+    p0 = Producer(ModelRolloutBackend(sampler, dict(max_new_tokens=3)), mk(), 2, producer_idx=0, num_producers=2)
+    p1 = Producer(ModelRolloutBackend(sampler, dict(max_new_tokens=5)), mk(), 2, producer_idx=1, num_producers=2)
+    r0, r1 = p0.rollout(), p1.rollout()
+    assert r0["sequences"][0, 1].item() == 10 and r1["sequences"][0, 1].item() == 12          # batches 0 and 1
+    r1["model_version"] = 3
+    m = merge_rollouts([r0, None, r1], pad_token_id=0)
+    assert m["sequences"].shape == (8, 3 + 5) and m["attention_mask"].shape[0] == 8 and m["model_version"] == 0
+    assert m["producer"] == [0] * 4 + [1] * 4 and (m["sequences"][:4, 6:] == 0).all()
+    out = cons.step(m)                                                                          # trains on the merged batch
+    assert out["kept"] >= 0.0 and cons.version == 5
+
+
+def _multi_producer_worker(rank, world_size, port):
+    import torch.distributed as dist
+
+    import colossalai_b200
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    prod = cons = None
+    if rank < 2:                                          # two producers, each with its shard of the prompts
+        prod = Producer(ModelRolloutBackend(_tiny(0, vocab_size=32), dict(max_new_tokens=4)), _prompt_loader(),
+                        num_generations=4, producer_idx=rank, num_producers=2)
+    else:
+        policy = _tiny(0, vocab_size=32)
+        cons = GRPOConsumer(policy, torch.optim.AdamW(policy.parameters(), lr=3e-3), _count_reward, num_generations=4)
+    torch.manual_seed(rank)
+    h = launch_distributed(prod, cons, num_steps=3, sync_every=1, producer_ranks=(0, 1))
+    if cons is not None:
+        assert len(h) == 3 and cons.version == 3 and all("reward" in x for x in h)
+        ref = torch.cat([p.detach().flatten() for p in cons.policy.parameters()])
+    else:
+        assert prod.model_version == 3
+        ref = torch.cat([p.detach().flatten() for p in prod.backend.model.parameters()])
+    got = [torch.empty_like(ref) for _ in range(world_size)]
+    dist.all_gather(got, ref)
+    assert torch.equal(got[0], got[2]) and torch.equal(got[1], got[2])      # both producers hold the consumer's weights
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+def test_two_producers_one_consumer_processes():
+    from colossalai_b200.testing import spawn
+
+    spawn(_multi_producer_worker, 3)

@@ -20,10 +20,13 @@ def _build(family):
     kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
               num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=False)
     cfg_cls = {"llama": transformers.LlamaConfig, "mistral": transformers.MistralConfig, "qwen2": transformers.Qwen2Config,
-               "cohere": transformers.CohereConfig, "qwen3": transformers.Qwen3Config}[family]
+               "cohere": transformers.CohereConfig, "qwen3": transformers.Qwen3Config,
+               "glm": transformers.GlmConfig}[family]
     model_cls = {"llama": transformers.LlamaForCausalLM, "mistral": transformers.MistralForCausalLM,
                  "qwen2": transformers.Qwen2ForCausalLM, "cohere": transformers.CohereForCausalLM,
-                 "qwen3": transformers.Qwen3ForCausalLM}[family]
+                 "qwen3": transformers.Qwen3ForCausalLM, "glm": transformers.GlmForCausalLM}[family]
+    if family == "glm":
+        kw.update(head_dim=16, pad_token_id=0)               # (GLM: fused gate|up MLP, partial interleaved rotary)
     cfg = cfg_cls(**kw)
     cfg._attn_implementation = "eager"
     torch.manual_seed(0)
@@ -312,6 +315,105 @@ def _check_t5(gated, tied):
     assert n > 30
 
 
+def _compare_grads(tag, sharded, org, atol=2e-4, rtol=2e-3, min_n=10, relative_to_max=False):
+    ref = {n: p.grad for n, p in org.named_parameters()}
+    n = 0
+    for name, p in sharded.named_parameters():
+        if p.grad is None:
+            assert ref[name] is None, f"{tag} {name}: no gradient on the sharded model"
+            continue
+        full = _gather_grad(p)
+        r = ref[name]
+        if full.shape != r.shape:
+            full = full[: r.shape[0]]
+        a = atol * max(1.0, float(r.abs().max())) if relative_to_max else atol
+        torch.testing.assert_close(full, r, atol=a, rtol=rtol, msg=lambda m: f"{tag} {name}: {m}")
+        n += 1
+    assert n >= min_n, (tag, n)
+
+
+def _check_sam():
+    """SAM in place: windowed + global vision layers (fused qkv split per projection, decomposed relative-position
+    tables with their gradient summed over the group), two-way mask decoder attention, masks + IoU head vs unsharded."""
+    import transformers
+    from transformers.models.sam.configuration_sam import SamMaskDecoderConfig, SamPromptEncoderConfig, SamVisionConfig
+
+    v = SamVisionConfig(hidden_size=32, output_channels=16, num_hidden_layers=2, num_attention_heads=4, image_size=32,
+                        patch_size=8, window_size=2, global_attn_indexes=[1], mlp_dim=64, num_pos_feats=8)
+    pe = SamPromptEncoderConfig(hidden_size=16, image_size=32, patch_size=8, num_point_embeddings=4)
+    d = SamMaskDecoderConfig(hidden_size=16, num_hidden_layers=2, num_attention_heads=4, mlp_dim=32,
+                             iou_head_hidden_dim=16, attention_downsample_rate=2)
+    for impl in ("eager", "sdpa"):
+        cfg = transformers.SamConfig(vision_config=v, prompt_encoder_config=pe, mask_decoder_config=d)
+        cfg._attn_implementation = impl
+        cfg.vision_config._attn_implementation = impl
+        torch.manual_seed(0)
+        org = transformers.SamModel(cfg).float()
+        with torch.no_grad():                                  # (the relative-position tables are zero-initialised)
+            for n, p in org.named_parameters():
+                if "rel_pos" in n:
+                    p.normal_(0, 0.5)
+        sharded = copy.deepcopy(org)
+        sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+        sharded, _ = ShardFormer(sc).optimize(sharded)
+        attn = sharded.vision_encoder.layers[0].attn
+        assert type(attn.qkv).__name__ == "FusedLinear1D_Col" and attn.qkv.weight.shape[0] == 48 and attn.num_attention_heads == 2
+        blk = sharded.mask_decoder.transformer.layers[0]
+        assert type(blk.self_attn.q_proj).__name__ == "Linear1D_Col" and type(blk.mlp.lin2).__name__ == "Linear1D_Row"
+        torch.manual_seed(6)
+        px, pts = torch.randn(2, 3, 32, 32), torch.rand(2, 1, 2, 2) * 32
+        outs = []
+        for m in (org, sharded):
+            o = m(pixel_values=px, input_points=pts, multimask_output=True)
+            outs.append(o)
+            (o.pred_masks.square().mean() + o.iou_scores.sum()).backward()
+        torch.testing.assert_close(outs[1].pred_masks, outs[0].pred_masks, atol=2e-4, rtol=2e-4)
+        torch.testing.assert_close(outs[1].iou_scores, outs[0].iou_scores, atol=2e-4, rtol=2e-4)
+        _compare_grads(f"sam/{impl}", sharded, org, atol=1e-4, rtol=2e-3)
+
+
+def _check_blip2():
+    """BLIP-2 in place: vision tower (rebound attention forward), Q-Former (self + cross attention), OPT language model
+    through its own in-place policy (tied, vocab-parallel head): LM loss and gradients vs unsharded."""
+    import transformers
+    from transformers.models.blip_2.configuration_blip_2 import Blip2QFormerConfig, Blip2VisionConfig
+
+    vis = Blip2VisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                            image_size=16, patch_size=8, attention_dropout=0.0)
+    qf = Blip2QFormerConfig(vocab_size=64, hidden_size=32, num_hidden_layers=2, num_attention_heads=4,
+                            intermediate_size=64, encoder_hidden_size=32, cross_attention_frequency=1,
+                            hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=32)
+    txt = transformers.OPTConfig(vocab_size=320, hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4,
+                                 max_position_embeddings=64, word_embed_proj_dim=64, dropout=0.0, attention_dropout=0.0,
+                                 activation_dropout=0.0, layerdrop=0.0)
+    cfg = transformers.Blip2Config(vision_config=vis, qformer_config=qf, text_config=txt, num_query_tokens=4,
+                                   image_token_index=319)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    org = transformers.Blip2ForConditionalGeneration(cfg).float().eval()
+    sharded = copy.deepcopy(org)
+    sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
+    sharded, _ = ShardFormer(sc).optimize(sharded)
+    lay = sharded.vision_model.encoder.layers[0]
+    assert lay.self_attn.forward.__func__.__name__ == "_blip2_attention_forward" and lay.self_attn.num_heads == 2
+    ql = sharded.qformer.encoder.layer[0]
+    assert type(ql.attention.attention.query).__name__ == "Linear1D_Col" and \
+        type(ql.crossattention.output.dense).__name__ == "Linear1D_Row" and ql.attention.attention.all_head_size == 16
+    assert type(sharded.language_model.model.decoder.layers[0].fc1).__name__ == "Linear1D_Col"
+    torch.manual_seed(8)
+    px = torch.randn(2, 3, 16, 16)
+    ids = torch.randint(0, 300, (2, 12))
+    ids[:, :4] = 319                                             # the placeholders the query outputs are scattered into
+    ref = org(pixel_values=px, input_ids=ids, labels=ids)
+    out = sharded(pixel_values=px, input_ids=ids, labels=ids)
+    torch.testing.assert_close(out.loss, ref.loss, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(out.logits[..., :320], ref.logits, atol=2e-4, rtol=2e-4)
+    ref.loss.backward()
+    out.loss.backward()
+    # (the random tiny tower has gradients in the hundreds on the patch embedding: tolerance relative to the tensor's max)
+    _compare_grads("blip2", sharded, org, min_n=40, relative_to_max=True)
+
+
 def _moe_model(family):
     import transformers
 
@@ -583,19 +685,21 @@ def _check_pipeline_in_place(family, tied):
 
 def _worker(rank, world_size, port):
     colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
-    for family in ("llama", "mistral", "qwen2", "cohere", "qwen3"):
+    for family in ("llama", "mistral", "qwen2", "cohere", "qwen3", "glm"):
         _check(family)
     for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new", "falcon-mha"):
         _check_tied(family)
     _check_bert()
     _check_vit()
     _check_whisper()
+    _check_sam()
+    _check_blip2()
     for gated, tied in ((False, True), (True, False)):
         _check_t5(gated, tied)
     for family in ("mixtral", "qwen3_moe", "qwen2_moe", "deepseek_v2", "deepseek_v3"):
         _check_moe_ep(family)
     _check_booster_in_place()
-    for family in ("llama", "qwen3", "cohere", "mistral"):
+    for family in ("llama", "qwen3", "cohere", "mistral", "glm"):
         _check_sequence_parallel_in_place(family)
     _check_zero_and_ddp_keep_hf_module()
     for family, tied in (("llama", False), ("qwen2", True)):
