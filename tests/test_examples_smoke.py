@@ -34,3 +34,46 @@ def test_long_context_ring_attention_example():
     out = _torchrun("examples/language/long_context/train_ring_attention.py", "--steps", "2", "--seq", "128", port=29753)
     lines = [l for l in out.splitlines() if l.startswith("step ")]
     assert len(lines) == 2 and "sp 2" in lines[0] and "nan" not in out
+
+
+def _python(script, *args, timeout=240):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, script), *args], capture_output=True, text=True,
+                         timeout=timeout, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+@pytest.mark.dist
+def test_sequence_parallel_tutorial_matches_single_process():
+    """Every SP mode prints the loss curve of the single-process run (same seed, same data)."""
+    def losses(out):
+        return [l.split("loss ")[1].split(" ")[0] for l in out.splitlines() if l.startswith("step ")]
+
+    script = "examples/tutorial/sequence_parallel/train.py"
+    ref = losses(_python(script, "--mode", "none", "--steps", "3"))
+    assert len(ref) == 3
+    for i, mode in enumerate(("split_gather", "all_to_all")):
+        assert losses(_torchrun(script, "--mode", mode, "--steps", "3", port=29755 + i)) == ref, mode
+    ref = losses(_python(script, "--mode", "none", "--model", "llama-tiny", "--steps", "3"))
+    got = losses(_torchrun(script, "--mode", "ring_attn", "--model", "llama-tiny", "--steps", "3", port=29757))
+    assert got == ref
+
+
+@pytest.mark.dist
+def test_large_batch_optimizer_tutorial():
+    out = _torchrun("examples/tutorial/large_batch_optimizer/train.py", "--optimizer", "lars", "--plugin", "zero1",
+                    "--steps", "21", "--batch", "64", port=29758)
+    lines = [l for l in out.splitlines() if l.startswith("step ")]
+    first, last = float(lines[0].split("loss ")[1].split(" ")[0]), float(lines[-1].split("loss ")[1].split(" ")[0])
+    assert "global batch 64" in lines[0] and last < first
+
+
+def test_inference_examples_cpu():
+    out = _python("examples/inference/stable_diffusion/sd3_generation.py", "--model", "sd3-tiny", "--steps", "2")
+    assert "generated (1, 3, 64, 64)" in out and "finite True" in out
+    out = _python("examples/inference/benchmark_ops/benchmark_ops.py")
+    assert out.count(" ok") >= 8                                   # every op agrees with its PyTorch formulation
+    pytest.importorskip("uvicorn")
+    out = _python("examples/inference/client/run_client.py", "--self-host", "--concurrency", "4")
+    assert "Healthy" in out and "16/16 ok" in out
