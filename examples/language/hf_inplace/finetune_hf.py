@@ -53,7 +53,7 @@ def main():
     args = ap.parse_args()
     colossalai_b200.launch_from_torch()
     cuda = torch.cuda.is_available()
-    precision = "bf16" if cuda else "fp32"
+    precision = "bf16" if (cuda or args.zero) else "fp32"         # (ZeRO keeps fp32 masters of low-precision params)
     if args.pretrained:
         import transformers as tf
 
