@@ -57,3 +57,35 @@ def test_referenced_files_exist(doc):
             if not (doc.parent / m.group(1)).exists():
                 missing.append("profiles/" + m.group(1))
     assert not missing, f"{doc.name} refers to files that do not exist: {sorted(set(missing))}"
+
+
+def _expand_braces(p):
+    m = re.search(r"\{([^{}]*)\}", p)
+    if not m:
+        return [p]
+    out = []
+    for alt in m.group(1).split(","):
+        out += _expand_braces(p[:m.start()] + alt.strip() + p[m.end():])
+    return out
+
+
+@pytest.mark.parametrize("doc", DOCS, ids=lambda p: p.name)
+def test_source_paths_cited_in_docs_exist(doc):
+    """Every backticked source path (`zero/gemini/chunk/manager.py`, `models/{transformer,moe}.py`, `coati/trainer/*.py`,
+    optionally with `:line`) resolves under the repo, the package, one of its sub-packages or an application root."""
+    pkg = ROOT / "colossalai_b200"
+    bases = [ROOT, pkg, pkg / "kernel" / "csrc", pkg / "shardformer", pkg / "inference", ROOT / "tests",
+             ROOT / "applications"] + sorted(p for p in (ROOT / "applications").iterdir() if p.is_dir())
+    missing = []
+    for m in re.finditer(r"`([A-Za-z0-9_./\-{},* ]+?)`", doc.read_text()):
+        tok = m.group(1).replace(", ", ",")
+        if "/" not in tok or " " in tok:
+            continue
+        for p in _expand_braces(tok):
+            p = p.split(":")[0]
+            if not re.search(r"\.(py|cu|cuh|cpp|sh)$", p) or p.startswith("."):
+                continue
+            found = any(list(b.glob(p)) for b in bases) if "*" in p else any((b / p).exists() for b in bases)
+            if not found:
+                missing.append(p)
+    assert not missing, f"{doc.name} cites source files that do not exist: {sorted(set(missing))}"
