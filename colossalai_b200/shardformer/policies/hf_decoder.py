@@ -30,7 +30,7 @@ existing `nn.Module` the framework knows nothing about and rewrite it through th
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn
@@ -39,7 +39,7 @@ from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabP
 from ..layer.qkv_fused_linear import FusedLinear1D_Col
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
 
-__all__ = ["HFDecoderPolicy", "HFDecoderPipelineMixin", "HF_FAMILIES"]
+__all__ = ["HFDecoderPolicy", "HFDecoderPipelineMixin", "HF_FAMILIES", "sequence_parallel_hooks"]
 
 # transformers module path -> class-name prefix
 HF_FAMILIES = {"llama": "Llama", "mistral": "Mistral", "qwen2": "Qwen2", "qwen3": "Qwen3", "cohere": "Cohere",
@@ -156,6 +156,52 @@ class HFDecoderPipelineMixin:
         return [{0: emb_w, sm.num_stages - 1: head_w}]
 
 
+def sequence_parallel_hooks(group, layers_attr: str = "layers", attn_attr: Optional[str] = "self_attn",
+                            mlp_attr: Optional[str] = "mlp", norm_attrs=("input_layernorm", "post_attention_layernorm",
+                                                                         "pre_feedforward_layernorm",
+                                                                         "post_feedforward_layernorm")):
+    """Parameter-replacement hook for the backbone module of an HF decoder under `split_gather` sequence parallelism:
+    split the sequence in front of the first block, gather it behind the last one (autograd-aware), gather ONCE in front
+    of every attention / MLP sub-module (all-gather forward, reduce-scatter backward; only their first argument - BLOOM
+    passes the sequence-sharded residual as the second), mark the in-block norm parameters SP-partial."""
+    from ..layer._operation import (gather_forward_reducescatter_backward, gather_forward_split_backward,
+                                    split_forward_gather_backward)
+    from ..layer.utils import SeqParallelUtils
+
+    def first_arg(fn):
+        def hook(module, args, kwargs):
+            if args:
+                return (fn(args[0]),) + tuple(args[1:]), kwargs
+            kwargs = dict(kwargs)
+            kwargs["hidden_states"] = fn(kwargs["hidden_states"])
+            return args, kwargs
+        return hook
+
+    def gather_out(module, args, output):
+        if isinstance(output, tuple):
+            return (gather_forward_split_backward(output[0], 1, group),) + tuple(output[1:])
+        return gather_forward_split_backward(output, 1, group)
+
+    def install(backbone: nn.Module) -> None:
+        layers = list(getattr(backbone, layers_attr))
+        if not layers:
+            return
+        layers[0].register_forward_pre_hook(first_arg(lambda t: split_forward_gather_backward(t, 1, group)),
+                                            with_kwargs=True)
+        layers[-1].register_forward_hook(gather_out)
+        gather_in = first_arg(lambda t: gather_forward_reducescatter_backward(t, group, 1))
+        for layer in layers:
+            for attr in (attn_attr, mlp_attr):
+                if attr is not None:
+                    getattr(layer, attr).register_forward_pre_hook(gather_in, with_kwargs=True)
+            for name in norm_attrs:
+                norm = getattr(layer, name, None)
+                if norm is not None:
+                    for prm in norm.parameters(recurse=False):
+                        SeqParallelUtils.marked_as_sp_partial_derived_param(prm)
+    return install
+
+
 class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
     """Works for `<Family>Model`, `<Family>ForCausalLM` of the families in HF_FAMILIES (matched by class NAME, so the
     policy never imports transformers itself)."""
@@ -178,50 +224,7 @@ class HFDecoderPolicy(HFDecoderPipelineMixin, Policy):
         return self.model
 
     def _sp_hooks(self):
-        """Parameter-replacement hook for `<Family>Model`: split the sequence in front of the first decoder layer,
-        gather it behind the last one (autograd-aware), mark the in-layer norm weights SP-partial."""
-        from ..layer._operation import (gather_forward_reducescatter_backward, gather_forward_split_backward,
-                                        split_forward_gather_backward)
-        from ..layer.utils import SeqParallelUtils
-
-        group = self.shard_config.tensor_parallel_process_group
-
-        def install(backbone: nn.Module) -> None:
-            layers = list(backbone.layers)
-            if not layers:
-                return
-
-            def split_in(module, args, kwargs):
-                if args:
-                    return (split_forward_gather_backward(args[0], 1, group),) + tuple(args[1:]), kwargs
-                kwargs = dict(kwargs)
-                kwargs["hidden_states"] = split_forward_gather_backward(kwargs["hidden_states"], 1, group)
-                return args, kwargs
-
-            def gather_out(module, args, output):
-                if isinstance(output, tuple):
-                    return (gather_forward_split_backward(output[0], 1, group),) + tuple(output[1:])
-                return gather_forward_split_backward(output, 1, group)
-
-            def gather_block_input(module, args, kwargs):
-                if args:
-                    return (gather_forward_reducescatter_backward(args[0], group, 1),) + tuple(args[1:]), kwargs
-                kwargs = dict(kwargs)
-                kwargs["hidden_states"] = gather_forward_reducescatter_backward(kwargs["hidden_states"], group, 1)
-                return args, kwargs
-
-            layers[0].register_forward_pre_hook(split_in, with_kwargs=True)
-            layers[-1].register_forward_hook(gather_out)
-            for layer in layers:
-                layer.self_attn.register_forward_pre_hook(gather_block_input, with_kwargs=True)
-                layer.mlp.register_forward_pre_hook(gather_block_input, with_kwargs=True)
-                for name in ("input_layernorm", "post_attention_layernorm", "pre_feedforward_layernorm",
-                             "post_feedforward_layernorm"):
-                    norm = getattr(layer, name, None)
-                    if norm is not None:
-                        for prm in norm.parameters(recurse=False):
-                            SeqParallelUtils.marked_as_sp_partial_derived_param(prm)
-        return install
+        return sequence_parallel_hooks(self.shard_config.tensor_parallel_process_group)
 
     def _prefix(self) -> str:
         name = self.model.__class__.__name__

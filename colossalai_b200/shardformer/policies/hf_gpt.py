@@ -9,8 +9,11 @@ These two families need more than the llama-like decoders of `hf_decoder.py`:
     local value;
   * both tie the LM head to the token embedding: both sides are sharded along the vocabulary identically and re-tied;
     the learned position embeddings stay replicated.
-LayerNorms are left to PyTorch (replicated parameters, tiny).  Pipeline / sequence parallelism of HF modules: use the
-native zoo (`models.hf_io`), as for `hf_decoder.py`."""
+LayerNorms are left to PyTorch (replicated parameters, tiny).  `split_gather` sequence parallelism works as in
+`hf_decoder.py` (`sequence_parallel_hooks`: the blocks run on sequence shards, one gather in front of each attention /
+MLP module, row linears reduce-scatter; OPT has no MLP module and flattens [batch, seq] in its layer, so `fc1` / `fc2`
+gather and scatter the rows themselves along dim 0 - the MLP is row-wise, the row order does not matter).  Pipeline
+parallelism of these families: native zoo (`models.hf_io`)."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -31,8 +34,28 @@ class _HFTiedDecoderPolicy(Policy):
         if self.shard_config.enable_tensor_parallelism:
             heads = getattr(cfg, "num_attention_heads", None) or cfg.n_head
             assert heads % tp == 0, "the number of attention heads must be divisible by the TP size"
-        assert not self.shard_config.enable_sequence_parallelism, \
-            "sequence parallelism of HF modules is not supported; build the model from the native zoo (models.hf_io)"
+        if self.shard_config.enable_sequence_parallelism:
+            assert self.shard_config.sequence_parallelism_mode == "split_gather" and \
+                self.shard_config.enable_tensor_parallelism, (
+                    "HF modules support sequence parallelism in `split_gather` mode (with tensor parallelism); the "
+                    "all_to_all / ring_attn modes need the native zoo (models.hf_io)")
+
+    # where the blocks live and what they are made of (`split_gather` sequence parallelism, see `hf_decoder.py`)
+    _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "h", "attn", "mlp", ("ln_1", "ln_2")
+
+    def _sp_kwargs(self):
+        """(column kwargs, row kwargs, backbone hook list or None)."""
+        sc = self.shard_config
+        col = dict(fp8_communication=sc.fp8_communication)
+        row = dict(col)
+        if not sc.enable_sequence_parallelism:
+            return col, row, None
+        col.update(seq_parallel_mode="pre_gathered")
+        row.update(seq_parallel_mode="split_gather", seq_parallel_dim=1)
+        from .hf_decoder import sequence_parallel_hooks
+
+        return col, row, [sequence_parallel_hooks(sc.tensor_parallel_process_group, self._sp_layers, self._sp_attn,
+                                                  self._sp_mlp, self._sp_norms)]
 
     def preprocess(self) -> nn.Module:
         self.tie_weight = self.tie_weight_check()
@@ -70,19 +93,20 @@ class HFGPT2Policy(_HFTiedDecoderPolicy):
         cfg, tp = self.model.config, sc.tensor_parallel_size
         hidden = cfg.hidden_size
         inner = cfg.n_inner if getattr(cfg, "n_inner", None) is not None else 4 * hidden
-        fp8 = dict(fp8_communication=sc.fp8_communication)
+        col, row, hooks = self._sp_kwargs()
         policy["GPT2Attention"] = ModulePolicyDescription(attribute_replacement={
             "embed_dim": hidden // tp, "split_size": hidden // tp, "num_heads": cfg.num_attention_heads // tp})
         policy["GPT2Block"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("attn.c_attn", GPT2FusedLinearConv1D_Col,
-                                            kwargs=dict(split_sizes=[hidden] * 3, **fp8)),
-            SubModuleReplacementDescription("attn.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(fp8)),
+                                            kwargs=dict(split_sizes=[hidden] * 3, **col)),
+            SubModuleReplacementDescription("attn.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(row)),
             SubModuleReplacementDescription("mlp.c_fc", GPT2FusedLinearConv1D_Col,
-                                            kwargs=dict(split_sizes=[inner], **fp8)),
-            SubModuleReplacementDescription("mlp.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(fp8)),
+                                            kwargs=dict(split_sizes=[inner], **col)),
+            SubModuleReplacementDescription("mlp.c_proj", GPT2FusedLinearConv1D_Row, kwargs=dict(row)),
         ])
         policy["GPT2Model"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())],
+            param_replacement=hooks)
         policy["GPT2LMHeadModel"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
@@ -91,6 +115,10 @@ class HFGPT2Policy(_HFTiedDecoderPolicy):
 
 class HFOPTPolicy(_HFTiedDecoderPolicy):
     """`OPTModel`, `OPTForCausalLM` (models without `project_in / project_out`, i.e. word_embed_proj_dim == hidden)."""
+
+    # the OPT layer flattens [batch, seq] before `fc1`: its MLP is row-wise, so fc1 / fc2 gather and scatter those rows
+    # themselves (dim 0, any row order) instead of through a hook on an MLP module (there is none)
+    _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "layers", "self_attn", None, ("self_attn_layer_norm", "final_layer_norm")
 
     def config_sanity_check(self) -> None:
         super().config_sanity_check()
@@ -104,19 +132,21 @@ class HFOPTPolicy(_HFTiedDecoderPolicy):
         if not sc.enable_tensor_parallelism:
             return policy
         cfg, tp = self.model.config, sc.tensor_parallel_size
-        fp8 = dict(fp8_communication=sc.fp8_communication)
+        col, row, hooks = self._sp_kwargs()
+        flat = dict(row, seq_parallel_dim=0) if hooks else dict(row)
         policy["OPTAttention"] = ModulePolicyDescription(attribute_replacement={
             "embed_dim": cfg.hidden_size // tp, "num_heads": cfg.num_attention_heads // tp})
         policy["OPTDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("self_attn.out_proj", Linear1D_Row, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("fc1", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("fc2", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attn.q_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("self_attn.k_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("self_attn.v_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("self_attn.out_proj", Linear1D_Row, kwargs=dict(row)),
+            SubModuleReplacementDescription("fc1", Linear1D_Col, kwargs=dict(flat)),
+            SubModuleReplacementDescription("fc2", Linear1D_Row, kwargs=dict(flat)),
         ])
         policy["OPTDecoder"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+            SubModuleReplacementDescription("embed_tokens", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())],
+            param_replacement=hooks)
         policy["OPTForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
@@ -128,25 +158,28 @@ class HFGPTJPolicy(_HFTiedDecoderPolicy):
     rotary slice is per head, so splitting heads over ranks leaves it untouched).  The LM head is not tied and has a
     bias; it becomes a gathered vocab-parallel head."""
 
+    _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "h", "attn", "mlp", ("ln_1",)
+
     def module_policy(self) -> Dict[str, ModulePolicyDescription]:
         sc = self.shard_config
         policy: Dict[str, ModulePolicyDescription] = {}
         if not sc.enable_tensor_parallelism:
             return policy
         cfg, tp = self.model.config, sc.tensor_parallel_size
-        fp8 = dict(fp8_communication=sc.fp8_communication)
+        col, row, hooks = self._sp_kwargs()
         policy["GPTJAttention"] = ModulePolicyDescription(attribute_replacement={
             "embed_dim": cfg.hidden_size // tp, "num_attention_heads": cfg.num_attention_heads // tp})
         policy["GPTJBlock"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("attn.q_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("attn.k_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("attn.v_proj", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("attn.out_proj", Linear1D_Row, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.fc_in", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.fc_out", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("attn.q_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("attn.k_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("attn.v_proj", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("attn.out_proj", Linear1D_Row, kwargs=dict(row)),
+            SubModuleReplacementDescription("mlp.fc_in", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("mlp.fc_out", Linear1D_Row, kwargs=dict(row)),
         ])
         policy["GPTJModel"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+            SubModuleReplacementDescription("wte", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())],
+            param_replacement=hooks)
         policy["GPTJForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
@@ -170,6 +203,8 @@ class HFBloomPolicy(_HFTiedDecoderPolicy):
     linear applies; `num_heads` / `hidden_size` become local values and the attention forward is wrapped to slice the
     ALiBi bias of its heads.  Assumes `pretraining_tp == 1` (the HF default for fine-tuning)."""
 
+    _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "h", "self_attention", "mlp", ("input_layernorm", "post_attention_layernorm")
+
     def config_sanity_check(self) -> None:
         super().config_sanity_check()
         cfg = self.model.config
@@ -190,14 +225,16 @@ class HFBloomPolicy(_HFTiedDecoderPolicy):
             attribute_replacement={"num_heads": cfg.n_head // tp, "hidden_size": cfg.hidden_size // tp,
                                    "_cb200_tp_size": tp, "_cb200_tp_rank": rank},
             method_replacement={"forward": _bloom_attention_forward})
+        col, row, hooks = self._sp_kwargs()
         policy["BloomBlock"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(row)),
+            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(row)),
         ])
         policy["BloomModel"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())],
+            param_replacement=hooks)
         policy["BloomForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])
@@ -212,6 +249,9 @@ class HFFalconPolicy(_HFTiedDecoderPolicy):
     would leave K / V replicated inside a column-parallel weight, which this in-place policy does not do (use the native
     zoo: `models.hf_io` imports Falcon checkpoints with the KV head replicated per rank).  ALiBi variants (falcon-rw) are
     likewise left to the native zoo."""
+
+    _sp_layers, _sp_attn, _sp_mlp = "h", "self_attention", "mlp"
+    _sp_norms = ("input_layernorm", "post_attention_layernorm", "ln_attn", "ln_mlp")
 
     def config_sanity_check(self) -> None:
         super().config_sanity_check()
@@ -238,14 +278,16 @@ class HFFalconPolicy(_HFTiedDecoderPolicy):
         elif not cfg.multi_query:
             attrs["num_kv_heads"] = cfg.num_attention_heads // tp
         policy["FalconAttention"] = ModulePolicyDescription(attribute_replacement=attrs)
+        col, row, hooks = self._sp_kwargs()
         policy["FalconDecoderLayer"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(fp8)),
-            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(fp8)),
+            SubModuleReplacementDescription("self_attention.query_key_value", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("self_attention.dense", Linear1D_Row, kwargs=dict(row)),
+            SubModuleReplacementDescription("mlp.dense_h_to_4h", Linear1D_Col, kwargs=dict(col)),
+            SubModuleReplacementDescription("mlp.dense_4h_to_h", Linear1D_Row, kwargs=dict(row)),
         ])
         policy["FalconModel"] = ModulePolicyDescription(sub_module_replacement=[
-            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())])
+            SubModuleReplacementDescription("word_embeddings", VocabParallelEmbedding1D, kwargs=self._vocab_kwargs())],
+            param_replacement=hooks)
         policy["FalconForCausalLM"] = ModulePolicyDescription(sub_module_replacement=[
             SubModuleReplacementDescription("lm_head", VocabParallelLMHead1D,
                                             kwargs=dict(gather_output=True, **self._vocab_kwargs()))])

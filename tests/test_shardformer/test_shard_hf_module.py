@@ -77,8 +77,7 @@ def _check(family):
     assert n > 10
 
 
-def _check_tied(family):
-    """GPT-2 (fused Conv1D q|k|v, `split_size` attribute) and OPT (`num_heads` attribute), both with tied LM heads."""
+def _build_tied(family):
     import transformers
 
     torch.manual_seed(0)
@@ -110,6 +109,12 @@ def _check_tied(family):
                                      max_position_embeddings=64, word_embed_proj_dim=64, dropout=0.0)
         cfg._attn_implementation = "eager"
         org = transformers.OPTForCausalLM(cfg).float()
+    return org
+
+
+def _check_tied(family):
+    """GPT-2 (fused Conv1D q|k|v, `split_size` attribute) and OPT (`num_heads` attribute), both with tied LM heads."""
+    org = _build_tied(family)
     sharded = copy.deepcopy(org)
     sc = ShardConfig(tensor_parallel_process_group=dist.group.WORLD, enable_tensor_parallelism=True)
     sharded, _ = ShardFormer(sc).optimize(sharded)
@@ -544,6 +549,51 @@ def _check_booster_in_place():
     dist.barrier()
 
 
+def _check_sequence_parallel_tied(family):
+    """`split_gather` sequence parallelism of the GPT-style HF decoders through the plugin: blocks run on sequence
+    shards, two SGD steps track the single-process model (loss, block norms, final norm, position embeddings)."""
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    org = _build_tied(family)
+    model = copy.deepcopy(org)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    ref_opt = torch.optim.SGD(org.parameters(), lr=0.05)
+    plugin = HybridParallelPlugin(tp_size=2, pp_size=1, precision="fp32", enable_sequence_parallelism=True,
+                                  sequence_parallelism_mode="split_gather")
+    booster = Booster(plugin=plugin, convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    blocks = inner.model.decoder.layers if family == "opt" else inner.transformer.h
+    seen = {}
+    blocks[0].register_forward_hook(
+        lambda m, a, o: seen.update(block=tuple((o[0] if isinstance(o, tuple) else o).shape)))
+    torch.manual_seed(3)
+    ids = torch.randint(0, 320, (2, 16))
+    for step in range(2):
+        loss = model(input_ids=ids, labels=ids).loss
+        booster.backward(loss, opt)
+        opt.step()
+        opt.zero_grad()
+        ref = org(input_ids=ids, labels=ids).loss
+        ref.backward()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        torch.testing.assert_close(loss.detach(), ref.detach(), atol=1e-5, rtol=1e-5,
+                                   msg=lambda m: f"sp {family} step {step}: {m}")
+    assert seen["block"][1] == (16 if len(blocks) == 1 else 8), seen       # first block: sequence shard out
+    ref_params = dict(org.named_parameters())
+    n = 0
+    for name, p in inner.named_parameters():
+        if hasattr(p, "dist_shard") or hasattr(p, "gather_fn") or p.shape != ref_params[name].shape:
+            continue                                             # replicated parameters: norms, positions, row biases
+        torch.testing.assert_close(p.detach(), ref_params[name].detach(), atol=1e-6, rtol=1e-5,
+                                   msg=lambda m: f"sp {family} {name}: {m}")
+        n += 1
+    assert n >= 5, (family, n)
+    del plugin
+
+
 def _check_sequence_parallel_in_place(family):
     """`split_gather` sequence parallelism of a user's HF decoder (TP2 + SP inside the TP group): the layers run on
     sequence shards (checked with a hook), the norm-weight gradients are summed over the group by the plugin, and two
@@ -701,6 +751,8 @@ def _worker(rank, world_size, port):
     _check_booster_in_place()
     for family in ("llama", "qwen3", "cohere", "mistral", "glm"):
         _check_sequence_parallel_in_place(family)
+    for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new", "falcon-mha"):
+        _check_sequence_parallel_tied(family)
     _check_zero_and_ddp_keep_hf_module()
     for family, tied in (("llama", False), ("qwen2", True)):
         _check_pipeline_in_place(family, tied)
