@@ -53,14 +53,17 @@ def _pp_stage_forward(self, input_ids=None, hidden_states=None, labels=None, att
                       **kwargs):
     """Stage-aware forward bound to the user's `<Family>ForCausalLM` / `<Family>Model` under pipeline parallelism."""
     sm = self._cb200_stage_manager
-    backbone = self.model if hasattr(self, "lm_head") else self
+    backbone = self._cb200_backbone
     inner = type(backbone).forward                       # the HF backbone's own forward
+    kw = dict(attention_mask=attention_mask, position_ids=position_ids, use_cache=False)
     if sm.is_first_stage():
-        out = inner(backbone, input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, use_cache=False)
+        kw["input_ids"] = input_ids
     else:
-        out = inner(backbone, inputs_embeds=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
-                    use_cache=False)
-    h = out.last_hidden_state
+        kw["inputs_embeds"] = hidden_states
+    accepted = self._cb200_backbone_params
+    if accepted is not None:                             # (BLOOM / Falcon backbones take no `position_ids`)
+        kw = {k: v for k, v in kw.items() if k in accepted}
+    h = inner(backbone, **kw).last_hidden_state
     if not sm.is_last_stage():
         return {"hidden_states": h}
     if not hasattr(self, "lm_head"):
@@ -73,6 +76,14 @@ def _pp_stage_forward(self, input_ids=None, hidden_states=None, labels=None, att
     if labels is not None:
         loss = self.loss_function(logits=logits, labels=labels, vocab_size=self.config.vocab_size)
     return {"loss": loss, "logits": logits}
+
+
+class _ZeroPositions(nn.Module):
+    """Stands in for a learned position embedding on the stages behind the first one: the HF backbone ADDS the position
+    embedding to `inputs_embeds`, which on those stages are hidden states that already carry it."""
+
+    def forward(self, *args, **kwargs) -> torch.Tensor:
+        return torch.zeros(())
 
 
 def _fused_rmsnorm_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
@@ -105,15 +116,30 @@ def mark_head_norms(tp_group):
 
 
 class HFDecoderPipelineMixin:
-    """1F1B pipeline stages for HF decoders whose backbone (`<Family>Model`) has `embed_tokens`, `layers`, `norm`,
-    `rotary_emb` and accepts `inputs_embeds` (llama-likes and the MoE families built on them)."""
+    """1F1B pipeline stages for HF decoders whose backbone accepts `inputs_embeds`: a stage keeps its slice of the
+    block list and the HF loop walks just that.  The class attributes name the family's modules: the path from the LM
+    wrapper to the backbone, the block list, the modules only the first stage needs, the final norm, modules every
+    stage needs (rotary tables), and what the backbone applies to `inputs_embeds` BEFORE the first block - on the
+    stages behind the first one those are replaced by neutral elements (learned positions -> zeros, embedding dropout /
+    embedding LayerNorm -> identity), because their input is a hidden state, not an embedding."""
+
+    _pp_backbone = ("model",)
+    _pp_layers = "layers"
+    _pp_first = ("embed_tokens",)
+    _pp_final = "norm"
+    _pp_every = ("rotary_emb",)
+    _pp_neutral = {}                     # attribute -> "zero" | "identity"
 
     def _backbone(self) -> nn.Module:
-        return self.model.model if hasattr(self.model, "lm_head") else self.model
+        m = self.model
+        if hasattr(m, "lm_head"):
+            for attr in self._pp_backbone:
+                m = getattr(m, attr)
+        return m
 
     def _stage_layers(self):
         sm = self.pipeline_stage_manager
-        layers = self._backbone().layers
+        layers = getattr(self._backbone(), self._pp_layers)
         assert not sm.is_interleave, "HF modules support the 1F1B schedule (one model chunk per stage)"
         start, end = sm.get_stage_index(sm.distribute_layers(len(layers)))
         return list(layers[start:end])
@@ -122,12 +148,21 @@ class HFDecoderPipelineMixin:
         sm = self.pipeline_stage_manager
         if sm is None or sm.num_stages == 1:
             return
+        import inspect
         from types import MethodType
 
         backbone = self._backbone()
-        backbone.layers = nn.ModuleList(self._held_decoder_layers)     # the HF loop now walks this stage's layers
+        setattr(backbone, self._pp_layers, nn.ModuleList(self._held_decoder_layers))   # the HF loop walks this stage only
         if not sm.is_last_stage():
-            backbone.norm = nn.Identity()
+            setattr(backbone, self._pp_final, nn.Identity())
+        if not sm.is_first_stage():
+            for attr, kind in self._pp_neutral.items():
+                if hasattr(backbone, attr):
+                    setattr(backbone, attr, _ZeroPositions() if kind == "zero" else nn.Identity())
+        params = inspect.signature(type(backbone).forward).parameters
+        var_kw = any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+        self.model._cb200_backbone_params = None if var_kw else set(params)
+        self.model._cb200_backbone = backbone
         self.model._cb200_stage_manager = sm
         self.model.forward = MethodType(_pp_stage_forward, self.model)
 
@@ -138,12 +173,11 @@ class HFDecoderPipelineMixin:
         backbone = self._backbone()
         self._held_decoder_layers = self._stage_layers()
         held: List[nn.Module] = list(self._held_decoder_layers)
-        if hasattr(backbone, "rotary_emb"):
-            held.append(backbone.rotary_emb)
+        held += [getattr(backbone, a) for a in self._pp_every if hasattr(backbone, a)]
         if sm.is_first_stage():
-            held.append(backbone.embed_tokens)
+            held += [getattr(backbone, a) for a in self._pp_first if hasattr(backbone, a)]
         if sm.is_last_stage():
-            held.append(backbone.norm)
+            held.append(getattr(backbone, self._pp_final))
             if hasattr(self.model, "lm_head"):
                 held.append(self.model.lm_head)
         return held
@@ -152,7 +186,7 @@ class HFDecoderPipelineMixin:
         sm = self.pipeline_stage_manager
         if sm is None or sm.num_stages == 1 or not getattr(self, "tie_weight", False) or not hasattr(self.model, "lm_head"):
             return []
-        emb_w, head_w = self._backbone().embed_tokens.weight, self.model.lm_head.weight
+        emb_w, head_w = self.model.get_input_embeddings().weight, self.model.lm_head.weight
         return [{0: emb_w, sm.num_stages - 1: head_w}]
 
 

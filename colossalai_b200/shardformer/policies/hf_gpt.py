@@ -13,7 +13,10 @@ LayerNorms are left to PyTorch (replicated parameters, tiny).  `split_gather` se
 `hf_decoder.py` (`sequence_parallel_hooks`: the blocks run on sequence shards, one gather in front of each attention /
 MLP module, row linears reduce-scatter; OPT has no MLP module and flattens [batch, seq] in its layer, so `fc1` / `fc2`
 gather and scatter the rows themselves along dim 0 - the MLP is row-wise, the row order does not matter).  Pipeline
-parallelism of these families: native zoo (`models.hf_io`)."""
+stages (1F1B) come from `HFDecoderPipelineMixin`: these backbones ADD learned positions to `inputs_embeds` (GPT-2, OPT),
+or apply embedding dropout (GPT-2, GPT-J) or an embedding LayerNorm (BLOOM) to it, so on the stages behind the first
+one those modules are replaced by neutral elements; the tied head on the last stage is kept in step with the first
+stage's embedding by the plugin's shared-parameter all-reduce."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -23,11 +26,16 @@ import torch.nn as nn
 from ..layer import Linear1D_Col, Linear1D_Row, VocabParallelEmbedding1D, VocabParallelLMHead1D
 from ..layer.qkv_fused_linear import GPT2FusedLinearConv1D_Col, GPT2FusedLinearConv1D_Row
 from .base_policy import ModulePolicyDescription, Policy, SubModuleReplacementDescription
+from .hf_decoder import HFDecoderPipelineMixin
 
 __all__ = ["HFGPT2Policy", "HFOPTPolicy", "HFGPTJPolicy", "HFBloomPolicy", "HFFalconPolicy"]
 
 
-class _HFTiedDecoderPolicy(Policy):
+class _HFTiedDecoderPolicy(HFDecoderPipelineMixin, Policy):
+    # pipeline stages (`HFDecoderPipelineMixin`): GPT-2 naming by default
+    _pp_backbone, _pp_layers, _pp_final, _pp_every = ("transformer",), "h", "ln_f", ()
+    _pp_first, _pp_neutral = ("wte", "wpe"), {"wpe": "zero", "drop": "identity"}
+
     def config_sanity_check(self) -> None:
         cfg = self.model.config
         tp = self.shard_config.tensor_parallel_size
@@ -62,20 +70,14 @@ class _HFTiedDecoderPolicy(Policy):
         return self.model
 
     def postprocess(self) -> nn.Module:
-        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism:
+        sm = self.pipeline_stage_manager
+        single_stage = sm is None or sm.num_stages == 1
+        if getattr(self, "tie_weight", False) and self.shard_config.enable_tensor_parallelism and single_stage:
             emb, head = self.model.get_input_embeddings(), self.model.get_output_embeddings()
             if head is not None and emb is not None and head.weight.shape == emb.weight.shape:
                 head.weight = emb.weight
+        self._install_pipeline_stage()
         return self.model
-
-    def get_held_layers(self) -> List[nn.Module]:
-        if self.pipeline_stage_manager is not None:
-            raise NotImplementedError("pipeline parallelism of HuggingFace modules: import the weights into the native "
-                                      "zoo (`models.hf_io.load_hf_checkpoint`) and use its policy")
-        return []
-
-    def get_shared_params(self):
-        return []
 
     def _vocab_kwargs(self) -> dict:
         sc = self.shard_config
@@ -119,6 +121,8 @@ class HFOPTPolicy(_HFTiedDecoderPolicy):
     # the OPT layer flattens [batch, seq] before `fc1`: its MLP is row-wise, so fc1 / fc2 gather and scatter those rows
     # themselves (dim 0, any row order) instead of through a hook on an MLP module (there is none)
     _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "layers", "self_attn", None, ("self_attn_layer_norm", "final_layer_norm")
+    _pp_backbone, _pp_layers, _pp_final = ("model", "decoder"), "layers", "final_layer_norm"
+    _pp_first, _pp_neutral = ("embed_tokens", "embed_positions"), {"embed_positions": "zero"}
 
     def config_sanity_check(self) -> None:
         super().config_sanity_check()
@@ -159,6 +163,7 @@ class HFGPTJPolicy(_HFTiedDecoderPolicy):
     bias; it becomes a gathered vocab-parallel head."""
 
     _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "h", "attn", "mlp", ("ln_1",)
+    _pp_first, _pp_neutral = ("wte",), {"drop": "identity"}
 
     def module_policy(self) -> Dict[str, ModulePolicyDescription]:
         sc = self.shard_config
@@ -204,6 +209,7 @@ class HFBloomPolicy(_HFTiedDecoderPolicy):
     ALiBi bias of its heads.  Assumes `pretraining_tp == 1` (the HF default for fine-tuning)."""
 
     _sp_layers, _sp_attn, _sp_mlp, _sp_norms = "h", "self_attention", "mlp", ("input_layernorm", "post_attention_layernorm")
+    _pp_first, _pp_neutral = ("word_embeddings", "word_embeddings_layernorm"), {"word_embeddings_layernorm": "identity"}
 
     def config_sanity_check(self) -> None:
         super().config_sanity_check()
@@ -252,6 +258,7 @@ class HFFalconPolicy(_HFTiedDecoderPolicy):
 
     _sp_layers, _sp_attn, _sp_mlp = "h", "self_attention", "mlp"
     _sp_norms = ("input_layernorm", "post_attention_layernorm", "ln_attn", "ln_mlp")
+    _pp_first, _pp_neutral, _pp_every = ("word_embeddings",), {}, ("rotary_emb",)
 
     def config_sanity_check(self) -> None:
         super().config_sanity_check()

@@ -45,7 +45,7 @@ def main():
     ap.add_argument("--pretrained", default=None, help="HuggingFace checkpoint directory (AutoModelForCausalLM)")
     ap.add_argument("--tp", type=int, default=1)
     ap.add_argument("--ep", type=int, default=1)
-    ap.add_argument("--pp", type=int, default=1, help="pipeline stages (llama-like families)")
+    ap.add_argument("--pp", type=int, default=1, help="pipeline stages (decoder families)")
     ap.add_argument("--sp", action="store_true", help="split_gather sequence parallelism inside the TP group (decoder families)")
     ap.add_argument("--zero", type=int, default=0)
     ap.add_argument("--steps", type=int, default=5)

@@ -77,35 +77,35 @@ def _check(family):
     assert n > 10
 
 
-def _build_tied(family):
+def _build_tied(family, layers=2):
     import transformers
 
     torch.manual_seed(0)
     if family.startswith("falcon"):
         new_arch = family == "falcon-new"
-        cfg = transformers.FalconConfig(vocab_size=320, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+        cfg = transformers.FalconConfig(vocab_size=320, hidden_size=64, num_hidden_layers=layers, num_attention_heads=4,
                                         num_kv_heads=2 if new_arch else None, new_decoder_architecture=new_arch,
                                         multi_query=False, parallel_attn=True, bias=False, alibi=False,
                                         hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=64)
         cfg._attn_implementation = "eager"
         org = transformers.FalconForCausalLM(cfg).float()
     elif family == "bloom":
-        cfg = transformers.BloomConfig(vocab_size=320, hidden_size=64, n_layer=2, n_head=4, hidden_dropout=0.0,
+        cfg = transformers.BloomConfig(vocab_size=320, hidden_size=64, n_layer=layers, n_head=4, hidden_dropout=0.0,
                                        attention_dropout=0.0)
         cfg._attn_implementation = "eager"
         org = transformers.BloomForCausalLM(cfg).float()
     elif family == "gptj":
-        cfg = transformers.GPTJConfig(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, rotary_dim=8,
+        cfg = transformers.GPTJConfig(vocab_size=320, n_positions=64, n_embd=64, n_layer=layers, n_head=4, rotary_dim=8,
                                       resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
         cfg._attn_implementation = "eager"
         org = transformers.GPTJForCausalLM(cfg).float()
     elif family == "gpt2":
-        cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
+        cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=layers, n_head=4, resid_pdrop=0.0,
                                       embd_pdrop=0.0, attn_pdrop=0.0)
         cfg._attn_implementation = "eager"
         org = transformers.GPT2LMHeadModel(cfg).float()
     else:
-        cfg = transformers.OPTConfig(vocab_size=320, hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4,
+        cfg = transformers.OPTConfig(vocab_size=320, hidden_size=64, ffn_dim=128, num_hidden_layers=layers, num_attention_heads=4,
                                      max_position_embeddings=64, word_embed_proj_dim=64, dropout=0.0)
         cfg._attn_implementation = "eager"
         org = transformers.OPTForCausalLM(cfg).float()
@@ -673,6 +673,60 @@ def _check_zero_and_ddp_keep_hf_module():
         torch.testing.assert_close(w, other, atol=1e-6, rtol=1e-6)
 
 
+def _check_pipeline_tied(family):
+    """1F1B pipeline stages of the GPT-style HF decoders in place (4 blocks over 2 stages, 2 micro-batches): learned
+    position embeddings / embedding dropout / embedding LayerNorm act on the first stage only, the tied head on the last
+    stage keeps its gradient in step with the first stage's embedding; two SGD steps track the single-process model."""
+    import re
+
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    org = _build_tied(family, layers=4)
+    tied = org.get_output_embeddings().weight is org.get_input_embeddings().weight
+    model = copy.deepcopy(org)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    ref_opt = torch.optim.SGD(org.parameters(), lr=0.05)
+    plugin = HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2)
+    booster = Booster(plugin=plugin, convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    r = dist.get_rank()
+    blocks = inner.model.decoder.layers if family == "opt" else inner.transformer.h
+    assert len(blocks) == 2
+    torch.manual_seed(12)
+    ids = torch.randint(0, 320, (2, 16))
+    for _ in range(2):
+        out = booster.execute_pipeline(iter([{"input_ids": ids, "labels": ids}]), model, lambda o, b: o["loss"], opt,
+                                       return_loss=True)
+        opt.step()
+        opt.zero_grad()
+        total = 0.0
+        for i in range(2):
+            l = org(input_ids=ids[i:i + 1], labels=ids[i:i + 1]).loss / 2
+            l.backward()
+            total += l.item()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        if out["loss"] is not None:
+            assert abs(out["loss"].item() - total) < 1e-4, (family, out["loss"].item(), total)
+    ref_params = dict(org.named_parameters())
+    emb_name = [n for n, p in org.named_parameters() if p is org.get_input_embeddings().weight][0]
+    n = 0
+    for name, p in inner.named_parameters():
+        if p is None:
+            continue
+        # the stage's blocks are renumbered from 0: map back to the global block index
+        ref_name = re.sub(r"\.(h|layers)\.(\d+)\.", lambda m: f".{m.group(1)}.{int(m.group(2)) + 2 * r}.", name)
+        if ref_name not in ref_params and "lm_head" in ref_name and tied:
+            ref_name = emb_name
+        torch.testing.assert_close(p.detach(), ref_params[ref_name].detach(), atol=2e-5, rtol=1e-4,
+                                   msg=lambda m: f"pp {family} {name}: {m}")
+        n += 1
+    assert n >= 10, (family, n)
+    del plugin
+
+
 def _check_pipeline_in_place(family, tied):
     """Pipeline parallelism of a user's HF decoder without converting it: stage 0 keeps the embedding + first layers,
     stage 1 the rest + norm + head (tied head: gradients of the two copies are synchronised); two 1F1B steps with two
@@ -756,6 +810,8 @@ def _worker(rank, world_size, port):
     _check_zero_and_ddp_keep_hf_module()
     for family, tied in (("llama", False), ("qwen2", True)):
         _check_pipeline_in_place(family, tied)
+    for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new"):
+        _check_pipeline_tied(family)
     dist.destroy_process_group()
 
 
