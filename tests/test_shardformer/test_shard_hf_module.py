@@ -209,6 +209,65 @@ def _check_bert():
     assert n > 20
 
 
+def _check_bert_pipeline():
+    """BERT in place as two 1F1B stages: embeddings on the first, pooler + classifier + loss (the model's own forward on
+    `inputs_embeds`) on the last; padded batch, two micro-batches, two SGD steps vs the single-process model."""
+    import re
+
+    import transformers
+
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+
+    torch.manual_seed(0)
+    cfg = transformers.BertConfig(vocab_size=320, hidden_size=64, num_hidden_layers=4, num_attention_heads=4,
+                                  intermediate_size=128, max_position_embeddings=64, hidden_dropout_prob=0.0,
+                                  attention_probs_dropout_prob=0.0, num_labels=3)
+    cfg._attn_implementation = "eager"
+    org = transformers.BertForSequenceClassification(cfg).float()
+    model = copy.deepcopy(org)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    ref_opt = torch.optim.SGD(org.parameters(), lr=0.05)
+    plugin = HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2)
+    booster = Booster(plugin=plugin, convert_hf_models=False)
+    model, opt, *_ = booster.boost(model, opt)
+    inner = model.unwrap()
+    r = dist.get_rank()
+    assert len(inner.bert.encoder.layer) == 2 and (inner.bert.pooler is None) == (r == 0)
+    torch.manual_seed(8)
+    ids = torch.randint(0, 320, (4, 16))
+    mask = torch.ones(4, 16, dtype=torch.long)
+    mask[0, 10:] = 0
+    types = torch.randint(0, 2, (4, 16))
+    labels = torch.tensor([0, 2, 1, 1])
+    for _ in range(2):
+        batch = {"input_ids": ids, "attention_mask": mask, "token_type_ids": types, "labels": labels}
+        out = booster.execute_pipeline(iter([batch]), model, lambda o, b: o["loss"], opt, return_loss=True)
+        opt.step()
+        opt.zero_grad()
+        total = 0.0
+        for i in range(2):
+            sl = slice(2 * i, 2 * i + 2)
+            l = org(input_ids=ids[sl], attention_mask=mask[sl], token_type_ids=types[sl], labels=labels[sl]).loss / 2
+            l.backward()
+            total += l.item()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        if out["loss"] is not None:
+            assert abs(out["loss"].item() - total) < 1e-4, (out["loss"].item(), total)
+    ref_params = dict(org.named_parameters())
+    n = 0
+    for name, p in inner.named_parameters():
+        if p is None:
+            continue
+        ref_name = re.sub(r"\.layer\.(\d+)\.", lambda m: f".layer.{int(m.group(1)) + 2 * r}.", name)
+        torch.testing.assert_close(p.detach(), ref_params[ref_name].detach(), atol=2e-5, rtol=1e-4,
+                                   msg=lambda m: f"pp bert {name}: {m}")
+        n += 1
+    assert n >= 30, n
+    del plugin
+
+
 def _check_vit():
     import transformers
 
@@ -641,13 +700,14 @@ def _check_sequence_parallel_in_place(family):
 
 def _check_zero_and_ddp_keep_hf_module():
     """Data-parallel plugins need no policy: with `convert_hf_models=False` the user's module is wrapped as it is
-    (ZeRO-1 in bf16, torch DDP in fp32) and trains."""
+    (ZeRO-1 in bf16, torch DDP in fp32, Gemini chunks in bf16) and trains."""
     import transformers
 
     from colossalai_b200.booster import Booster
-    from colossalai_b200.booster.plugin import LowLevelZeroPlugin, TorchDDPPlugin
+    from colossalai_b200.booster.plugin import GeminiPlugin, LowLevelZeroPlugin, TorchDDPPlugin
 
-    for plugin, steps in ((LowLevelZeroPlugin(stage=1, precision="bf16"), 4), (TorchDDPPlugin(), 4)):
+    for plugin, steps in ((LowLevelZeroPlugin(stage=1, precision="bf16"), 4), (TorchDDPPlugin(), 4),
+                          (GeminiPlugin(precision="bf16", placement_policy="static", initial_scale=1), 4)):
         torch.manual_seed(0)
         cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
                                       embd_pdrop=0.0, attn_pdrop=0.0)
@@ -666,6 +726,8 @@ def _check_zero_and_ddp_keep_hf_module():
             opt.zero_grad()
             losses.append(float(loss))
         assert all(l == l for l in losses) and losses[-1] < losses[0], (type(plugin).__name__, losses)
+        if isinstance(plugin, GeminiPlugin):                      # parameters live in chunks, sharded over the ranks
+            continue
         # replicas stay identical across the data-parallel ranks
         w = model.unwrap().transformer.h[0].mlp.c_fc.weight.detach().float().clone()
         other = w.clone()
@@ -812,6 +874,7 @@ def _worker(rank, world_size, port):
         _check_pipeline_in_place(family, tied)
     for family in ("gpt2", "opt", "gptj", "bloom", "falcon-new"):
         _check_pipeline_tied(family)
+    _check_bert_pipeline()
     dist.destroy_process_group()
 
 
