@@ -77,3 +77,37 @@ def test_inference_examples_cpu():
     pytest.importorskip("uvicorn")
     out = _python("examples/inference/client/run_client.py", "--self-host", "--concurrency", "4")
     assert "Healthy" in out and "16/16 ok" in out
+
+
+@pytest.mark.dist
+def test_colossal_llama_train_and_resume(tmp_path):
+    """The continual-pretraining driver: spliced data, ZeRO-2, checkpoint at step 3, resume reproduces step 4's loss."""
+    script = "applications/Colossal-LLaMA/train.py"
+    common = ("--model", "llama-tiny", "--plugin", "zero2", "--max_length", "64", "--steps", "5", "--synthetic_docs", "120")
+    out = _torchrun(script, *common, "--save_dir", str(tmp_path), "--save_interval", "3", "--log_file",
+                    str(tmp_path / "log.jsonl"), port=29759)
+    first = {l.split()[1]: l.split()[3] for l in out.splitlines() if l.startswith("step ")}
+    assert len(first) == 5 and float(first["5"]) < float(first["1"]) and (tmp_path / "epoch-0_step-3").is_dir()
+    assert len((tmp_path / "log.jsonl").read_text().splitlines()) == 5
+    out = _torchrun(script, *common, "--load_checkpoint", str(tmp_path / "epoch-0_step-3"), port=29760)
+    assert "resumed from" in out
+    resumed = {l.split()[1]: l.split()[3] for l in out.splitlines() if l.startswith("step ")}
+    assert sorted(resumed) == ["4", "5"] and abs(float(resumed["4"]) - float(first["4"])) < 2e-3
+
+
+@pytest.mark.dist
+def test_colossal_moe_train_then_infer(tmp_path):
+    """Expert-parallel training with load monitoring + checkpoint; the expert-parallel decode loop and the single-rank
+    paged-KV engine produce the same greedy completion from that checkpoint."""
+    out = _torchrun("applications/ColossalMoE/train.py", "--model", "mixtral-tiny", "--ep", "2", "--steps", "4",
+                    "--log_interval", "2", "--max_length", "32", "--save_dir", str(tmp_path), "--save_interval", "4",
+                    port=29764)
+    lines = [l for l in out.splitlines() if l.startswith("step ")]
+    assert len(lines) == 2 and "expert load" in lines[0] and "imbalance" in lines[0] and "nan" not in lines[0]
+    ckpt = str(tmp_path / "epoch-0_step-4")
+    prompt = ("--prompt", "The capital of France is", "--max_new_tokens", "5")
+    ep = _torchrun("applications/ColossalMoE/infer.py", "--model", "mixtral-tiny", "--ep", "2", "--checkpoint", ckpt,
+                   *prompt, port=29765)
+    single = _python("applications/ColossalMoE/infer.py", "--model", "mixtral-tiny", "--engine", "--checkpoint", ckpt, *prompt)
+    pick = lambda text: [l for l in text.splitlines() if l.startswith("[output]")]      # noqa: E731
+    assert pick(ep) and pick(ep) == pick(single)
