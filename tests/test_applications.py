@@ -506,3 +506,63 @@ def test_two_producers_one_consumer_processes():
     from colossalai_b200.testing import spawn
 
     spawn(_multi_producer_worker, 3)
+
+
+def test_colossal_eval_batched_pipeline_and_judge(tmp_path):
+    """`EvalModel` (right-padded batches) agrees with the one-item-at-a-time functions; the two-phase pipeline writes
+    answers and scores them offline; the LLM-as-judge path parses scores / battles from a stub judge."""
+    import json
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "ColossalEval"))
+    from colossal_eval import (EvalModel, Evaluator, format_table, judge_battle, judge_scores, parse_battle, parse_score,
+                               run_evaluation, run_inference, score_choices_by_loglikelihood)
+
+    model = _tiny(3, vocab_size=300).eval()
+    dec = lambda ids: bytes(max(0, min(255, i - 3)) for i in ids if i >= 3).decode(errors="replace")     # noqa: E731
+    em = EvalModel(model, _tok, dec, batch_size=3, max_new_tokens=5, eos_token_id=2)
+    # per-choice losses: batched == sequential (length-normalised log-likelihood, sign flipped)
+    items = [{"instruction": f"Q{i}: pick", "choices": [" a", " bb", " ccc" * (i + 1)], "answer": i % 3, "category": f"c{i % 2}"}
+             for i in range(5)]
+    scored = em.score_choices(items)
+    for it, s in zip(items, scored):
+        ref = score_choices_by_loglikelihood(model, _tok, it["instruction"], it["choices"])
+        torch.testing.assert_close(torch.tensor(s["choice_losses"]), -torch.tensor(ref), atol=1e-4, rtol=1e-4)
+        assert s["output"] == max(range(3), key=ref.__getitem__)
+    # generation: rows of different lengths in one right-padded batch == one at a time
+    prompts = ["hi", "a much longer prompt than the others", "mid size"]
+    single = Evaluator(model, _tok, dec, max_new_tokens=5)
+    assert em.generate(prompts) == [single.generate(p) for p in prompts]
+    # masked target loss == cross entropy over the target tokens only
+    l = em.get_loss(["The quick", "x"], [" brown fox", " yz"])
+    ids = torch.tensor([_tok("The quick") + _tok(" brown fox")])
+    lp = torch.log_softmax(get_logits(model, ids)[0, :-1].float(), -1).gather(-1, ids[0, 1:, None]).squeeze(-1)
+    assert abs(l[0] - float(-lp[len(_tok("The quick")) - 1:].mean())) < 1e-4
+    # two-phase pipeline
+    datasets = {"choice": items, "gen": [{"instruction": p, "target": "x", "category": "g"} for p in prompts],
+                "lm": [{"instruction": "The quick", "target": " brown fox", "calculate_loss": True}]}
+    paths = run_inference(em, datasets, str(tmp_path / "answers"))
+    blob = json.loads(open(paths["choice"]).read())
+    assert blob["num_items"] == 5 and [it["index"] for it in blob["items"]] == list(range(5))
+    res = run_evaluation(str(tmp_path / "answers"), {"gen": ["exact_match", "f1"]}, str(tmp_path / "results.json"))
+    acc = sum(int(s["output"] == s["answer"]) for s in scored) / 5
+    assert abs(res["choice"]["micro_avg"]["accuracy"] - acc) < 1e-9 and set(res["choice"]) == {"c0", "c1", "macro_avg", "micro_avg"}
+    assert abs(res["lm"]["micro_avg"]["loss"] - l[0]) < 1e-4 and "f1" in res["gen"]["g"]
+    assert "perplexity" in format_table(res) and (tmp_path / "results.json").exists()
+    # judge
+    assert parse_score("fine.\nScore: 4/5") == 4 and parse_score("no verdict") is None
+    assert parse_battle("B is vague. Winner: A") == "a" and parse_battle("Winner: Tie") == "tie"
+
+    def stub(prompt):                                   # prefers long answers; always names the longer assistant
+        if "[Assistant A]" in prompt:
+            a = prompt.split("[Assistant A]\n")[1].split("\n[Assistant B]")[0]
+            b = prompt.split("[Assistant B]\n")[1].split("\n\n")[0]
+            return "Winner: " + ("A" if len(a) > len(b) else "B" if len(b) > len(a) else "tie")
+        ans = prompt.split("[Assistant's answer]\n")[1].split("\n\n")[0]
+        return f"ok. Score: {min(5, 1 + len(ans) // 4)}" if ans != "??" else "cannot say"
+
+    rep = judge_scores(stub, [{"instruction": "q1", "output": "short", "category": "x"},
+                              {"instruction": "q2", "output": "a considerably longer answer", "category": "y"},
+                              {"instruction": "q3", "output": "??", "category": "y"}], criteria=("correctness",))
+    assert rep["failed"] == 1 and rep["overall"]["correctness"] == (2 + 5) / 2 and rep["by_category"]["y"]["correctness"] == 5
+    b = judge_battle(stub, ["q"] * 3, ["long answer here", "s", "same"], ["s", "long answer here", "same"])
+    assert b["win_rate_a"] == b["win_rate_b"] == b["tie_rate"] == 1 / 3 and b["failed"] == 0

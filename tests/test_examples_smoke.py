@@ -111,3 +111,14 @@ def test_colossal_moe_train_then_infer(tmp_path):
     single = _python("applications/ColossalMoE/infer.py", "--model", "mixtral-tiny", "--engine", "--checkpoint", ckpt, *prompt)
     pick = lambda text: [l for l in text.splitlines() if l.startswith("[output]")]      # noqa: E731
     assert pick(ep) and pick(ep) == pick(single)
+
+
+@pytest.mark.dist
+def test_colossal_eval_two_phase_example(tmp_path):
+    cfg = "applications/ColossalEval/examples/dataset_evaluation/config.json"
+    out = _torchrun("applications/ColossalEval/examples/dataset_evaluation/inference.py", "--config", cfg, "--out_dir",
+                    str(tmp_path / "answers"), port=29766)
+    assert out.count("_inference.json") == 3
+    table = _python("applications/ColossalEval/examples/dataset_evaluation/eval_dataset.py", "--inference_dir",
+                    str(tmp_path / "answers"), "--config", cfg, "--out", str(tmp_path / "results.json"))
+    assert "accuracy" in table and "perplexity" in table and "rouge_l" in table and (tmp_path / "results.json").exists()
