@@ -566,3 +566,46 @@ def test_colossal_eval_batched_pipeline_and_judge(tmp_path):
     assert rep["failed"] == 1 and rep["overall"]["correctness"] == (2 + 5) / 2 and rep["by_category"]["y"]["correctness"] == 5
     b = judge_battle(stub, ["q"] * 3, ["long answer here", "s", "same"], ["s", "long answer here", "same"])
     assert b["win_rate_a"] == b["win_rate_b"] == b["tie_rate"] == 1 / 3 and b["failed"] == 0
+
+
+def test_colossalqa_universal_conversation(tmp_path):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "applications", "ColossalQA"))
+    from colossalqa import (LocalLLM, UniversalRetrievalConversation, classify_intent, detect_language, load_table,
+                            split_chinese_text)
+
+    assert detect_language("What is the warranty?") == "en" and detect_language("保修期是多久？") == "zh"
+    zh = "极光笔记本的保修期为二十四个月。电池损耗仅在前十二个月内保修！退货须在收货后三十天内提出，且产品未使用、包装完好。"
+    chunks = split_chinese_text(zh, 24)
+    assert "".join(chunks) == zh and all(len(c) <= 24 for c in chunks) and chunks[0].endswith("。")
+    (tmp_path / "t.csv").write_text("name,price,stock\nwidget,9.5,3\ngadget,20,\n")
+    rows = load_table(tmp_path / "t.csv")
+    assert rows[0]["text"] == "name: widget; price: 9.5; stock: 3" and rows[1]["text"] == "name: gadget; price: 20"
+
+    seen = []
+
+    def fake_model(prompt):                              # echoes the prompt like some engines do, then answers
+        seen.append(prompt)
+        if "intent:" in prompt:
+            return prompt + " Refund."
+        return prompt + (" 24 months\nquestion: something else" if "question:" in prompt else " 二十四个月\n\n多余")
+
+    llm = LocalLLM(fake_model)
+    conv = UniversalRetrievalConversation(llm, k=2, intents={"refund": "wants money back", "product": "asks about a product"},
+                                          intent_replies={"refund": "Please open a refund ticket."})
+    added = conv.add_documents(["The Aurora laptop has a warranty period of 24 months. Returns within 30 days.", zh], "kb")
+    assert added["en"] >= 1 and added["zh"] >= 1
+    assert classify_intent(lambda p: "Product.", "how long is the warranty", conv.intents) == "product"
+    assert classify_intent(lambda p: "no idea", "??", conv.intents) == "other"
+    ans, src, meta = conv.run("I want my money back")                 # intent routed: canned reply, no retrieval
+    assert ans == "Please open a refund ticket." and src == [] and meta["intent"] == "refund"
+    conv.intents = None
+    ans, src, meta = conv.run("What is the warranty period of the laptop?")
+    assert ans == "24 months" and meta["language"] == "en" and "warranty" in src[0]["text"] and "context:" in seen[-1]
+    ans, src, meta = conv.run("笔记本的保修期是多久？")
+    assert ans == "二十四个月" and meta["language"] == "zh" and "保修" in src[0]["text"] and "资料：" in seen[-1]
+    n = llm.calls
+    ans, src, _ = conv.run("Jupiter?")                                  # nothing relevant retrieved: refuse, no model call
+    assert ans == "I do not know." and src == [] and llm.calls == n
+    assert "warranty period" in conv.chains["en"].memory.render()
+    conv.reset()
+    assert conv.chains["en"].memory.render().strip() == ""

@@ -74,6 +74,9 @@ def test_inference_examples_cpu():
     assert "generated (1, 3, 64, 64)" in out and "finite True" in out
     out = _python("examples/inference/benchmark_ops/benchmark_ops.py")
     assert out.count(" ok") >= 8                                   # every op agrees with its PyTorch formulation
+    out = _python("applications/ColossalQA/examples/retrieval_conversation_universal.py", "--ask",
+                  "What is the warranty period?", "保修期是多久？", "--max_new_tokens", "3")
+    assert "[en] What is the warranty" in out and "[zh]" in out and out.count("source :") >= 2
     pytest.importorskip("uvicorn")
     out = _python("examples/inference/client/run_client.py", "--self-host", "--concurrency", "4")
     assert "Healthy" in out and "16/16 ok" in out
