@@ -121,7 +121,12 @@ class _AsyncInferenceEngine(InferenceEngine):
         eng = self.engine
         loop = asyncio.get_event_loop()
         finished = await loop.run_in_executor(None, eng.step)
-        return finished, eng.request_handler.total_requests_in_batch_bucket() > 0
+        # "still busy" must include the WAITING list: a step can retire every running sequence while requests admitted
+        # at its start are still queued (decode has priority over prefill); looking at the batch buckets only would
+        # park the loop on the new-request event with work pending - and with every client blocked on its own
+        # unfinished request that event never fires
+        rh = eng.request_handler
+        return finished, rh.check_unfinished_reqs() or rh.total_requests_in_batch_bucket() > 0
 
     def add_single_request(self, request_id: int, prompt: str, prompt_token_ids=None, generation_config=None) -> None:
         self.engine.add_request(request_ids=request_id, prompts=prompt, prompts_token_ids=prompt_token_ids,

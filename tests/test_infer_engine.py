@@ -334,3 +334,31 @@ def test_engine_sliding_window_matches_naive_greedy():
                           generation_config=GenerationConfig(max_new_tokens=10))
     for p, got in zip(prompts, ids):
         assert got == _naive_greedy(model, p, 10), (p, got)
+
+
+def test_async_engine_drains_waiting_requests():
+    """More concurrent requests than batch slots: the background loop must keep stepping while requests are WAITING
+    even when a step retired every running sequence (it used to park on the new-request event and hang)."""
+    import asyncio
+
+    from colossalai_b200.inference.core.async_engine import AsyncInferenceEngine
+
+    torch.manual_seed(0)
+    model = build_model("llama-tiny").float().eval()
+    cfg = InferenceConfig(max_batch_size=2, max_input_len=32, max_output_len=4, block_size=8, dtype="fp32")
+
+    async def one(eng, rid):
+        out = None
+        async for o in eng.generate(rid, f"prompt number {rid}", generation_config=GenerationConfig(max_new_tokens=2 + rid % 3)):
+            out = o
+        return out
+
+    async def run():
+        eng = AsyncInferenceEngine(start_engine_loop=True, model_or_path=model, tokenizer=None, inference_config=cfg)
+        for wave in range(3):                           # waves: clients only send the next request after an answer
+            outs = await asyncio.wait_for(asyncio.gather(*[one(eng, 10 * wave + i) for i in range(7)]), timeout=120)
+            assert len(outs) == 7 and all(isinstance(o, str) for o in outs)
+        rh = eng.engine.engine.request_handler
+        assert not rh.check_unfinished_reqs() and rh.total_requests_in_batch_bucket() == 0
+
+    asyncio.run(run())
