@@ -188,7 +188,11 @@ class RequestHandler(NaiveRequestHandler):
                                          alloc_block_tables_fn=self.cache_manager.allocate_context_from_block_tables)
                 self.running_list.move_prefill_to_decoding([s.request_id for s in seqs])
                 return self.prefill_bb
-        if not self.running_bb.is_empty:
+        # room for this step's token(s) of every running sequence.  The cache is sized for the worst case, so this
+        # only fails under over-subscription (speculative look-ahead); then the youngest sequence goes back to the
+        # waiting list and the allocation is RETRIED - the failed pass stopped at the first sequence without a block,
+        # the ones behind it have none yet either (allocation of an already assigned slot is a no-op)
+        while not self.running_bb.is_empty:
             try:
                 n_new = self.running_bb.num_tokens_to_verify + 1 if self.running_bb.use_spec_dec else 1
                 if n_new == 1:
@@ -199,6 +203,7 @@ class RequestHandler(NaiveRequestHandler):
                     self.cache_manager.allocate_n_tokens_from_block_tables(
                         self.running_bb.block_tables, self.running_bb.seq_lengths,
                         self.running_bb.current_batch_size, n_new)
+                break
             except RuntimeError:
                 self._recycle_last()
         return self.running_bb
