@@ -16,6 +16,14 @@ from torch.utils._pytree import tree_map
 __all__ = ["PipelineSchedule"]
 
 
+def _shape_signature(batch: Any, microbatch_size: int):
+    """(shape beyond the batch dim, dtype) of every tensor of the batch + the micro-batch size."""
+    from torch.utils._pytree import tree_flatten
+
+    leaves, _ = tree_flatten(batch)
+    return (microbatch_size,) + tuple((tuple(x.shape[1:]), str(x.dtype)) for x in leaves if torch.is_tensor(x))
+
+
 class PipelineSchedule:
     def __init__(self, stage_manager: PipelineStageManager) -> None:
         self.stage_manager = stage_manager
@@ -35,18 +43,26 @@ class PipelineSchedule:
         self.microbatch_offset = [0 for _ in range(getattr(self, "num_model_chunks", 1))]
         self.batch = batch
         self.batch_size = get_batch_size(batch)
-        if self.microbatch_size is None:
+        # the user fixed ONE of (number of micro-batches, micro-batch size); the other follows the batch - every batch,
+        # not only the first one (a larger batch must not silently lose its tail, a smaller one must not over-read)
+        if not hasattr(self, "_derive"):
+            self._derive = "size" if self.microbatch_size is None else ("num" if self.num_microbatch is None else None)
+        if self._derive == "size":
             assert self.batch_size % self.num_microbatch == 0, "Batch size should divided by # microbatches"
             self.microbatch_size = self.batch_size // self.num_microbatch
-        if self.num_microbatch is None:
+        elif self._derive == "num":
             assert self.batch_size % self.microbatch_size == 0, "Batch size should divided by the microbatch size"
             self.num_microbatch = self.batch_size // self.microbatch_size
-        if self.last_batch_size is None:
-            self.last_batch_size = self.batch_size
-        elif self.last_batch_size != self.batch_size:
-            self.enable_metadata_cache = False    # shapes changed: resend metadata
+        else:
+            assert self.num_microbatch * self.microbatch_size == self.batch_size, (
+                f"batch of {self.batch_size} != {self.num_microbatch} micro-batches x {self.microbatch_size}")
+        # cached P2P metadata (shapes / dtypes of what a stage sends) is only valid while the micro-batches keep their
+        # shape: every stage sees the same batch, so all of them drop the cache together and re-exchange it once
+        sig = _shape_signature(batch, self.microbatch_size)
+        if getattr(self, "_batch_signature", None) is not None and sig != self._batch_signature:
             self.reset_metadata_cache()
-            self.last_batch_size = self.batch_size
+        self._batch_signature = sig
+        self.last_batch_size = self.batch_size
 
     def reset_metadata_cache(self) -> None:
         pass

@@ -130,3 +130,49 @@ def test_pipeline_schedules_cpu():
 if __name__ == "__main__":
     test_schedule_graphs_are_complete()
     test_pipeline_schedules_cpu()
+
+
+def _variable_shape_worker(rank, world_size, port):
+    """Sequence length and batch size change from step to step: the cached P2P metadata is re-exchanged when the
+    micro-batch shape changes, and the micro-batch size follows the batch (fixed number of micro-batches) - every
+    step's loss equals the single-process loss on the same data."""
+    import copy
+
+    import torch.distributed as dist
+
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import HybridParallelPlugin
+    from colossalai_b200.models import build_model
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    torch.manual_seed(0)
+    base = build_model("llama-tiny").float()
+    model = copy.deepcopy(base)
+    opt, ref_opt = torch.optim.SGD(model.parameters(), lr=0.05), torch.optim.SGD(base.parameters(), lr=0.05)
+    booster = Booster(plugin=HybridParallelPlugin(tp_size=1, pp_size=2, precision="fp32", num_microbatches=2))
+    model, opt, *_ = booster.boost(model, opt)
+    g = torch.Generator().manual_seed(1)
+    for B, S in [(2, 16), (2, 24), (4, 8), (2, 16), (6, 12)]:
+        ids = torch.randint(0, 256, (B, S), generator=g)
+        out = booster.execute_pipeline(iter([{"input_ids": ids, "labels": ids}]), model, lambda o, b: o["loss"], opt,
+                                       return_loss=True)
+        opt.step()
+        opt.zero_grad()
+        total, mb = 0.0, B // 2
+        for i in range(2):
+            l = base(input_ids=ids[i * mb:(i + 1) * mb], labels=ids[i * mb:(i + 1) * mb])["loss"] / 2
+            l.backward()
+            total += l.item()
+        ref_opt.step()
+        ref_opt.zero_grad()
+        if out["loss"] is not None:
+            assert abs(out["loss"].item() - total) < 1e-4, ((B, S), out["loss"].item(), total)
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+def test_pipeline_variable_batch_shapes():
+    from colossalai_b200.testing import spawn
+
+    spawn(_variable_shape_worker, 2)
