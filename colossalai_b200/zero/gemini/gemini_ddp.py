@@ -351,6 +351,13 @@ class GeminiDDP(ModelWrapper):
                 cache[chunk] = self._gather_chunk_tensors(chunk, dtype)
             if rank0 or not only_rank_0:
                 dst[prefix + name] = cache[chunk][src].cpu()
+        # a parameter registered under several names (tied head, a module reused twice) appears under every one of them
+        # in `nn.Module.state_dict`; `named_parameters()` only yields the first - add the aliases (same tensor)
+        first = {id(p): n for n, p in self.module.named_parameters()}
+        for name, p in self.module.named_parameters(remove_duplicate=False):
+            canon = first[id(p)]
+            if name != canon and prefix + canon in dst and prefix + name not in dst:
+                dst[prefix + name] = dst[prefix + canon]
         for name, b in self.module.named_buffers():
             mod_path, _, bname = name.rpartition(".")
             owner = self.module.get_submodule(mod_path) if mod_path else self.module
@@ -359,8 +366,8 @@ class GeminiDDP(ModelWrapper):
         return dst
 
     def load_state_dict(self, state_dict: "OrderedDict[str, torch.Tensor]", strict: bool = True):
-        missing, unexpected = [], [k for k in state_dict if k not in dict(self.module.named_parameters())
-                                   and k not in dict(self.module.named_buffers())]
+        known = dict(self.module.named_parameters(remove_duplicate=False))
+        missing, unexpected = [], [k for k in state_dict if k not in known and k not in dict(self.module.named_buffers())]
         p2master = dict(zip(self.fp16_params, self.fp32_params)) if self.fp32_params else {}
         for name, p in self.module.named_parameters():
             if name not in state_dict:

@@ -83,3 +83,44 @@ def test_gemini_cpu():
 if __name__ == "__main__":
     test_search_chunk_configuration()
     test_gemini_cpu()
+
+
+def _alias_worker(rank, world_size, port):
+    """A module registered under two names: the Gemini state dict carries both keys (like `nn.Module.state_dict`), loads
+    strictly into a plain copy of the model and back into the Gemini-wrapped one."""
+    import torch.nn as nn
+
+    import colossalai_b200
+    from colossalai_b200.booster import Booster
+    from colossalai_b200.booster.plugin import GeminiPlugin
+    from colossalai_b200.nn.optimizer import HybridAdam
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(16, 32), nn.Linear(32, 16)
+            self.shared = self.a
+
+        def forward(self, x):
+            return self.b(torch.relu(self.shared(x)))
+
+    colossalai_b200.launch(rank, world_size, "127.0.0.1", port, backend="gloo", verbose=False)
+    torch.manual_seed(0)
+    model = Net()
+    opt = HybridAdam(model.parameters(), lr=1e-2)
+    booster = Booster(plugin=GeminiPlugin(precision="bf16", placement_policy="static", initial_scale=1))
+    model, opt, *_ = booster.boost(model, opt)
+    loss = model(torch.randn(4, 16)).square().mean()
+    booster.backward(loss, opt)
+    opt.step()
+    sd = model.state_dict(only_rank_0=False)
+    assert set(sd) == set(Net().state_dict()) and sd["shared.weight"] is sd["a.weight"]
+    plain = Net()
+    plain.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    model.load_state_dict(sd, strict=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.dist
+def test_gemini_state_dict_keeps_aliased_parameter_names():
+    spawn(_alias_worker, 2)
