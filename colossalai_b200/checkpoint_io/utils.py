@@ -159,7 +159,17 @@ def save_state_dict(state_dict: Mapping, checkpoint_file_path: str, use_safetens
     if use_safetensors:
         from safetensors.torch import save_file
 
-        save_file(_flatten_for_safetensors(cpu_sd), checkpoint_file_path, metadata={"format": "pt"})
+        # safetensors refuses tensors that share memory: a tied / shared parameter is stored under its first name only
+        # (the HuggingFace convention; loaders re-tie, `load_state_dict` of the wrappers treats the alias as present)
+        seen, unique = set(), {}
+        for k, v in cpu_sd.items():
+            if torch.is_tensor(v) and v.numel() > 0:
+                key = (v.untyped_storage().data_ptr(), v.storage_offset(), tuple(v.shape), tuple(v.stride()))
+                if key in seen:
+                    continue
+                seen.add(key)
+            unique[k] = v
+        save_file(_flatten_for_safetensors(unique), checkpoint_file_path, metadata={"format": "pt"})
     else:
         torch.save(cpu_sd, checkpoint_file_path)
 

@@ -403,7 +403,12 @@ class GeminiDDP(ModelWrapper):
         from ...checkpoint_io.utils import StateDictSharder
 
         sharder = StateDictSharder(max_shard_size)
+        seen = set()
         for k, v in self.state_dict(prefix=prefix, only_rank_0=only_rank_0, dtype=dtype).items():
+            if torch.is_tensor(v):
+                if id(v) in seen:               # alias of a tied / shared parameter: stored once (HF convention)
+                    continue
+                seen.add(id(v))
             block, size = sharder.append_param(k, v)
             if block is not None:
                 yield block, size
