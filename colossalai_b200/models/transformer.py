@@ -466,6 +466,17 @@ class TransformerModel(nn.Module):
         else:
             assert batch is not None and seqlen is not None, "later PP stages need batch/seqlen"
             B, S, device = batch, seqlen, hidden_states.device
+        if sp > 1:
+            # fail here with a sentence, not inside a collective with mismatched shard sizes
+            if sp_mode == "ring_attn":
+                assert S % (2 * sp) == 0, (f"ring attention splits every sequence into 2 x sp = {2 * sp} zigzag blocks: "
+                                           f"pad the sequence length {S} to a multiple of {2 * sp}")
+            elif sp_mode == "all_to_all":
+                assert S % sp == 0, (f"all_to_all sequence parallelism shards the sequence over {sp} ranks: pad the "
+                                     f"sequence length {S} to a multiple of {sp}")
+            elif sp_mode in ("split_gather", "ring"):
+                assert (B * S) % sp == 0, (f"{sp_mode} sequence parallelism shards the {B} x {S} tokens over {sp} ranks: "
+                                           f"pad batch x sequence to a multiple of {sp}")
         if meta is None:
             # positions seen by rope/attention
             if position_ids is not None:
