@@ -9,15 +9,12 @@ __all__ = ["seed_all"]
 
 
 def seed_all(seed: int, cuda_deterministic: bool = False) -> None:
-    random.seed(seed)
-    np.random.seed(seed)
+    """Seed python / numpy / torch (all devices).  `cuda_deterministic` trades cuDNN autotuning for run-to-run
+    reproducibility; the default keeps autotuning on, which is what the performance tests want."""
     os.environ["PYTHONHASHSEED"] = str(seed)
-    torch.manual_seed(seed)
+    for seeder in (random.seed, np.random.seed, torch.manual_seed):
+        seeder(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(seed)
-    if cuda_deterministic:
-        torch.backends.cudnn.deterministic = True
-        torch.backends.cudnn.benchmark = False
-    else:
-        torch.backends.cudnn.deterministic = False
-        torch.backends.cudnn.benchmark = True
+    cudnn = torch.backends.cudnn
+    cudnn.deterministic, cudnn.benchmark = bool(cuda_deterministic), not cuda_deterministic
