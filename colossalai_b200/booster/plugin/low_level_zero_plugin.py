@@ -148,7 +148,8 @@ class LowLevelZeroPlugin(DPPluginBase):
                  hysteresis: int = 2, max_scale: float = 2**32, max_norm: float = 0.0, norm_type: float = 2.0,
                  reduce_bucket_size_in_m: int = 12, communication_dtype: Optional[torch.dtype] = None,
                  overlap_communication: bool = True, overlap_allgather: bool = False, cpu_offload: bool = False, offload_optim_frac: float = 1.0,
-                 master_weights: bool = True, verbose: bool = False, cast_inputs: bool = True,
+                 master_weights: bool = True, skip_untouched_params: bool = False, verbose: bool = False,
+                 cast_inputs: bool = True,
                  fp8_communication: bool = False, use_fp8: bool = False, extra_dp_size: int = 1) -> None:
         super().__init__()
         assert stage in (1, 2), "LowLevelZeroPlugin only supports stage 1/2 training"
@@ -170,7 +171,7 @@ class LowLevelZeroPlugin(DPPluginBase):
             max_scale=max_scale, clip_grad_norm=max_norm, reduce_bucket_size=reduce_bucket_size_in_m * 1024 * 1024,
             communication_dtype=communication_dtype, overlap_communication=overlap_communication,
             partition_grad=(stage == 2), cpu_offload=cpu_offload, offload_optim_frac=offload_optim_frac,
-            master_weights=master_weights,
+            master_weights=master_weights, skip_untouched_params=skip_untouched_params,
             overlap_allgather=overlap_allgather, fp8_communication=fp8_communication)
         self.verbose = verbose
         self.cast_inputs = cast_inputs

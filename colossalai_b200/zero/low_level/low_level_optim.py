@@ -75,6 +75,7 @@ class _Bucket:
         self.n_ready = 0
         self.reduced = False
         self.work = None
+        self.touched = [False] * len(params)         # which params received a gradient since the last step
 
     @property
     def my_slice(self) -> slice:
@@ -94,8 +95,14 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                  dp_process_group: Optional[ProcessGroup] = None, extra_dp_group: Optional[ProcessGroup] = None,
                  forced_dtype: Optional[torch.dtype] = None, master_weights: bool = True,
                  overlap_allgather: bool = False, fp8_communication: bool = False, backward_context=None,
-                 offload_optim_frac: float = 1.0) -> None:
+                 offload_optim_frac: float = 1.0, skip_untouched_params: bool = False) -> None:
         super().__init__(optim=optimizer)
+        # flat buckets step a parameter that received no gradient with a ZERO gradient (moments decay, momentum moves
+        # it, weight decay applies).  `skip_untouched_params=True` gives `torch.optim` / reference semantics instead -
+        # such a parameter and its moments are left exactly as they were - for one small all-reduce and host read per
+        # step (the ranks must agree on what "received no gradient anywhere" means), hence opt-in.  (Adam's bias
+        # correction still uses the bucket's step count: a flat state has one counter, not one per parameter.)
+        self._skip_untouched = bool(skip_untouched_params)
         # cpu_offload: fraction of the optimizer state (fp32 master + moments, by element count) that lives in pinned
         # host memory and is stepped by the AVX-512 CPU Adam; the rest stays in HBM on the fused multi-tensor path.
         # 1.0 = everything (the reference's `cpu_offload=True`), smaller values tier the state between HBM and DRAM.
@@ -218,6 +225,7 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             o = b.offsets[idx]
             b.grad_full[o:o + p.numel()].add_(g.reshape(-1).to(b.grad_full.dtype))
             p.grad = None
+            b.touched[idx] = True
             b.n_ready += 1
             if b.n_ready == len(b.params):
                 b.n_ready = 0
@@ -313,6 +321,7 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             b.grad_shard = None
             b.grad_full = None
             b.n_ready = 0
+            b.touched = [False] * len(b.params)
             for p in b.params:
                 p.grad = None
             b.master.grad = None
@@ -355,6 +364,7 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             clip_coef = (self._clip_grad_norm / (norm + 1e-6)).clamp(max=1.0).float().reshape(1)
         live = [b for b in self.buckets if b.grad_shard is not None]
         self._stepped_groups = set()
+        kept = self._snapshot_untouched(live) if self._skip_untouched else []
         fused = (live and use_native(live[0].grad_shard) and self._is_adam())
         if fused and self._cpu_offload:
             # tiered optimizer state: HBM-resident buckets on the fused GPU kernel (asynchronous), host-resident
@@ -378,8 +388,17 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
             for b in live:
                 b.working_shard().copy_(b.master.data.to(b.device))
                 b.master.grad = None
+        for b, lo, hi, saved in kept:                  # parameters without a gradient anywhere: as if never stepped
+            st = self.optim.state[b.master]
+            b.master.data[lo:hi].copy_(saved[0])
+            for key, v in st.items():
+                if torch.is_tensor(v) and v.shape == b.master.data.shape:
+                    # a state created by this very step (first step of the bucket) had no value before: zero
+                    v[lo:hi].copy_(saved[1][key]) if key in saved[1] else v[lo:hi].zero_()
+            b.working_shard()[lo:hi].copy_(b.master.data[lo:hi].to(b.device))
         for b in self.buckets:
             b.grad_shard = None
+            b.touched = [False] * len(b.params)
         # all-gather the updated working params (one collective per bucket, straight into param storage)
         for b in self.buckets:
             if b.ws > 1:
@@ -389,6 +408,28 @@ class LowLevelZeroOptimizer(OptimizerWrapper):
                     all_gather_fp8(list(b.flat.chunk(b.ws)), b.working_shard().clone(), group=b.pg)
                 else:
                     dist.all_gather_into_tensor(b.flat, b.working_shard().clone(), group=b.pg)
+
+    def _snapshot_untouched(self, live: List[_Bucket]):
+        """[(bucket, lo, hi, (master, exp_avg, exp_avg_sq) copies)] for the part of this rank's shard that belongs to
+        parameters no rank produced a gradient for in this step."""
+        out = []
+        for b in live:
+            flags = torch.tensor([int(t) for t in b.touched], dtype=torch.int32, device=b.device)
+            if b.ws > 1:
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=b.pg)
+            start = b.rank * b.shard_size
+            for idx, hit in enumerate(flags.tolist()):
+                if hit:
+                    continue
+                lo = max(b.offsets[idx], start) - start
+                hi = min(b.offsets[idx] + b.params[idx].numel(), start + b.shard_size) - start
+                if lo >= hi:
+                    continue
+                st = self.optim.state[b.master]
+                states = {k: v[lo:hi].clone() for k, v in st.items()
+                          if torch.is_tensor(v) and v.shape == b.master.data.shape}     # moments / momentum buffers
+                out.append((b, lo, hi, (b.master.data[lo:hi].clone(), states)))
+        return out
 
     def _bump_step(self, gid: int, group: dict) -> None:
         """Advance a param group's Adam step counter once per optimizer step (both state tiers share it)."""
