@@ -6,6 +6,10 @@ and a TorchFunctionMode records every in-place initialiser call (`normal_`, `uni
 on them; parallel layers built from a meta module inherit the op log (initialisers are shape-agnostic), and
 `materialize` allocates the *local shard* on the target device and replays the log under the layer's per-rank RNG.
 This lets a 70B model be constructed on 8 GPUs without ever holding a full weight anywhere.
+`materialize(module, reproduce_eager=True)` is the reproducibility path: a second, complete log (constructor defaults
+through `torch.nn.init.*`, tensors the model dropped again) is replayed for the whole model in recording order, which
+consumes the RNG exactly like eager construction - lazy and eager builds are then equal value for value
+(reference `tests/test_lazy/test_models.py`).
 """
 from __future__ import annotations
 
@@ -39,10 +43,42 @@ def copy_lazy_ops(src: Optional[torch.Tensor], dst: Optional[torch.Tensor]) -> N
 
 
 class _Recorder(TorchFunctionMode):
+    """Two logs per meta tensor.  `_lazy_ops`: the tensor-level in-place initialisers, replayed shard by shard.
+    `_lazy_full_log`: EVERY random-or-not initialiser that touched the tensor, `torch.nn.init.*` defaults of the module
+    constructors included, each with a global sequence number - replaying all tensors' full logs in that order consumes
+    the RNG exactly like eager construction did (`materialize(..., reproduce_eager=True)`)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.seq = 0
+        self.all_tensors: List[torch.Tensor] = []      # every logged meta tensor, also ones the model later drops
+
+    def _log_full(self, t: torch.Tensor, name: str, rest, kwargs) -> None:
+        log = getattr(t, "_lazy_full_log", None)
+        if log is None:
+            log = []
+            try:
+                t._lazy_full_log = log
+                t._lazy_all_tensors = self.all_tensors
+            except Exception:
+                return
+            self.all_tensors.append(t)
+        log.append((self.seq, name, rest, dict(kwargs)))
+        self.seq += 1
+
     def __torch_function__(self, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         out = func(*args, **kwargs)
         name = getattr(func, "__name__", "")
+        if getattr(func, "__module__", "") == "torch.nn.init" and hasattr(nn.init, name):
+            # the wrappers dispatch with the tensor as keyword (`tensor=`) or first positional argument
+            t = kwargs.get("tensor", args[0] if args else None)
+            if isinstance(t, torch.Tensor) and t.device.type == "meta":
+                kw = {k: v for k, v in kwargs.items() if k != "tensor"}
+                self._log_full(t, "init:" + name, tuple(args[1:]) if args else (), kw)
+        elif name in _INPLACE_INIT and args and isinstance(args[0], torch.Tensor) and args[0].device.type == "meta" \
+                and not any(isinstance(a, torch.Tensor) and a.device.type == "meta" for a in args[1:]):
+            self._log_full(args[0], name, tuple(args[1:]), kwargs)
         # NB: `torch.nn.init.*` wrappers dispatch as a whole (name e.g. "kaiming_uniform_") and are deliberately NOT
         # recorded: module constructors call them as throw-away defaults.  Only tensor-level in-place initialisers
         # (`w.normal_()`, `w.fill_()`, ...) are replayed; everything else gets `_default_fill` (or the model's own
@@ -111,12 +147,68 @@ class LazyInitContext:
                     getattr(real, fn)(*args, **kwargs)
 
     @staticmethod
-    def materialize(module: nn.Module, device: Optional[torch.device] = None, verbose: bool = False) -> nn.Module:
-        """Allocate every meta parameter/buffer of `module` on `device` and replay its initialiser log."""
+    def _materialize_like_eager(module: nn.Module, device) -> None:
+        """Allocate ALL meta parameters / buffers and replay their full logs in the global order they were recorded in:
+        under the seed the context was entered with this yields bit-identical values to eager construction (needs the
+        whole model on `device` at once - it is the debugging / reproducibility path, not the 70B one)."""
+        entries, seen = [], {}
+        for mod_name, mod in module.named_modules():
+            for store in (mod._parameters, mod._buffers):
+                for name, t in list(store.items()):
+                    if t is None or t.device.type != "meta":
+                        continue
+                    if id(t) not in seen:
+                        real = torch.zeros(t.shape, dtype=t.dtype, device=device)
+                        if isinstance(t, nn.Parameter):
+                            newp = nn.Parameter(real, requires_grad=t.requires_grad)
+                            for attr, val in vars(t).items():
+                                if attr not in ("_lazy_ops", "_lazy_full_log"):      # (`_lazy_all_tensors` is copied on purpose)
+                                    try:
+                                        setattr(newp, attr, val)
+                                    except Exception:
+                                        pass
+                            real = newp
+                        seen[id(t)] = real
+                        full = f"{mod_name}.{name}" if mod_name else name
+                        log = getattr(t, "_lazy_full_log", None)
+                        if log:
+                            entries += [(seq, real, fn, a, k) for seq, fn, a, k in log]
+                        elif isinstance(t, nn.Parameter):
+                            entries.append((float("inf"), real, "default:" + full, (), {}))
+                    store[name] = seen[id(t)]
+        # tensors that were initialised during construction but are no longer part of the model (a head's own weight
+        # replaced by the tied embedding, ...) consumed random numbers in the eager run: burn the same ones on scratch
+        registry = None
+        for real in seen.values():
+            registry = vars(real).pop("_lazy_all_tensors", registry) if isinstance(real, nn.Parameter) else registry
+        if registry is not None:
+            for t in registry:
+                if id(t) not in seen:
+                    scratch = torch.zeros(t.shape, dtype=t.dtype, device=device)
+                    entries += [(seq, scratch, fn, a, k) for seq, fn, a, k in t._lazy_full_log]
+        with torch.no_grad():
+            for _, real, fn, a, k in sorted(entries, key=lambda e: e[0]):
+                data = real.data
+                if fn.startswith("init:"):
+                    getattr(nn.init, fn[5:])(data, *a, **k)
+                elif fn.startswith("default:"):
+                    LazyInitContext._default_fill(fn[8:], data)
+                else:
+                    getattr(data, fn)(*a, **k)
+
+    @staticmethod
+    def materialize(module: nn.Module, device: Optional[torch.device] = None, verbose: bool = False,
+                    reproduce_eager: bool = False) -> nn.Module:
+        """Allocate every meta parameter/buffer of `module` on `device` and replay its initialiser log.
+        `reproduce_eager`: replay the full log of the whole model in recording order (same RNG stream as eager
+        construction under the same seed) instead of per-module, shard-friendly replay."""
         if device is None:
             from ..accelerator import get_accelerator
 
             device = get_accelerator().get_current_device()
+        if reproduce_eager:
+            LazyInitContext._materialize_like_eager(module, device)
+            return module
         memo = {}
         n = 0
         for mod_name, mod in module.named_modules():

@@ -71,9 +71,8 @@ class GroupedExperts(nn.Module):
         up_out = 2 * intermediate if cfg.glu else intermediate
         self.w_up = nn.Parameter(torch.empty(num_local_experts, up_out, H))      # gate|up fused
         self.w_down = nn.Parameter(torch.empty(num_local_experts, H, intermediate))
-        if self.w_up.device.type != "meta":
-            nn.init.normal_(self.w_up, std=cfg.initializer_range)
-            nn.init.normal_(self.w_down, std=cfg.initializer_range)
+        nn.init.normal_(self.w_up, std=cfg.initializer_range)        # (on meta: recorded by the lazy-init log only)
+        nn.init.normal_(self.w_down, std=cfg.initializer_range)
 
     def forward(self, x_sorted: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
         """x_sorted [N, H] rows grouped by local expert; counts [E_local] rows per expert."""

@@ -551,17 +551,16 @@ class TransformerLMHeadModel(nn.Module):
 
     def _init_weights(self, m: nn.Module) -> None:
         std = self.cfg.initializer_range
+        # (on the meta device these calls only land in the lazy-init log: `materialize(reproduce_eager=True)` replays them)
         if isinstance(m, nn.Linear):
-            if m.weight.device.type != "meta":
-                nn.init.normal_(m.weight, mean=0.0, std=std)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
+            nn.init.normal_(m.weight, mean=0.0, std=std)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
         elif isinstance(m, nn.Embedding):
-            if m.weight.device.type != "meta":
-                nn.init.normal_(m.weight, mean=0.0, std=std)
-                if m.padding_idx is not None:
-                    with torch.no_grad():
-                        m.weight[m.padding_idx].zero_()
+            nn.init.normal_(m.weight, mean=0.0, std=std)
+            if m.padding_idx is not None and m.weight.device.type != "meta":
+                with torch.no_grad():
+                    m.weight[m.padding_idx].zero_()
 
     def gradient_checkpointing_enable(self, *a, **k) -> None:
         self.model.gradient_checkpointing = True
