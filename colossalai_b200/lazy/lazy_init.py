@@ -228,7 +228,7 @@ class LazyInitContext:
                     LazyInitContext._replay(full, p, real)
                 newp = nn.Parameter(real, requires_grad=p.requires_grad)
                 for attr, val in vars(p).items():
-                    if attr in ("_lazy_ops",):
+                    if attr in ("_lazy_ops", "_lazy_full_log", "_lazy_all_tensors"):
                         continue
                     try:
                         setattr(newp, attr, val)
