@@ -21,7 +21,9 @@ def _torchrun(script, *args, nproc=2, port=29750, timeout=240):
 @pytest.mark.dist
 @pytest.mark.parametrize("args,port,nproc", [(("--family", "gpt2", "--tp", "2", "--steps", "2"), 29751, 2),
                                              (("--family", "mixtral", "--ep", "2", "--steps", "2"), 29752, 2),
-                                             (("--family", "llama", "--tp", "2", "--pp", "2", "--steps", "2"), 29754, 4)])
+                                             (("--family", "llama", "--tp", "2", "--pp", "2", "--steps", "2"), 29754, 4),
+                                             (("--family", "bloom", "--tp", "2", "--sp", "--steps", "2"), 29767, 2),
+                                             (("--family", "opt", "--pp", "2", "--steps", "2"), 29768, 2)])
 def test_hf_inplace_example(args, port, nproc):
     pytest.importorskip("transformers")
     out = _torchrun("examples/language/hf_inplace/finetune_hf.py", *args, port=port, nproc=nproc)
